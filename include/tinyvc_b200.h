@@ -1,0 +1,127 @@
+/* tinyvc_b200 -- C-ABI of the B200-native TinyVC inference path.
+ *
+ * The reference (uthree/tinyvc) is pure Python on torch and has no FFI of its own; the
+ * boundary it offers is its Python class surface.  Each entry point below
+ * replaces the arithmetic behind one of those Python callables -- cited as
+ * /root/reference-relative file:line -- and is what `tinyvc_b200/tinyvc/*.py` (the drop-in
+ * mirror of `module.tinyvc`) binds with ctypes.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C: opaque handles, raw pointers, sizes; no torch types.
+ *   - every tensor pointer is a DEVICE pointer to contiguous fp32 in the reference's
+ *     channels-first layout [B][C][T] unless stated otherwise; the caller owns all buffers.
+ *   - `workspace` is caller-provided scratch (device, 256-byte aligned) of at least
+ *     `*_workspace_bytes(...)` bytes; no entry point allocates on the hot path.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); calls are asynchronous.
+ *   - return value 0 = ok; otherwise tvc_last_error() gives a thread-local message.  No entry
+ *     point throws, and none falls back to the CPU.
+ *   - frame = 480 samples @ 24 kHz; an utterance has Lf frames and L = 480*Lf samples.
+ */
+#ifndef TINYVC_B200_H
+#define TINYVC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tvc_decoder* tvc_decoder_t;
+typedef struct tvc_encoder* tvc_encoder_t;
+typedef struct tvc_index* tvc_index_t;
+
+const char* tvc_last_error(void);
+const char* tvc_version(void);
+/* Runtime switches, e.g. ("conv_impl","fp32"|"mma").  Returns non-zero for unknown keys. */
+int tvc_set_option(const char* key, const char* value);
+
+/* ---- parameter contract: flat fp32 buffers in torch state_dict() order ------------------- */
+/* kind: 0 = Decoder (module/tinyvc/decoder.py:236-251), 1 = Encoder (encoder.py:100-106).     */
+int tvc_param_count(int kind);
+const char* tvc_param_name(int kind, int i);
+int64_t tvc_param_numel(int kind, int i);
+int64_t tvc_param_total(int kind);
+
+/* ---- Decoder (module/tinyvc/decoder.py) --------------------------------------------------- */
+/* `params`: host or device pointer to tvc_param_total(0) floats (replaces
+ * decoder.load_state_dict, infer.py:36-37).  Weights are repacked once into kernel layout.   */
+int tvc_decoder_create(const float* params, int64_t numel, tvc_decoder_t* out);
+int tvc_decoder_destroy(tvc_decoder_t h);
+size_t tvc_decoder_workspace_bytes(int B, int Lf);
+
+/* Decoder.infer(content, f0, energy)  (decoder.py:253-257).
+ *   content [B,768,Lf]  f0 [B,1,Lf]  energy [B,1,L]  rand01 [B,961,Lf]  ->  out [B,L]
+ * `rand01` is the uniform [0,1) draw that decoder.py:78 takes from torch's generator; passing
+ * it in makes the noise branch reproducible against the CPU reference.                       */
+int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, const float* energy,
+                      const float* rand01, float* out, int B, int Lf, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* SourceNet.forward (decoder.py:126-134): -> amps [B,15,Lf], kernel [B,961,Lf].              */
+int tvc_source_net(tvc_decoder_t h, const float* content, const float* f0, const float* energy,
+                   float* amps, float* kernel, int B, int Lf, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* Decoder.dsp (decoder.py:259-266; oscillate_harmonics :24-54, oscillate_noise :63-85):
+ *   f0 [B,1,Lf], amps [B,15,Lf], kernel [B,961,Lf], rand01 [B,961,Lf] -> source [B,16,L].     */
+int tvc_dsp(tvc_decoder_t h, const float* f0, const float* amps, const float* kernel,
+            const float* rand01, float* source, int B, int Lf, void* workspace, size_t workspace_bytes,
+            void* stream);
+
+/* FilterNet.forward (decoder.py:222-233): source [B,16,L] -> out [B,1,L].                    */
+int tvc_filter_net(tvc_decoder_t h, const float* content, const float* f0, const float* energy,
+                   const float* source, float* out, int B, int Lf, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* oscillate_harmonics phase only (decoder.py:39-50): theta [B,15,L]; parity probe.           */
+int tvc_harmonic_theta(const float* f0, float* theta, int B, int Lf, void* stream);
+
+/* ---- Encoder (module/tinyvc/encoder.py) --------------------------------------------------- */
+int tvc_encoder_create(const float* params, int64_t numel, tvc_encoder_t* out);
+int tvc_encoder_destroy(tvc_encoder_t h);
+size_t tvc_encoder_workspace_bytes(int B, int Lf);
+
+/* Encoder.forward / Encoder.infer (encoder.py:108-116).  spec [B,961,Lf] ->
+ *   z [B,768,Lf] (SSLFeatureEstimator, :89-97), logits [B,512,Lf] (PitchEstimator.forward,
+ *   :33-38) and f0 [B,1,Lf] (PitchEstimator.decode, :61-67).  Any output pointer may be NULL. */
+int tvc_encoder_forward(tvc_encoder_t h, const float* spec, float* z, float* logits, float* f0,
+                        int B, int Lf, void* workspace, size_t workspace_bytes, void* stream);
+
+/* PitchEstimator.decode (encoder.py:61-67) on caller-provided logits [B,512,Lf] (k = 4).     */
+int tvc_pitch_decode(const float* logits, float* f0, int B, int Lf, void* stream);
+
+/* ---- kNN content match (module/tinyvc/feature_retrieval.py:15-33) ------------------------- */
+/* metric: 0 = 'cos', 1 = 'IP', 2 = 'L2'.  `index` is the index.pt tensor [1,768,N]
+ * (extract_index.py:58), device pointer; a normalised copy and a row-major copy are built once. */
+int tvc_index_create(const float* index, int N, int metric, tvc_index_t* out);
+int tvc_index_destroy(tvc_index_t h);
+size_t tvc_match_workspace_bytes(tvc_index_t h, int B, int Lf);
+/* match_features(source, reference, k, alpha, metrics): source [B,768,Lf] -> out [B,768,Lf];
+ * idx_out (nullable) int32 [B,Lf,k] receives topk indices in descending-similarity order.    */
+int tvc_match_features(tvc_index_t h, const float* source, float* out, int32_t* idx_out, int B, int Lf,
+                       int k, float alpha, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- signal front end (module/utils) ------------------------------------------------------ */
+/* spectrogram (utils/spectrogram.py:8-15): wf [B,L] (L multiple of 480) -> spec [B,961,Lf].  */
+size_t tvc_spectrogram_workspace_bytes(int B, int L);
+int tvc_spectrogram(const float* wf, float* spec, int B, int L, void* workspace, size_t workspace_bytes,
+                    void* stream);
+/* estimate_energy (utils/energy_estimation.py:9-14): wf [B,L] -> energy [B,1,L].             */
+size_t tvc_energy_workspace_bytes(int B, int L);
+int tvc_estimate_energy(const float* wf, float* energy, int B, int L, void* workspace, size_t workspace_bytes,
+                        void* stream);
+/* shift_frequency (utils/pitch_shift.py:5-15): n elements, in place allowed.                 */
+int tvc_shift_frequency(const float* f0, float* out, int64_t n, float semitones, void* stream);
+
+/* ---- streaming (module/infer/stream.py:68-95) --------------------------------------------- */
+/* SOLA search + cross-fade for S independent streams.  y [S,y_len] is the converted window;
+ * sola_buf [S,cross] is read and replaced; out_block [S,block]; shift_out int32 [S].
+ * fade_in [cross] as built by StreamInfer.init_buffer (stream.py:61).                        */
+int tvc_sola(const float* y, int y_len, float* sola_buf, const float* fade_in, float* out_block,
+             int32_t* shift_out, int S, int block, int cross, int search, int delay, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TINYVC_B200_H */

@@ -1,0 +1,173 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REAL reference (/root/reference) on torch-CPU.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference imports `torchfcpe` and `pyworld` at module scope (module/utils/__init__.py:2 ->
+f0_estimation.py:6,9) although the inference path never calls them; both are absent here, so two
+empty stub modules are registered before the import.  Nothing from the reference
+is copied into this repo -- only the tensors it produces.
+
+Weights are `tinyvc_b200.weights.synth_state_dict(seed)` loaded into the reference's own
+Encoder()/Decoder(); inputs are `tinyvc_b200.synth.*`.  Fixtures record torch's version.
+"""
+import os
+import sys
+import types
+import warnings
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+
+sys.dont_write_bytecode = True
+for _n in ("torchfcpe", "pyworld"):
+    _m = types.ModuleType(_n)
+    _m.spawn_bundled_infer_model = lambda *a, **k: None
+    sys.modules[_n] = _m
+# The reference's `module` is a namespace package (no __init__.py), so the repo's own `module/`
+# shim would shadow it wherever it sits on sys.path: import the reference FIRST, with the repo
+# root not importable, and only then add the repo root for `tinyvc_b200`.
+sys.path = [p for p in sys.path if os.path.abspath(p or os.getcwd()) != REPO]
+sys.path.insert(0, REF)
+warnings.filterwarnings("ignore")
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from module.tinyvc import Encoder, Decoder, match_features  # noqa: E402  (reference)
+from module.infer import Generator, StreamInfer  # noqa: E402  (reference)
+from module.utils import spectrogram, estimate_energy, shift_frequency, autopad_waveform  # noqa: E402
+import module as _ref_module  # noqa: E402
+
+assert list(_ref_module.__path__)[0].startswith(REF), _ref_module.__path__
+sys.path.append(REPO)
+
+from tinyvc_b200.weights import synth_state_dict, state_checksum  # noqa: E402
+from tinyvc_b200 import synth  # noqa: E402
+
+WEIGHT_SEED = 7
+torch.set_num_threads(8)
+
+
+def build():
+    enc, dec = Encoder().eval(), Decoder().eval()
+    enc.load_state_dict(synth_state_dict(enc.state_dict(), WEIGHT_SEED))
+    dec.load_state_dict(synth_state_dict(dec.state_dict(), WEIGHT_SEED))
+    return enc, dec
+
+
+def meta(enc, dec):
+    return dict(torch_version=np.array(torch.__version__), weight_seed=np.array(WEIGHT_SEED),
+                enc_checksum=np.array(state_checksum(enc.state_dict())),
+                dec_checksum=np.array(state_checksum(dec.state_dict())))
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+@torch.inference_mode()
+def golden_decoder(enc, dec):
+    """Decoder.infer on B=2, Lf=18 (the bench workload's chunk shape) with a known noise draw."""
+    inp = synth.decoder_inputs(2, 18, seed=1235)
+    torch.manual_seed(4242)
+    rand01 = torch.rand(2, 961, 18)              # what decoder.py:78 will draw under this seed
+    amps, kern = dec.source_net(inp["content"], inp["f0"], inp["energy"])
+    torch.manual_seed(4242)
+    src = dec.dsp(inp["f0"], amps, kern)
+    torch.manual_seed(4242)
+    out = dec.infer(inp["content"], inp["f0"], inp["energy"])
+    np.savez(os.path.join(HERE, "decoder_b2_lf18.npz"), content=npy(inp["content"]), f0=npy(inp["f0"]),
+             energy=npy(inp["energy"]), rand01=npy(rand01), amps=npy(amps), kernel=npy(kern),
+             source_b0=npy(src[0]), out=npy(out), **meta(enc, dec))
+    print("decoder:", out.shape, float(out.pow(2).mean().sqrt()))
+
+
+@torch.inference_mode()
+def golden_pipeline(enc, dec):
+    """Generator.convert on ragged-length audio (autopad path) with a 300-vector index."""
+    gen = Generator(enc, dec)
+    inp = synth.pipeline_inputs(2, 4700, 300, seed=1236)
+    wf, index = inp["wf"], inp["index"]
+    wfp = autopad_waveform(wf)
+    spec = spectrogram(wfp)
+    energy = estimate_energy(wfp)
+    z, f0 = enc.infer(spec)
+    logits = enc.pitch_estimator(spec)
+    tgt = index.expand(2, -1, -1)                # bmm needs the batch expanded
+    zm = match_features(z, tgt)
+    sims = torch.bmm((z.transpose(1, 2) / (torch.norm(z.transpose(1, 2), dim=2, keepdim=True) + 1e-6)),
+                     (tgt.transpose(1, 2) / (torch.norm(tgt.transpose(1, 2), dim=2, keepdim=True) + 1e-6)).transpose(1, 2))
+    idx = torch.topk(sims, 4, dim=2).indices
+    f0s = shift_frequency(f0, 3.0)
+    torch.manual_seed(99)
+    rand01 = torch.rand(2, 961, spec.shape[2])
+    torch.manual_seed(99)
+    out = gen.convert(wf, tgt, 3.0)
+    tz, tf0 = gen.encode(wf)
+    np.savez(os.path.join(HERE, "pipeline_b2_t4700.npz"), wf=npy(wf), index=npy(index), spec=npy(spec),
+             energy=npy(energy), z=npy(z), f0=npy(f0), logits_b0=npy(logits[0]), zm=npy(zm), idx=npy(idx),
+             f0s=npy(f0s), rand01=npy(rand01), out=npy(out), enc_z=npy(tz), enc_f0=npy(tf0),
+             pitch_shift=np.array(3.0), **meta(enc, dec))
+    print("pipeline:", out.shape, float(out.pow(2).mean().sqrt()), "f0 range", float(f0.min()), float(f0.max()))
+
+
+@torch.inference_mode()
+def golden_match(enc, dec):
+    """match_features: all three metrics and an alpha blend."""
+    g = torch.Generator().manual_seed(55)
+    src = torch.randn(1, 768, 23, generator=g)
+    ref = torch.randn(1, 768, 130, generator=g)
+    out = {}
+    for m in ("cos", "IP", "L2"):
+        out["out_" + m] = npy(match_features(src, ref, k=4, alpha=0.0, metrics=m))
+    out["out_cos_a03"] = npy(match_features(src, ref, k=4, alpha=0.3, metrics="cos"))
+    out["out_cos_k2"] = npy(match_features(src, ref, k=2, alpha=0.0, metrics="cos"))
+    np.savez(os.path.join(HERE, "match_features.npz"), source=npy(src), reference=npy(ref), **out,
+             torch_version=np.array(torch.__version__))
+    print("match: ok")
+
+
+@torch.inference_mode()
+def golden_stream(enc, dec):
+    """StreamInfer.audio_callback over 4 ticks (SOLA cross-fade) and 2 with the phase vocoder."""
+    gen = Generator(enc, dec)
+    g = torch.Generator().manual_seed(77)
+    index = torch.randn(1, 768, 64, generator=g)
+    blocks = 0.1 * torch.randn(4, 1920, generator=g)
+    res = {}
+    for tag, pv in (("sola", False), ("pv", True)):
+        si = StreamInfer(gen, target=index, pitch_shift=0.0, use_phase_vocoder=pv)
+        si.init_buffer()
+        torch.manual_seed(777)
+        outs = []
+        for i in range(4 if not pv else 2):
+            outs.append(si.audio_callback(blocks[i].clone()).clone())
+        res["out_" + tag] = npy(torch.stack(outs))
+    np.savez(os.path.join(HERE, "stream_4ticks.npz"), index=npy(index), blocks=npy(blocks),
+             rand_seed=np.array(777), **res, **meta(enc, dec))
+    print("stream:", res["out_sola"].shape, res["out_pv"].shape)
+
+
+def golden_keys(enc, dec):
+    """state_dict key order and shapes of the reference's Encoder / Decoder."""
+    import json
+    doc = {"encoder": [[k, list(v.shape)] for k, v in enc.state_dict().items()],
+           "decoder": [[k, list(v.shape)] for k, v in dec.state_dict().items()]}
+    with open(os.path.join(HERE, "state_keys.json"), "w") as f:
+        json.dump(doc, f, indent=0)
+    print("keys:", len(doc["encoder"]), len(doc["decoder"]))
+
+
+if __name__ == "__main__":
+    enc, dec = build()
+    golden_keys(enc, dec)
+    golden_decoder(enc, dec)
+    golden_pipeline(enc, dec)
+    golden_match(enc, dec)
+    golden_stream(enc, dec)
+    tot = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith(".npz"))
+    print("fixtures total bytes:", tot)

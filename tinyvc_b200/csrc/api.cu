@@ -1,0 +1,373 @@
+// extern "C" entry points declared in include/tinyvc_b200.h.
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "../../include/tinyvc_b200.h"
+#include "nets.cuh"
+
+namespace tvc {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static std::once_flag g_init_once;
+static int g_init_status = 0;
+static int global_init() {
+    std::call_once(g_init_once, [] { g_init_status = conv1d_init(); });
+    return g_init_status;
+}
+
+static ParamTable& table_of(int kind) {
+    static ParamTable dec, enc;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        build_decoder_table(dec);
+        build_encoder_table(enc);
+    });
+    return kind == 0 ? dec : enc;
+}
+
+struct IndexModel {
+    float* index_w = nullptr;    // [C][NP] (normalised for cos)
+    float* index_nc = nullptr;   // [N][C] raw
+    float* bias = nullptr;       // [N]
+    int N = 0, NP = 0, metric = 0;
+    ConvW as_conv;
+    ~IndexModel() {
+        if (index_w) cudaFree(index_w);
+        if (index_nc) cudaFree(index_nc);
+        if (bias) cudaFree(bias);
+    }
+};
+
+}  // namespace tvc
+
+using namespace tvc;
+
+struct tvc_decoder { DecoderModel m; };
+struct tvc_encoder { EncoderModel m; };
+struct tvc_index { IndexModel m; };
+
+#define API_BEGIN try {
+#define API_END                                              \
+    }                                                        \
+    catch (const std::exception& e) {                        \
+        tvc::set_error("exception: %s", e.what());           \
+        return 3;                                            \
+    }                                                        \
+    catch (...) {                                            \
+        tvc::set_error("unknown exception");                 \
+        return 3;                                            \
+    }
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* tvc_last_error(void) { return g_err; }
+const char* tvc_version(void) { return "tinyvc_b200 0.1 (sm_100a)"; }
+
+int tvc_set_option(const char* key, const char* value) {
+    if (!key || !value) return 2;
+    if (!strcmp(key, "conv_impl")) {
+        if (!strcmp(value, "fp32")) { g_conv_impl = CONV_IMPL_FP32; return 0; }
+        if (!strcmp(value, "mma")) { g_conv_impl = CONV_IMPL_MMA; return 0; }
+        set_error("conv_impl: unknown value '%s'", value);
+        return 2;
+    }
+    set_error("unknown option '%s'", key);
+    return 2;
+}
+
+int tvc_param_count(int kind) { return (kind == 0 || kind == 1) ? (int)table_of(kind).specs.size() : -1; }
+const char* tvc_param_name(int kind, int i) {
+    if (kind != 0 && kind != 1) return nullptr;
+    ParamTable& t = table_of(kind);
+    return (i >= 0 && i < (int)t.specs.size()) ? t.specs[i].name.c_str() : nullptr;
+}
+int64_t tvc_param_numel(int kind, int i) {
+    if (kind != 0 && kind != 1) return -1;
+    ParamTable& t = table_of(kind);
+    return (i >= 0 && i < (int)t.specs.size()) ? t.specs[i].numel : -1;
+}
+int64_t tvc_param_total(int kind) { return (kind == 0 || kind == 1) ? table_of(kind).total : -1; }
+
+// ---------------------------------------------------------------------------------------------- decoder
+int tvc_decoder_create(const float* params, int64_t numel, tvc_decoder_t* out) {
+    API_BEGIN
+    TVC_REQUIRE(out, "tvc_decoder_create: null out pointer");
+    TVC_TRY(global_init());
+    tvc_decoder* h = new (std::nothrow) tvc_decoder();
+    TVC_REQUIRE(h, "tvc_decoder_create: out of host memory");
+    const int r = h->m.init(params, numel);
+    if (r) { delete h; return r; }
+    *out = h;
+    return 0;
+    API_END
+}
+int tvc_decoder_destroy(tvc_decoder_t h) { delete h; return 0; }
+
+static void shapes_ok_msg(int B, int Lf) { set_error("invalid shape B=%d Lf=%d", B, Lf); }
+#define CHECK_SHAPES() do { if (B <= 0 || Lf <= 0 || (long long)B * Lf * 480 > (1LL << 31) - 1) { shapes_ok_msg(B, Lf); return 2; } } while (0)
+
+size_t tvc_decoder_workspace_bytes(int B, int Lf) {
+    if (B <= 0 || Lf <= 0) return 0;
+    static DecoderModel shape_only;   // dry runs never touch weights
+    Arena A(nullptr, 0, true);
+    if (shape_only.infer(A, 0, nullptr, nullptr, nullptr, nullptr, nullptr, B, Lf)) return 0;
+    return A.peak + 256;
+}
+
+int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, const float* energy,
+                      const float* rand01, float* out, int B, int Lf, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+    API_BEGIN
+    TVC_REQUIRE(h && content && f0 && energy && rand01 && out && workspace, "tvc_decoder_infer: null argument");
+    CHECK_SHAPES();
+    Arena A(workspace, workspace_bytes, false);
+    return h->m.infer(A, (cudaStream_t)stream, content, f0, energy, rand01, out, B, Lf);
+    API_END
+}
+
+int tvc_source_net(tvc_decoder_t h, const float* content, const float* f0, const float* energy, float* amps,
+                   float* kernel, int B, int Lf, void* workspace, size_t workspace_bytes, void* stream) {
+    API_BEGIN
+    TVC_REQUIRE(h && content && f0 && energy && amps && kernel && workspace, "tvc_source_net: null argument");
+    CHECK_SHAPES();
+    Arena A(workspace, workspace_bytes, false);
+    cudaStream_t s = (cudaStream_t)stream;
+    float* e_fr = A.f32((int64_t)B * Lf);
+    float* lf0 = A.f32((int64_t)B * Lf);
+    TVC_REQUIRE(!A.overflow, "workspace too small");
+    TVC_TRY(frame_prep(energy, f0, e_fr, lf0, B, Lf, s));
+    return h->m.source_net(A, s, content, e_fr, lf0, amps, kernel, B, Lf);
+    API_END
+}
+
+int tvc_dsp(tvc_decoder_t h, const float* f0, const float* amps, const float* kernel, const float* rand01,
+            float* source, int B, int Lf, void* workspace, size_t workspace_bytes, void* stream) {
+    API_BEGIN
+    TVC_REQUIRE(h && f0 && amps && kernel && rand01 && source && workspace, "tvc_dsp: null argument");
+    CHECK_SHAPES();
+    Arena A(workspace, workspace_bytes, false);
+    return h->m.dsp(A, (cudaStream_t)stream, f0, amps, kernel, rand01, source, 16LL * Lf * kFrame, B, Lf);
+    API_END
+}
+
+int tvc_filter_net(tvc_decoder_t h, const float* content, const float* f0, const float* energy, const float* source,
+                   float* out, int B, int Lf, void* workspace, size_t workspace_bytes, void* stream) {
+    API_BEGIN
+    TVC_REQUIRE(h && content && f0 && energy && source && out && workspace, "tvc_filter_net: null argument");
+    CHECK_SHAPES();
+    Arena A(workspace, workspace_bytes, false);
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long L = (long long)Lf * kFrame;
+    float* e_fr = A.f32((int64_t)B * Lf);
+    float* lf0 = A.f32((int64_t)B * Lf);
+    float* src17 = A.f32((int64_t)B * 17 * L);
+    TVC_REQUIRE(!A.overflow, "workspace too small");
+    TVC_TRY(frame_prep(energy, f0, e_fr, lf0, B, Lf, s));
+    TVC_CUDA(cudaMemcpy2DAsync(src17, sizeof(float) * 17 * L, source, sizeof(float) * 16 * L, sizeof(float) * 16 * L, B,
+                               cudaMemcpyDeviceToDevice, s));
+    TVC_CUDA(cudaMemcpy2DAsync(src17 + 16 * L, sizeof(float) * 17 * L, energy, sizeof(float) * L, sizeof(float) * L, B,
+                               cudaMemcpyDeviceToDevice, s));
+    return h->m.filter_net(A, s, content, lf0, src17, out, B, Lf);
+    API_END
+}
+
+int tvc_harmonic_theta(const float* f0, float* theta, int B, int Lf, void* stream) {
+    API_BEGIN
+    TVC_REQUIRE(f0 && theta, "tvc_harmonic_theta: null argument");
+    CHECK_SHAPES();
+    return harmonic_theta(f0, theta, B, Lf, (cudaStream_t)stream);
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------- encoder
+int tvc_encoder_create(const float* params, int64_t numel, tvc_encoder_t* out) {
+    API_BEGIN
+    TVC_REQUIRE(out, "tvc_encoder_create: null out pointer");
+    TVC_TRY(global_init());
+    tvc_encoder* h = new (std::nothrow) tvc_encoder();
+    TVC_REQUIRE(h, "tvc_encoder_create: out of host memory");
+    const int r = h->m.init(params, numel);
+    if (r) { delete h; return r; }
+    *out = h;
+    return 0;
+    API_END
+}
+int tvc_encoder_destroy(tvc_encoder_t h) { delete h; return 0; }
+
+size_t tvc_encoder_workspace_bytes(int B, int Lf) {
+    if (B <= 0 || Lf <= 0) return 0;
+    // x, t1 [B,384,Lf]; t2 [B,768,Lf]; sc [B,768]; logits [B,512,Lf]  (+ alignment slack)
+    const size_t f = sizeof(float);
+    return (size_t)B * Lf * f * (384 + 384 + 768 + 512) + (size_t)B * 768 * f + 16 * 256;
+}
+
+int tvc_encoder_forward(tvc_encoder_t h, const float* spec, float* z, float* logits, float* f0, int B, int Lf,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    API_BEGIN
+    TVC_REQUIRE(h && spec && workspace, "tvc_encoder_forward: null argument");
+    CHECK_SHAPES();
+    Arena A(workspace, workspace_bytes, false);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (z) TVC_TRY(h->m.run_stack(A, s, h->m.ssl, spec, z, B, Lf));
+    if (logits || f0) {
+        float* lg = logits ? logits : A.f32((int64_t)B * 512 * Lf);
+        TVC_REQUIRE(!A.overflow, "workspace too small");
+        TVC_TRY(h->m.run_stack(A, s, h->m.pitch, spec, lg, B, Lf));
+        if (f0) TVC_TRY(pitch_decode(lg, f0, B, 512, Lf, s));
+    }
+    return 0;
+    API_END
+}
+
+int tvc_pitch_decode(const float* logits, float* f0, int B, int Lf, void* stream) {
+    API_BEGIN
+    TVC_REQUIRE(logits && f0, "tvc_pitch_decode: null argument");
+    CHECK_SHAPES();
+    return pitch_decode(logits, f0, B, 512, Lf, (cudaStream_t)stream);
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------- kNN
+int tvc_index_create(const float* index, int N, int metric, tvc_index_t* out) {
+    API_BEGIN
+    TVC_REQUIRE(index && out, "tvc_index_create: null argument");
+    TVC_REQUIRE(N >= 1, "tvc_index_create: empty index");
+    TVC_REQUIRE(metric >= 0 && metric <= 2, "tvc_index_create: unknown metric %d (0 cos, 1 IP, 2 L2)", metric);
+    TVC_TRY(global_init());
+    tvc_index* h = new (std::nothrow) tvc_index();
+    TVC_REQUIRE(h, "tvc_index_create: out of host memory");
+    IndexModel& m = h->m;
+    m.N = N; m.NP = (int)align_up(N, 4); m.metric = metric;
+    int r = 0;
+    do {
+        if (cudaMalloc(&m.index_w, sizeof(float) * (size_t)kContent * m.NP) != cudaSuccess ||
+            cudaMalloc(&m.index_nc, sizeof(float) * (size_t)kContent * N) != cudaSuccess ||
+            cudaMalloc(&m.bias, sizeof(float) * (size_t)m.NP) != cudaSuccess) {
+            set_error("tvc_index_create: cudaMalloc failed for N=%d", N);
+            r = 1;
+            break;
+        }
+        if (cudaMemset(m.index_w, 0, sizeof(float) * (size_t)kContent * m.NP) != cudaSuccess) { r = 1; break; }
+        r = knn_prepare(index, m.index_w, m.index_nc, m.bias, kContent, N, m.NP, metric, 0);
+        if (!r && cudaStreamSynchronize(0) != cudaSuccess) { set_error("tvc_index_create: prepare kernel failed"); r = 1; }
+    } while (0);
+    if (r) { delete h; return r; }
+    m.as_conv.w = m.index_w; m.as_conv.b = m.bias; m.as_conv.Cin = kContent; m.as_conv.Cout = N; m.as_conv.CoutP = m.NP;
+    m.as_conv.K = 1;
+    *out = h;
+    return 0;
+    API_END
+}
+int tvc_index_destroy(tvc_index_t h) { delete h; return 0; }
+
+static int match_chunk_utts(int N, int Lf) {
+    const long long budget = 512LL << 20;   // similarity scratch per pass
+    long long per_utt = (long long)N * Lf * (long long)sizeof(float);
+    long long c = budget / (per_utt > 0 ? per_utt : 1);
+    return (int)(c < 1 ? 1 : c);
+}
+
+size_t tvc_match_workspace_bytes(tvc_index_t h, int B, int Lf) {
+    if (!h || B <= 0 || Lf <= 0) return 0;
+    const int N = h->m.N;
+    const int bc = std::min(B, match_chunk_utts(N, Lf));
+    const size_t f = sizeof(float);
+    size_t tot = 0;
+    tot += align_up((size_t)B * kContent * Lf * f, 256);                    // normalised queries
+    tot += align_up((size_t)bc * N * Lf * f, 256);                          // sims chunk
+    tot += 2 * align_up((size_t)16 * bc * Lf * 8 * f, 256);                 // partial top-k (values, indices)
+    tot += align_up((size_t)B * Lf * 8 * sizeof(int), 256);                 // indices
+    return tot + 1024;
+}
+
+int tvc_match_features(tvc_index_t h, const float* source, float* out, int32_t* idx_out, int B, int Lf, int k,
+                       float alpha, void* workspace, size_t workspace_bytes, void* stream) {
+    API_BEGIN
+    TVC_REQUIRE(h && source && out && workspace, "tvc_match_features: null argument");
+    CHECK_SHAPES();
+    const IndexModel& m = h->m;
+    TVC_REQUIRE(k >= 1 && k <= 8, "match_features: k=%d unsupported (1..8)", k);
+    TVC_REQUIRE(k <= m.N, "match_features: k=%d exceeds the index size %d", k, m.N);
+    cudaStream_t s = (cudaStream_t)stream;
+    Arena A(workspace, workspace_bytes, false);
+    const int bc = std::min(B, match_chunk_utts(m.N, Lf));
+    float* qn = A.f32((int64_t)B * kContent * Lf);
+    float* sims = A.f32((int64_t)bc * m.N * Lf);
+    float* pv = A.f32((int64_t)16 * bc * Lf * 8);
+    int* pi = A.i32((int64_t)16 * bc * Lf * 8);
+    int* idx = idx_out ? idx_out : A.i32((int64_t)B * Lf * k);
+    TVC_REQUIRE(!A.overflow, "workspace too small: need at least %zu bytes, got %zu", A.peak, A.cap);
+    TVC_TRY(knn_normalize_queries(source, qn, B, kContent, Lf, m.metric, s));
+    for (int b0 = 0; b0 < B; b0 += bc) {
+        const int nb = std::min(bc, B - b0);
+        TVC_TRY(conv_run(A, s, m.as_conv, qn + (long long)b0 * kContent * Lf, (long long)kContent * Lf, sims,
+                         (long long)m.N * Lf, nb, Lf, 1, PRE_NONE, EPI_NONE));
+        TVC_TRY(knn_topk(sims, pv, pi, idx + (long long)b0 * Lf * k, nb, Lf, m.N, k, s));
+    }
+    return knn_gather_mean(source, m.index_nc, idx, out, B, kContent, Lf, k, alpha, s);
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------- front end
+size_t tvc_spectrogram_workspace_bytes(int B, int L) {
+    if (B <= 0 || L <= 0 || L % kFrame) return 0;
+    Arena A(nullptr, 0, true);
+    if (spectrogram_run(A, 0, nullptr, nullptr, B, L)) return 0;
+    return A.peak + 256;
+}
+int tvc_spectrogram(const float* wf, float* spec, int B, int L, void* workspace, size_t workspace_bytes, void* stream) {
+    API_BEGIN
+    TVC_REQUIRE(wf && spec && workspace, "tvc_spectrogram: null argument");
+    TVC_REQUIRE(B > 0 && L > 0, "tvc_spectrogram: invalid shape B=%d L=%d", B, L);
+    TVC_TRY(global_init());
+    Arena A(workspace, workspace_bytes, false);
+    return spectrogram_run(A, (cudaStream_t)stream, wf, spec, B, L);
+    API_END
+}
+
+size_t tvc_energy_workspace_bytes(int B, int L) {
+    if (B <= 0 || L < 64) return 0;
+    return align_up((size_t)B * energy_pooled_len(L) * sizeof(float), 256) + 256;
+}
+int tvc_estimate_energy(const float* wf, float* energy, int B, int L, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+    API_BEGIN
+    TVC_REQUIRE(wf && energy && workspace, "tvc_estimate_energy: null argument");
+    TVC_REQUIRE(B > 0 && L > 0, "tvc_estimate_energy: invalid shape B=%d L=%d", B, L);
+    Arena A(workspace, workspace_bytes, false);
+    float* pooled = A.f32((int64_t)B * energy_pooled_len(L));
+    TVC_REQUIRE(!A.overflow, "workspace too small: need at least %zu bytes, got %zu", A.peak, A.cap);
+    return energy_estimate(wf, energy, pooled, B, L, (cudaStream_t)stream);
+    API_END
+}
+
+int tvc_shift_frequency(const float* f0, float* out, int64_t n, float semitones, void* stream) {
+    API_BEGIN
+    TVC_REQUIRE(f0 && out, "tvc_shift_frequency: null argument");
+    return shift_frequency(f0, out, n, semitones, (cudaStream_t)stream);
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------- streaming
+int tvc_sola(const float* y, int y_len, float* sola_buf, const float* fade_in, float* out_block, int32_t* shift_out,
+             int S, int block, int cross, int search, int delay, void* stream) {
+    API_BEGIN
+    TVC_REQUIRE(y && sola_buf && fade_in && out_block && shift_out, "tvc_sola: null argument");
+    TVC_REQUIRE(S > 0 && block > 0 && cross > 0 && search >= 0 && delay >= 0, "tvc_sola: invalid sizes");
+    return sola_run(y, y_len, sola_buf, fade_in, out_block, shift_out, S, block, cross, search, delay, (cudaStream_t)stream);
+    API_END
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

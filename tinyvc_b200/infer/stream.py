@@ -1,0 +1,92 @@
+"""Drop-in for `module.infer.stream.StreamInfer` (reference module/infer/stream.py:30-95), plus a
+batched variant for many concurrent streams on one GPU.
+
+Per tick the reference rolls a 13 440-sample window, runs the whole `Generator.convert` on it,
+finds the SOLA offset by normalised cross-correlation against the previous tail, cross-fades and
+emits `block_size` samples (stream.py:68-95).  Here the window stays on the device, convert runs on
+the CUDA path, and the SOLA search + cross-fade + tail update is one kernel (`tvc_sola`) with no
+`.item()` host round trip.  Results depend on the 13 440-sample window exactly as in the reference
+(GRN normalises over the window).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from .. import _lib
+from .generator import Generator
+
+
+class BatchedStreamInfer:
+    """S independent streams sharing one target index; state tensors are [S, ...] on `device`."""
+
+    def __init__(self, generator: Generator, num_streams: int, target=None, pitch_shift: float = 0.0,
+                 device=torch.device("cuda"), block_size: int = 1920, extra_size: int = 0,
+                 use_phase_vocoder: bool = False, f0_estimation: str = "default"):
+        if use_phase_vocoder:
+            raise NotImplementedError("phase-vocoder cross-fade (reference stream.py:9-26,83-89) is not built yet; "
+                                      "use the default SOLA cross-fade")
+        self.generator = generator
+        self.num_streams = int(num_streams)
+        self.target = target
+        self.pitch_shift = pitch_shift
+        self.device = torch.device(device)
+        self.block_size = block_size
+        self.extra_size = extra_size
+        self.sola_search_size = 1920
+        self.last_dilay_size = 3840          # (sic) attribute name kept from the reference, stream.py:48
+        self.crossfade_size = 1920
+        self.use_phase_vocoder = use_phase_vocoder
+        self.f0_estimation = f0_estimation
+        self.input_size = max(self.block_size + self.crossfade_size + self.sola_search_size + 2 * self.last_dilay_size,
+                              self.block_size + self.extra_size)
+        self.last_shift: Optional[torch.Tensor] = None
+
+    def init_buffer(self) -> None:
+        if self.device.type != "cuda":
+            raise RuntimeError(f"StreamInfer: device {self.device} is not CUDA; there is no CPU path")
+        cf = self.crossfade_size
+        # stream.py:61-62 (built once on the host side of the device; not on the per-tick path)
+        self.fade_in_window = (torch.sin(math.pi * torch.arange(0, 1, 1 / cf, device=self.device) / 2) ** 2).contiguous()
+        self.fade_out_window = 1 - self.fade_in_window
+        self.input_wav = torch.zeros(self.num_streams, self.input_size, device=self.device)
+        self.sola_buffer = torch.zeros(self.num_streams, cf, device=self.device)
+        self._shift = torch.zeros(self.num_streams, dtype=torch.int32, device=self.device)
+
+    @torch.inference_mode()
+    def audio_callback(self, blocks: torch.Tensor, *, rand01: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """blocks [S, block_size] -> converted [S, block_size]."""
+        S, bs = self.num_streams, self.block_size
+        blocks = _lib.dev_f32(blocks, "block")
+        if tuple(blocks.shape) != (S, bs):
+            raise RuntimeError(f"audio_callback: expected {(S, bs)}, got {tuple(blocks.shape)}")
+        # stream.py:69-70: slide the window left by one block and append the new samples
+        nxt = torch.empty_like(self.input_wav)
+        nxt[:, : self.input_size - bs] = self.input_wav[:, bs:]
+        nxt[:, self.input_size - bs:] = blocks
+        self.input_wav = nxt
+        y = self.generator.convert(self.input_wav, self.target, self.pitch_shift, rand01=rand01).contiguous()
+        out = torch.empty(S, bs, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().tvc_sola(y.data_ptr(), y.shape[1], self.sola_buffer.data_ptr(),
+                                           self.fade_in_window.data_ptr(), out.data_ptr(), self._shift.data_ptr(), S, bs,
+                                           self.crossfade_size, self.sola_search_size, self.last_dilay_size,
+                                           _lib.stream_ptr(self.device)), "tvc_sola")
+        self.last_shift = self._shift
+        return out
+
+
+class StreamInfer(BatchedStreamInfer):
+    """Single-stream API of the reference: audio_callback(block [block_size]) -> [block_size]."""
+
+    def __init__(self, generator: Generator, target=None, pitch_shift: float = 0.0, device=torch.device("cpu"),
+                 block_size: int = 1920, extra_size: int = 0, use_phase_vocoder: bool = False,
+                 f0_estimation: str = "default"):
+        super().__init__(generator, 1, target, pitch_shift, device, block_size, extra_size, use_phase_vocoder,
+                         f0_estimation)
+
+    @torch.inference_mode()
+    def audio_callback(self, block: torch.Tensor, *, rand01: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return super().audio_callback(block.reshape(1, -1), rand01=rand01)[0]

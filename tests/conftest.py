@@ -66,3 +66,25 @@ def rmse(a: torch.Tensor, b: torch.Tensor) -> float:
 
 def max_abs(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a.double().cpu() - b.double().cpu()).abs().max())
+
+
+class _Report:
+    """Collects measured parity numbers; dumped to gpurun_out/parity_report.json at session end."""
+
+    def __init__(self):
+        self.rows = {}
+
+    def add(self, key: str, **vals):
+        self.rows[key] = {k: (float(v) if isinstance(v, (int, float)) else v) for k, v in vals.items()}
+        print(f"[parity] {key}: " + ", ".join(f"{k}={v:.3e}" if isinstance(v, float) else f"{k}={v}" for k, v in vals.items()))
+
+
+@pytest.fixture(scope="session")
+def report():
+    r = _Report()
+    yield r
+    if r.rows:
+        out = os.path.join(REPO, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_report.json"), "w") as f:
+            json.dump(r.rows, f, indent=1, sort_keys=True)

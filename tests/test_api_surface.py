@@ -1,0 +1,93 @@
+"""Drop-in boundary checks that need no GPU: the C-ABI library loads and exports every symbol the
+header declares, the Python mirror has the reference's state_dict keys / signatures, and there is no
+silent CPU fallback."""
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import REPO
+
+
+def _header_symbols():
+    txt = open(os.path.join(REPO, "include", "tinyvc_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(tvc_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from tinyvc_b200 import _lib
+    syms = _header_symbols()
+    assert len(syms) >= 25
+    L = _lib.lib()
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/tinyvc_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == syms, "ctypes signature table out of sync with the header"
+    assert b"sm_100a" in L.tvc_version()
+
+
+def test_state_dict_contract(state_keys):
+    from tinyvc_b200 import _lib
+    from tinyvc_b200.tinyvc import Decoder, Encoder
+    for kind, cls, kid in (("encoder", Encoder, 1), ("decoder", Decoder, 0)):
+        sd = cls().state_dict()
+        assert [[k, list(v.shape)] for k, v in sd.items()] == state_keys[kind], f"{kind} keys differ from the reference"
+        assert tuple((k, v.numel()) for k, v in sd.items()) == _lib.param_names(kid)
+        assert sum(v.numel() for v in sd.values()) == _lib.lib().tvc_param_total(kid)
+
+
+def test_reference_import_paths_and_signatures():
+    from module.tinyvc import Encoder, Decoder, match_features
+    from module.infer import Generator, StreamInfer
+    from module.utils import spectrogram, shift_frequency, estimate_energy, autopad_waveform
+    assert list(inspect.signature(Decoder.__init__).parameters)[1:] == ["sample_rate", "n_fft", "frame_size", "num_harmonics"]
+    assert list(inspect.signature(Encoder.__init__).parameters)[1:] == ["n_fft", "hop_size"]
+    assert list(inspect.signature(match_features).parameters)[:5] == ["source", "reference", "k", "alpha", "metrics"]
+    assert list(inspect.signature(Generator.convert).parameters)[1:6] == ["wf", "tgt", "pitch_shift", "f0_estimation", "device"]
+    assert list(inspect.signature(StreamInfer.__init__).parameters)[1:] == [
+        "generator", "target", "pitch_shift", "device", "block_size", "extra_size", "use_phase_vocoder", "f0_estimation"]
+    d = Decoder()
+    for attr in ("source_net", "filter_net", "frame_size", "sample_rate", "num_harmonics", "n_fft", "dsp", "infer"):
+        assert hasattr(d, attr)
+    e = Encoder()
+    for attr in ("n_fft", "hop_size", "ssl_feature_estimator", "pitch_estimator"):
+        assert hasattr(e, attr)
+    for attr in ("freq2id", "id2freq", "decode", "num_classes"):
+        assert hasattr(e.pitch_estimator, attr)
+    assert autopad_waveform(torch.zeros(2, 700)).shape == (2, 960)
+    assert autopad_waveform(torch.zeros(2, 960)).shape == (2, 960)
+
+
+def test_no_cpu_fallback():
+    from tinyvc_b200.tinyvc import Decoder, match_features
+    from tinyvc_b200.utils import spectrogram
+    from tinyvc_b200 import synth
+    inp = synth.decoder_inputs(1, 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Decoder().infer(inp["content"], inp["f0"], inp["energy"])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        spectrogram(torch.zeros(1, 4800))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        match_features(torch.zeros(1, 768, 4), torch.zeros(1, 768, 16))
+
+
+def test_workspace_queries_are_monotone():
+    from tinyvc_b200 import _lib
+    L = _lib.lib()
+    a, b, c = (L.tvc_decoder_workspace_bytes(*s) for s in ((1, 18), (4, 18), (4, 36)))
+    assert 0 < a < b < c
+    assert L.tvc_decoder_workspace_bytes(0, 5) == 0
+    assert L.tvc_encoder_workspace_bytes(2, 10) > 0
+    assert L.tvc_spectrogram_workspace_bytes(2, 4800) > 0 and L.tvc_spectrogram_workspace_bytes(2, 4801) == 0
+
+
+def test_product_path_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under tinyvc_b200/ or module/ may reference it."""
+    for root in ("tinyvc_b200", "module"):
+        for dp, _, files in os.walk(os.path.join(REPO, root)):
+            for f in files:
+                if f.endswith(".py"):
+                    src = open(os.path.join(dp, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dp, f)

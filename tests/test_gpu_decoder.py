@@ -1,0 +1,149 @@
+"""Decoder parity on the GPU: every stage of Decoder.infer through the C-ABI vs the CPU oracle.
+
+Bar (BASELINE.json north_star): waveform fp32 RMSE < 1e-4 against the reference's CPU path on the
+same inputs (same weights, same noise draw); the oscillator phase bit-equal."""
+import pytest
+import torch
+
+from conftest import load_golden, t, rmse, max_abs
+from oracle import tinyvc_oracle as O
+from tinyvc_b200 import synth
+
+pytestmark = pytest.mark.gpu
+RMSE_BAR = 1e-4
+
+
+def _cuda(*xs):
+    return [x.to("cuda") for x in xs]
+
+
+@pytest.mark.parametrize("lf,seed", [(18, 0), (57, 1), (200, 2)])
+def test_oscillator_phase_bit_exact(lf, seed, report):
+    from tinyvc_b200.tinyvc.decoder import harmonic_theta
+    f0 = synth.synth_f0(2, lf, torch.Generator().manual_seed(seed))
+    _, theta_ref = O.oscillate_harmonics(f0, return_theta=True)
+    theta = harmonic_theta(f0.cuda()).cpu()
+    nbad = int((theta != theta_ref).sum())
+    report.add(f"theta_lf{lf}", mismatches=nbad, max_abs=max_abs(theta, theta_ref))
+    assert nbad == 0, f"{nbad} of {theta.numel()} phase samples differ from the CPU reference"
+
+
+def test_oscillator_phase_high_pitch_bit_exact(report):
+    from tinyvc_b200.tinyvc.decoder import harmonic_theta
+    f0 = torch.rand(1, 1, 40, generator=torch.Generator().manual_seed(5)) * 14000.0
+    _, theta_ref = O.oscillate_harmonics(f0, return_theta=True)
+    theta = harmonic_theta(f0.cuda()).cpu()
+    nbad = int((theta != theta_ref).sum())
+    report.add("theta_high_pitch", mismatches=nbad)
+    assert nbad == 0
+
+
+@torch.inference_mode()
+def test_source_net(cuda_models, weights, report):
+    _, dec = cuda_models
+    g = load_golden("decoder_b2_lf18.npz")
+    content, f0, energy = t(g["content"]), t(g["f0"]), t(g["energy"])
+    amps, kern = dec.source_net(*_cuda(content, f0, energy))
+    ea, ek = max_abs(amps, t(g["amps"])), max_abs(kern, t(g["kernel"]))
+    report.add("source_net", amps_max_abs=ea, kernel_max_abs=ek)
+    assert ea < 2e-5 and ek < 2e-5
+
+
+@torch.inference_mode()
+def test_dsp(cuda_models, report):
+    _, dec = cuda_models
+    g = load_golden("decoder_b2_lf18.npz")
+    f0, amps, kern, rand01 = t(g["f0"]), t(g["amps"]), t(g["kernel"]), t(g["rand01"])
+    src = dec.dsp(*_cuda(f0, amps, kern), rand01=rand01.cuda()).cpu()
+    ref = t(g["source_b0"])
+    eh, en = max_abs(src[0, :15], ref[:15]), max_abs(src[0, 15], ref[15])
+    report.add("dsp", harmonics_max_abs=eh, noise_max_abs=en, noise_rms=float(ref[15].pow(2).mean().sqrt()))
+    assert eh < 5e-6, "harmonics"
+    assert en < 2e-5, "noise"
+
+
+@torch.inference_mode()
+def test_filter_net(cuda_models, weights, report):
+    _, dec = cuda_models
+    g = load_golden("decoder_b2_lf18.npz")
+    content, f0, energy, rand01 = t(g["content"]), t(g["f0"]), t(g["energy"]), t(g["rand01"])
+    src = O.decoder_dsp(f0, t(g["amps"]), t(g["kernel"]), rand01)
+    ref = O.filter_net(weights[1], content, f0, energy, src)
+    out = dec.filter_net(*_cuda(content, f0, energy, src)).cpu()
+    e = rmse(out, ref)
+    report.add("filter_net", rmse=e, ref_rms=float(ref.pow(2).mean().sqrt()), max_abs=max_abs(out, ref))
+    assert e < RMSE_BAR
+
+
+@torch.inference_mode()
+def test_decoder_infer_golden(cuda_models, report):
+    _, dec = cuda_models
+    g = load_golden("decoder_b2_lf18.npz")
+    out = dec.infer(*_cuda(t(g["content"]), t(g["f0"]), t(g["energy"])), rand01=t(g["rand01"]).cuda()).cpu()
+    ref = t(g["out"])
+    e = rmse(out, ref)
+    report.add("decoder_golden", rmse=e, ref_rms=float(ref.pow(2).mean().sqrt()), max_abs=max_abs(out, ref))
+    assert out.shape == ref.shape
+    assert e < RMSE_BAR
+
+
+@pytest.mark.parametrize("batch,lf", [(3, 1), (2, 2), (2, 3), (2, 5), (3, 33), (1, 100)])
+@torch.inference_mode()
+def test_decoder_ragged_lengths(cuda_models, weights, batch, lf, report):
+    """Edge cases: utterances shorter than the dilations (replicate padding dominates), odd frame counts."""
+    _, dec = cuda_models
+    inp = synth.decoder_inputs(batch, lf, seed=100 + lf)
+    ref = O.decoder_infer(weights[1], inp["content"], inp["f0"], inp["energy"], inp["rand01"])
+    out = dec.infer(*_cuda(inp["content"], inp["f0"], inp["energy"]), rand01=inp["rand01"].cuda()).cpu()
+    e = rmse(out, ref)
+    report.add(f"decoder_b{batch}_lf{lf}", rmse=e, ref_rms=float(ref.pow(2).mean().sqrt()))
+    assert e < RMSE_BAR
+
+
+@torch.inference_mode()
+def test_decoder_unvoiced_and_silent(cuda_models, weights, report):
+    """All-unvoiced f0 (oscillator gated off) and zero energy."""
+    _, dec = cuda_models
+    inp = synth.decoder_inputs(2, 12, seed=77)
+    inp["f0"].zero_()
+    inp["energy"][1].zero_()
+    ref = O.decoder_infer(weights[1], inp["content"], inp["f0"], inp["energy"], inp["rand01"])
+    out = dec.infer(*_cuda(inp["content"], inp["f0"], inp["energy"]), rand01=inp["rand01"].cuda()).cpu()
+    e = rmse(out, ref)
+    report.add("decoder_unvoiced", rmse=e)
+    assert e < RMSE_BAR
+
+
+@torch.inference_mode()
+def test_decoder_batch_invariance(cuda_models):
+    """An utterance's waveform must not depend on what else is in the batch (sharding invariant)."""
+    _, dec = cuda_models
+    inp = synth.decoder_inputs(5, 18, seed=9)
+    c, f, e, r = _cuda(inp["content"], inp["f0"], inp["energy"], inp["rand01"])
+    full = dec.infer(c, f, e, rand01=r)
+    for b in (0, 3, 4):
+        one = dec.infer(c[b:b + 1], f[b:b + 1], e[b:b + 1], rand01=r[b:b + 1])
+        assert torch.equal(one[0], full[b]), f"utterance {b} differs when run alone"
+    again = dec.infer(c, f, e, rand01=r)
+    assert torch.equal(again, full), "run-to-run nondeterminism"
+
+
+@torch.inference_mode()
+def test_bench_shape_properties(cuda_models, weights, report):
+    """BASELINE config 2 shape (B=64, Lf=18): oracle parity on 8 utterances, finite everywhere."""
+    _, dec = cuda_models
+    inp = synth.decoder_inputs(64, 18, seed=1234 + 2)
+    out = dec.infer(*_cuda(inp["content"], inp["f0"], inp["energy"]), rand01=inp["rand01"].cuda()).cpu()
+    assert out.shape == (64, 8640) and torch.isfinite(out).all()
+    sel = [0, 9, 18, 27, 36, 45, 54, 63]
+    ref = O.decoder_infer(weights[1], inp["content"][sel], inp["f0"][sel], inp["energy"][sel], inp["rand01"][sel])
+    e = rmse(out[sel], ref)
+    report.add("decoder_config2_8utt", rmse=e, ref_rms=float(ref.pow(2).mean().sqrt()))
+    assert e < RMSE_BAR
+
+
+def test_cpu_tensor_is_rejected(cuda_models):
+    _, dec = cuda_models
+    inp = synth.decoder_inputs(1, 4, seed=1)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        dec.infer(inp["content"], inp["f0"], inp["energy"])

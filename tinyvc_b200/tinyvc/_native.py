@@ -21,7 +21,12 @@ class NativeHandle:
         self._device: Optional[torch.device] = None
 
     def _fingerprint(self) -> Tuple:
-        return tuple((p.data_ptr(), p._version) for p in self._module.parameters())
+        def ver(p):
+            try:
+                return p._version
+            except RuntimeError:    # inference tensors do not track a version counter
+                return -1
+        return tuple((p.data_ptr(), ver(p)) for p in self._module.parameters())
 
     def get(self) -> ctypes.c_void_p:
         key = self._fingerprint()

@@ -43,8 +43,15 @@ class _Index:
 _cache: "OrderedDict[Tuple, _Index]" = OrderedDict()
 
 
+def _version(t: torch.Tensor) -> int:
+    try:
+        return t._version
+    except RuntimeError:        # inference tensors do not track a version counter
+        return -1
+
+
 def _prepared(ref2d: torch.Tensor, metric: int) -> _Index:
-    key = (ref2d.data_ptr(), ref2d._version, ref2d.shape[1], metric, ref2d.device.index)
+    key = (ref2d.data_ptr(), _version(ref2d), ref2d.shape[1], metric, ref2d.device.index)
     hit = _cache.get(key)
     if hit is not None:
         _cache.move_to_end(key)

@@ -35,6 +35,11 @@ const char* tvc_last_error(void);
 const char* tvc_version(void);
 /* Runtime switches, e.g. ("conv_impl","fp32"|"mma").  Returns non-zero for unknown keys. */
 int tvc_set_option(const char* key, const char* value);
+/* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
+unsigned long long tvc_launch_count(void);
+/* With option ("profile","1"): per-launcher CUDA-event times since the last report, as a JSON
+ * object {"name": {"launches": n, "ms": total}} written to buf.  Synchronises the device.      */
+int tvc_profile_report(char* buf, size_t n);
 
 /* ---- parameter contract: flat fp32 buffers in torch state_dict() order ------------------- */
 /* kind: 0 = Decoder (module/tinyvc/decoder.py:236-251), 1 = Encoder (encoder.py:100-106).     */

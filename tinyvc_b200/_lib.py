@@ -29,6 +29,8 @@ _SIGNATURES = {
     "tvc_last_error": (c_char_p, []),
     "tvc_version": (c_char_p, []),
     "tvc_set_option": (c_int, [c_char_p, c_char_p]),
+    "tvc_launch_count": (ctypes.c_ulonglong, []),
+    "tvc_profile_report": (c_int, [c_char_p, c_size_t]),
     "tvc_param_count": (c_int, [c_int]),
     "tvc_param_name": (c_char_p, [c_int, c_int]),
     "tvc_param_numel": (c_int64, [c_int, c_int]),
@@ -88,6 +90,18 @@ def check(status: int, what: str) -> None:
 
 def set_option(key: str, value: str) -> None:
     check(lib().tvc_set_option(key.encode(), value.encode()), f"tvc_set_option({key})")
+
+
+def launch_count() -> int:
+    return int(lib().tvc_launch_count())
+
+
+def profile_report() -> dict:
+    """Per-launcher event times accumulated since the last call (needs set_option('profile','1'))."""
+    import json
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib().tvc_profile_report(buf, len(buf)), "tvc_profile_report")
+    return json.loads(buf.value.decode())
 
 
 def param_names(kind: int) -> Tuple[Tuple[str, int], ...]:

@@ -3,6 +3,9 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <atomic>
+#include <map>
+#include <vector>
 
 #include "../../include/tinyvc_b200.h"
 #include "nets.cuh"
@@ -16,6 +19,32 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- event profiler ----------------------------------------------------------------------------
+struct ProfEntry { std::string name; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::mutex g_prof_mu;
+static std::vector<ProfEntry> g_prof;
+
+ProfScope::ProfScope(const char* name, cudaStream_t s) : stream(s) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    ProfEntry e;
+    const char* paren = strchr(name, '(');
+    e.name = paren ? std::string(name, paren - name) : std::string(name);
+    if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+    cudaEventRecord(e.a, s);
+    slot = (int)g_prof.size();
+    g_prof.push_back(e);
+}
+ProfScope::~ProfScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    cudaEventRecord(g_prof[slot].b, stream);
 }
 
 static std::once_flag g_init_once;
@@ -82,8 +111,45 @@ int tvc_set_option(const char* key, const char* value) {
         set_error("conv_impl: unknown value '%s'", value);
         return 2;
     }
+    if (!strcmp(key, "profile")) {
+        std::lock_guard<std::mutex> lock(g_prof_mu);
+        g_prof_on = !strcmp(value, "1");
+        return 0;
+    }
     set_error("unknown option '%s'", key);
     return 2;
+}
+
+unsigned long long tvc_launch_count(void) { return g_launches.load(); }
+
+int tvc_profile_report(char* buf, size_t n) {
+    API_BEGIN
+    TVC_REQUIRE(buf && n > 2, "tvc_profile_report: need a buffer");
+    TVC_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    std::map<std::string, std::pair<long long, double>> acc;
+    for (ProfEntry& e : g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+            acc[e.name].first += 1;
+            acc[e.name].second += ms;
+        }
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    g_prof.clear();
+    std::string js = "{";
+    for (auto& kv : acc) {
+        char tmp[256];
+        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f}", js.size() > 1 ? ", " : "",
+                 kv.first.c_str(), kv.second.first, kv.second.second);
+        js += tmp;
+    }
+    js += "}";
+    TVC_REQUIRE(js.size() + 1 <= n, "tvc_profile_report: buffer of %zu bytes too small (%zu needed)", n, js.size() + 1);
+    memcpy(buf, js.c_str(), js.size() + 1);
+    return 0;
+    API_END
 }
 
 int tvc_param_count(int kind) { return (kind == 0 || kind == 1) ? (int)table_of(kind).specs.size() : -1; }

@@ -189,9 +189,12 @@ void* Arena::bytes(size_t n) {
     return base + o;
 }
 
-#define RUN(expr)                 \
-    do {                          \
-        if (!A.dry) TVC_TRY(expr); \
+#define RUN(expr)                    \
+    do {                             \
+        if (!A.dry) {                \
+            ProfScope ps__(#expr, s); \
+            TVC_TRY(expr);           \
+        }                            \
     } while (0)
 #define ARENA_OK() TVC_REQUIRE(!A.overflow, "workspace too small: need at least %zu bytes, got %zu", A.peak, A.cap)
 
@@ -205,6 +208,7 @@ int conv_run(Arena& A, cudaStream_t s, const ConvW& W, const float* x, long long
     p.pre_scale = pre_scale; p.pre_shift = pre_shift;
     p.B = B; p.T = T; p.Cin = W.Cin; p.Cout = W.Cout; p.CoutP = W.CoutP; p.K = W.K; p.dil = dil;
     p.pre = pre; p.epi = epi;
+    ProfScope ps(W.K == 1 ? "conv1d_k1(" : "conv1d_k3(", s);
     return conv1d_launch(p, s);
 }
 

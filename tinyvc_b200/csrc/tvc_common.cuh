@@ -18,7 +18,23 @@ void set_error(const char* fmt, ...);
             return 1;                                                                          \
         }                                                                                      \
     } while (0)
-#define TVC_LAUNCH_CHECK() TVC_CUDA(cudaGetLastError())
+// Every kernel launch of this library goes through TVC_LAUNCH_CHECK(): it counts the launch
+// (tvc_launch_count(), reported by bench.py as `gpu_launches`) and surfaces launch errors.
+void count_launch();
+#define TVC_LAUNCH_CHECK()            \
+    do {                              \
+        ::tvc::count_launch();        \
+        TVC_CUDA(cudaGetLastError()); \
+    } while (0)
+
+// Optional per-kernel CUDA-event timing (tvc_set_option("profile","1"); tvc_profile_report()).
+// A ProfScope brackets one launcher call with two events on the launch stream; disabled = no-op.
+struct ProfScope {
+    int slot = -1;
+    cudaStream_t stream = 0;
+    ProfScope(const char* name, cudaStream_t s);
+    ~ProfScope();
+};
 #define TVC_TRY(expr)                                                                          \
     do {                                                                                       \
         int r__ = (expr);                                                                      \

@@ -126,6 +126,20 @@ int tvc_shift_frequency(const float* f0, float* out, int64_t n, float semitones,
 int tvc_sola(const float* y, int y_len, float* sola_buf, const float* fade_in, float* out_block,
              int32_t* shift_out, int S, int block, int cross, int search, int delay, void* stream);
 
+/* ---- parity probes (tests only) ------------------------------------------------------------ */
+/* One dense Conv1d through the tcgen05 tensor-core kernel (csrc/tc_conv.cu) with channels-first fp32
+ * device tensors at the boundary, as nn.Conv1d(Cin, Cout, K, dilation=dil, padding=dil*(K-1)/2,
+ * padding_mode='replicate') evaluates it (decoder.py:143-146,165-171).  `w` [Cout][Cin][K], `bias`
+ * [Cout], `aux_w`, `aux_b` are HOST pointers in torch layout.  aux_mode 0 = none; 1 = a 1x1 conv of
+ * aux_x accumulated into the output (Downsample.down_res, decoder.py:143,157); 2 = FiLM
+ * (decoder.py:88-97): aux_w [2][Cout][aux_cin] = to_scale rows then to_shift rows.  res (nullable)
+ * is added last.  epi_act/out_act: 0 none, 1 leaky_relu(0.1), 2 GELU, 3 ELU+1.  y receives the fp32
+ * output, y_planes the re-split bf16 hi+lo copy with out_act applied (both [B][Cout][T], nullable). */
+int tvc_tc_conv_probe(const float* x, const float* w, const float* bias, int B, int T, int Cin, int Cout, int K,
+                      int dil, const float* aux_x, const float* aux_w, const float* aux_b, int aux_cin,
+                      int aux_mode, const float* res, int epi_act, int out_act, int NT, float* y, float* y_planes,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,7 @@
 
 #include "../../include/tinyvc_b200.h"
 #include "nets.cuh"
+#include "tc_conv.cuh"
 
 namespace tvc {
 
@@ -50,7 +51,10 @@ ProfScope::~ProfScope() {
 static std::once_flag g_init_once;
 static int g_init_status = 0;
 static int global_init() {
-    std::call_once(g_init_once, [] { g_init_status = conv1d_init(); });
+    std::call_once(g_init_once, [] {
+        g_init_status = conv1d_init();
+        if (!g_init_status) g_init_status = tc_conv_init();
+    });
     return g_init_status;
 }
 
@@ -432,6 +436,61 @@ int tvc_sola(const float* y, int y_len, float* sola_buf, const float* fade_in, f
     TVC_REQUIRE(y && sola_buf && fade_in && out_block && shift_out, "tvc_sola: null argument");
     TVC_REQUIRE(S > 0 && block > 0 && cross > 0 && search >= 0 && delay >= 0, "tvc_sola: invalid sizes");
     return sola_run(y, y_len, sola_buf, fade_in, out_block, shift_out, S, block, cross, search, delay, (cudaStream_t)stream);
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------- parity probes
+int tvc_tc_conv_probe(const float* x, const float* w, const float* bias, int B, int T, int Cin, int Cout, int K, int dil,
+                      const float* aux_x, const float* aux_w, const float* aux_b, int aux_cin, int aux_mode,
+                      const float* res, int epi_act, int out_act, int NT, float* y, float* y_planes, void* stream) {
+    API_BEGIN
+    TVC_TRY(global_init());
+    TVC_REQUIRE(x && w && B > 0 && T > 0 && Cin > 0 && Cout > 0, "tvc_tc_conv_probe: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    TcConvW W;
+    TVC_TRY(tc_pack_conv(w, bias, Cout, Cin, K, aux_w, aux_b, aux_cin, aux_mode, NT, W));
+    const long long rows = (long long)B * T;
+    const int a_cs = (int)align_up(Cin, 8), x_cs = (int)align_up(aux_cin > 0 ? aux_cin : 8, 8), o_cs = (int)align_up(Cout, 8);
+    bf16 *a_hi = nullptr, *a_lo = nullptr, *x_hi = nullptr, *x_lo = nullptr, *y_hi = nullptr, *y_lo = nullptr;
+    float *res_cl = nullptr, *y_cl = nullptr;
+    int rc = 0;
+    auto cleanup = [&] {
+        cudaStreamSynchronize(s);
+        cudaFree(a_hi); cudaFree(a_lo); cudaFree(x_hi); cudaFree(x_lo); cudaFree(y_hi); cudaFree(y_lo);
+        cudaFree(res_cl); cudaFree(y_cl);
+        W.free_all();
+    };
+#define PROBE_CUDA(e) do { if ((e) != cudaSuccess) { set_error("probe: %s failed: %s", #e, cudaGetErrorString(cudaGetLastError())); cleanup(); return 1; } } while (0)
+#define PROBE_TRY(e) do { rc = (e); if (rc) { cleanup(); return rc; } } while (0)
+    PROBE_CUDA(cudaMalloc(&a_hi, rows * a_cs * 2)); PROBE_CUDA(cudaMalloc(&a_lo, rows * a_cs * 2));
+    PROBE_CUDA(cudaMalloc(&y_hi, rows * o_cs * 2)); PROBE_CUDA(cudaMalloc(&y_lo, rows * o_cs * 2));
+    PROBE_CUDA(cudaMalloc(&y_cl, rows * o_cs * 4));
+    PROBE_CUDA(cudaMemsetAsync(y_cl, 0, rows * o_cs * 4, s));
+    PROBE_CUDA(cudaMemsetAsync(y_hi, 0, rows * o_cs * 2, s)); PROBE_CUDA(cudaMemsetAsync(y_lo, 0, rows * o_cs * 2, s));
+    PROBE_TRY(cf_to_planes(x, a_hi, a_lo, B, Cin, T, a_cs, TC_ACT_NONE, s));
+    TcConvArgs a;
+    a.a_hi = a_hi; a.a_lo = a_lo; a.a_cs = a_cs; a.dil = dil; a.B = B; a.T = T;
+    if (aux_mode != TC_AUX_NONE) {
+        TVC_REQUIRE(aux_x && aux_w, "tvc_tc_conv_probe: aux input missing");
+        PROBE_CUDA(cudaMalloc(&x_hi, rows * x_cs * 2)); PROBE_CUDA(cudaMalloc(&x_lo, rows * x_cs * 2));
+        PROBE_TRY(cf_to_planes(aux_x, x_hi, x_lo, B, aux_cin, T, x_cs, TC_ACT_NONE, s));
+        a.x_hi = x_hi; a.x_lo = x_lo; a.x_cs = x_cs;
+    }
+    if (res) {
+        PROBE_CUDA(cudaMalloc(&res_cl, rows * o_cs * 4));
+        PROBE_TRY(cf_to_cl(res, res_cl, B, Cout, T, o_cs, s));
+        a.res = res_cl; a.res_cs = o_cs;
+    }
+    a.y32 = y_cl; a.y32_cs = o_cs; a.y_hi = y_hi; a.y_lo = y_lo; a.y_cs = o_cs;
+    a.epi_act = epi_act; a.out_act = out_act;
+    PROBE_TRY(tc_conv_launch(W, a, s));
+    if (y) PROBE_TRY(cl_to_cf(y_cl, y, B, Cout, T, o_cs, s));
+    if (y_planes) PROBE_TRY(planes_to_cf(y_hi, y_lo, y_planes, B, Cout, T, o_cs, s));
+    PROBE_CUDA(cudaStreamSynchronize(s));
+    cleanup();
+    return 0;
+#undef PROBE_CUDA
+#undef PROBE_TRY
     API_END
 }
 

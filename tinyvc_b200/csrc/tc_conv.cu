@@ -1,0 +1,496 @@
+// Dense Conv1d on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), sm_100a.
+//
+// One CTA computes a [128 time rows] x [NT output channels] tile of
+//     y[row, co] = epi( bias[co] + sum_{tap,ci} W[co,ci,tap] * x[clamp_T(row + (tap-(taps-1)/2)*dil), ci]  (+ aux) )
+// for the decoder's dense convolutions (module/tinyvc/decoder.py:93-94 FiLM 1x1s, :119-124 SourceNet
+// heads, :143-146 Downsample, :165-171 Upsample, :201 content_in, :206 downs.0) as an implicit GEMM:
+//     M = 128 rows (time), N = NT channels, K = taps * Cin, processed in K-stages of KB channels of one tap.
+//
+// Warp roles (160 threads):
+//   warps 0-3  producers, then epilogue.  Thread r owns tile row r: it gathers that row's 16-byte
+//              channel chunks of both split planes for the stage's tap (time index clamped inside the
+//              utterance = replicate padding) straight into the UMMA K-major core-matrix layout
+//              smem[plane][chunk][row][16 B]; fence.proxy.async; arrive on the stage's `full` mbarrier.
+//              Thread 0 also launches the stage's weight image with one cp.async.bulk (TMA bulk copy,
+//              complete_tx on the same mbarrier); weights are pre-packed in exactly the smem layout.
+//   warp 4     lane 0 waits `full`, issues 3 x KB/16 tcgen05.mma (hi*hi, hi*lo, lo*hi; fp32 accumulate in
+//              TMEM), tcgen05.commit -> the stage's `empty` mbarrier; after the last stage commit -> `acc`.
+//   epilogue   thread r reads TMEM lane r with tcgen05.ld (32x32b), adds bias, applies FiLM
+//              (x*scale+shift from a second accumulator fed by the aux 1x1 on the skip tensor), the
+//              residual, the activation, and writes fp32 and/or re-split bf16 planes, channels-last.
+// Every mbarrier wait is bounded (trap after ~2 s) so a protocol bug cannot hang the GPU.
+#include <cstring>
+#include <vector>
+
+#include "tc_conv.cuh"
+
+namespace tvc {
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 160;
+constexpr uint32_t kChunkStride = kTileM * 16;   // bytes between consecutive 8-channel chunks of the A tile (LBO)
+
+struct TcKParams {
+    const bf16 *a_hi, *a_lo, *x_hi, *x_lo, *w;
+    const float *bias, *film_bias, *res;
+    float* y32;
+    bf16 *y_hi, *y_lo;
+    long long rows;
+    long long tile_elems;
+    int a_cs, x_cs, res_cs, y32_cs, y_cs;
+    int T, dil, taps, nkb, aux_nkb, aux_mode, KB, NT, NTp, Cout;
+    int ring;                      // smem ring depth
+    uint32_t a_stage_bytes, b_stage_bytes;
+    uint32_t tmem_cols;
+    int epi_act, out_act;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate, single-CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(addr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (stride between the two 8-element
+//   K chunks of one MMA) | [32,46) stride byte offset >> 4 (stride between 8-row groups) |
+//   [46,48) version = 1 | [61,64) layout type = 0.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10,
+// a/b K-major (0) @15/@16, N>>3 @17, M>>4 @24.
+__device__ __forceinline__ uint32_t umma_idesc(uint32_t M, uint32_t N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case TC_ACT_LRELU: return leaky01(v);
+        case TC_ACT_GELU: return gelu_erf(v);
+        case TC_ACT_ELU1: return elu_plus1(v);
+        default: return v;
+    }
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(bf16 a, bf16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) tc_conv_kernel(const TcKParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + (uint32_t)p.ring * stage_bytes;   // full[ring], empty[ring], acc
+    const uint32_t acc_bar = bar_base + 16u * (uint32_t)p.ring;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)p.ring * stage_bytes + 16 * p.ring + 8);
+
+    const int n_main = p.taps * p.nkb;
+    const int n_stage = n_main + p.aux_nkb;
+    const int chunks = p.KB >> 3;                   // 16-byte chunks per row per plane in one stage
+    const uint32_t plane_a = (uint32_t)chunks * kChunkStride;
+
+    if (tid == 128) {
+        for (int s = 0; s < p.ring; ++s) {
+            mbar_init(bar_base + 8u * s, kTileM + 1);              // full: 128 gather arrivals + 1 expect_tx
+            mbar_init(bar_base + 8u * (p.ring + s), 1);            // empty: one tcgen05.commit
+        }
+        mbar_init(acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const long long row0 = (long long)blockIdx.x * kTileM;
+    const int n_tile = blockIdx.y;
+
+    if (warp < 4) {
+        // ================= producer: gather A, launch B =================
+        const long long row = row0 + tid;
+        const bool valid = row < p.rows;
+        const long long b = valid ? row / p.T : 0;
+        const int t = valid ? (int)(row - b * p.T) : 0;
+        const bf16* wt = p.w + (long long)n_tile * p.tile_elems;
+        long long w_off = 0;   // bf16 elements consumed so far
+        for (int i = 0; i < n_stage; ++i) {
+            const int s = i % p.ring, use = i / p.ring;
+            const uint32_t full = bar_base + 8u * s, empty = bar_base + 8u * (p.ring + s);
+            const bool is_aux = i >= n_main;
+            const uint32_t n_rows = (is_aux && p.aux_mode == TC_AUX_FILM) ? 2u * p.NTp : (uint32_t)p.NTp;
+            const uint32_t b_bytes = 4u * (uint32_t)p.KB * n_rows;       // hi + lo images
+            if (use > 0) mbar_wait(empty, (uint32_t)(use - 1) & 1u);
+            const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
+            if (tid == 0) {
+                mbar_arrive_expect_tx(full, b_bytes);
+                bulk_g2s(a_dst + p.a_stage_bytes, wt + w_off, b_bytes, full);
+            }
+            w_off += b_bytes >> 1;
+            // source row of this thread for this stage
+            int kb;
+            const bf16 *src_hi, *src_lo;
+            int cs;
+            long long srow;
+            if (!is_aux) {
+                const int tap = i / p.nkb;
+                kb = i - tap * p.nkb;
+                int tt = t + (tap - ((p.taps - 1) >> 1)) * p.dil;
+                tt = tt < 0 ? 0 : (tt > p.T - 1 ? p.T - 1 : tt);
+                srow = b * p.T + tt;
+                src_hi = p.a_hi; src_lo = p.a_lo; cs = p.a_cs;
+            } else {
+                kb = i - n_main;
+                srow = row;
+                src_hi = p.x_hi; src_lo = p.x_lo; cs = p.x_cs;
+            }
+            const int c0 = kb * chunks, cmax = cs >> 3;
+            const uint4* gh = reinterpret_cast<const uint4*>(src_hi + srow * cs);
+            const uint4* gl = reinterpret_cast<const uint4*>(src_lo + srow * cs);
+            uint8_t* dst = smem + (size_t)s * stage_bytes + (size_t)tid * 16;
+            for (int c = 0; c < chunks; c += 4) {
+                uint4 vh[4], vl[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool ok = valid && (c + u) < chunks && (c0 + c + u) < cmax;
+                    vh[u] = ok ? __ldg(gh + c0 + c + u) : make_uint4(0, 0, 0, 0);
+                    vl[u] = ok ? __ldg(gl + c0 + c + u) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (c + u < chunks) {
+                        *reinterpret_cast<uint4*>(dst + (size_t)(c + u) * kChunkStride) = vh[u];
+                        *reinterpret_cast<uint4*>(dst + plane_a + (size_t)(c + u) * kChunkStride) = vl[u];
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(full);
+        }
+
+        // ================= epilogue =================
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        const bool film = p.aux_mode == TC_AUX_FILM;
+        const float* bias = p.bias + n_tile * p.NTp;               // padded channel space
+        const float* fbias = film ? p.film_bias + 2 * n_tile * p.NTp : nullptr;
+        const int ch0 = n_tile * p.NT;                             // first real output channel of this tile
+        for (int cg = 0; cg < (p.NT >> 3); ++cg) {
+            float v[8], sc[8], sh[8];
+            tmem_ld8(lane_addr + (uint32_t)(cg * 8), v);
+            if (film) {
+                tmem_ld8(lane_addr + (uint32_t)(p.NTp + cg * 8), sc);
+                tmem_ld8(lane_addr + (uint32_t)(2 * p.NTp + cg * 8), sh);
+            }
+            tmem_ld_wait();
+            const int ch = ch0 + cg * 8;
+            if (!valid || ch >= p.Cout) continue;                  // warp-uniform in ch; `valid` only masks stores below
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __fadd_rn(v[i], __ldg(bias + cg * 8 + i));
+            if (film) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float scale = __fadd_rn(sc[i], __ldg(fbias + cg * 8 + i));
+                    const float shift = __fadd_rn(sh[i], __ldg(fbias + p.NTp + cg * 8 + i));
+                    v[i] = __fadd_rn(__fmul_rn(v[i], scale), shift);       // FiLM: x * scale + shift (decoder.py:97)
+                }
+            }
+            if (p.res) {
+                const float* rp = p.res + row * p.res_cs + ch;
+                if (ch + 8 <= p.res_cs) {
+                    const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
+                    const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp) + 1);
+                    v[0] = __fadd_rn(v[0], r0.x); v[1] = __fadd_rn(v[1], r0.y); v[2] = __fadd_rn(v[2], r0.z); v[3] = __fadd_rn(v[3], r0.w);
+                    v[4] = __fadd_rn(v[4], r1.x); v[5] = __fadd_rn(v[5], r1.y); v[6] = __fadd_rn(v[6], r1.z); v[7] = __fadd_rn(v[7], r1.w);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (ch + i < p.res_cs) v[i] = __fadd_rn(v[i], __ldg(rp + i));
+                }
+            }
+            if (p.epi_act != TC_ACT_NONE) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], p.epi_act);
+            }
+            if (p.y32) {
+                float* yp = p.y32 + row * p.y32_cs + ch;
+                if (ch + 8 <= p.y32_cs) {
+                    reinterpret_cast<float4*>(yp)[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    reinterpret_cast<float4*>(yp)[1] = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (ch + i < p.y32_cs) yp[i] = v[i];
+                }
+            }
+            if (p.y_hi && ch + 8 <= p.y_cs) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float a0 = apply_act(v[2 * i], p.out_act), a1 = apply_act(v[2 * i + 1], p.out_act);
+                    const bf16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
+                    const bf16 l0 = __float2bfloat16_rn(__fsub_rn(a0, __bfloat162float(h0)));
+                    const bf16 l1 = __float2bfloat16_rn(__fsub_rn(a1, __bfloat162float(h1)));
+                    h[i] = pack_bf16x2(h0, h1);
+                    l[i] = pack_bf16x2(l0, l1);
+                }
+                *reinterpret_cast<uint4*>(p.y_hi + row * p.y_cs + ch) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(p.y_lo + row * p.y_cs + ch) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+        }
+    } else if (lane == 0) {
+        // ================= MMA issuer (one thread) =================
+        const uint32_t idesc_main = umma_idesc(kTileM, (uint32_t)p.NTp);
+        const uint32_t idesc_film = umma_idesc(kTileM, 2u * (uint32_t)p.NTp);
+        for (int i = 0; i < n_stage; ++i) {
+            const int s = i % p.ring, use = i / p.ring;
+            const uint32_t full = bar_base + 8u * s, empty = bar_base + 8u * (p.ring + s);
+            const bool is_film = i >= n_main && p.aux_mode == TC_AUX_FILM;
+            const uint32_t n_rows = is_film ? 2u * p.NTp : (uint32_t)p.NTp;
+            const uint32_t idesc = is_film ? idesc_film : idesc_main;
+            const uint32_t d = tmem + (is_film ? (uint32_t)p.NTp : 0u);
+            const bool first = is_film ? (i == n_main) : (i == 0);
+            mbar_wait(full, (uint32_t)use & 1u);
+            tc_fence_after();
+            const uint32_t a_base = smem_base + (uint32_t)s * stage_bytes;
+            const uint32_t b_base = a_base + p.a_stage_bytes;
+            const uint32_t b_lbo = n_rows * 16u;                  // bytes between 8-channel chunks of the weight image
+            const uint32_t plane_b = (uint32_t)chunks * b_lbo;
+            for (int ks = 0; ks < (p.KB >> 4); ++ks) {
+                const uint64_t a_h = umma_desc(a_base + (uint32_t)(2 * ks) * kChunkStride, kChunkStride, 128);
+                const uint64_t a_l = umma_desc(a_base + plane_a + (uint32_t)(2 * ks) * kChunkStride, kChunkStride, 128);
+                const uint64_t b_h = umma_desc(b_base + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
+                const uint64_t b_l = umma_desc(b_base + plane_b + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
+                umma_bf16(d, a_h, b_h, idesc, (first && ks == 0) ? 0u : 1u);
+                umma_bf16(d, a_h, b_l, idesc, 1u);
+                umma_bf16(d, a_l, b_h, idesc, 1u);
+            }
+            umma_commit(empty);                                    // frees the smem stage once these MMAs retire
+        }
+        umma_commit(acc_bar);                                      // accumulators complete -> epilogue
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem, p.tmem_cols);
+}
+
+// ---- host side --------------------------------------------------------------------------------
+inline uint16_t f2bf_host(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+inline float bf2f_host(uint16_t h) {
+    const uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+int pick_kb(int cin) {
+    const int c16 = (int)align_up(cin, 16);
+    if (c16 <= 64) return c16;
+    if (c16 % 64 == 0) return 64;
+    if (c16 % 48 == 0) return 48;
+    return 64;   // K is zero-padded up to a multiple of 64
+}
+
+}  // namespace
+
+void TcConvW::free_all() {
+    if (w) cudaFree(w);
+    if (bias) cudaFree(bias);
+    if (film_bias) cudaFree(film_bias);
+    w = nullptr; bias = nullptr; film_bias = nullptr;
+}
+
+int tc_pack_conv(const float* w, const float* b, int Cout, int Cin, int taps, const float* aux_w, const float* aux_b,
+                 int aux_cin, int aux_mode, int NT, TcConvW& o) {
+    TVC_REQUIRE(Cout > 0 && Cin > 0 && (taps == 1 || taps == 3), "tc_pack_conv: bad shape Cout=%d Cin=%d taps=%d", Cout, Cin, taps);
+    TVC_REQUIRE(NT % 8 == 0 && NT >= 8, "tc_pack_conv: NT=%d must be a multiple of 8", NT);
+    o.Cin = Cin; o.Cout = Cout; o.taps = taps; o.aux_cin = aux_mode ? aux_cin : 0; o.aux_mode = aux_mode;
+    o.KB = pick_kb(aux_mode ? (Cin > aux_cin ? Cin : aux_cin) : Cin);
+    o.nkb = cdiv(align_up(Cin, 16), o.KB);
+    o.aux_nkb = aux_mode ? cdiv(align_up(aux_cin, 16), o.KB) : 0;
+    o.NT = NT; o.NTp = (int)align_up(NT, 16); o.n_tiles = cdiv(Cout, NT);
+    const int film_rows = 2 * o.NTp;
+    TVC_REQUIRE(o.NTp <= 256 && (aux_mode != TC_AUX_FILM || film_rows <= 256), "tc_pack_conv: NT=%d too wide", NT);
+    const int chunks = o.KB / 8;
+    const size_t main_stage = (size_t)2 * chunks * o.NTp * 8;                                   // bf16 elements, hi+lo
+    const size_t aux_stage = (size_t)2 * chunks * (aux_mode == TC_AUX_FILM ? film_rows : o.NTp) * 8;
+    o.tile_elems = main_stage * taps * o.nkb + aux_stage * o.aux_nkb;
+    std::vector<uint16_t> img(o.tile_elems * o.n_tiles, 0);
+    std::vector<float> hb((size_t)o.n_tiles * o.NTp, 0.f), hf;
+    if (aux_mode == TC_AUX_FILM) hf.assign((size_t)o.n_tiles * film_rows, 0.f);
+
+    auto put = [&](uint16_t* stage, int n_rows, int c, int n, int e, float v) {
+        const uint16_t h = f2bf_host(v);
+        const uint16_t l = f2bf_host(v - bf2f_host(h));
+        const size_t plane = (size_t)chunks * n_rows * 8;
+        const size_t off = ((size_t)c * n_rows + n) * 8 + e;
+        stage[off] = h;
+        stage[plane + off] = l;
+    };
+    for (int nt = 0; nt < o.n_tiles; ++nt) {
+        uint16_t* tile = img.data() + o.tile_elems * nt;
+        size_t so = 0;
+        for (int tap = 0; tap < taps; ++tap)
+            for (int kb = 0; kb < o.nkb; ++kb, so += main_stage)
+                for (int c = 0; c < chunks; ++c)
+                    for (int n = 0; n < NT; ++n)
+                        for (int e = 0; e < 8; ++e) {
+                            const int co = nt * NT + n, ci = kb * o.KB + c * 8 + e;
+                            if (co < Cout && ci < Cin) put(tile + so, o.NTp, c, n, e, w[((size_t)co * Cin + ci) * taps + tap]);
+                        }
+        for (int kb = 0; kb < o.aux_nkb; ++kb, so += aux_stage)
+            for (int c = 0; c < chunks; ++c)
+                for (int n = 0; n < NT; ++n)
+                    for (int e = 0; e < 8; ++e) {
+                        const int co = nt * NT + n, ci = kb * o.KB + c * 8 + e;
+                        if (co >= Cout || ci >= aux_cin) continue;
+                        if (aux_mode == TC_AUX_ACC) {
+                            put(tile + so, o.NTp, c, n, e, aux_w[(size_t)co * aux_cin + ci]);
+                        } else {
+                            put(tile + so, film_rows, c, n, e, aux_w[(size_t)co * aux_cin + ci]);                          // scale
+                            put(tile + so, film_rows, c, o.NTp + n, e, aux_w[((size_t)Cout + co) * aux_cin + ci]);     // shift
+                        }
+                    }
+        for (int n = 0; n < NT; ++n) {
+            const int co = nt * NT + n;
+            if (co >= Cout) break;
+            float bv = b ? b[co] : 0.f;
+            if (aux_mode == TC_AUX_ACC && aux_b) bv += aux_b[co];
+            hb[(size_t)nt * o.NTp + n] = bv;
+            if (aux_mode == TC_AUX_FILM && aux_b) {
+                hf[(size_t)nt * film_rows + n] = aux_b[co];
+                hf[(size_t)nt * film_rows + o.NTp + n] = aux_b[Cout + co];
+            }
+        }
+    }
+    TVC_CUDA(cudaMalloc(&o.w, img.size() * sizeof(uint16_t)));
+    TVC_CUDA(cudaMemcpy(o.w, img.data(), img.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    TVC_CUDA(cudaMalloc(&o.bias, hb.size() * sizeof(float)));
+    TVC_CUDA(cudaMemcpy(o.bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (!hf.empty()) {
+        TVC_CUDA(cudaMalloc(&o.film_bias, hf.size() * sizeof(float)));
+        TVC_CUDA(cudaMemcpy(o.film_bias, hf.data(), hf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+constexpr int kTcMaxSmem = 200 * 1024;
+
+int tc_conv_init() {
+    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
+    return 0;
+}
+
+int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
+    TVC_REQUIRE(W.w && a.a_hi && a.a_lo, "tc_conv: missing weights or input");
+    TVC_REQUIRE(a.B > 0 && a.T > 0, "tc_conv: empty problem B=%d T=%d", a.B, a.T);
+    TVC_REQUIRE(a.a_cs % 8 == 0 && a.a_cs >= W.Cin, "tc_conv: input channel stride %d (need multiple of 8 >= %d)", a.a_cs, W.Cin);
+    TVC_REQUIRE(W.aux_mode == TC_AUX_NONE || (a.x_hi && a.x_lo && a.x_cs % 8 == 0 && a.x_cs >= W.aux_cin), "tc_conv: aux input missing / bad stride");
+    TVC_REQUIRE(!a.y_hi || (a.y_lo && a.y_cs % 8 == 0), "tc_conv: plane output needs both planes and a stride multiple of 8");
+    TVC_REQUIRE(!a.y32 || a.y32_cs % 4 == 0, "tc_conv: fp32 output stride must be a multiple of 4");
+    TVC_REQUIRE(!a.res || a.res_cs % 4 == 0, "tc_conv: residual stride must be a multiple of 4");
+    TcKParams p;
+    p.a_hi = a.a_hi; p.a_lo = a.a_lo; p.x_hi = a.x_hi; p.x_lo = a.x_lo; p.w = W.w;
+    p.bias = W.bias; p.film_bias = W.film_bias; p.res = a.res; p.y32 = a.y32; p.y_hi = a.y_hi; p.y_lo = a.y_lo;
+    p.rows = (long long)a.B * a.T; p.tile_elems = (long long)W.tile_elems;
+    p.a_cs = a.a_cs; p.x_cs = a.x_cs; p.res_cs = a.res_cs; p.y32_cs = a.y32_cs; p.y_cs = a.y_cs;
+    p.T = a.T; p.dil = a.dil; p.taps = W.taps; p.nkb = W.nkb; p.aux_nkb = W.aux_nkb; p.aux_mode = W.aux_mode;
+    p.KB = W.KB; p.NT = W.NT; p.NTp = W.NTp; p.Cout = W.Cout;
+    p.epi_act = a.epi_act; p.out_act = a.out_act;
+    const int n_rows_max = W.aux_mode == TC_AUX_FILM ? 2 * W.NTp : W.NTp;
+    p.a_stage_bytes = 512u * (uint32_t)W.KB;                     // 2 planes x KB/8 chunks x 128 rows x 16 B
+    p.b_stage_bytes = 4u * (uint32_t)W.KB * (uint32_t)n_rows_max;
+    const uint32_t stage = p.a_stage_bytes + p.b_stage_bytes;
+    const int n_stage = W.taps * W.nkb + W.aux_nkb;
+    int ring = (kTcMaxSmem - 256) / (int)stage;
+    ring = ring > 4 ? 4 : ring;
+    ring = ring > n_stage ? n_stage : ring;
+    TVC_REQUIRE(ring >= 1, "tc_conv: a K-stage of %u bytes does not fit shared memory", stage);
+    p.ring = ring;
+    const uint32_t cols = (uint32_t)(W.aux_mode == TC_AUX_FILM ? 3 * W.NTp : W.NTp);
+    uint32_t tc = 32;
+    while (tc < cols) tc <<= 1;
+    TVC_REQUIRE(tc <= 512, "tc_conv: %u TMEM columns needed (> 512)", cols);
+    p.tmem_cols = tc;
+    const size_t smem = (size_t)ring * stage + 16 * ring + 16;
+    dim3 grid((unsigned)cdiv(p.rows, kTileM), (unsigned)W.n_tiles, 1);
+    tc_conv_kernel<<<grid, kThreads, smem, s>>>(p);
+    TVC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace tvc

@@ -1,0 +1,67 @@
+// Tensor-core (tcgen05 / TMEM) dense Conv1d for the TinyVC decoder -- declarations.
+//
+// Activations on this path are channels-last "split planes": a tensor [rows = B*T][C] is stored
+// as two bf16 matrices hi = bf16(v), lo = bf16(v - hi) with channel stride `cs` (a multiple of
+// 8 elements = one 16-byte UMMA core-matrix row; channels [C, cs) hold finite padding, their
+// weights are zero).  A conv is evaluated as three bf16 tensor-core products accumulated in
+// fp32 in TMEM:  x*w ~= x_hi*w_hi + x_hi*w_lo + x_lo*w_hi  (relative error ~2^-16, against
+// 2^-11 for one TF32 product, which SURVEY.md section 0 shows is not enough for RMSE < 1e-4).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "tvc_common.cuh"
+
+namespace tvc {
+
+typedef __nv_bfloat16 bf16;
+
+enum TcAux { TC_AUX_NONE = 0, TC_AUX_ACC = 1, TC_AUX_FILM = 2 };
+enum TcAct { TC_ACT_NONE = 0, TC_ACT_LRELU = 1, TC_ACT_GELU = 2, TC_ACT_ELU1 = 3 };
+
+// Packed weights of one conv (device memory, built once at load by tc_pack_conv).
+struct TcConvW {
+    bf16* w = nullptr;           // per n-tile, per K-stage: [hi image][lo image] in UMMA K-major core-matrix order
+    float* bias = nullptr;       // [n_tiles * NTp]   (main bias, + aux bias for TC_AUX_ACC)
+    float* film_bias = nullptr;  // [n_tiles * 2*NTp] (scale bias | shift bias), TC_AUX_FILM only
+    int Cin = 0, Cout = 0, taps = 1;
+    int aux_cin = 0, aux_mode = TC_AUX_NONE;
+    int KB = 0, nkb = 0, aux_nkb = 0;   // K-stage = KB channels of one tap
+    int NT = 0, NTp = 0, n_tiles = 0;   // output channels per CTA, padded to 16
+    size_t tile_elems = 0;              // bf16 elements of packed weights per n-tile
+    void free_all();
+};
+
+// `w` host [Cout][Cin][taps] (torch Conv1d layout), `b` host [Cout] (nullable).
+// aux (1x1 on a second input, host pointers):
+//   TC_AUX_ACC : aux_w [Cout][aux_cin], aux_b [Cout]  -> accumulated into the same output
+//   TC_AUX_FILM: aux_w [2][Cout][aux_cin] (scale rows then shift rows), aux_b [2][Cout]
+//                -> out = conv * (scale) + shift (+ res)            (decoder.py:88-97)
+int tc_pack_conv(const float* w, const float* b, int Cout, int Cin, int taps, const float* aux_w, const float* aux_b,
+                 int aux_cin, int aux_mode, int NT, TcConvW& out);
+
+struct TcConvArgs {
+    const bf16 *a_hi = nullptr, *a_lo = nullptr;   // main input planes [B*T][a_cs]
+    int a_cs = 0;
+    const bf16 *x_hi = nullptr, *x_lo = nullptr;   // aux input planes [B*T][x_cs]
+    int x_cs = 0;
+    int dil = 1;
+    int B = 0, T = 0;                  // taps are clamped inside each utterance of T rows (replicate padding)
+    const float* res = nullptr;        // fp32 residual [B*T][res_cs], added after bias / FiLM
+    int res_cs = 0;
+    float* y32 = nullptr;              // fp32 output [B*T][y32_cs] (nullable)
+    int y32_cs = 0;
+    bf16 *y_hi = nullptr, *y_lo = nullptr;   // split-plane output [B*T][y_cs] (nullable)
+    int y_cs = 0;
+    int epi_act = TC_ACT_NONE;         // applied to the value (both outputs)
+    int out_act = TC_ACT_NONE;         // applied additionally to the split-plane copy only
+};
+int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s);
+int tc_conv_init();
+
+// layout helpers (tc_ops.cu)
+int cf_to_planes(const float* x, bf16* hi, bf16* lo, int B, int C, int T, int cs, int act, cudaStream_t s);
+int cf_to_cl(const float* x, float* y, int B, int C, int T, int cs, cudaStream_t s);
+int cl_to_cf(const float* x, float* y, int B, int C, int T, int cs, cudaStream_t s);
+int planes_to_cf(const bf16* hi, const bf16* lo, float* y, int B, int C, int T, int cs, cudaStream_t s);
+
+}  // namespace tvc

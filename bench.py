@@ -252,7 +252,7 @@ def run_ours(args) -> None:
         value = world * samples / (ms_step * 1e-3)
         e2e_val = world * samples / (ms_e2e / args.steps * 1e-3)
         peak, peak_src = measured_peak_hbm()
-        conv_ms = sum(v["ms_per_step"] for k, v in prof.items() if k.startswith("conv1d"))
+        conv_ms = sum(v["ms_per_step"] for k, v in prof.items() if k.startswith(("conv1d", "tc_")))
         prof_ms = sum(v["ms_per_step"] for v in prof.values())
         per_gpu_rate = samples / (ms_step * 1e-3)
         traffic = None
@@ -264,7 +264,7 @@ def run_ours(args) -> None:
                 traffic = None
         achieved = CONV1D_BYTES_PER_SAMPLE * samples / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else None
         roofline = {
-            "bound": "hbm", "kernel": "conv1d dense-conv launches of one step (all Conv1d layers)",
+            "bound": "hbm", "kernel": "dense-conv launches of one step (all Conv1d layers: tc_conv_kernel / conv1d_f32_kernel)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
             "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_step": CONV1D_BYTES_PER_SAMPLE * samples,
@@ -305,14 +305,13 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--conv-impl", default=os.environ.get("TVC_CONV_IMPL", "fp32"), choices=["fp32", "mma"])
+    ap.add_argument("--conv-impl", default=os.environ.get("TVC_CONV_IMPL", "tc"), choices=["fp32", "tc"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
         return
-    if args.conv_impl != "fp32":
-        from tinyvc_b200 import _lib
-        _lib.set_option("conv_impl", args.conv_impl)
+    from tinyvc_b200 import _lib
+    _lib.set_option("conv_impl", args.conv_impl)
     run_ours(args)
 
 

@@ -87,6 +87,22 @@ def test_decoder_infer_golden(cuda_models, report):
     assert e < RMSE_BAR
 
 
+@torch.inference_mode()
+def test_decoder_infer_golden_fp32_plan(cuda_models, report):
+    """The exact-fp32 CUDA-core plan (option conv_impl=fp32) stays available and matches to ~1e-7."""
+    from tinyvc_b200 import _lib
+    _, dec = cuda_models
+    g = load_golden("decoder_b2_lf18.npz")
+    _lib.set_option("conv_impl", "fp32")
+    try:
+        out = dec.infer(*_cuda(t(g["content"]), t(g["f0"]), t(g["energy"])), rand01=t(g["rand01"]).cuda()).cpu()
+    finally:
+        _lib.set_option("conv_impl", "tc")
+    e = rmse(out, t(g["out"]))
+    report.add("decoder_golden_fp32_plan", rmse=e)
+    assert e < 1e-6
+
+
 @pytest.mark.parametrize("batch,lf", [(3, 1), (2, 2), (2, 3), (2, 5), (3, 33), (1, 100)])
 @torch.inference_mode()
 def test_decoder_ragged_lengths(cuda_models, weights, batch, lf, report):

@@ -80,6 +80,9 @@ def lib() -> ctypes.CDLL:
                     fn = getattr(h, name)   # AttributeError if the export is missing
                     fn.restype = res
                     fn.argtypes = args
+                impl = os.environ.get("TVC_CONV_IMPL")
+                if impl and h.tvc_set_option(b"conv_impl", impl.encode()) != 0:
+                    raise RuntimeError(f"tinyvc_b200: TVC_CONV_IMPL={impl!r} is not a known conv implementation")
                 _lib = h
     return _lib
 

@@ -111,7 +111,7 @@ int tvc_set_option(const char* key, const char* value) {
     if (!key || !value) return 2;
     if (!strcmp(key, "conv_impl")) {
         if (!strcmp(value, "fp32")) { g_conv_impl = CONV_IMPL_FP32; return 0; }
-        if (!strcmp(value, "mma")) { g_conv_impl = CONV_IMPL_MMA; return 0; }
+        if (!strcmp(value, "tc")) { g_conv_impl = CONV_IMPL_TC; return 0; }
         set_error("conv_impl: unknown value '%s'", value);
         return 2;
     }
@@ -190,9 +190,18 @@ static void shapes_ok_msg(int B, int Lf) { set_error("invalid shape B=%d Lf=%d",
 size_t tvc_decoder_workspace_bytes(int B, int Lf) {
     if (B <= 0 || Lf <= 0) return 0;
     static DecoderModel shape_only;   // dry runs never touch weights
-    Arena A(nullptr, 0, true);
-    if (shape_only.infer(A, 0, nullptr, nullptr, nullptr, nullptr, nullptr, B, Lf)) return 0;
-    return A.peak + 256;
+    // the larger of the two execution plans, so the caller's buffer fits whichever option is active
+    size_t need = 0;
+    const int saved = g_conv_impl;
+    for (int impl : {CONV_IMPL_FP32, CONV_IMPL_TC}) {
+        g_conv_impl = impl;
+        Arena A(nullptr, 0, true);
+        const int r = shape_only.infer(A, 0, nullptr, nullptr, nullptr, nullptr, nullptr, B, Lf);
+        g_conv_impl = saved;
+        if (r) return 0;
+        need = A.peak > need ? A.peak : need;
+    }
+    return need + 256;
 }
 
 int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, const float* energy,

@@ -24,7 +24,7 @@
 
 namespace tvc {
 
-int g_conv_impl = CONV_IMPL_FP32;
+int g_conv_impl = CONV_IMPL_TC;   // Decoder.infer runs on the tcgen05 path unless ("conv_impl","fp32") is set
 
 template <int NTY, int TM, int NTX, int BK, int KT>
 __global__ void __launch_bounds__(NTY* NTX) conv1d_f32_kernel(ConvParams p) {

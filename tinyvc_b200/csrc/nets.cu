@@ -1,5 +1,6 @@
 // Parameter tables, weight packing and the launch sequences of the TinyVC networks.
 #include "nets.cuh"
+#include "nets_tc.cuh"
 
 #include <cmath>
 #include <cstring>
@@ -228,6 +229,7 @@ int convnext_forward(Arena& A, cudaStream_t s, const CnxtW& L, float* x, float* 
 // =============================================================================================
 DecoderModel::~DecoderModel() {
     if (dft_buf) cudaFree(dft_buf);
+    delete tc;
 }
 
 int DecoderModel::init(const float* params, int64_t numel) {
@@ -287,6 +289,8 @@ int DecoderModel::init(const float* params, int64_t numel) {
     dft_sin = dft_cos;
     dft_sin.w = dft_buf + (size_t)kBins * P;
     TVC_CUDA(cudaStreamSynchronize(s));
+    tc = new DecoderTC();
+    TVC_TRY(tc->init(store));
     return 0;
 }
 
@@ -405,6 +409,11 @@ int DecoderModel::filter_net(Arena& A, cudaStream_t s, const float* content, con
 // Decoder.infer (decoder.py:253-257).
 int DecoderModel::infer(Arena& A, cudaStream_t s, const float* content, const float* f0, const float* energy,
                         const float* rand01, float* out, int B, int Lf) {
+    if (g_conv_impl == CONV_IMPL_TC) {
+        static const DecoderTC shape_only;   // dry runs (workspace sizing) never touch weights
+        TVC_REQUIRE(A.dry || (tc && tc->ready), "decoder: tensor-core plan not initialised");
+        return (A.dry && !tc ? shape_only : *tc).infer(A, s, content, f0, energy, rand01, out, B, Lf);
+    }
     const int L = Lf * kFrame;
     const size_t m = A.mark();
     float* e_fr = A.f32((int64_t)B * Lf);

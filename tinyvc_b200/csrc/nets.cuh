@@ -69,8 +69,11 @@ struct Arena {
     void release(size_t m) { off = m; }
 };
 
+struct DecoderTC;   // nets_tc.cuh: tensor-core execution plan
+
 struct DecoderModel {
     WeightStore store;
+    DecoderTC* tc = nullptr;
     // SourceNet (decoder.py:102-134)
     ConvW sn_content_in, sn_to_amps, sn_to_kernel;
     const float *sn_energy_w = nullptr, *sn_energy_b = nullptr, *sn_f0_w = nullptr, *sn_f0_b = nullptr;

@@ -1,0 +1,329 @@
+// Decoder.infer on the tensor-core path: every dense conv of SourceNet / dsp / FilterNet
+// (module/tinyvc/decoder.py:102-257) runs on tc_conv_kernel (tcgen05, split bf16 x3, fp32 TMEM
+// accumulate); activations stay channels-last between layers (fp32 where a residual or a
+// resampler needs the exact value, split bf16 planes where the consumer is a conv).
+#include "nets_tc.cuh"
+
+#include <cmath>
+#include <string>
+#include <vector>
+
+namespace tvc {
+
+namespace {
+
+const int kUpCh[5] = {384, 192, 96, 48, 24};      // decoder.py:195
+const int kUpOut[5] = {192, 96, 48, 24, 24};
+const int kUpFac[5] = {2, 3, 4, 4, 5};            // decoder.py:196
+const int kDownIn[4] = {24, 48, 96, 192};
+const int kDownOut[4] = {48, 96, 192, 384};
+const int kDownFac[4] = {5, 4, 4, 3};
+// output channels per CTA (tc_conv N tile), chosen so the low-rate levels still spread over the SMs
+const int kDownNT12[4] = {24, 48, 32, 32};
+const int kDownNT3[4] = {48, 48, 64, 48};
+const int kUpNT[5] = {48, 64, 48, 48, 24};
+const int kUpNT5[5] = {32, 32, 48, 24, 24};
+
+constexpr int kHeadsCout = 983;    // kernel 961 | 7 zero rows | amps 15  (amps start on a 16-byte chunk)
+constexpr int kHeadsCs = 984;
+constexpr int kAmpsOff = 968;
+constexpr int kBinsCs = 968;
+constexpr int kFrameInK = kContent + 2;
+constexpr int kFrameInCs = 776;
+
+struct Pl {
+    bf16 *hi = nullptr, *lo = nullptr;
+    int cs = 0;
+};
+Pl planes(Arena& A, long long rows, int cs) {
+    Pl p;
+    p.hi = (bf16*)A.bytes((size_t)rows * cs * sizeof(bf16));
+    p.lo = (bf16*)A.bytes((size_t)rows * cs * sizeof(bf16));
+    p.cs = cs;
+    return p;
+}
+
+struct HostW {
+    std::vector<float> flat;
+    const ParamTable* table = nullptr;
+    const float* get(const std::string& name, int64_t* numel = nullptr) const {
+        const ParamSpec* s = table->find(name);
+        if (!s) return nullptr;
+        if (numel) *numel = s->numel;
+        return flat.data() + s->offset;
+    }
+};
+
+int pack_named(const HostW& H, const std::string& prefix, int NT, TcConvW& out, const std::string& aux_prefix = "",
+               int aux_mode = TC_AUX_NONE) {
+    const ParamSpec* w = H.table->find(prefix + ".weight");
+    TVC_REQUIRE(w && H.get(prefix + ".bias"), "tc weights: no conv named %s", prefix.c_str());
+    const int Cout = w->d0, Cin = w->d1, K = w->d2;
+    if (aux_mode == TC_AUX_NONE) return tc_pack_conv(H.get(prefix + ".weight"), H.get(prefix + ".bias"), Cout, Cin, K, nullptr, nullptr, 0, 0, NT, out);
+    if (aux_mode == TC_AUX_ACC) {
+        const ParamSpec* aw = H.table->find(aux_prefix + ".weight");
+        TVC_REQUIRE(aw && aw->d0 == Cout && aw->d2 == 1, "tc weights: bad residual conv %s", aux_prefix.c_str());
+        return tc_pack_conv(H.get(prefix + ".weight"), H.get(prefix + ".bias"), Cout, Cin, K, H.get(aux_prefix + ".weight"),
+                            H.get(aux_prefix + ".bias"), aw->d1, TC_AUX_ACC, NT, out);
+    }
+    // FiLM: aux_prefix.to_scale / aux_prefix.to_shift, both Conv1d(C, C, 1)  (decoder.py:88-97)
+    const ParamSpec* sw = H.table->find(aux_prefix + ".to_scale.weight");
+    const ParamSpec* hw = H.table->find(aux_prefix + ".to_shift.weight");
+    TVC_REQUIRE(sw && hw && sw->d0 == Cout && hw->d0 == Cout && sw->d1 == hw->d1, "tc weights: bad FiLM %s", aux_prefix.c_str());
+    const int ac = sw->d1;
+    std::vector<float> fw((size_t)2 * Cout * ac), fb((size_t)2 * Cout);
+    memcpy(fw.data(), H.get(aux_prefix + ".to_scale.weight"), sizeof(float) * Cout * ac);
+    memcpy(fw.data() + (size_t)Cout * ac, H.get(aux_prefix + ".to_shift.weight"), sizeof(float) * Cout * ac);
+    memcpy(fb.data(), H.get(aux_prefix + ".to_scale.bias"), sizeof(float) * Cout);
+    memcpy(fb.data() + Cout, H.get(aux_prefix + ".to_shift.bias"), sizeof(float) * Cout);
+    return tc_pack_conv(H.get(prefix + ".weight"), H.get(prefix + ".bias"), Cout, Cin, K, fw.data(), fb.data(), ac, TC_AUX_FILM, NT, out);
+}
+
+}  // namespace
+
+DecoderTC::~DecoderTC() {
+    frame_in.free_all(); heads.free_all(); dft_cos.free_all(); dft_sin.free_all(); down0.free_all();
+    for (auto& m : mid) { m.c2.free_all(); m.c3.free_all(); }
+    for (auto& d : down) { d.c1.free_all(); d.c2.free_all(); d.c3.free_all(); }
+    for (auto& u : up) { u.c1.free_all(); u.c2.free_all(); u.c3.free_all(); u.c4.free_all(); u.c5.free_all(); }
+    if (w7_buf) cudaFree(w7_buf);
+}
+
+int DecoderTC::init(const WeightStore& store) {
+    HostW H;
+    H.table = &store.table;
+    H.flat.resize((size_t)store.table.total);
+    TVC_CUDA(cudaMemcpy(H.flat.data(), store.flat, sizeof(float) * H.flat.size(), cudaMemcpyDeviceToHost));
+    const std::string sn = "source_net", fn = "filter_net";
+
+    // ---- frame_in: content_in (+ energy_in + f0_in) of both nets as one product over [content | e_fr | log f0]
+    {
+        const int Cout = 128 + 384, K = kFrameInK;
+        std::vector<float> w((size_t)Cout * K, 0.f), b((size_t)Cout, 0.f);
+        const float *sw = H.get(sn + ".content_in.weight"), *sb = H.get(sn + ".content_in.bias");
+        const float *ew = H.get(sn + ".energy_in.weight"), *eb = H.get(sn + ".energy_in.bias");
+        const float *fw = H.get(sn + ".f0_in.weight"), *fb = H.get(sn + ".f0_in.bias");
+        const float *cw = H.get(fn + ".content_in.weight"), *cb = H.get(fn + ".content_in.bias");
+        const float *gw = H.get(fn + ".f0_in.weight"), *gb = H.get(fn + ".f0_in.bias");
+        TVC_REQUIRE(sw && sb && ew && eb && fw && fb && cw && cb && gw && gb, "tc weights: missing frame-rate input convs");
+        for (int co = 0; co < 128; ++co) {
+            memcpy(&w[(size_t)co * K], sw + (size_t)co * kContent, sizeof(float) * kContent);
+            w[(size_t)co * K + kContent] = ew[co];
+            w[(size_t)co * K + kContent + 1] = fw[co];
+            b[co] = (sb[co] + eb[co]) + fb[co];            // decoder.py:128 adds in this order
+        }
+        for (int co = 0; co < 384; ++co) {
+            memcpy(&w[(size_t)(128 + co) * K], cw + (size_t)co * kContent, sizeof(float) * kContent);
+            w[(size_t)(128 + co) * K + kContent + 1] = gw[co];
+            b[128 + co] = cb[co] + gb[co];                 // decoder.py:223
+        }
+        TVC_TRY(tc_pack_conv(w.data(), b.data(), Cout, K, 1, nullptr, nullptr, 0, 0, 64, frame_in));
+    }
+    // ---- SourceNet ConvNeXt blocks
+    {
+        std::vector<float> w7((size_t)3 * 7 * 128);
+        for (int i = 0; i < 3; ++i) {
+            const std::string p = sn + ".mid_layers." + std::to_string(i);
+            const float* dw = H.get(p + ".c1.weight");     // [128][1][7]
+            TVC_REQUIRE(dw, "tc weights: missing %s.c1", p.c_str());
+            for (int c = 0; c < 128; ++c)
+                for (int j = 0; j < 7; ++j) w7[((size_t)i * 7 + j) * 128 + c] = dw[c * 7 + j];
+        }
+        TVC_CUDA(cudaMalloc(&w7_buf, sizeof(float) * w7.size()));
+        TVC_CUDA(cudaMemcpy(w7_buf, w7.data(), sizeof(float) * w7.size(), cudaMemcpyHostToDevice));
+        for (int i = 0; i < 3; ++i) {
+            const std::string p = sn + ".mid_layers." + std::to_string(i);
+            mid[i].w7 = w7_buf + (size_t)i * 7 * 128;
+            mid[i].wb = store.raw(p + ".c1.bias");
+            mid[i].ln_g = store.raw(p + ".norm.gamma"); mid[i].ln_b = store.raw(p + ".norm.beta");
+            mid[i].grn_g = store.raw(p + ".grn.gamma"); mid[i].grn_b = store.raw(p + ".grn.beta");
+            TVC_REQUIRE(mid[i].wb && mid[i].ln_g && mid[i].ln_b && mid[i].grn_g && mid[i].grn_b, "tc weights: incomplete %s", p.c_str());
+            TVC_TRY(pack_named(H, p + ".c2", 64, mid[i].c2));
+            TVC_TRY(pack_named(H, p + ".c3", 32, mid[i].c3));
+        }
+    }
+    // ---- heads: to_kernel rows [0,961), to_amps rows [968,983)
+    {
+        std::vector<float> w((size_t)kHeadsCout * 128, 0.f), b((size_t)kHeadsCout, 0.f);
+        const float *kw = H.get(sn + ".to_kernel.weight"), *kb = H.get(sn + ".to_kernel.bias");
+        const float *aw = H.get(sn + ".to_amps.weight"), *ab = H.get(sn + ".to_amps.bias");
+        TVC_REQUIRE(kw && kb && aw && ab, "tc weights: missing SourceNet heads");
+        memcpy(w.data(), kw, sizeof(float) * kBins * 128);
+        memcpy(b.data(), kb, sizeof(float) * kBins);
+        memcpy(w.data() + (size_t)kAmpsOff * 128, aw, sizeof(float) * kOsc * 128);
+        memcpy(b.data() + kAmpsOff, ab, sizeof(float) * kOsc);
+        TVC_TRY(tc_pack_conv(w.data(), b.data(), kHeadsCout, 128, 1, nullptr, nullptr, 0, 0, 64, heads));
+    }
+    // ---- inverse real-DFT bases (fp64 on the host, rounded once):  C[p] = sum_f w_f cos(2 pi f p / N) / N * Re Y[f]
+    {
+        std::vector<float> wc((size_t)kBins * kBins), ws((size_t)kBins * kBins);
+        for (int p = 0; p < kBins; ++p)
+            for (int f = 0; f < kBins; ++f) {
+                const double wf = (f == 0 || f == kNfft / 2) ? 1.0 : 2.0;
+                const int r = (int)(((long long)f * p) % kNfft);
+                const double ang = 2.0 * M_PI * (double)r / (double)kNfft;
+                wc[(size_t)p * kBins + f] = (float)(wf * std::cos(ang) / (double)kNfft);
+                ws[(size_t)p * kBins + f] = (float)(wf * std::sin(ang) / (double)kNfft);
+            }
+        TVC_TRY(tc_pack_conv(wc.data(), nullptr, kBins, kBins, 1, nullptr, nullptr, 0, 0, 64, dft_cos));
+        TVC_TRY(tc_pack_conv(ws.data(), nullptr, kBins, kBins, 1, nullptr, nullptr, 0, 0, 64, dft_sin));
+    }
+    // ---- FilterNet
+    TVC_TRY(pack_named(H, fn + ".downs.0", 24, down0));
+    for (int i = 0; i < 4; ++i) {
+        const std::string p = fn + ".downs." + std::to_string(i + 1);
+        TVC_TRY(pack_named(H, p + ".c1", kDownNT12[i], down[i].c1));
+        TVC_TRY(pack_named(H, p + ".c2", kDownNT12[i], down[i].c2));
+        TVC_TRY(pack_named(H, p + ".c3", kDownNT3[i], down[i].c3, p + ".down_res", TC_AUX_ACC));
+    }
+    for (int i = 0; i < 5; ++i) {
+        const std::string p = fn + ".ups." + std::to_string(i);
+        TVC_TRY(pack_named(H, p + ".c1", kUpNT[i], up[i].c1));
+        TVC_TRY(pack_named(H, p + ".c2", kUpNT[i], up[i].c2, p + ".film1", TC_AUX_FILM));
+        TVC_TRY(pack_named(H, p + ".c3", kUpNT[i], up[i].c3));
+        TVC_TRY(pack_named(H, p + ".c4", kUpNT[i], up[i].c4, p + ".film2", TC_AUX_FILM));
+        TVC_TRY(pack_named(H, p + ".c5", kUpNT5[i], up[i].c5));
+    }
+    out_w = store.raw(fn + ".output_layer.weight");
+    out_b = store.raw(fn + ".output_layer.bias");
+    TVC_REQUIRE(out_w && out_b, "tc weights: missing output layer");
+    ready = true;
+    return 0;
+}
+
+#define RUN(expr)                     \
+    do {                              \
+        if (!A.dry) {                 \
+            ProfScope ps__(#expr, s); \
+            TVC_TRY(expr);            \
+        }                             \
+    } while (0)
+#define ARENA_OK() TVC_REQUIRE(!A.overflow, "workspace too small: need at least %zu bytes, got %zu", A.peak, A.cap)
+
+namespace {
+struct ConvCall {
+    TcConvArgs a;
+    ConvCall(const Pl& in, int B, int T, int dil = 1) {
+        a.a_hi = in.hi; a.a_lo = in.lo; a.a_cs = in.cs; a.B = B; a.T = T; a.dil = dil;
+    }
+    ConvCall& aux(const Pl& x) { a.x_hi = x.hi; a.x_lo = x.lo; a.x_cs = x.cs; return *this; }
+    ConvCall& res(const float* r, int cs) { a.res = r; a.res_cs = cs; return *this; }
+    ConvCall& f32(float* y, int cs) { a.y32 = y; a.y32_cs = cs; return *this; }
+    ConvCall& out(const Pl& y, int act) { a.y_hi = y.hi; a.y_lo = y.lo; a.y_cs = y.cs; a.out_act = act; return *this; }
+    ConvCall& epi(int act) { a.epi_act = act; return *this; }
+};
+int tc_conv_k(const char* name, const TcConvW& W, const ConvCall& c, cudaStream_t s) {
+    ProfScope ps(name, s);
+    return tc_conv_launch(W, c.a, s);
+}
+}  // namespace
+#define CONV(name, W, call)                                   \
+    do {                                                      \
+        if (!A.dry) TVC_TRY(tc_conv_k(name, W, call, s));     \
+    } while (0)
+
+int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float* f0, const float* energy,
+                     const float* rand01, float* out, int B, int Lf) const {
+    const int L = Lf * kFrame;
+    const long long rowsF = (long long)B * Lf, rowsL = (long long)B * L;
+    const size_t m0 = A.mark();
+
+    // ---- frame-rate inputs -> [SourceNet x (128) | FilterNet x0 (384)], channels-last fp32 [rowsF][512]
+    float* e_fr = A.f32(rowsF);
+    float* lf0 = A.f32(rowsF);
+    float* fx = A.f32(rowsF * 512);
+    Pl src = planes(A, rowsL, 24);
+    {
+        const size_t m = A.mark();
+        Pl cin = planes(A, rowsF, kFrameInCs);
+        ARENA_OK();
+        RUN(frame_prep(energy, f0, e_fr, lf0, B, Lf, s));
+        RUN(cf_to_planes(content, cin.hi, cin.lo, B, kContent, Lf, kFrameInCs, TC_ACT_NONE, s, e_fr, lf0));
+        CONV("tc_frame_in(", frame_in, ConvCall(cin, B, Lf).f32(fx, 512));
+        A.release(m);
+    }
+    // ---- SourceNet (decoder.py:126-134) + dsp (decoder.py:259-266)
+    {
+        const size_t m = A.mark();
+        Pl t1 = planes(A, rowsF, 128), xp = planes(A, rowsF, 128), t2p = planes(A, rowsF, 256);
+        float* t2 = A.f32(rowsF * 256);
+        float* hk = A.f32(rowsF * kHeadsCs);
+        Pl yr = planes(A, rowsF, kBinsCs), yi = planes(A, rowsF, kBinsCs);
+        float* cc = A.f32(rowsF * kBinsCs);
+        float* ss = A.f32(rowsF * kBinsCs);
+        float* noise = A.f32(rowsL);
+        void* osc = A.bytes(osc_scratch_bytes(B, Lf));
+        ARENA_OK();
+        for (int i = 0; i < 3; ++i) {
+            const Cnxt& c = mid[i];
+            RUN(dwconv_ln_cl(fx, 512, c.w7, c.wb, c.ln_g, c.ln_b, t1.hi, t1.lo, B, Lf, s));
+            CONV("tc_cnxt_c2(", c.c2, ConvCall(t1, B, Lf).f32(t2, 256).epi(TC_ACT_GELU));
+            RUN(grn_apply_cl(t2, c.grn_g, c.grn_b, t2p.hi, t2p.lo, B, 256, Lf, s));
+            CONV("tc_cnxt_c3(", c.c3, ConvCall(t2p, B, Lf).res(fx, 512).f32(fx, 512).out(xp, TC_ACT_NONE));
+        }
+        CONV("tc_heads(", heads, ConvCall(xp, B, Lf).f32(hk, kHeadsCs).epi(TC_ACT_ELU1));
+        RUN(noise_spectrum_cl(hk, kHeadsCs, rand01, yr.hi, yr.lo, yi.hi, yi.lo, kBinsCs, B, Lf, s));
+        CONV("tc_idft(", dft_cos, ConvCall(yr, B, Lf).f32(cc, kBinsCs));
+        CONV("tc_idft(", dft_sin, ConvCall(yi, B, Lf).f32(ss, kBinsCs));
+        RUN(noise_ola_cl(cc, ss, kBinsCs, noise, B, Lf, s));
+        RUN(harmonic_source_cl(f0, hk + kAmpsOff, kHeadsCs, noise, energy, src.hi, src.lo, 24, osc, B, Lf, s));
+        A.release(m);
+    }
+    // ---- FilterNet down path (decoder.py:206-213,225-229): skips at L, L/5, L/20, L/80, L/240
+    float* skip32[5];
+    Pl skipP[5];
+    int skipT[5];
+    skipT[0] = L;
+    skip32[0] = A.f32(rowsL * 24);
+    skipP[0] = planes(A, rowsL, 24);
+    ARENA_OK();
+    CONV("tc_down0(", down0, ConvCall(src, B, L).f32(skip32[0], 24).out(skipP[0], TC_ACT_NONE));
+    for (int i = 0; i < 4; ++i) {
+        const int cin = kDownIn[i], cout = kDownOut[i], fac = kDownFac[i];
+        const int tin = skipT[i], tout = tin / fac;       // exact: L = 480 * Lf
+        const long long rows = (long long)B * tout;
+        skipT[i + 1] = tout;
+        skip32[i + 1] = A.f32(rows * cout);
+        skipP[i + 1] = planes(A, rows, cout);
+        const size_t m = A.mark();
+        Pl xr = planes(A, rows, cin), xa = planes(A, rows, cin), a = planes(A, rows, cin), c = planes(A, rows, cin);
+        ARENA_OK();
+        const float scale = (float)(1.0 / (1.0 / (double)fac));   // F.interpolate(scale_factor=1/f)
+        RUN(interp_cl(skip32[i], cin, B, tin, tout, scale, cin, nullptr, 0, xr.hi, xr.lo, xa.hi, xa.lo, cin, s));
+        CONV("tc_down_c1(", down[i].c1, ConvCall(xa, B, tout, 1).out(a, TC_ACT_LRELU));
+        CONV("tc_down_c2(", down[i].c2, ConvCall(a, B, tout, 2).out(c, TC_ACT_LRELU));
+        CONV("tc_down_c3(", down[i].c3, ConvCall(c, B, tout, 4).aux(xr).f32(skip32[i + 1], cout).out(skipP[i + 1], TC_ACT_NONE));
+        A.release(m);
+    }
+    // ---- FilterNet up path (decoder.py:214-219,230-233)
+    const float* x = fx + 128;
+    int x_cs = 512, tin = Lf;
+    for (int i = 0; i < 5; ++i) {
+        const Up& u = up[i];
+        const int c = kUpCh[i], cn = kUpOut[i], fac = kUpFac[i];
+        const int tout = tin * fac;
+        const long long rows = (long long)B * tout;
+        const Pl& cond = skipP[4 - i];
+        TVC_REQUIRE(skipT[4 - i] == tout && cond.cs == c, "filter_net: skip %d shape mismatch", 4 - i);
+        float* xo = A.f32(rows * cn);
+        const size_t m = A.mark();
+        float* xi = A.f32(rows * c);
+        float* y = A.f32(rows * c);
+        Pl p0 = planes(A, rows, c), p1 = planes(A, rows, c);
+        ARENA_OK();
+        const float scale = (float)(1.0 / (double)fac);           // F.interpolate(scale_factor=f)
+        RUN(interp_cl(x, x_cs, B, tin, tout, scale, c, xi, c, nullptr, nullptr, p0.hi, p0.lo, c, s));
+        CONV("tc_up_c1(", u.c1, ConvCall(p0, B, tout, 1).out(p1, TC_ACT_LRELU));
+        CONV("tc_up_c2(", u.c2, ConvCall(p1, B, tout, 3).aux(cond).res(xi, c).f32(y, c).out(p0, TC_ACT_LRELU));
+        CONV("tc_up_c3(", u.c3, ConvCall(p0, B, tout, 9).out(p1, TC_ACT_LRELU));
+        CONV("tc_up_c4(", u.c4, ConvCall(p1, B, tout, 27).aux(cond).res(y, c).out(p0, TC_ACT_NONE));
+        CONV("tc_up_c5(", u.c5, ConvCall(p0, B, tout, 1).f32(xo, cn));
+        A.release(m);
+        x = xo; x_cs = cn; tin = tout;
+    }
+    RUN(out_conv_k7_cl(x, out_w, out_b, out, B, L, s));
+    A.release(m0);
+    return 0;
+}
+
+}  // namespace tvc

@@ -1,0 +1,29 @@
+// Tensor-core (tcgen05) execution plan of the Decoder: packed weights + launch sequence.
+#pragma once
+#include "nets.cuh"
+#include "tc_kernels.cuh"
+
+namespace tvc {
+
+struct DecoderTC {
+    TcConvW frame_in;             // [content 768 | e_fr | log f0] -> [SourceNet 128 | FilterNet 384]
+    struct Cnxt {
+        const float *w7 = nullptr, *wb = nullptr, *ln_g = nullptr, *ln_b = nullptr, *grn_g = nullptr, *grn_b = nullptr;
+        TcConvW c2, c3;
+    } mid[3];
+    TcConvW heads;                // 128 -> [kernel 961 | 7 pad | amps 15]
+    TcConvW dft_cos, dft_sin;     // inverse real-DFT bases, 961 -> 961
+    TcConvW down0;
+    struct Down { TcConvW c1, c2, c3; } down[4];
+    struct Up { TcConvW c1, c2, c3, c4, c5; } up[5];
+    const float *out_w = nullptr, *out_b = nullptr;
+    float* w7_buf = nullptr;      // depth-wise weights repacked [3][7][128]
+    bool ready = false;
+    ~DecoderTC();
+    int init(const WeightStore& store);
+    // Decoder.infer (decoder.py:253-257) on the tensor-core path.
+    int infer(Arena& A, cudaStream_t s, const float* content, const float* f0, const float* energy, const float* rand01,
+              float* out, int B, int Lf) const;
+};
+
+}  // namespace tvc

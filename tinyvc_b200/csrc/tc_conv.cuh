@@ -59,7 +59,9 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s);
 int tc_conv_init();
 
 // layout helpers (tc_ops.cu)
-int cf_to_planes(const float* x, bf16* hi, bf16* lo, int B, int C, int T, int cs, int act, cudaStream_t s);
+// extra0/extra1 (nullable, [B*T]) are appended as channels C and C+1 (frame-rate scalars such as log-f0).
+int cf_to_planes(const float* x, bf16* hi, bf16* lo, int B, int C, int T, int cs, int act, cudaStream_t s,
+                 const float* extra0 = nullptr, const float* extra1 = nullptr);
 int cf_to_cl(const float* x, float* y, int B, int C, int T, int cs, cudaStream_t s);
 int cl_to_cf(const float* x, float* y, int B, int C, int T, int cs, cudaStream_t s);
 int planes_to_cf(const bf16* hi, const bf16* lo, float* y, int B, int C, int T, int cs, cudaStream_t s);

@@ -1,0 +1,206 @@
+// Channels-last kernels of the tensor-core decoder path that are not dense convs:
+// linear resampling, ConvNeXt depth-wise conv + LayerNorm, GRN, and the k=7 output conv.
+#include "tc_conv.cuh"
+#include "tc_kernels.cuh"
+
+namespace tvc {
+
+namespace {
+
+__device__ __forceinline__ void split_bf16(float v, bf16& h, bf16& l) {
+    h = __float2bfloat16_rn(v);
+    l = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(h)));
+}
+__device__ __forceinline__ uint32_t pack2(bf16 a, bf16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+// store 4 consecutive channels of both planes (8 bytes each)
+__device__ __forceinline__ void store_planes4(bf16* hi, bf16* lo, long long off, const float v[4]) {
+    bf16 h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_bf16(v[i], h[i], l[i]);
+    *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
+    *reinterpret_cast<uint2*>(lo + off) = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// interp_cl:  F.interpolate(x, scale_factor=..., mode='linear') along time for channels-last
+// fp32 input [B*Tin][x_cs] (decoder.py:148 Downsample, :174 Upsample), exact ATen coordinate
+// arithmetic (tvc_common.cuh lin_coord/lin_blend).  Writes any of: fp32 [B*Tout][y_cs],
+// raw split planes, leaky_relu(0.1) split planes (the convs that follow apply leaky_relu first).
+// One thread per (output row, 4-channel group).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) interp_cl_kernel(const float* __restrict__ x, int x_cs, int Tin, int Tout,
+                                                        float scale, int C4, float* __restrict__ y32, int y_cs,
+                                                        bf16* __restrict__ r_hi, bf16* __restrict__ r_lo,
+                                                        bf16* __restrict__ a_hi, bf16* __restrict__ a_lo, int p_cs,
+                                                        long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int g = (int)(i % C4);
+    const long long row = i / C4;
+    const long long b = row / Tout;
+    const int t = (int)(row - b * Tout);
+    const LinCoord c = lin_coord(t, scale, Tin);
+    const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + (b * Tin + c.i0) * x_cs) + g);
+    const float4 x1 = __ldg(reinterpret_cast<const float4*>(x + (b * Tin + c.i1) * x_cs) + g);
+    float v[4] = {lin_blend(x0.x, x1.x, c), lin_blend(x0.y, x1.y, c), lin_blend(x0.z, x1.z, c), lin_blend(x0.w, x1.w, c)};
+    if (y32) *reinterpret_cast<float4*>(y32 + row * y_cs + g * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    if (r_hi) store_planes4(r_hi, r_lo, row * p_cs + g * 4, v);
+    if (a_hi) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = leaky01(v[k]);
+        store_planes4(a_hi, a_lo, row * p_cs + g * 4, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dwconv_ln_cl (C = 128): depth-wise k=7 conv (dilation 1, replicate padding) + LayerNorm over
+// channels (convnext.py:42-43,52-53) on channels-last fp32 rows -> split planes.  One warp per
+// row, 4 channels per lane; the LayerNorm statistics are two warp-shuffle reductions.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dwconv_ln_cl_kernel(const float* __restrict__ x, int x_cs,
+                                                           const float* __restrict__ w7,   // [7][128] repacked
+                                                           const float* __restrict__ wb, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, bf16* __restrict__ hi,
+                                                           bf16* __restrict__ lo, int T, long long rows) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const long long b = row / T;
+    const int t = (int)(row - b * T);
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(wb) + lane);
+    float v[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        int tt = t + j - 3;
+        tt = tt < 0 ? 0 : (tt > T - 1 ? T - 1 : tt);
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (b * T + tt) * x_cs) + lane);
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w7 + j * 128) + lane);
+        v[0] = fmaf(wv.x, xv.x, v[0]); v[1] = fmaf(wv.y, xv.y, v[1]);
+        v[2] = fmaf(wv.z, xv.z, v[2]); v[3] = fmaf(wv.w, xv.w, v[3]);
+    }
+    float s = (v[0] + v[1]) + (v[2] + v[3]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / 128.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float d = v[k] - mean;
+        q = fmaf(d, d, q);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = 1.0f / sqrtf(q * (1.0f / 128.0f) + 1e-5f);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane);
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + lane);
+    float o4[4] = {fmaf((v[0] - mean) * rstd, g.x, be.x), fmaf((v[1] - mean) * rstd, g.y, be.y),
+                   fmaf((v[2] - mean) * rstd, g.z, be.z), fmaf((v[3] - mean) * rstd, g.w, be.w)};
+    store_planes4(hi, lo, row * 128 + lane * 4, o4);
+}
+
+// ---------------------------------------------------------------------------------------------
+// grn_apply_cl: GRN (convnext.py:23-34) on channels-last fp32 [B*T][C] -> split planes:
+//   g[c] = sqrt(sum_t y^2),  n = g / (mean_c g + 1e-6),  out = y * (gamma*n + 1) + beta
+// One block per utterance, thread = channel (coalesced over channels), fixed summation order.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grn_apply_cl_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, bf16* __restrict__ hi,
+                                                           bf16* __restrict__ lo, int C, int T) {
+    __shared__ float part[8];
+    const int b = blockIdx.x, c = threadIdx.x, lane = c & 31, warp = c >> 5;
+    const float* yb = y + (long long)b * T * C;
+    float s = 0.f;
+    if (c < C)
+        for (int t = 0; t < T; ++t) {
+            const float v = __ldg(yb + (long long)t * C + c);
+            s = fmaf(v, v, s);
+        }
+    const float g = sqrtf(s);
+    float tot = c < C ? g : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0) part[warp] = tot;
+    __syncthreads();
+    float all = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) all += part[i];
+    if (c >= C) return;
+    const float scale = fmaf(__ldg(gamma + c), g / (all / (float)C + 1e-6f), 1.0f);
+    const float bt = __ldg(beta + c);
+    for (int t = 0; t < T; ++t) {
+        const long long o = ((long long)b * T + t) * C + c;
+        bf16 h, l;
+        split_bf16(fmaf(__ldg(y + o), scale, bt), h, l);
+        hi[o] = h;
+        lo[o] = l;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// out_conv_k7_cl: FilterNet.output_layer, Conv1d(24 -> 1, k = 7, replicate pad 3) (decoder.py:220,233)
+// on channels-last fp32 [B*T][24] -> waveform [B][T].  One thread per output sample.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) out_conv_k7_cl_kernel(const float* __restrict__ x, const float* __restrict__ w,   // [24][7] torch layout
+                                                             const float* __restrict__ bias, float* __restrict__ y, int T,
+                                                             long long rows) {
+    __shared__ float ws[7][24];
+    for (int e = threadIdx.x; e < 24 * 7; e += blockDim.x) ws[e % 7][e / 7] = __ldg(w + e);
+    __syncthreads();
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const long long b = row / T;
+    const int t = (int)(row - b * T);
+    float acc = __ldg(bias);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        int tt = t + j - 3;
+        tt = tt < 0 ? 0 : (tt > T - 1 ? T - 1 : tt);
+        const float4* xr = reinterpret_cast<const float4*>(x + (b * T + tt) * 24);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const float4 v = __ldg(xr + q);
+            acc = fmaf(ws[j][q * 4 + 0], v.x, acc);
+            acc = fmaf(ws[j][q * 4 + 1], v.y, acc);
+            acc = fmaf(ws[j][q * 4 + 2], v.z, acc);
+            acc = fmaf(ws[j][q * 4 + 3], v.w, acc);
+        }
+    }
+    y[row] = acc;
+}
+
+}  // namespace
+
+int interp_cl(const float* x, int x_cs, int B, int Tin, int Tout, float scale, int C, float* y32, int y_cs, bf16* r_hi,
+              bf16* r_lo, bf16* a_hi, bf16* a_lo, int p_cs, cudaStream_t s) {
+    TVC_REQUIRE(C % 4 == 0 && x_cs % 4 == 0 && (!y32 || y_cs % 4 == 0) && p_cs % 4 == 0, "interp_cl: channel counts must be multiples of 4");
+    const long long total = (long long)B * Tout * (C / 4);
+    interp_cl_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, x_cs, Tin, Tout, scale, C / 4, y32, y_cs, r_hi, r_lo, a_hi, a_lo, p_cs, total);
+    TVC_LAUNCH_CHECK();
+    return 0;
+}
+
+int dwconv_ln_cl(const float* x, int x_cs, const float* w7, const float* wb, const float* gamma, const float* beta,
+                 bf16* hi, bf16* lo, int B, int T, cudaStream_t s) {
+    const long long rows = (long long)B * T;
+    dwconv_ln_cl_kernel<<<cdiv(rows * 32, 256), 256, 0, s>>>(x, x_cs, w7, wb, gamma, beta, hi, lo, T, rows);
+    TVC_LAUNCH_CHECK();
+    return 0;
+}
+
+int grn_apply_cl(const float* y, const float* gamma, const float* beta, bf16* hi, bf16* lo, int B, int C, int T,
+                 cudaStream_t s) {
+    TVC_REQUIRE(C <= 256, "grn_apply_cl: C=%d > 256", C);
+    grn_apply_cl_kernel<<<B, 256, 0, s>>>(y, gamma, beta, hi, lo, C, T);
+    TVC_LAUNCH_CHECK();
+    return 0;
+}
+
+int out_conv_k7_cl(const float* x, const float* w, const float* bias, float* y, int B, int T, cudaStream_t s) {
+    const long long rows = (long long)B * T;
+    out_conv_k7_cl_kernel<<<cdiv(rows, 256), 256, 0, s>>>(x, w, bias, y, T, rows);
+    TVC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace tvc

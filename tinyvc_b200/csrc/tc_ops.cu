@@ -24,13 +24,20 @@ __device__ __forceinline__ void split_bf16(float v, bf16& h, bf16& l) {
 template <int MODE>
 __global__ void __launch_bounds__(256) cf_to_cl_kernel(const float* __restrict__ x, float* __restrict__ y32,
                                                        bf16* __restrict__ hi, bf16* __restrict__ lo, int C, int T,
-                                                       int cs, int act) {
+                                                       int cs, int act, const float* __restrict__ extra0,
+                                                       const float* __restrict__ extra1) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int j = ty; j < 32; j += 8) {
         const int c = c0 + j, t = t0 + tx;
-        tile[j][tx] = (c < C && t < T) ? __ldg(x + ((long long)b * C + c) * T + t) : 0.f;
+        float v = 0.f;
+        if (t < T) {
+            if (c < C) v = __ldg(x + ((long long)b * C + c) * T + t);
+            else if (c == C && extra0) v = __ldg(extra0 + (long long)b * T + t);       // per-row scalars appended as
+            else if (c == C + 1 && extra1) v = __ldg(extra1 + (long long)b * T + t);   // channels C, C+1
+        }
+        tile[j][tx] = v;
     }
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
@@ -75,15 +82,16 @@ __global__ void __launch_bounds__(256) cl_to_cf_kernel(const float* __restrict__
 
 }  // namespace
 
-int cf_to_planes(const float* x, bf16* hi, bf16* lo, int B, int C, int T, int cs, int act, cudaStream_t s) {
+int cf_to_planes(const float* x, bf16* hi, bf16* lo, int B, int C, int T, int cs, int act, cudaStream_t s,
+                 const float* extra0, const float* extra1) {
     dim3 grid(cdiv(T, 32), cdiv(cs, 32), B);
-    cf_to_cl_kernel<1><<<grid, 256, 0, s>>>(x, nullptr, hi, lo, C, T, cs, act);
+    cf_to_cl_kernel<1><<<grid, 256, 0, s>>>(x, nullptr, hi, lo, C, T, cs, act, extra0, extra1);
     TVC_LAUNCH_CHECK();
     return 0;
 }
 int cf_to_cl(const float* x, float* y, int B, int C, int T, int cs, cudaStream_t s) {
     dim3 grid(cdiv(T, 32), cdiv(cs, 32), B);
-    cf_to_cl_kernel<0><<<grid, 256, 0, s>>>(x, y, nullptr, nullptr, C, T, cs, 0);
+    cf_to_cl_kernel<0><<<grid, 256, 0, s>>>(x, y, nullptr, nullptr, C, T, cs, 0, nullptr, nullptr);
     TVC_LAUNCH_CHECK();
     return 0;
 }

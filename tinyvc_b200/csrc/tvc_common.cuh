@@ -116,7 +116,7 @@ int conv1d_launch(const ConvParams& p, cudaStream_t stream);
 int conv1d_init();   // one-time cudaFuncSetAttribute calls
 
 // Conv implementation selector (set through tvc_set_option("conv_impl", ...)).
-enum ConvImpl { CONV_IMPL_FP32 = 0, CONV_IMPL_MMA = 1 };
+enum ConvImpl { CONV_IMPL_FP32 = 0, CONV_IMPL_TC = 1 };
 extern int g_conv_impl;
 
 }  // namespace tvc

@@ -41,7 +41,7 @@ CASES = [
     (2, 300, 24, 24, 3, 27, 24, 2, True, 0, 1, 24),
     (3, 100, 48, 96, 3, 4, 48, 1, False, 0, 0, 96),
     (8, 18, 768, 512, 1, 1, 0, 0, False, 0, 0, 128),
-    (4, 36, 384, 384, 3, 9, 384, 2, True, 0, 1, 96),
+    (4, 36, 384, 384, 3, 9, 384, 2, True, 0, 1, 64),
     (5, 18, 128, 976, 1, 1, 0, 0, False, 3, 0, 128),
     (2, 777, 17, 24, 3, 1, 0, 0, False, 0, 0, 24),
     (3, 18, 961, 961, 1, 1, 0, 0, False, 0, 0, 128),

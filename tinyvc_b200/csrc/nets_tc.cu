@@ -290,9 +290,12 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         ARENA_OK();
         const float scale = (float)(1.0 / (1.0 / (double)fac));   // F.interpolate(scale_factor=1/f)
         RUN(interp_cl(skip32[i], cin, B, tin, tout, scale, cin, nullptr, 0, xr.hi, xr.lo, xa.hi, xa.lo, cin, s));
-        CONV("tc_down_c1(", down[i].c1, ConvCall(xa, B, tout, 1).out(a, TC_ACT_LRELU));
-        CONV("tc_down_c2(", down[i].c2, ConvCall(a, B, tout, 2).out(c, TC_ACT_LRELU));
-        CONV("tc_down_c3(", down[i].c3, ConvCall(c, B, tout, 4).aux(xr).f32(skip32[i + 1], cout).out(skipP[i + 1], TC_ACT_NONE));
+        const char* const n1[4] = {"tc_down1_c1(", "tc_down2_c1(", "tc_down3_c1(", "tc_down4_c1("};
+        const char* const n2[4] = {"tc_down1_c2(", "tc_down2_c2(", "tc_down3_c2(", "tc_down4_c2("};
+        const char* const n3[4] = {"tc_down1_c3(", "tc_down2_c3(", "tc_down3_c3(", "tc_down4_c3("};
+        CONV(n1[i], down[i].c1, ConvCall(xa, B, tout, 1).out(a, TC_ACT_LRELU));
+        CONV(n2[i], down[i].c2, ConvCall(a, B, tout, 2).out(c, TC_ACT_LRELU));
+        CONV(n3[i], down[i].c3, ConvCall(c, B, tout, 4).aux(xr).f32(skip32[i + 1], cout).out(skipP[i + 1], TC_ACT_NONE));
         A.release(m);
     }
     // ---- FilterNet up path (decoder.py:214-219,230-233)
@@ -313,11 +316,16 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         ARENA_OK();
         const float scale = (float)(1.0 / (double)fac);           // F.interpolate(scale_factor=f)
         RUN(interp_cl(x, x_cs, B, tin, tout, scale, c, xi, c, nullptr, nullptr, p0.hi, p0.lo, c, s));
-        CONV("tc_up_c1(", u.c1, ConvCall(p0, B, tout, 1).out(p1, TC_ACT_LRELU));
-        CONV("tc_up_c2(", u.c2, ConvCall(p1, B, tout, 3).aux(cond).res(xi, c).f32(y, c).out(p0, TC_ACT_LRELU));
-        CONV("tc_up_c3(", u.c3, ConvCall(p0, B, tout, 9).out(p1, TC_ACT_LRELU));
-        CONV("tc_up_c4(", u.c4, ConvCall(p1, B, tout, 27).aux(cond).res(y, c).out(p0, TC_ACT_NONE));
-        CONV("tc_up_c5(", u.c5, ConvCall(p0, B, tout, 1).f32(xo, cn));
+        const char* const un[5][5] = {{"tc_up0_c1(", "tc_up0_c2(", "tc_up0_c3(", "tc_up0_c4(", "tc_up0_c5("},
+                                      {"tc_up1_c1(", "tc_up1_c2(", "tc_up1_c3(", "tc_up1_c4(", "tc_up1_c5("},
+                                      {"tc_up2_c1(", "tc_up2_c2(", "tc_up2_c3(", "tc_up2_c4(", "tc_up2_c5("},
+                                      {"tc_up3_c1(", "tc_up3_c2(", "tc_up3_c3(", "tc_up3_c4(", "tc_up3_c5("},
+                                      {"tc_up4_c1(", "tc_up4_c2(", "tc_up4_c3(", "tc_up4_c4(", "tc_up4_c5("}};
+        CONV(un[i][0], u.c1, ConvCall(p0, B, tout, 1).out(p1, TC_ACT_LRELU));
+        CONV(un[i][1], u.c2, ConvCall(p1, B, tout, 3).aux(cond).res(xi, c).f32(y, c).out(p0, TC_ACT_LRELU));
+        CONV(un[i][2], u.c3, ConvCall(p0, B, tout, 9).out(p1, TC_ACT_LRELU));
+        CONV(un[i][3], u.c4, ConvCall(p1, B, tout, 27).aux(cond).res(y, c).out(p0, TC_ACT_NONE));
+        CONV(un[i][4], u.c5, ConvCall(p0, B, tout, 1).f32(xo, cn));
         A.release(m);
         x = xo; x_cs = cn; tin = tout;
     }

@@ -29,7 +29,7 @@ namespace tvc {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 160;
+constexpr int kThreads = 544;   // 12 epilogue warps + 1 MMA warp + 4 producer warps
 constexpr uint32_t kChunkStride = kTileM * 16;   // bytes between consecutive 8-channel chunks of the A tile (LBO)
 
 struct TcKParams {
@@ -42,6 +42,8 @@ struct TcKParams {
     int a_cs, x_cs, res_cs, y32_cs, y_cs;
     int T, dil, taps, nkb, aux_nkb, aux_mode, KB, NT, NTp, Cout;
     int ring;                      // smem ring depth
+    long long row_tiles;
+    int n_tiles;
     uint32_t a_stage_bytes, b_stage_bytes;
     uint32_t tmem_cols;
     int epi_act, out_act;
@@ -82,6 +84,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+// 16-byte cp.async (LDGSTS) with zero fill when src_bytes == 0
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival once all prior cp.async of this thread have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -142,204 +152,278 @@ __device__ __forceinline__ uint32_t pack_bf16x2(bf16 a, bf16 b) {
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) tc_conv_kernel(const TcKParams p) {
+// Epilogue specialisations.  The element-wise tail is the instruction-bound part of the small-channel
+// convs, so the combinations the decoder uses are compiled with their flags as constants; the generic
+// instantiation (flags read from the parameters) serves everything else (parity probes).
+// ---------------------------------------------------------------------------------------------
+struct EpiSpec { int film, res, y32, planes, epi_act, out_act; };
+constexpr int kNumSpecs = 8;
+__host__ __device__ constexpr EpiSpec epi_spec(int i) {
+    return i == 0 ? EpiSpec{0, 0, 1, 0, TC_ACT_NONE, TC_ACT_NONE}      // plain fp32 output
+         : i == 1 ? EpiSpec{0, 0, 1, 0, TC_ACT_GELU, TC_ACT_NONE}      // ConvNeXt c2
+         : i == 2 ? EpiSpec{0, 1, 1, 1, TC_ACT_NONE, TC_ACT_NONE}      // ConvNeXt c3 (+residual)
+         : i == 3 ? EpiSpec{0, 0, 1, 0, TC_ACT_ELU1, TC_ACT_NONE}      // SourceNet heads
+         : i == 4 ? EpiSpec{0, 0, 1, 1, TC_ACT_NONE, TC_ACT_NONE}      // skip tensors (downs.0, Downsample c3)
+         : i == 5 ? EpiSpec{0, 0, 0, 1, TC_ACT_NONE, TC_ACT_LRELU}     // c1/c3 of Up, c1/c2 of Down
+         : i == 6 ? EpiSpec{1, 1, 1, 1, TC_ACT_NONE, TC_ACT_LRELU}     // Upsample c2 + FiLM1 + residual
+                  : EpiSpec{1, 1, 0, 1, TC_ACT_NONE, TC_ACT_NONE};     // Upsample c4 + FiLM2 + residual
+}
+
+constexpr int kEpiWarps = 12;      // 4 TMEM lane quarters x 3 column slots
+constexpr int kMmaWarp = 12;
+constexpr int kProdWarp0 = 13;
+
+// split two fp32 values into packed bf16 hi / lo pairs
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(__fsub_rn(a, ha), __fsub_rn(b, hb));
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent, warp-specialised: each CTA walks tiles (row tile, channel tile) round-robin.
+//   warps 0-11   epilogue: TMEM lane quarter = warp & 3, column slot = warp >> 2 (8-channel groups
+//                slot, slot+3, ...); accumulators are double-buffered in TMEM
+//   warp  12     TMEM allocation + single-thread tcgen05.mma issue
+//   warps 13-16  producers (thread = tile row): cp.async 16-byte gathers into the smem ring, completion
+//                signalled with cp.async.mbarrier.arrive.noinc, so a producer never waits for its loads
+// ---------------------------------------------------------------------------------------------
+template <int SPEC>
+__global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bar_base = smem_base + (uint32_t)p.ring * stage_bytes;   // full[ring], empty[ring], acc
-    const uint32_t acc_bar = bar_base + 16u * (uint32_t)p.ring;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)p.ring * stage_bytes + 16 * p.ring + 8);
+    // barriers: full[ring], empty[ring], acc_full[2], acc_empty[2]
+    const uint32_t bar_base = smem_base + (uint32_t)p.ring * stage_bytes;
+    const uint32_t acc_full = bar_base + 16u * (uint32_t)p.ring;
+    const uint32_t acc_empty = acc_full + 16u;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)p.ring * stage_bytes + 16 * p.ring + 32);
 
+    constexpr bool kGeneric = SPEC < 0;
+    constexpr EpiSpec kS = epi_spec(SPEC < 0 ? 0 : SPEC);
+    const bool film = kGeneric ? p.aux_mode == TC_AUX_FILM : kS.film != 0;
     const int n_main = p.taps * p.nkb;
     const int n_stage = n_main + p.aux_nkb;
     const int chunks = p.KB >> 3;                   // 16-byte chunks per row per plane in one stage
     const uint32_t plane_a = (uint32_t)chunks * kChunkStride;
+    const uint32_t acc_cols = (uint32_t)(film ? 3 * p.NTp : p.NTp);
+    const long long n_tiles_total = p.row_tiles * p.n_tiles;
 
-    if (tid == 128) {
+    if (tid == 0) {
         for (int s = 0; s < p.ring; ++s) {
             mbar_init(bar_base + 8u * s, kTileM + 1);              // full: 128 gather arrivals + 1 expect_tx
             mbar_init(bar_base + 8u * (p.ring + s), 1);            // empty: one tcgen05.commit
         }
-        mbar_init(acc_bar, 1);
+        mbar_init(acc_full, 1); mbar_init(acc_full + 8, 1);
+        mbar_init(acc_empty, kEpiWarps); mbar_init(acc_empty + 8, kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    const long long row0 = (long long)blockIdx.x * kTileM;
-    const int n_tile = blockIdx.y;
-
-    if (warp < 4) {
-        // ================= producer: gather A, launch B =================
-        const long long row = row0 + tid;
-        const bool valid = row < p.rows;
-        const long long b = valid ? row / p.T : 0;
-        const int t = valid ? (int)(row - b * p.T) : 0;
-        const bf16* wt = p.w + (long long)n_tile * p.tile_elems;
-        long long w_off = 0;   // bf16 elements consumed so far
-        for (int i = 0; i < n_stage; ++i) {
-            const int s = i % p.ring, use = i / p.ring;
-            const uint32_t full = bar_base + 8u * s, empty = bar_base + 8u * (p.ring + s);
-            const bool is_aux = i >= n_main;
-            const uint32_t n_rows = (is_aux && p.aux_mode == TC_AUX_FILM) ? 2u * p.NTp : (uint32_t)p.NTp;
-            const uint32_t b_bytes = 4u * (uint32_t)p.KB * n_rows;       // hi + lo images
-            if (use > 0) mbar_wait(empty, (uint32_t)(use - 1) & 1u);
-            const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
-            if (tid == 0) {
-                mbar_arrive_expect_tx(full, b_bytes);
-                bulk_g2s(a_dst + p.a_stage_bytes, wt + w_off, b_bytes, full);
-            }
-            w_off += b_bytes >> 1;
-            // source row of this thread for this stage
-            int kb;
-            const bf16 *src_hi, *src_lo;
-            int cs;
-            long long srow;
-            if (!is_aux) {
-                const int tap = i / p.nkb;
-                kb = i - tap * p.nkb;
-                int tt = t + (tap - ((p.taps - 1) >> 1)) * p.dil;
-                tt = tt < 0 ? 0 : (tt > p.T - 1 ? p.T - 1 : tt);
-                srow = b * p.T + tt;
-                src_hi = p.a_hi; src_lo = p.a_lo; cs = p.a_cs;
-            } else {
-                kb = i - n_main;
-                srow = row;
-                src_hi = p.x_hi; src_lo = p.x_lo; cs = p.x_cs;
-            }
-            const int c0 = kb * chunks, cmax = cs >> 3;
-            const uint4* gh = reinterpret_cast<const uint4*>(src_hi + srow * cs);
-            const uint4* gl = reinterpret_cast<const uint4*>(src_lo + srow * cs);
-            uint8_t* dst = smem + (size_t)s * stage_bytes + (size_t)tid * 16;
-            for (int c = 0; c < chunks; c += 4) {
-                uint4 vh[4], vl[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const bool ok = valid && (c + u) < chunks && (c0 + c + u) < cmax;
-                    vh[u] = ok ? __ldg(gh + c0 + c + u) : make_uint4(0, 0, 0, 0);
-                    vl[u] = ok ? __ldg(gl + c0 + c + u) : make_uint4(0, 0, 0, 0);
+    if (warp >= kProdWarp0) {
+        // ================= producers =================
+        const int r = tid - kProdWarp0 * 32;
+        uint32_t s = 0, ph = 0;    // ring slot and the parity of its *previous* use
+        bool wrapped = false;
+        const int half = (p.taps - 1) >> 1;
+        const uint32_t b_main = 4u * (uint32_t)p.KB * (uint32_t)p.NTp;
+        const uint32_t b_aux = film ? 2u * b_main : b_main;
+        for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+            const long long row_tile = tile / p.n_tiles;
+            const int n_tile = (int)(tile - row_tile * p.n_tiles);
+            const long long row = row_tile * kTileM + r;
+            const bool valid = row < p.rows;
+            const long long b = valid ? row / p.T : 0;
+            const int t = valid ? (int)(row - b * p.T) : 0;
+            const bf16* wt = p.w + (long long)n_tile * p.tile_elems;
+            int tap = 0, kb = 0;
+            for (int i = 0; i < n_stage; ++i) {
+                const uint32_t full = bar_base + 8u * s, empty = bar_base + 8u * (p.ring + s);
+                const bool is_aux = i >= n_main;
+                const uint32_t b_bytes = is_aux ? b_aux : b_main;
+                if (wrapped) mbar_wait(empty, ph);
+                const uint32_t a_dst = smem_base + s * stage_bytes;
+                if (r == 0) {
+                    mbar_arrive_expect_tx(full, b_bytes);
+                    bulk_g2s(a_dst + p.a_stage_bytes, wt, b_bytes, full);
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (c + u < chunks) {
-                        *reinterpret_cast<uint4*>(dst + (size_t)(c + u) * kChunkStride) = vh[u];
-                        *reinterpret_cast<uint4*>(dst + plane_a + (size_t)(c + u) * kChunkStride) = vl[u];
-                    }
+                wt += b_bytes >> 1;
+                const bf16 *src_hi, *src_lo;
+                int cs;
+                long long srow;
+                if (!is_aux) {
+                    int tt = t + (tap - half) * p.dil;
+                    tt = tt < 0 ? 0 : (tt > p.T - 1 ? p.T - 1 : tt);
+                    srow = b * p.T + tt;
+                    src_hi = p.a_hi; src_lo = p.a_lo; cs = p.a_cs;
+                } else {
+                    srow = valid ? row : 0;
+                    src_hi = p.x_hi; src_lo = p.x_lo; cs = p.x_cs;
                 }
+                const int c0 = kb * chunks;
+                const int nok = valid ? min(chunks, (cs >> 3) - c0) : 0;     // chunks that exist in memory
+                const bf16* gh = src_hi + srow * cs + c0 * 8;
+                const bf16* gl = src_lo + srow * cs + c0 * 8;
+                const uint32_t dst = a_dst + (uint32_t)r * 16u;
+                for (int c = 0; c < chunks; ++c) {
+                    const uint32_t nb = c < nok ? 16u : 0u;                 // 0 -> zero fill
+                    cp_async16(dst + (uint32_t)c * kChunkStride, nb ? gh + c * 8 : src_hi, nb);
+                    cp_async16(dst + plane_a + (uint32_t)c * kChunkStride, nb ? gl + c * 8 : src_lo, nb);
+                }
+                cp_async_arrive_noinc(full);
+                if (++kb == (is_aux ? p.aux_nkb : p.nkb)) { kb = 0; ++tap; }
+                if (i + 1 == n_main) { kb = 0; }
+                if (++s == (uint32_t)p.ring) { s = 0; ph = wrapped ? ph ^ 1u : 0u; wrapped = true; }
             }
-            fence_proxy_async();
-            mbar_arrive(full);
         }
-
-        // ================= epilogue =================
-        mbar_wait(acc_bar, 0);
-        tc_fence_after();
-        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-        const bool film = p.aux_mode == TC_AUX_FILM;
-        const float* bias = p.bias + n_tile * p.NTp;               // padded channel space
-        const float* fbias = film ? p.film_bias + 2 * n_tile * p.NTp : nullptr;
-        const int ch0 = n_tile * p.NT;                             // first real output channel of this tile
-        for (int cg = 0; cg < (p.NT >> 3); ++cg) {
-            float v[8], sc[8], sh[8];
-            tmem_ld8(lane_addr + (uint32_t)(cg * 8), v);
-            if (film) {
-                tmem_ld8(lane_addr + (uint32_t)(p.NTp + cg * 8), sc);
-                tmem_ld8(lane_addr + (uint32_t)(2 * p.NTp + cg * 8), sh);
-            }
-            tmem_ld_wait();
-            const int ch = ch0 + cg * 8;
-            if (!valid || ch >= p.Cout) continue;                  // warp-uniform in ch; `valid` only masks stores below
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __fadd_rn(v[i], __ldg(bias + cg * 8 + i));
-            if (film) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float scale = __fadd_rn(sc[i], __ldg(fbias + cg * 8 + i));
-                    const float shift = __fadd_rn(sh[i], __ldg(fbias + p.NTp + cg * 8 + i));
-                    v[i] = __fadd_rn(__fmul_rn(v[i], scale), shift);       // FiLM: x * scale + shift (decoder.py:97)
+    } else if (warp == kMmaWarp) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            const uint32_t idesc_main = umma_idesc(kTileM, (uint32_t)p.NTp);
+            const uint32_t idesc_film = umma_idesc(kTileM, 2u * (uint32_t)p.NTp);
+            uint32_t s = 0, ph = 0, tcount = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tcount) {
+                const uint32_t buf = tcount & 1u, buse = tcount >> 1;
+                if (buse > 0) {                                         // epilogue must have drained this accumulator
+                    mbar_wait(acc_empty + 8u * buf, (buse - 1) & 1u);
+                    tc_fence_after();
                 }
+                const uint32_t d_base = tmem + buf * acc_cols;
+                for (int i = 0; i < n_stage; ++i) {
+                    const uint32_t full = bar_base + 8u * s, empty = bar_base + 8u * (p.ring + s);
+                    const bool is_film = i >= n_main && film;
+                    const uint32_t n_rows = is_film ? 2u * p.NTp : (uint32_t)p.NTp;
+                    const uint32_t idesc = is_film ? idesc_film : idesc_main;
+                    const uint32_t d = d_base + (is_film ? (uint32_t)p.NTp : 0u);
+                    const bool first = is_film ? (i == n_main) : (i == 0);
+                    mbar_wait(full, ph);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_base + s * stage_bytes;
+                    const uint32_t b_base = a_base + p.a_stage_bytes;
+                    const uint32_t b_lbo = n_rows * 16u;              // bytes between 8-channel chunks of the weight image
+                    const uint32_t plane_b = (uint32_t)chunks * b_lbo;
+                    for (int ks = 0; ks < (p.KB >> 4); ++ks) {
+                        const uint64_t a_h = umma_desc(a_base + (uint32_t)(2 * ks) * kChunkStride, kChunkStride, 128);
+                        const uint64_t a_l = umma_desc(a_base + plane_a + (uint32_t)(2 * ks) * kChunkStride, kChunkStride, 128);
+                        const uint64_t b_h = umma_desc(b_base + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
+                        const uint64_t b_l = umma_desc(b_base + plane_b + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
+                        umma_bf16(d, a_h, b_h, idesc, (first && ks == 0) ? 0u : 1u);
+                        umma_bf16(d, a_h, b_l, idesc, 1u);
+                        umma_bf16(d, a_l, b_h, idesc, 1u);
+                    }
+                    umma_commit(empty);                                // frees the smem stage once these MMAs retire
+                    if (++s == (uint32_t)p.ring) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(acc_full + 8u * buf);                      // accumulators complete -> epilogue
             }
-            if (p.res) {
-                const float* rp = p.res + row * p.res_cs + ch;
-                if (ch + 8 <= p.res_cs) {
-                    const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
-                    const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp) + 1);
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue =================
+        const bool has_res = kGeneric ? p.res != nullptr : kS.res != 0;
+        const bool has_y32 = kGeneric ? p.y32 != nullptr : kS.y32 != 0;
+        const bool has_pl = kGeneric ? p.y_hi != nullptr : kS.planes != 0;
+        const int epi_act = kGeneric ? p.epi_act : kS.epi_act;
+        const int out_act = kGeneric ? p.out_act : kS.out_act;
+        const int quarter = warp & 3, slot = warp >> 2;
+        const int rloc = quarter * 32 + lane;
+        const int n_groups = p.NT >> 3;
+        uint32_t tcount = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tcount) {
+            const uint32_t buf = tcount & 1u, buse = tcount >> 1;
+            const long long row_tile = tile / p.n_tiles;
+            const int n_tile = (int)(tile - row_tile * p.n_tiles);
+            const long long row = row_tile * kTileM + rloc;
+            const bool valid = row < p.rows;
+            const uint32_t lane_addr = tmem + buf * acc_cols + ((uint32_t)(quarter * 32) << 16);
+            const float* bias = p.bias + n_tile * p.NTp;               // padded channel space
+            const float* fbias = film ? p.film_bias + 2 * n_tile * p.NTp : nullptr;
+            const int ch0 = n_tile * p.NT;                             // first real output channel of this tile
+            bool waited = false;
+            for (int cg = slot; cg < n_groups; cg += 3) {
+                const int ch = ch0 + cg * 8;
+                const bool live = valid && ch < p.Cout;
+                float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+                if (has_res && live) {                                 // issued before the accumulator wait
+                    const float4* rp = reinterpret_cast<const float4*>(p.res + row * p.res_cs + ch);
+                    r0 = __ldg(rp);
+                    r1 = __ldg(rp + 1);
+                }
+                if (!waited) {
+                    mbar_wait(acc_full + 8u * buf, buse & 1u);
+                    tc_fence_after();
+                    waited = true;
+                }
+                float v[8], sc[8], sh[8];
+                tmem_ld8(lane_addr + (uint32_t)(cg * 8), v);
+                if (film) {
+                    tmem_ld8(lane_addr + (uint32_t)(p.NTp + cg * 8), sc);
+                    tmem_ld8(lane_addr + (uint32_t)(2 * p.NTp + cg * 8), sh);
+                }
+                tmem_ld_wait();
+                if (!live) continue;
+                {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cg * 8));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cg * 8) + 1);
+                    v[0] = __fadd_rn(v[0], b0.x); v[1] = __fadd_rn(v[1], b0.y); v[2] = __fadd_rn(v[2], b0.z); v[3] = __fadd_rn(v[3], b0.w);
+                    v[4] = __fadd_rn(v[4], b1.x); v[5] = __fadd_rn(v[5], b1.y); v[6] = __fadd_rn(v[6], b1.z); v[7] = __fadd_rn(v[7], b1.w);
+                }
+                if (film) {
+                    const float4 s0 = __ldg(reinterpret_cast<const float4*>(fbias + cg * 8));
+                    const float4 s1 = __ldg(reinterpret_cast<const float4*>(fbias + cg * 8) + 1);
+                    const float4 h0 = __ldg(reinterpret_cast<const float4*>(fbias + p.NTp + cg * 8));
+                    const float4 h1 = __ldg(reinterpret_cast<const float4*>(fbias + p.NTp + cg * 8) + 1);
+                    const float sb[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                    const float hb[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)                        // FiLM: x * scale + shift (decoder.py:97)
+                        v[i] = __fadd_rn(__fmul_rn(v[i], __fadd_rn(sc[i], sb[i])), __fadd_rn(sh[i], hb[i]));
+                }
+                if (has_res) {
                     v[0] = __fadd_rn(v[0], r0.x); v[1] = __fadd_rn(v[1], r0.y); v[2] = __fadd_rn(v[2], r0.z); v[3] = __fadd_rn(v[3], r0.w);
                     v[4] = __fadd_rn(v[4], r1.x); v[5] = __fadd_rn(v[5], r1.y); v[6] = __fadd_rn(v[6], r1.z); v[7] = __fadd_rn(v[7], r1.w);
-                } else {
+                }
+                if (epi_act != TC_ACT_NONE) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (ch + i < p.res_cs) v[i] = __fadd_rn(v[i], __ldg(rp + i));
+                    for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], epi_act);
+                }
+                if (has_y32) {
+                    float* yp = p.y32 + row * p.y32_cs + ch;
+                    if (ch + 8 <= p.y32_cs) {
+                        reinterpret_cast<float4*>(yp)[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        reinterpret_cast<float4*>(yp)[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (ch + i < p.y32_cs) yp[i] = v[i];
+                    }
+                }
+                if (has_pl && ch + 8 <= p.y_cs) {
+                    uint32_t h[4], l[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) split2(apply_act(v[2 * i], out_act), apply_act(v[2 * i + 1], out_act), h[i], l[i]);
+                    *reinterpret_cast<uint4*>(p.y_hi + row * p.y_cs + ch) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4*>(p.y_lo + row * p.y_cs + ch) = make_uint4(l[0], l[1], l[2], l[3]);
                 }
             }
-            if (p.epi_act != TC_ACT_NONE) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], p.epi_act);
+            if (!waited) {                                             // a slot without column groups still takes part
+                mbar_wait(acc_full + 8u * buf, buse & 1u);
             }
-            if (p.y32) {
-                float* yp = p.y32 + row * p.y32_cs + ch;
-                if (ch + 8 <= p.y32_cs) {
-                    reinterpret_cast<float4*>(yp)[0] = make_float4(v[0], v[1], v[2], v[3]);
-                    reinterpret_cast<float4*>(yp)[1] = make_float4(v[4], v[5], v[6], v[7]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (ch + i < p.y32_cs) yp[i] = v[i];
-                }
-            }
-            if (p.y_hi && ch + 8 <= p.y_cs) {
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float a0 = apply_act(v[2 * i], p.out_act), a1 = apply_act(v[2 * i + 1], p.out_act);
-                    const bf16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
-                    const bf16 l0 = __float2bfloat16_rn(__fsub_rn(a0, __bfloat162float(h0)));
-                    const bf16 l1 = __float2bfloat16_rn(__fsub_rn(a1, __bfloat162float(h1)));
-                    h[i] = pack_bf16x2(h0, h1);
-                    l[i] = pack_bf16x2(l0, l1);
-                }
-                *reinterpret_cast<uint4*>(p.y_hi + row * p.y_cs + ch) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(p.y_lo + row * p.y_cs + ch) = make_uint4(l[0], l[1], l[2], l[3]);
-            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + 8u * buf);          // accumulator buffer may be overwritten
         }
-    } else if (lane == 0) {
-        // ================= MMA issuer (one thread) =================
-        const uint32_t idesc_main = umma_idesc(kTileM, (uint32_t)p.NTp);
-        const uint32_t idesc_film = umma_idesc(kTileM, 2u * (uint32_t)p.NTp);
-        for (int i = 0; i < n_stage; ++i) {
-            const int s = i % p.ring, use = i / p.ring;
-            const uint32_t full = bar_base + 8u * s, empty = bar_base + 8u * (p.ring + s);
-            const bool is_film = i >= n_main && p.aux_mode == TC_AUX_FILM;
-            const uint32_t n_rows = is_film ? 2u * p.NTp : (uint32_t)p.NTp;
-            const uint32_t idesc = is_film ? idesc_film : idesc_main;
-            const uint32_t d = tmem + (is_film ? (uint32_t)p.NTp : 0u);
-            const bool first = is_film ? (i == n_main) : (i == 0);
-            mbar_wait(full, (uint32_t)use & 1u);
-            tc_fence_after();
-            const uint32_t a_base = smem_base + (uint32_t)s * stage_bytes;
-            const uint32_t b_base = a_base + p.a_stage_bytes;
-            const uint32_t b_lbo = n_rows * 16u;                  // bytes between 8-channel chunks of the weight image
-            const uint32_t plane_b = (uint32_t)chunks * b_lbo;
-            for (int ks = 0; ks < (p.KB >> 4); ++ks) {
-                const uint64_t a_h = umma_desc(a_base + (uint32_t)(2 * ks) * kChunkStride, kChunkStride, 128);
-                const uint64_t a_l = umma_desc(a_base + plane_a + (uint32_t)(2 * ks) * kChunkStride, kChunkStride, 128);
-                const uint64_t b_h = umma_desc(b_base + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
-                const uint64_t b_l = umma_desc(b_base + plane_b + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
-                umma_bf16(d, a_h, b_h, idesc, (first && ks == 0) ? 0u : 1u);
-                umma_bf16(d, a_h, b_l, idesc, 1u);
-                umma_bf16(d, a_l, b_h, idesc, 1u);
-            }
-            umma_commit(empty);                                    // frees the smem stage once these MMAs retire
-        }
-        umma_commit(acc_bar);                                      // accumulators complete -> epilogue
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem, p.tmem_cols);
+    if (warp == kMmaWarp) tmem_dealloc(tmem, p.tmem_cols);
 }
 
 // ---- host side --------------------------------------------------------------------------------
@@ -450,8 +534,23 @@ int tc_pack_conv(const float* w, const float* b, int Cout, int Cin, int taps, co
 
 constexpr int kTcMaxSmem = 200 * 1024;
 
+static int g_num_sms = 148;
+bool g_force_generic = false;   // tests: run the runtime-flag instantiation
+
 int tc_conv_init() {
-    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
+    int dev = 0, n = 0;
+    TVC_CUDA(cudaGetDevice(&dev));
+    TVC_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    if (n > 0) g_num_sms = n;
+    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
+    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
+    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
+    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
+    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
+    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
+    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
+    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
+    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
     return 0;
 }
 
@@ -462,7 +561,7 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     TVC_REQUIRE(W.aux_mode == TC_AUX_NONE || (a.x_hi && a.x_lo && a.x_cs % 8 == 0 && a.x_cs >= W.aux_cin), "tc_conv: aux input missing / bad stride");
     TVC_REQUIRE(!a.y_hi || (a.y_lo && a.y_cs % 8 == 0), "tc_conv: plane output needs both planes and a stride multiple of 8");
     TVC_REQUIRE(!a.y32 || a.y32_cs % 4 == 0, "tc_conv: fp32 output stride must be a multiple of 4");
-    TVC_REQUIRE(!a.res || a.res_cs % 4 == 0, "tc_conv: residual stride must be a multiple of 4");
+    TVC_REQUIRE(!a.res || (a.res_cs % 4 == 0 && a.res_cs >= (int)align_up(W.Cout, 8)), "tc_conv: residual stride must be a multiple of 4 covering Cout rounded up to 8");
     TcKParams p;
     p.a_hi = a.a_hi; p.a_lo = a.a_lo; p.x_hi = a.x_hi; p.x_lo = a.x_lo; p.w = W.w;
     p.bias = W.bias; p.film_bias = W.film_bias; p.res = a.res; p.y32 = a.y32; p.y_hi = a.y_hi; p.y_lo = a.y_lo;
@@ -476,19 +575,42 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     p.b_stage_bytes = 4u * (uint32_t)W.KB * (uint32_t)n_rows_max;
     const uint32_t stage = p.a_stage_bytes + p.b_stage_bytes;
     const int n_stage = W.taps * W.nkb + W.aux_nkb;
+    (void)n_stage;
     int ring = (kTcMaxSmem - 256) / (int)stage;
-    ring = ring > 4 ? 4 : ring;
-    ring = ring > n_stage ? n_stage : ring;
+    ring = ring > 8 ? 8 : ring;
     TVC_REQUIRE(ring >= 1, "tc_conv: a K-stage of %u bytes does not fit shared memory", stage);
     p.ring = ring;
-    const uint32_t cols = (uint32_t)(W.aux_mode == TC_AUX_FILM ? 3 * W.NTp : W.NTp);
+    const uint32_t cols = 2u * (uint32_t)(W.aux_mode == TC_AUX_FILM ? 3 * W.NTp : W.NTp);   // double-buffered accumulators
     uint32_t tc = 32;
     while (tc < cols) tc <<= 1;
     TVC_REQUIRE(tc <= 512, "tc_conv: %u TMEM columns needed (> 512)", cols);
     p.tmem_cols = tc;
-    const size_t smem = (size_t)ring * stage + 16 * ring + 16;
-    dim3 grid((unsigned)cdiv(p.rows, kTileM), (unsigned)W.n_tiles, 1);
-    tc_conv_kernel<<<grid, kThreads, smem, s>>>(p);
+    p.row_tiles = (p.rows + kTileM - 1) / kTileM;
+    p.n_tiles = W.n_tiles;
+    const size_t smem = (size_t)ring * stage + 16 * ring + 64;
+    const long long tiles = p.row_tiles * p.n_tiles;
+    const unsigned grid = (unsigned)(tiles < g_num_sms ? tiles : g_num_sms);
+    int spec = -1;
+    for (int i = 0; i < kNumSpecs; ++i) {
+        const EpiSpec e = epi_spec(i);
+        if ((e.film != 0) == (W.aux_mode == TC_AUX_FILM) && (e.res != 0) == (a.res != nullptr) && (e.y32 != 0) == (a.y32 != nullptr) &&
+            (e.planes != 0) == (a.y_hi != nullptr) && e.epi_act == a.epi_act && (e.out_act == a.out_act || !a.y_hi)) {
+            spec = i;
+            break;
+        }
+    }
+    if (g_force_generic) spec = -1;
+    switch (spec) {
+        case 0: tc_conv_kernel<0><<<grid, kThreads, smem, s>>>(p); break;
+        case 1: tc_conv_kernel<1><<<grid, kThreads, smem, s>>>(p); break;
+        case 2: tc_conv_kernel<2><<<grid, kThreads, smem, s>>>(p); break;
+        case 3: tc_conv_kernel<3><<<grid, kThreads, smem, s>>>(p); break;
+        case 4: tc_conv_kernel<4><<<grid, kThreads, smem, s>>>(p); break;
+        case 5: tc_conv_kernel<5><<<grid, kThreads, smem, s>>>(p); break;
+        case 6: tc_conv_kernel<6><<<grid, kThreads, smem, s>>>(p); break;
+        case 7: tc_conv_kernel<7><<<grid, kThreads, smem, s>>>(p); break;
+        default: tc_conv_kernel<-1><<<grid, kThreads, smem, s>>>(p); break;
+    }
     TVC_LAUNCH_CHECK();
     return 0;
 }

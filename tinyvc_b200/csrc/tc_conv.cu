@@ -30,7 +30,6 @@ namespace {
 
 constexpr int kTileM = 128;
 constexpr int kThreads = 544;   // 12 epilogue warps + 1 MMA warp + 4 producer warps
-constexpr uint32_t kChunkStride = kTileM * 16;   // bytes between consecutive 8-channel chunks of the A tile (LBO)
 
 struct TcKParams {
     const bf16 *a_hi, *a_lo, *x_hi, *x_lo, *w;
@@ -44,6 +43,10 @@ struct TcKParams {
     int ring;                      // smem ring depth
     long long row_tiles;
     int n_tiles;
+    int halo;                      // 1: one stage holds a (128 + 2*dil)-row window shared by the 3 taps (tiles never straddle utterances)
+    int R;                         // rows per A stage (128, or 128 + 2*dil in halo mode)
+    int tiles_per_utt;             // halo mode
+    uint32_t lbo_a;                // bytes between consecutive 8-channel chunks of the A stage (odd multiple of 16)
     uint32_t a_stage_bytes, b_stage_bytes;
     uint32_t tmem_cols;
     int epi_act, out_act;
@@ -205,10 +208,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
     constexpr bool kGeneric = SPEC < 0;
     constexpr EpiSpec kS = epi_spec(SPEC < 0 ? 0 : SPEC);
     const bool film = kGeneric ? p.aux_mode == TC_AUX_FILM : kS.film != 0;
-    const int n_main = p.taps * p.nkb;
+    const int n_main = p.halo ? p.nkb : p.taps * p.nkb;
     const int n_stage = n_main + p.aux_nkb;
     const int chunks = p.KB >> 3;                   // 16-byte chunks per row per plane in one stage
-    const uint32_t plane_a = (uint32_t)chunks * kChunkStride;
+    const uint32_t plane_a = (uint32_t)chunks * p.lbo_a;
     const uint32_t acc_cols = (uint32_t)(film ? 3 * p.NTp : p.NTp);
     const long long n_tiles_total = p.row_tiles * p.n_tiles;
 
@@ -229,20 +232,41 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
 
     if (warp >= kProdWarp0) {
         // ================= producers =================
-        const int r = tid - kProdWarp0 * 32;
+        // Lane mapping: consecutive threads fetch consecutive 16-byte chunks of one row (coalesced global
+        // reads); the odd chunk stride lbo_a keeps the shared-memory side conflict-free.
+        const int j = tid - kProdWarp0 * 32;
+        const int rpi = kTileM / chunks;                 // rows covered per pass of the 128 producer threads
+        const bool act = j < rpi * chunks;
+        const int c = act ? j % chunks : 0, rsub = act ? j / chunks : 0;
         uint32_t s = 0, ph = 0;    // ring slot and the parity of its *previous* use
         bool wrapped = false;
         const int half = (p.taps - 1) >> 1;
-        const uint32_t b_main = 4u * (uint32_t)p.KB * (uint32_t)p.NTp;
-        const uint32_t b_aux = film ? 2u * b_main : b_main;
+        const uint32_t b_tap = 4u * (uint32_t)p.KB * (uint32_t)p.NTp;
+        const uint32_t b_main = p.halo ? (uint32_t)p.taps * b_tap : b_tap;
+        const uint32_t b_aux = film ? 2u * b_tap : b_tap;
+        const uint32_t dst_c = (uint32_t)c * p.lbo_a;
         for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
             const long long row_tile = tile / p.n_tiles;
             const int n_tile = (int)(tile - row_tile * p.n_tiles);
-            const long long row = row_tile * kTileM + r;
-            const bool valid = row < p.rows;
-            const long long b = valid ? row / p.T : 0;
-            const int t = valid ? (int)(row - b * p.T) : 0;
             const bf16* wt = p.w + (long long)n_tile * p.tile_elems;
+            // flat mode: (utterance base row, time) of the rows this thread serves; halo mode: window origin
+            int bT[8], tq[8];
+            int baseT = 0, tt0 = 0;
+            if (!p.halo) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int m = rsub + q * rpi;
+                    const long long g = row_tile * kTileM + m;
+                    const bool ok = act && m < kTileM && g < p.rows;
+                    const int bq = ok ? (int)(g / p.T) : 0;
+                    bT[q] = bq * p.T;
+                    tq[q] = ok ? (int)(g - (long long)bq * p.T) : -1;
+                }
+            } else {
+                const int bq = (int)(row_tile / p.tiles_per_utt);
+                tt0 = (int)(row_tile - (long long)bq * p.tiles_per_utt) * kTileM;
+                baseT = bq * p.T;
+            }
             int tap = 0, kb = 0;
             for (int i = 0; i < n_stage; ++i) {
                 const uint32_t full = bar_base + 8u * s, empty = bar_base + 8u * (p.ring + s);
@@ -250,36 +274,50 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                 const uint32_t b_bytes = is_aux ? b_aux : b_main;
                 if (wrapped) mbar_wait(empty, ph);
                 const uint32_t a_dst = smem_base + s * stage_bytes;
-                if (r == 0) {
+                if (j == 0) {
                     mbar_arrive_expect_tx(full, b_bytes);
                     bulk_g2s(a_dst + p.a_stage_bytes, wt, b_bytes, full);
                 }
                 wt += b_bytes >> 1;
-                const bf16 *src_hi, *src_lo;
-                int cs;
-                long long srow;
-                if (!is_aux) {
-                    int tt = t + (tap - half) * p.dil;
-                    tt = tt < 0 ? 0 : (tt > p.T - 1 ? p.T - 1 : tt);
-                    srow = b * p.T + tt;
-                    src_hi = p.a_hi; src_lo = p.a_lo; cs = p.a_cs;
+                const bf16* src_hi = is_aux ? p.x_hi : p.a_hi;
+                const bf16* src_lo = is_aux ? p.x_lo : p.a_lo;
+                const int cs = is_aux ? p.x_cs : p.a_cs;
+                const int gc = kb * chunks + c;
+                const bool c_ok = act && gc < (cs >> 3);
+                const uint32_t dst0 = a_dst + dst_c;
+                if (!p.halo) {
+                    const int shift = is_aux ? 0 : (tap - half) * p.dil;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int m = rsub + q * rpi;
+                        if (m < kTileM && act) {
+                            int tt = tq[q] + shift;
+                            tt = tt < 0 ? 0 : (tt > p.T - 1 ? p.T - 1 : tt);
+                            const long long off = ((long long)(bT[q] + tt)) * cs + gc * 8;
+                            const uint32_t nb = (c_ok && tq[q] >= 0) ? 16u : 0u;       // 0 -> zero fill
+                            const uint32_t dst = dst0 + (uint32_t)m * 16u;
+                            cp_async16(dst, nb ? src_hi + off : src_hi, nb);
+                            cp_async16(dst + plane_a, nb ? src_lo + off : src_lo, nb);
+                        }
+                    }
                 } else {
-                    srow = valid ? row : 0;
-                    src_hi = p.x_hi; src_lo = p.x_lo; cs = p.x_cs;
-                }
-                const int c0 = kb * chunks;
-                const int nok = valid ? min(chunks, (cs >> 3) - c0) : 0;     // chunks that exist in memory
-                const bf16* gh = src_hi + srow * cs + c0 * 8;
-                const bf16* gl = src_lo + srow * cs + c0 * 8;
-                const uint32_t dst = a_dst + (uint32_t)r * 16u;
-                for (int c = 0; c < chunks; ++c) {
-                    const uint32_t nb = c < nok ? 16u : 0u;                 // 0 -> zero fill
-                    cp_async16(dst + (uint32_t)c * kChunkStride, nb ? gh + c * 8 : src_hi, nb);
-                    cp_async16(dst + plane_a + (uint32_t)c * kChunkStride, nb ? gl + c * 8 : src_lo, nb);
+                    const int rows_s = is_aux ? kTileM : p.R;
+                    const int org = tt0 - (is_aux ? 0 : p.dil);
+                    for (int m = rsub; m < rows_s && act; m += rpi) {
+                        int tt = org + m;
+                        tt = tt < 0 ? 0 : (tt > p.T - 1 ? p.T - 1 : tt);                // replicate padding
+                        const long long off = ((long long)(baseT + tt)) * cs + gc * 8;
+                        const uint32_t nb = c_ok ? 16u : 0u;
+                        const uint32_t dst = dst0 + (uint32_t)m * 16u;
+                        cp_async16(dst, nb ? src_hi + off : src_hi, nb);
+                        cp_async16(dst + plane_a, nb ? src_lo + off : src_lo, nb);
+                    }
                 }
                 cp_async_arrive_noinc(full);
-                if (++kb == (is_aux ? p.aux_nkb : p.nkb)) { kb = 0; ++tap; }
-                if (i + 1 == n_main) { kb = 0; }
+                // stage order: K-block major, tap minor (flat); K-block only (halo); then the aux K-blocks
+                if (is_aux || p.halo) { ++kb; }
+                else if (++tap == p.taps) { tap = 0; ++kb; }
+                if (i + 1 == n_main) { kb = 0; tap = 0; }
                 if (++s == (uint32_t)p.ring) { s = 0; ph = wrapped ? ph ^ 1u : 0u; wrapped = true; }
             }
         }
@@ -309,14 +347,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                     const uint32_t b_base = a_base + p.a_stage_bytes;
                     const uint32_t b_lbo = n_rows * 16u;              // bytes between 8-channel chunks of the weight image
                     const uint32_t plane_b = (uint32_t)chunks * b_lbo;
-                    for (int ks = 0; ks < (p.KB >> 4); ++ks) {
-                        const uint64_t a_h = umma_desc(a_base + (uint32_t)(2 * ks) * kChunkStride, kChunkStride, 128);
-                        const uint64_t a_l = umma_desc(a_base + plane_a + (uint32_t)(2 * ks) * kChunkStride, kChunkStride, 128);
-                        const uint64_t b_h = umma_desc(b_base + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
-                        const uint64_t b_l = umma_desc(b_base + plane_b + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
-                        umma_bf16(d, a_h, b_h, idesc, (first && ks == 0) ? 0u : 1u);
-                        umma_bf16(d, a_h, b_l, idesc, 1u);
-                        umma_bf16(d, a_l, b_h, idesc, 1u);
+                    const int taps_here = (p.halo && i < n_main) ? p.taps : 1;
+                    for (int tap = 0; tap < taps_here; ++tap) {
+                        // halo mode: the tap is a row offset into the shared window (16 bytes per row)
+                        const uint32_t a_tap = a_base + (uint32_t)(tap * p.dil) * 16u;
+                        const uint32_t b_tapb = b_base + (uint32_t)tap * 2u * plane_b;
+                        for (int ks = 0; ks < (p.KB >> 4); ++ks) {
+                            const uint64_t a_h = umma_desc(a_tap + (uint32_t)(2 * ks) * p.lbo_a, p.lbo_a, 128);
+                            const uint64_t a_l = umma_desc(a_tap + plane_a + (uint32_t)(2 * ks) * p.lbo_a, p.lbo_a, 128);
+                            const uint64_t b_h = umma_desc(b_tapb + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
+                            const uint64_t b_l = umma_desc(b_tapb + plane_b + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
+                            umma_bf16(d, a_h, b_h, idesc, (first && tap == 0 && ks == 0) ? 0u : 1u);
+                            umma_bf16(d, a_h, b_l, idesc, 1u);
+                            umma_bf16(d, a_l, b_h, idesc, 1u);
+                        }
                     }
                     umma_commit(empty);                                // frees the smem stage once these MMAs retire
                     if (++s == (uint32_t)p.ring) { s = 0; ph ^= 1u; }
@@ -340,8 +384,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
             const uint32_t buf = tcount & 1u, buse = tcount >> 1;
             const long long row_tile = tile / p.n_tiles;
             const int n_tile = (int)(tile - row_tile * p.n_tiles);
-            const long long row = row_tile * kTileM + rloc;
-            const bool valid = row < p.rows;
+            long long row;
+            bool valid;
+            if (!p.halo) {
+                row = row_tile * kTileM + rloc;
+                valid = row < p.rows;
+            } else {
+                const long long bq = row_tile / p.tiles_per_utt;
+                const int t = (int)(row_tile - bq * p.tiles_per_utt) * kTileM + rloc;
+                row = bq * p.T + t;
+                valid = t < p.T;
+            }
             const uint32_t lane_addr = tmem + buf * acc_cols + ((uint32_t)(quarter * 32) << 16);
             const float* bias = p.bias + n_tile * p.NTp;               // padded channel space
             const float* fbias = film ? p.film_bias + 2 * n_tile * p.NTp : nullptr;
@@ -488,8 +541,8 @@ int tc_pack_conv(const float* w, const float* b, int Cout, int Cin, int taps, co
     for (int nt = 0; nt < o.n_tiles; ++nt) {
         uint16_t* tile = img.data() + o.tile_elems * nt;
         size_t so = 0;
-        for (int tap = 0; tap < taps; ++tap)
-            for (int kb = 0; kb < o.nkb; ++kb, so += main_stage)
+        for (int kb = 0; kb < o.nkb; ++kb)
+            for (int tap = 0; tap < taps; ++tap, so += main_stage)
                 for (int c = 0; c < chunks; ++c)
                     for (int n = 0; n < NT; ++n)
                         for (int e = 0; e < 8; ++e) {
@@ -536,6 +589,7 @@ constexpr int kTcMaxSmem = 200 * 1024;
 
 static int g_num_sms = 148;
 bool g_force_generic = false;   // tests: run the runtime-flag instantiation
+bool g_force_flat = false;      // tests: never use the shared-window (halo) mode
 
 int tc_conv_init() {
     int dev = 0, n = 0;
@@ -570,9 +624,18 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     p.T = a.T; p.dil = a.dil; p.taps = W.taps; p.nkb = W.nkb; p.aux_nkb = W.aux_nkb; p.aux_mode = W.aux_mode;
     p.KB = W.KB; p.NT = W.NT; p.NTp = W.NTp; p.Cout = W.Cout;
     p.epi_act = a.epi_act; p.out_act = a.out_act;
+    // halo mode: k=3 convs whose utterances fill their 128-row tiles well share one row window across the taps
+    const int tpu = cdiv(a.T, kTileM);
+    p.halo = (W.taps == 3 && (double)a.T / ((double)tpu * kTileM) >= 0.75 && !g_force_flat) ? 1 : 0;
+    p.tiles_per_utt = tpu;
+    p.R = p.halo ? kTileM + 2 * a.dil : kTileM;
+    TVC_REQUIRE(a.dil >= 1 && a.dil <= 64, "tc_conv: dilation %d out of range", a.dil);
+    p.lbo_a = (uint32_t)(p.R | 1) * 16u;                          // odd number of 16-byte slots: conflict-free stores
     const int n_rows_max = W.aux_mode == TC_AUX_FILM ? 2 * W.NTp : W.NTp;
-    p.a_stage_bytes = 512u * (uint32_t)W.KB;                     // 2 planes x KB/8 chunks x 128 rows x 16 B
-    p.b_stage_bytes = 4u * (uint32_t)W.KB * (uint32_t)n_rows_max;
+    p.a_stage_bytes = (uint32_t)align_up(2 * (W.KB / 8) * (int)p.lbo_a, 128);         // 2 planes x KB/8 chunks x rows x 16 B
+    uint32_t b_main = 4u * (uint32_t)W.KB * (uint32_t)W.NTp * (uint32_t)(p.halo ? W.taps : 1);
+    uint32_t b_aux = W.aux_mode ? 4u * (uint32_t)W.KB * (uint32_t)n_rows_max : 0u;
+    p.b_stage_bytes = b_main > b_aux ? b_main : b_aux;
     const uint32_t stage = p.a_stage_bytes + p.b_stage_bytes;
     const int n_stage = W.taps * W.nkb + W.aux_nkb;
     (void)n_stage;
@@ -585,7 +648,7 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     while (tc < cols) tc <<= 1;
     TVC_REQUIRE(tc <= 512, "tc_conv: %u TMEM columns needed (> 512)", cols);
     p.tmem_cols = tc;
-    p.row_tiles = (p.rows + kTileM - 1) / kTileM;
+    p.row_tiles = p.halo ? (long long)a.B * tpu : (p.rows + kTileM - 1) / kTileM;
     p.n_tiles = W.n_tiles;
     const size_t smem = (size_t)ring * stage + 16 * ring + 64;
     const long long tiles = p.row_tiles * p.n_tiles;

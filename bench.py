@@ -275,7 +275,7 @@ def run_ours(args) -> None:
             "per_kernel_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items())},
         }
         cpu = None
-        if world == 1:
+        if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             utts = 16
             rate, ts = oracle_decoder_rate(sd_cpu, host, utts, reps=5, threads=threads)
@@ -305,6 +305,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle timing (profiler runs)")
     ap.add_argument("--conv-impl", default=os.environ.get("TVC_CONV_IMPL", "tc"), choices=["fp32", "tc"])
     args = ap.parse_args()
     if args.impl == "reference":

@@ -163,3 +163,37 @@ def test_cpu_tensor_is_rejected(cuda_models):
     inp = synth.decoder_inputs(1, 4, seed=1)
     with pytest.raises(RuntimeError, match="CUDA only"):
         dec.infer(inp["content"], inp["f0"], inp["energy"])
+
+
+@torch.inference_mode()
+def test_decoder_graph_replay_matches_eager(cuda_models):
+    """tvc_decoder_infer captures a CUDA graph the second time it sees a buffer set; replays must read the
+    buffers' *current* contents and reproduce the eager launch sequence bit for bit."""
+    from tinyvc_b200 import _lib, synth
+    _, dec = cuda_models
+    a = {k: v.cuda() for k, v in synth.decoder_inputs(3, 7, seed=21).items()}
+    b = {k: v.cuda() for k, v in synth.decoder_inputs(3, 7, seed=22).items()}
+    _lib.set_option("graphs", "0")
+    try:
+        want_a = dec.infer(a["content"], a["f0"], a["energy"], rand01=a["rand01"]).clone()
+        want_b = dec.infer(b["content"], b["f0"], b["energy"], rand01=b["rand01"]).clone()
+    finally:
+        _lib.set_option("graphs", "1")
+    L, h = _lib.lib(), dec._native.get()
+    out = torch.empty_like(want_a)
+    ws = torch.empty(L.tvc_decoder_workspace_bytes(3, 7), dtype=torch.uint8, device="cuda")
+    stat = {k: v.clone() for k, v in a.items()}
+    n0 = _lib.launch_count()
+    per_call = []
+    for it in range(4):                       # call 0 eager, call 1 captures, calls 2.. replay
+        src = a if it % 2 == 0 else b
+        for k in stat:
+            stat[k].copy_(src[k])
+        _lib.check(L.tvc_decoder_infer(h, stat["content"].data_ptr(), stat["f0"].data_ptr(), stat["energy"].data_ptr(),
+                                       stat["rand01"].data_ptr(), out.data_ptr(), 3, 7, ws.data_ptr(), ws.numel(),
+                                       _lib.stream_ptr(out.device)), "tvc_decoder_infer")
+        torch.cuda.synchronize()
+        assert torch.equal(out, want_a if it % 2 == 0 else want_b), f"call {it} differs from the eager result"
+        per_call.append(_lib.launch_count() - n0)
+        n0 = _lib.launch_count()
+    assert len(set(per_call)) == 1 and per_call[0] > 50, per_call   # replays account for every captured kernel

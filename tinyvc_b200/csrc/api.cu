@@ -24,6 +24,7 @@ void set_error(const char* fmt, ...) {
 
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static bool g_use_graphs = true;
 
 // ---- event profiler ----------------------------------------------------------------------------
 struct ProfEntry { std::string name; cudaEvent_t a, b; };
@@ -85,7 +86,33 @@ struct IndexModel {
 
 using namespace tvc;
 
-struct tvc_decoder { DecoderModel m; };
+// A captured CUDA graph of one Decoder.infer launch sequence, valid for one exact set of buffers.
+struct DecoderGraphKey {
+    const void *content, *f0, *energy, *rand01, *out, *ws;
+    int B, Lf, impl;
+    bool operator==(const DecoderGraphKey& o) const {
+        return content == o.content && f0 == o.f0 && energy == o.energy && rand01 == o.rand01 && out == o.out &&
+               ws == o.ws && B == o.B && Lf == o.Lf && impl == o.impl;
+    }
+};
+struct DecoderGraph {
+    DecoderGraphKey key;
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long launches = 0, last_use = 0;
+};
+struct tvc_decoder {
+    DecoderModel m;
+    std::mutex mu;
+    std::vector<DecoderGraph> graphs;          // small LRU cache
+    std::vector<DecoderGraphKey> seen;         // buffer sets seen once (a second sighting triggers capture)
+    cudaStream_t cap_stream = nullptr;
+    unsigned long long tick = 0;
+    ~tvc_decoder() {
+        for (DecoderGraph& g : graphs)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (cap_stream) cudaStreamDestroy(cap_stream);
+    }
+};
 struct tvc_encoder { EncoderModel m; };
 struct tvc_index { IndexModel m; };
 
@@ -114,6 +141,10 @@ int tvc_set_option(const char* key, const char* value) {
         if (!strcmp(value, "tc")) { g_conv_impl = CONV_IMPL_TC; return 0; }
         set_error("conv_impl: unknown value '%s'", value);
         return 2;
+    }
+    if (!strcmp(key, "graphs")) {
+        g_use_graphs = !strcmp(value, "1");
+        return 0;
     }
     if (!strcmp(key, "profile")) {
         std::lock_guard<std::mutex> lock(g_prof_mu);
@@ -210,8 +241,61 @@ int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, co
     API_BEGIN
     TVC_REQUIRE(h && content && f0 && energy && rand01 && out && workspace, "tvc_decoder_infer: null argument");
     CHECK_SHAPES();
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!g_use_graphs || g_prof_on) {
+        Arena A(workspace, workspace_bytes, false);
+        return h->m.infer(A, s, content, f0, energy, rand01, out, B, Lf);
+    }
+    // CUDA-graph replay: the launch sequence for one exact set of buffers is captured the second time
+    // that set is seen (callers that reuse their buffers -- serving loops, the Python wrapper's cached
+    // workspace -- then pay one graph launch instead of ~100 kernel launches per call).
+    std::lock_guard<std::mutex> lock(h->mu);
+    const DecoderGraphKey key{content, f0, energy, rand01, out, workspace, B, Lf, g_conv_impl};
+    ++h->tick;
+    for (DecoderGraph& g : h->graphs)
+        if (g.key == key) {
+            g.last_use = h->tick;
+            TVC_CUDA(cudaGraphLaunch(g.exec, s));
+            g_launches.fetch_add(g.launches, std::memory_order_relaxed);
+            return 0;
+        }
+    bool seen_before = false;
+    for (const DecoderGraphKey& k : h->seen) seen_before = seen_before || k == key;
+    if (!seen_before) {
+        if (h->seen.size() >= 32) h->seen.erase(h->seen.begin());
+        h->seen.push_back(key);
+        Arena A(workspace, workspace_bytes, false);
+        return h->m.infer(A, s, content, f0, energy, rand01, out, B, Lf);
+    }
+    if (!h->cap_stream) TVC_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    const unsigned long long n0 = g_launches.load();
+    TVC_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
     Arena A(workspace, workspace_bytes, false);
-    return h->m.infer(A, (cudaStream_t)stream, content, f0, energy, rand01, out, B, Lf);
+    const int rc = h->m.infer(A, h->cap_stream, content, f0, energy, rand01, out, B, Lf);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+    if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    TVC_REQUIRE(ce == cudaSuccess && graph, "tvc_decoder_infer: graph capture failed: %s", cudaGetErrorString(ce));
+    DecoderGraph g;
+    g.key = key;
+    g.launches = g_launches.load() - n0;
+    g.last_use = h->tick;
+    const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    TVC_REQUIRE(ie == cudaSuccess, "tvc_decoder_infer: graph instantiation failed: %s", cudaGetErrorString(ie));
+    if (h->graphs.size() >= 8) {               // evict the least recently used
+        size_t victim = 0;
+        for (size_t i = 1; i < h->graphs.size(); ++i)
+            if (h->graphs[i].last_use < h->graphs[victim].last_use) victim = i;
+        cudaGraphExecDestroy(h->graphs[victim].exec);
+        h->graphs.erase(h->graphs.begin() + victim);
+    }
+    h->graphs.push_back(g);
+    TVC_CUDA(cudaGraphLaunch(g.exec, s));
+    return 0;
     API_END
 }
 

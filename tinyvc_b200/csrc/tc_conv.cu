@@ -19,6 +19,7 @@
 //              (x*scale+shift from a second accumulator fed by the aux 1x1 on the skip tensor), the
 //              residual, the activation, and writes fp32 and/or re-split bf16 planes, channels-last.
 // Every mbarrier wait is bounded (trap after ~2 s) so a protocol bug cannot hang the GPU.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -50,6 +51,7 @@ struct TcKParams {
     uint32_t a_stage_bytes, b_stage_bytes;
     uint32_t tmem_cols;
     int epi_act, out_act;
+    int dbg;   // ablation switches for profiling (TVC_TC_DBG): 1 no loads, 2 no MMAs, 4 no epilogue math/stores
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -68,10 +70,10 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x989680u)      // suspend-time hint (ns): sleep in hardware, do not spin
         : "memory");
     return ok;
 }
@@ -106,6 +108,13 @@ __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// One lane of a converged warp (the MMA warp runs its loops warp-uniformly so that descriptors stay in
+// uniform registers; only the tcgen05 instructions themselves are predicated on the elected lane).
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred;
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate, single-CTA.
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -176,6 +185,25 @@ constexpr int kEpiWarps = 12;      // 4 TMEM lane quarters x 3 column slots
 constexpr int kMmaWarp = 12;
 constexpr int kProdWarp0 = 13;
 
+// Walks consecutive tile ids (n_tile * row_tiles + row_tile) without per-tile divisions.
+struct TileWalk {
+    long long row_tile;
+    int n_tile, bq, tt0;     // halo mode: utterance index and first time step of the tile
+    __device__ TileWalk(const TcKParams& p, long long tile) {
+        n_tile = (int)(tile / p.row_tiles);
+        row_tile = tile - (long long)n_tile * p.row_tiles;
+        bq = p.halo ? (int)(row_tile / p.tiles_per_utt) : 0;
+        tt0 = p.halo ? (int)(row_tile - (long long)bq * p.tiles_per_utt) * kTileM : 0;
+    }
+    __device__ void next(const TcKParams& p) {
+        if (++row_tile == p.row_tiles) { row_tile = 0; ++n_tile; bq = 0; tt0 = 0; return; }
+        if (p.halo) {
+            tt0 += kTileM;
+            if (tt0 >= p.T) { tt0 = 0; ++bq; }
+        }
+    }
+};
+
 // split two fp32 values into packed bf16 hi / lo pairs
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -214,6 +242,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
     const uint32_t plane_a = (uint32_t)chunks * p.lbo_a;
     const uint32_t acc_cols = (uint32_t)(film ? 3 * p.NTp : p.NTp);
     const long long n_tiles_total = p.row_tiles * p.n_tiles;
+    // contiguous tile range of this CTA; tile id = n_tile * row_tiles + row_tile
+    const long long per_cta = (n_tiles_total + gridDim.x - 1) / gridDim.x;
+    const long long tile_beg = (long long)blockIdx.x * per_cta;
+    const long long tile_end = tile_beg + per_cta < n_tiles_total ? tile_beg + per_cta : n_tiles_total;
 
     if (tid == 0) {
         for (int s = 0; s < p.ring; ++s) {
@@ -245,27 +277,31 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
         const uint32_t b_main = p.halo ? (uint32_t)p.taps * b_tap : b_tap;
         const uint32_t b_aux = film ? 2u * b_tap : b_tap;
         const uint32_t dst_c = (uint32_t)c * p.lbo_a;
-        for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
-            const long long row_tile = tile / p.n_tiles;
-            const int n_tile = (int)(tile - row_tile * p.n_tiles);
-            const bf16* wt = p.w + (long long)n_tile * p.tile_elems;
+        TileWalk tw(p, tile_beg);
+        for (long long tile = tile_beg; tile < tile_end; ++tile, tw.next(p)) {
+            const long long row_tile = tw.row_tile;
+            const bf16* wt = p.w + (long long)tw.n_tile * p.tile_elems;
             // flat mode: (utterance base row, time) of the rows this thread serves; halo mode: window origin
             int bT[8], tq[8];
             int baseT = 0, tt0 = 0;
             if (!p.halo) {
+                // rows < 2^31 (checked at the API): 32-bit arithmetic, one division per tile, then increments
+                const unsigned g0 = (unsigned)(row_tile * kTileM) + (unsigned)rsub;
+                unsigned bcur = g0 / (unsigned)p.T;
+                int tcur = (int)(g0 - bcur * (unsigned)p.T);
+                int bTcur = (int)(bcur * (unsigned)p.T);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const int m = rsub + q * rpi;
-                    const long long g = row_tile * kTileM + m;
-                    const bool ok = act && m < kTileM && g < p.rows;
-                    const int bq = ok ? (int)(g / p.T) : 0;
-                    bT[q] = bq * p.T;
-                    tq[q] = ok ? (int)(g - (long long)bq * p.T) : -1;
+                    const bool ok = act && m < kTileM && (long long)g0 + q * rpi < p.rows;
+                    bT[q] = bTcur;
+                    tq[q] = ok ? tcur : -1;
+                    tcur += rpi;
+                    while (tcur >= p.T) { tcur -= p.T; bTcur += p.T; }
                 }
             } else {
-                const int bq = (int)(row_tile / p.tiles_per_utt);
-                tt0 = (int)(row_tile - (long long)bq * p.tiles_per_utt) * kTileM;
-                baseT = bq * p.T;
+                tt0 = tw.tt0;
+                baseT = tw.bq * p.T;
             }
             int tap = 0, kb = 0;
             for (int i = 0; i < n_stage; ++i) {
@@ -275,8 +311,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                 if (wrapped) mbar_wait(empty, ph);
                 const uint32_t a_dst = smem_base + s * stage_bytes;
                 if (j == 0) {
-                    mbar_arrive_expect_tx(full, b_bytes);
-                    bulk_g2s(a_dst + p.a_stage_bytes, wt, b_bytes, full);
+                    if (p.dbg & 1) mbar_arrive(full);
+                    else {
+                        mbar_arrive_expect_tx(full, b_bytes);
+                        bulk_g2s(a_dst + p.a_stage_bytes, wt, b_bytes, full);
+                    }
                 }
                 wt += b_bytes >> 1;
                 const bf16* src_hi = is_aux ? p.x_hi : p.a_hi;
@@ -285,7 +324,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                 const int gc = kb * chunks + c;
                 const bool c_ok = act && gc < (cs >> 3);
                 const uint32_t dst0 = a_dst + dst_c;
-                if (!p.halo) {
+                if (p.dbg & 1) {
+                } else if (!p.halo) {
                     const int shift = is_aux ? 0 : (tap - half) * p.dil;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
@@ -323,11 +363,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
         }
     } else if (warp == kMmaWarp) {
         // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
+        {
+            const uint32_t leader = elect_one();
             const uint32_t idesc_main = umma_idesc(kTileM, (uint32_t)p.NTp);
             const uint32_t idesc_film = umma_idesc(kTileM, 2u * (uint32_t)p.NTp);
+            const uint32_t desc_hi = (128u >> 4) | (1u << 14);      // SBO = 128 bytes, descriptor version 1
+            const uint32_t lbo_a16 = p.lbo_a >> 4, plane_a16 = plane_a >> 4;
+            const int ksteps = p.KB >> 4;
             uint32_t s = 0, ph = 0, tcount = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tcount) {
+            for (long long tile = tile_beg; tile < tile_end; ++tile, ++tcount) {
                 const uint32_t buf = tcount & 1u, buse = tcount >> 1;
                 if (buse > 0) {                                         // epilogue must have drained this accumulator
                     mbar_wait(acc_empty + 8u * buf, (buse - 1) & 1u);
@@ -343,29 +387,36 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                     const bool first = is_film ? (i == n_main) : (i == 0);
                     mbar_wait(full, ph);
                     tc_fence_after();
+                    // descriptors: hi word = SBO | version, lo word = start address | LBO (all in 16-byte units);
+                    // only the start address moves between MMAs
                     const uint32_t a_base = smem_base + s * stage_bytes;
-                    const uint32_t b_base = a_base + p.a_stage_bytes;
-                    const uint32_t b_lbo = n_rows * 16u;              // bytes between 8-channel chunks of the weight image
-                    const uint32_t plane_b = (uint32_t)chunks * b_lbo;
+                    const uint32_t b_lbo16 = n_rows;                    // weight-image chunk stride in 16-byte units
+                    const uint32_t a_lo0 = ((a_base & 0x3FFFFu) >> 4) | (lbo_a16 << 16);
+                    const uint32_t b_lo0 = (((a_base + p.a_stage_bytes) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
+                    const uint32_t plane_b16 = (uint32_t)chunks * b_lbo16;
                     const int taps_here = (p.halo && i < n_main) ? p.taps : 1;
+                    uint32_t acc = first ? 0u : 1u;
                     for (int tap = 0; tap < taps_here; ++tap) {
-                        // halo mode: the tap is a row offset into the shared window (16 bytes per row)
-                        const uint32_t a_tap = a_base + (uint32_t)(tap * p.dil) * 16u;
-                        const uint32_t b_tapb = b_base + (uint32_t)tap * 2u * plane_b;
-                        for (int ks = 0; ks < (p.KB >> 4); ++ks) {
-                            const uint64_t a_h = umma_desc(a_tap + (uint32_t)(2 * ks) * p.lbo_a, p.lbo_a, 128);
-                            const uint64_t a_l = umma_desc(a_tap + plane_a + (uint32_t)(2 * ks) * p.lbo_a, p.lbo_a, 128);
-                            const uint64_t b_h = umma_desc(b_tapb + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
-                            const uint64_t b_l = umma_desc(b_tapb + plane_b + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
-                            umma_bf16(d, a_h, b_h, idesc, (first && tap == 0 && ks == 0) ? 0u : 1u);
-                            umma_bf16(d, a_h, b_l, idesc, 1u);
-                            umma_bf16(d, a_l, b_h, idesc, 1u);
+                        // halo mode: the tap is a row offset into the shared window (one 16-byte slot per row)
+                        uint32_t a_lo = a_lo0 + (uint32_t)(tap * p.dil);
+                        uint32_t b_lo = b_lo0 + (uint32_t)tap * 2u * plane_b16;
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t a_h = ((uint64_t)desc_hi << 32) | a_lo, a_l = ((uint64_t)desc_hi << 32) | (a_lo + plane_a16);
+                            const uint64_t b_h = ((uint64_t)desc_hi << 32) | b_lo, b_l = ((uint64_t)desc_hi << 32) | (b_lo + plane_b16);
+                            if (leader && !(p.dbg & 2)) {
+                                umma_bf16(d, a_h, b_h, idesc, acc);
+                                umma_bf16(d, a_h, b_l, idesc, 1u);
+                                umma_bf16(d, a_l, b_h, idesc, 1u);
+                            }
+                            acc = 1u;
+                            a_lo += 2u * lbo_a16;
+                            b_lo += 2u * b_lbo16;
                         }
                     }
-                    umma_commit(empty);                                // frees the smem stage once these MMAs retire
+                    if (leader) umma_commit(empty);                    // frees the smem stage once these MMAs retire
                     if (++s == (uint32_t)p.ring) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(acc_full + 8u * buf);                      // accumulators complete -> epilogue
+                if (leader) umma_commit(acc_full + 8u * buf);          // accumulators complete -> epilogue
             }
         }
         __syncwarp();
@@ -380,19 +431,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
         const int rloc = quarter * 32 + lane;
         const int n_groups = p.NT >> 3;
         uint32_t tcount = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tcount) {
+        TileWalk tw(p, tile_beg);
+        for (long long tile = tile_beg; tile < tile_end; ++tile, ++tcount, tw.next(p)) {
             const uint32_t buf = tcount & 1u, buse = tcount >> 1;
-            const long long row_tile = tile / p.n_tiles;
-            const int n_tile = (int)(tile - row_tile * p.n_tiles);
+            const int n_tile = tw.n_tile;
             long long row;
             bool valid;
             if (!p.halo) {
-                row = row_tile * kTileM + rloc;
+                row = tw.row_tile * kTileM + rloc;
                 valid = row < p.rows;
             } else {
-                const long long bq = row_tile / p.tiles_per_utt;
-                const int t = (int)(row_tile - bq * p.tiles_per_utt) * kTileM + rloc;
-                row = bq * p.T + t;
+                const int t = tw.tt0 + rloc;
+                row = (long long)tw.bq * p.T + t;
                 valid = t < p.T;
             }
             const uint32_t lane_addr = tmem + buf * acc_cols + ((uint32_t)(quarter * 32) << 16);
@@ -402,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
             bool waited = false;
             for (int cg = slot; cg < n_groups; cg += 3) {
                 const int ch = ch0 + cg * 8;
-                const bool live = valid && ch < p.Cout;
+                const bool live = valid && ch < p.Cout && !(p.dbg & 4);
                 float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
                 if (has_res && live) {                                 // issued before the accumulator wait
                     const float4* rp = reinterpret_cast<const float4*>(p.res + row * p.res_cs + ch);
@@ -624,6 +674,8 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     p.T = a.T; p.dil = a.dil; p.taps = W.taps; p.nkb = W.nkb; p.aux_nkb = W.aux_nkb; p.aux_mode = W.aux_mode;
     p.KB = W.KB; p.NT = W.NT; p.NTp = W.NTp; p.Cout = W.Cout;
     p.epi_act = a.epi_act; p.out_act = a.out_act;
+    static const int dbg = getenv("TVC_TC_DBG") ? atoi(getenv("TVC_TC_DBG")) : 0;
+    p.dbg = dbg;
     // halo mode: k=3 convs whose utterances fill their 128-row tiles well share one row window across the taps
     const int tpu = cdiv(a.T, kTileM);
     p.halo = (W.taps == 3 && (double)a.T / ((double)tpu * kTileM) >= 0.75 && !g_force_flat) ? 1 : 0;

@@ -92,41 +92,34 @@ __global__ void __launch_bounds__(256) noise_ola_cl_kernel(const float* __restri
 // torch.cumsum (CPU) accumulates the fp32 increments in fp64 and rounds every prefix to fp32, so the
 // scan must be carried in fp64.  The fp64 sums are exact (or off in bit 53, far below the fp32
 // rounding) in any association, so the scan is done in three levels: per-frame totals (kernel 1),
-// an exclusive scan of the frame totals per (b,k) (kernel 2), and a block scan inside each frame
-// (kernel 3), which also evaluates the oscillators, multiplies the interpolated amplitudes and
+// an exclusive scan of the frame totals per (b,k) (kernel 2), and sequential runs + one warp scan inside
+// each frame (kernel 3), which also evaluates the oscillators, multiplies the interpolated amplitudes and
 // writes the FilterNet's 17-channel input (15 harmonics, noise, energy; decoder.py:224,265) as
 // channels-last split planes.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float osc_inc(const float* __restrict__ f0b, int n, float scale_size, int Lf, float kf,
-                                         LinCoord& c, float& fa, float& fb) {
-    c = lin_coord(n, scale_size, Lf);
-    fa = __ldg(f0b + c.i0);
-    fb = __ldg(f0b + c.i1);
-    return __fdiv_rn(__fmul_rn(lin_blend(fa, fb, c), kf), kSampleRate);
+// Thread layout shared by the two per-frame kernels: block = one frame (480 samples) of one utterance,
+// warp k = oscillator k+1, lane l = the 15 consecutive samples [15 l, 15 l + 15) of the frame, summed
+// sequentially in fp64; one warp scan over the 32 lane totals then gives every sample's prefix.
+constexpr int kRun = kFrame / 32;   // 15 samples per lane
+static_assert(kRun * 32 == kFrame, "frame must split into 32 equal runs");
+
+__device__ __forceinline__ float osc_increment(const float* __restrict__ f0b, int n, float scale_size, int Lf, float kf) {
+    const LinCoord c = lin_coord(n, scale_size, Lf);
+    return __fdiv_rn(__fmul_rn(lin_blend(__ldg(f0b + c.i0), __ldg(f0b + c.i1), c), kf), kSampleRate);
 }
 
-__global__ void __launch_bounds__(kFrame) osc_frame_sums_kernel(const float* __restrict__ f0, double* __restrict__ totals,
-                                                                int Lf, float scale_size) {
-    __shared__ double part[kFrame / 32][kOsc];
+__global__ void __launch_bounds__(kOsc * 32) osc_frame_sums_kernel(const float* __restrict__ f0, double* __restrict__ totals,
+                                                                   int Lf, float scale_size) {
     const int fr = blockIdx.x, b = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
     const float* f0b = f0 + (long long)b * Lf;
-    const int n = fr * kFrame + threadIdx.x;
-    LinCoord c = lin_coord(n, scale_size, Lf);
-    const float fi = lin_blend(__ldg(f0b + c.i0), __ldg(f0b + c.i1), c);
+    const int n0 = fr * kFrame + lane * kRun;
+    double v = 0.0;
 #pragma unroll
-    for (int k = 0; k < kOsc; ++k) {
-        double v = (double)__fdiv_rn(__fmul_rn(fi, (float)(k + 1)), kSampleRate);
+    for (int i = 0; i < kRun; ++i) v = __dadd_rn(v, (double)osc_increment(f0b, n0 + i, scale_size, Lf, (float)(k + 1)));
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if (lane == 0) part[warp][k] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < kOsc) {
-        double s = 0.0;
-        for (int w = 0; w < kFrame / 32; ++w) s = __dadd_rn(s, part[w][threadIdx.x]);
-        totals[((long long)b * Lf + fr) * kOsc + threadIdx.x] = s;
-    }
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) totals[((long long)b * Lf + fr) * kOsc + k] = v;
 }
 
 // in place: totals[b][fr][k] -> sum of totals[b][0..fr-1][k]
@@ -148,61 +141,64 @@ __global__ void __launch_bounds__(kOsc * 32) osc_scan_frames_kernel(double* __re
     }
 }
 
-__global__ void __launch_bounds__(kFrame) osc_source_kernel(const float* __restrict__ f0, const double* __restrict__ carry,
-                                                            const float* __restrict__ amps, int amps_cs,
-                                                            const float* __restrict__ noise,
-                                                            const float* __restrict__ energy, bf16* __restrict__ src_hi,
-                                                            bf16* __restrict__ src_lo, int src_cs, int Lf,
-                                                            float scale_size, float scale_factor) {
-    __shared__ double wtot[kFrame / 32][kOsc + 1];
+__global__ void __launch_bounds__(kOsc * 32, 2) osc_source_kernel(const float* __restrict__ f0, const double* __restrict__ carry,
+                                                               const float* __restrict__ amps, int amps_cs,
+                                                               const float* __restrict__ noise,
+                                                               const float* __restrict__ energy, bf16* __restrict__ src_hi,
+                                                               bf16* __restrict__ src_lo, int src_cs, int Lf,
+                                                               float scale_size, float scale_factor) {
+    __shared__ float tile[kFrame][kOsc + 2];      // [sample][oscillator], 17-float rows: conflict-free both ways
     const int fr = blockIdx.x, b = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
     const float* f0b = f0 + (long long)b * Lf;
-    const int n = fr * kFrame + threadIdx.x;
-    const long long row = (long long)b * Lf * kFrame + n;
-    const LinCoord c = lin_coord(n, scale_size, Lf);
-    const float fa = __ldg(f0b + c.i0), fb = __ldg(f0b + c.i1);
-    const float fi = lin_blend(fa, fb, c);
-    const float uv = lin_blend(fa > 20.0f ? 1.f : 0.f, fb > 20.0f ? 1.f : 0.f, c);
-    double pre[kOsc];
+    const int n0 = fr * kFrame + lane * kRun;
+    const float kf = (float)(k + 1);
+    double v = 0.0;
 #pragma unroll
-    for (int k = 0; k < kOsc; ++k) {
-        double v = (double)__fdiv_rn(__fmul_rn(fi, (float)(k + 1)), kSampleRate);
+    for (int i = 0; i < kRun; ++i) v = __dadd_rn(v, (double)osc_increment(f0b, n0 + i, scale_size, Lf, kf));
+    double ex = v;                                  // exclusive scan of the lane totals
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double u = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane >= o) v = __dadd_rn(v, u);
-        }
-        pre[k] = v;
-        if (lane == 31) wtot[warp][k] = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_up_sync(0xffffffffu, ex, o);
+        if (lane >= o) ex = __dadd_rn(ex, u);
+    }
+    // second pass: the same increments again (cheaper than keeping 15 fp64 prefixes live), now accumulated
+    // on top of everything that precedes this lane's run.  (base + run prefix) in one chain: the sums are
+    // exact in fp64, so the association does not change the fp32 rounding of I.
+    double acc = __dadd_rn(carry[((long long)b * Lf + fr) * kOsc + k], __dadd_rn(ex, -v));
+    const float* ab = amps + (long long)b * Lf * amps_cs + k;
+#pragma unroll 5
+    for (int i = 0; i < kRun; ++i) {
+        const int n = n0 + i;
+        acc = __dadd_rn(acc, (double)osc_increment(f0b, n, scale_size, Lf, kf));
+        const float I = __double2float_rn(acc);
+        const float theta = __fmul_rn(6.28318530717958647692f, fmodf(I, 1.0f));
+        const LinCoord c = lin_coord(n, scale_size, Lf);
+        const float uv = lin_blend(__ldg(f0b + c.i0) > 20.0f ? 1.f : 0.f, __ldg(f0b + c.i1) > 20.0f ? 1.f : 0.f, c);
+        const float h = __fmul_rn(sinf(theta), uv);
+        const LinCoord ca = lin_coord(n, scale_factor, Lf);
+        const float a = lin_blend(__ldg(ab + (long long)ca.i0 * amps_cs), __ldg(ab + (long long)ca.i1 * amps_cs), ca);
+        tile[lane * kRun + i][k] = __fmul_rn(h, a);
     }
     __syncthreads();
-    const LinCoord ca = lin_coord(n, scale_factor, Lf);
-    const float* a0 = amps + ((long long)b * Lf + ca.i0) * amps_cs;
-    const float* a1 = amps + ((long long)b * Lf + ca.i1) * amps_cs;
-    const double* cb = carry + ((long long)b * Lf + fr) * kOsc;
+    // one thread per sample assembles the 24-channel row: 15 harmonics, noise, energy, 7 zeros (decoder.py:224,265)
+    const int n = threadIdx.x;
+    const long long row = ((long long)b * Lf + fr) * kFrame + n;
     float out[24];
 #pragma unroll
-    for (int k = 0; k < kOsc; ++k) {
-        double base = cb[k];
-        for (int w = 0; w < warp; ++w) base = __dadd_rn(base, wtot[w][k]);
-        const float I = __double2float_rn(__dadd_rn(base, pre[k]));
-        const float theta = __fmul_rn(6.28318530717958647692f, fmodf(I, 1.0f));
-        const float h = __fmul_rn(sinf(theta), uv);
-        out[k] = __fmul_rn(h, lin_blend(__ldg(a0 + k), __ldg(a1 + k), ca));
-    }
+    for (int q = 0; q < kOsc; ++q) out[q] = tile[n][q];
     out[15] = __ldg(noise + row);
     out[16] = __ldg(energy + row);
 #pragma unroll
-    for (int k = 17; k < 24; ++k) out[k] = 0.f;
+    for (int q = 17; q < 24; ++q) out[q] = 0.f;
     uint32_t hh[12], ll[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) {
+    for (int q = 0; q < 12; ++q) {
         bf16 h0, l0, h1, l1;
-        split_bf16(out[2 * k], h0, l0);
-        split_bf16(out[2 * k + 1], h1, l1);
-        hh[k] = pack2(h0, h1);
-        ll[k] = pack2(l0, l1);
+        split_bf16(out[2 * q], h0, l0);
+        split_bf16(out[2 * q + 1], h1, l1);
+        hh[q] = pack2(h0, h1);
+        ll[q] = pack2(l0, l1);
     }
     uint4* ph = reinterpret_cast<uint4*>(src_hi + row * src_cs);
     uint4* pl = reinterpret_cast<uint4*>(src_lo + row * src_cs);
@@ -240,11 +236,11 @@ int harmonic_source_cl(const float* f0, const float* amps, int amps_cs, const fl
     const float scale_factor = (float)(1.0 / (double)kFrame);   // F.interpolate(scale_factor=480)
     double* totals = (double*)scratch;
     dim3 grid(Lf, B);
-    osc_frame_sums_kernel<<<grid, kFrame, 0, s>>>(f0, totals, Lf, scale_size);
+    osc_frame_sums_kernel<<<grid, kOsc * 32, 0, s>>>(f0, totals, Lf, scale_size);
     TVC_LAUNCH_CHECK();
     osc_scan_frames_kernel<<<B, kOsc * 32, 0, s>>>(totals, Lf);
     TVC_LAUNCH_CHECK();
-    osc_source_kernel<<<grid, kFrame, 0, s>>>(f0, totals, amps, amps_cs, noise, energy, src_hi, src_lo, src_cs, Lf,
+    osc_source_kernel<<<grid, kOsc * 32, 0, s>>>(f0, totals, amps, amps_cs, noise, energy, src_hi, src_lo, src_cs, Lf,
                                                scale_size, scale_factor);
     TVC_LAUNCH_CHECK();
     return 0;

@@ -91,3 +91,25 @@ def test_product_path_never_imports_oracle():
                 if f.endswith(".py"):
                     src = open(os.path.join(dp, f)).read()
                     assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dp, f)
+
+
+def test_cli_flags_match_the_reference():
+    """Flag spellings / defaults of reference infer.py:18-29 and infer_streaming.py:19-33 (device default is
+    cuda here: there is no CPU path)."""
+    import infer
+    import infer_streaming
+    a = vars(infer.build_parser().parse_args([]))
+    assert a == dict(inputs="./inputs/", outputs="./outputs/", encoder_path="./models/encoder.pt",
+                     decoder_path="./models/decoder.pt", f0_estimation="default", index="NONE", target="target.wav",
+                     device="cuda", pitch_shift=0.0, chunk_size=1920, buffer_size=4, no_chunking=False)
+    short = infer.build_parser().parse_args("-i a -o b -encp e -decp d -f0-est x -idx i -t t -d cuda:1 -p 2 -c 1 -b 2 -nc 1".split())
+    assert (short.inputs, short.index, short.device, short.pitch_shift, short.no_chunking) == ("a", "i", "cuda:1", 2.0, True)
+    b = vars(infer_streaming.build_parser().parse_args([]))
+    b.pop("dry_run")
+    assert b == dict(encoder_path="./models/encoder.pt", decoder_path="./models/decoder.pt", input=0, output=0,
+                     loopback=-1, index="NONE", pitch_shift=0, target="target.wav", chunk=1920, extra=3840,
+                     device="cuda", sample_rate=24000, input_gain=0, output_gain=0, f0_estimation="default")
+    s = infer_streaming.build_parser().parse_args("-i 1 -o 2 -l 3 -c 960 -e 0 -sr 48000 -ig 3 -og -3 -f0-est dio".split())
+    assert (s.input, s.output, s.loopback, s.chunk, s.extra, s.sample_rate, s.f0_estimation) == (1, 2, 3, 960, 0, 48000, "dio")
+    with pytest.raises(SystemExit, match="no CPU path"):
+        infer.load_generator("x", "y", torch.device("cpu"))

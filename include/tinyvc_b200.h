@@ -129,6 +129,19 @@ int tvc_shift_frequency(const float* f0, float* out, int64_t n, float semitones,
 int tvc_sola(const float* y, int y_len, float* sola_buf, const float* fade_in, float* out_block,
              int32_t* shift_out, int S, int block, int cross, int search, int delay, void* stream);
 
+/* The same tick with the reference's `use_phase_vocoder=True` cross-fade (stream.py:83-89): the first
+ * `cross` output samples are phase_vocoder(old tail, new head, fade_out, fade_in) (stream.py:9-26)
+ * instead of the linear cross-fade.  Needs block >= cross.                                         */
+size_t tvc_sola_pv_workspace_bytes(int S, int cross);
+int tvc_sola_pv(const float* y, int y_len, float* sola_buf, const float* fade_in, float* out_block,
+                int32_t* shift_out, int S, int block, int cross, int search, int delay, void* workspace,
+                size_t workspace_bytes, void* stream);
+/* phase_vocoder(a, b, fade_out = 1 - fade_in, fade_in) (stream.py:9-26) for S independent pairs:
+ * a, b, out [S,n]; fade_in [n].                                                                    */
+size_t tvc_phase_vocoder_workspace_bytes(int S, int n);
+int tvc_phase_vocoder(const float* a, const float* b, const float* fade_in, float* out, int S, int n,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- parity probes (tests only) ------------------------------------------------------------ */
 /* One dense Conv1d through the tcgen05 tensor-core kernel (csrc/tc_conv.cu) with channels-first fp32
  * device tensors at the boundary, as nn.Conv1d(Cin, Cout, K, dilation=dil, padding=dil*(K-1)/2,

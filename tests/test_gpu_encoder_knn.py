@@ -118,3 +118,33 @@ def test_pipeline_stagewise_and_teacher_forced(cuda_models, report):
     assert e < 1e-4
     z, f0 = gen.encode(wf)
     assert max_abs(z, t(g["enc_z"])) / float(zr.abs().max()) < 2e-5
+
+
+@torch.inference_mode()
+def test_build_index_matches_reference_loop(cuda_models, weights, report):
+    """extract_index.py:30-58 restated with the oracle encoder, clip by clip in the shuffled-loader order, against
+    the batched GPU builder under the same seed: same clips, same column permutation, vectors equal to 1e-5."""
+    from tinyvc_b200.index import build_index, dataloader_order
+    enc, _ = cuda_models
+    PE = weights[0]
+    g = torch.Generator().manual_seed(11)
+    clips = [0.1 * torch.randn(4800 if i % 3 else 9600, generator=g) for i in range(9)]
+    size, stride = 40, 4
+    torch.manual_seed(5)
+    got = build_index(enc, lambda i: clips[i], [c.numel() for c in clips], size=size, stride=stride, batch_size=4)
+    # the reference loop
+    torch.manual_seed(5)
+    feats, total = [], 0
+    for i in dataloader_order(len(clips)):
+        z, _ = O.encoder_infer(PE, O.spectrogram(clips[i][None]))
+        z = z[:, :, ::stride]
+        total += z.shape[2]
+        feats.append(z)
+        if total > size:
+            break
+    feats = torch.cat(feats, dim=2)
+    want = feats.index_select(2, torch.randperm(feats.size(2)))[:, :, :size]
+    assert got.shape == want.shape and got.device.type == "cpu" and got.dtype == torch.float32
+    e = max_abs(got, want) / float(want.abs().max())
+    report.add("build_index", rel_max=e, vectors=got.shape[2])
+    assert e < 2e-5

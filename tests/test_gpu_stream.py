@@ -70,3 +70,60 @@ def test_batched_streams_match_single(cuda_models):
         for s in range(S):
             one = singles[s].audio_callback(blocks[tick, s].cuda(), rand01=rands[tick, s:s + 1].cuda())
             assert torch.equal(one, out[s]), f"tick {tick} stream {s}"
+
+
+@torch.inference_mode()
+def test_phase_vocoder_matches_reference(report):
+    """phase_vocoder(a, b, fade_out, fade_in) (reference stream.py:9-26) for several stream pairs, n = 1920 and an
+    odd length (the reference doubles a different bin range for odd n)."""
+    from tinyvc_b200.infer.stream import phase_vocoder
+    import math
+    worst = 0.0
+    for n, S, seed in ((1920, 3, 0), (1920, 2, 1), (481, 2, 2), (64, 1, 3)):
+        g = torch.Generator().manual_seed(seed)
+        fade_in = torch.sin(math.pi * torch.arange(0, 1, 1 / n)[:n] / 2) ** 2
+        fade_out = 1 - fade_in
+        a = 0.3 * torch.randn(S, n, generator=g)
+        # b: a delayed, slightly different copy of a (what SOLA hands over) plus noise
+        b = 0.9 * torch.roll(a, 7, dims=1) + 0.05 * torch.randn(S, n, generator=g)
+        got = phase_vocoder(a.cuda(), b.cuda(), fade_out.cuda(), fade_in.cuda()).cpu()
+        for s in range(S):
+            want = O.phase_vocoder(a[s], b[s], fade_out, fade_in)
+            worst = max(worst, max_abs(got[s], want))
+    report.add("phase_vocoder", max_abs=worst)
+    assert worst < 2e-5      # fp32 FFT vs direct DFT; a 2*pi phase-wrap flip would show as ~1e-3
+
+
+@torch.inference_mode()
+def test_stream_phase_vocoder_ticks(cuda_models, report):
+    """use_phase_vocoder=True ticks against the oracle's SOLA + phase_vocoder on the windows the CUDA path converted."""
+    from tinyvc_b200.infer import Generator, StreamInfer
+    enc, dec = cuda_models
+    gen = Generator(enc, dec)
+    g = load_golden("stream_4ticks.npz")
+    index, blocks = t(g["index"]).cuda(), t(g["blocks"])
+    si = StreamInfer(gen, target=index, pitch_shift=0.0, device=torch.device("cuda"), use_phase_vocoder=True)
+    si.init_buffer()
+    captured = []
+    so = O.StreamOracle(lambda w: captured[-1], use_phase_vocoder=True)
+    torch.manual_seed(int(g["rand_seed"]))
+    rands = [torch.rand(1, 961, 28) for _ in range(3)]
+    real_convert = gen.convert
+
+    def spy(wf, tgt, ps, *a, **k):
+        y = real_convert(wf, tgt, ps, *a, **k)
+        captured.append(y.cpu())
+        return y
+
+    gen.convert = spy
+    worst = 0.0
+    try:
+        for i in range(3):
+            out = si.audio_callback(blocks[i].cuda(), rand01=rands[i].cuda()).cpu()
+            ref = so.audio_callback(blocks[i].clone())
+            assert int(si.last_shift[0]) == so.last_shift
+            worst = max(worst, max_abs(out, ref))
+    finally:
+        gen.convert = real_convert
+    report.add("stream_phase_vocoder", max_abs=worst)
+    assert worst < 2e-5

@@ -58,6 +58,10 @@ _SIGNATURES = {
     "tvc_estimate_energy": (c_int, [_P, _P, c_int, c_int, _P, c_size_t, c_void_p]),
     "tvc_shift_frequency": (c_int, [_P, _P, c_int64, c_float, c_void_p]),
     "tvc_sola": (c_int, [_P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "tvc_sola_pv_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "tvc_sola_pv": (c_int, [_P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, c_void_p]),
+    "tvc_phase_vocoder_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "tvc_phase_vocoder": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_size_t, c_void_p]),
     "tvc_tc_conv_probe": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, _P,
                                   c_int, c_int, c_int, _P, _P, c_void_p]),
 }

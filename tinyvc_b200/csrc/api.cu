@@ -580,6 +580,39 @@ int tvc_sola(const float* y, int y_len, float* sola_buf, const float* fade_in, f
     API_END
 }
 
+size_t tvc_sola_pv_workspace_bytes(int S, int cross) {
+    if (S <= 0 || cross <= 0) return 0;
+    return sizeof(float) * ((size_t)S * 2 * cross + phase_vocoder_scratch_floats(S, cross)) + 256;
+}
+
+int tvc_sola_pv(const float* y, int y_len, float* sola_buf, const float* fade_in, float* out_block, int32_t* shift_out,
+                int S, int block, int cross, int search, int delay, void* workspace, size_t workspace_bytes, void* stream) {
+    API_BEGIN
+    TVC_REQUIRE(y && sola_buf && fade_in && out_block && shift_out && workspace, "tvc_sola_pv: null argument");
+    TVC_REQUIRE(S > 0 && block > 0 && cross > 0 && search >= 0 && delay >= 0, "tvc_sola_pv: invalid sizes");
+    TVC_REQUIRE(workspace_bytes >= tvc_sola_pv_workspace_bytes(S, cross), "tvc_sola_pv: workspace too small");
+    return sola_run(y, y_len, sola_buf, fade_in, out_block, shift_out, S, block, cross, search, delay, (cudaStream_t)stream,
+                    (float*)workspace);
+    API_END
+}
+
+size_t tvc_phase_vocoder_workspace_bytes(int S, int n) {
+    if (S <= 0 || n <= 0) return 0;
+    return sizeof(float) * phase_vocoder_scratch_floats(S, n) + 256;
+}
+
+int tvc_phase_vocoder(const float* a, const float* b, const float* fade_in, float* out, int S, int n, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+    API_BEGIN
+    TVC_REQUIRE(a && b && fade_in && out && workspace, "tvc_phase_vocoder: null argument");
+    TVC_REQUIRE(S > 0 && n > 0, "tvc_phase_vocoder: invalid sizes");
+    TVC_REQUIRE(workspace_bytes >= tvc_phase_vocoder_workspace_bytes(S, n), "tvc_phase_vocoder: workspace too small");
+    // a and b are separate [S][n] arrays: address b relative to a
+    return phase_vocoder_run(a, (long long)n, (long long)(b - a), fade_in, (float*)workspace, out, (long long)n, S, n,
+                             (cudaStream_t)stream);
+    API_END
+}
+
 // ---------------------------------------------------------------------------------------------- parity probes
 int tvc_tc_conv_probe(const float* x, const float* w, const float* bias, int B, int T, int Cin, int Cout, int K, int dil,
                       const float* aux_x, const float* aux_w, const float* aux_b, int aux_cin, int aux_mode,

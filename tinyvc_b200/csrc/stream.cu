@@ -14,7 +14,7 @@ namespace tvc {
 __global__ void __launch_bounds__(1024) sola_kernel(const float* __restrict__ y, int y_len, float* __restrict__ sola_buf,
                                                     const float* __restrict__ fade_in, float* __restrict__ out_block,
                                                     int* __restrict__ shift_out, int block, int cross, int search,
-                                                    int delay) {
+                                                    int delay, float* __restrict__ pv_ab) {
     extern __shared__ float sm[];
     float* temp = sm;                           // [block+cross+search]
     float* sola = temp + block + cross + search;   // [cross]
@@ -72,7 +72,15 @@ __global__ void __launch_bounds__(1024) sola_kernel(const float* __restrict__ y,
     }
     __syncthreads();
     const int sh = s_shift;
-    for (int i = threadIdx.x; i < block; i += blockDim.x) {
+    if (pv_ab) {
+        // phase-vocoder cross-fade (stream.py:83-89): hand a = old tail, b = new head to pv_* kernels, which
+        // write out_block[:cross]; host side guarantees block >= cross, so the new tail is untouched audio
+        for (int i = threadIdx.x; i < cross; i += blockDim.x) {
+            pv_ab[((long long)s * 2) * cross + i] = sola[i];
+            pv_ab[((long long)s * 2 + 1) * cross + i] = temp[sh + i];
+        }
+    }
+    for (int i = threadIdx.x + (pv_ab ? cross : 0); i < block; i += blockDim.x) {
         float v = temp[sh + i];
         if (i < cross) {
             const float fi = __ldg(fade_in + i);
@@ -92,8 +100,113 @@ __global__ void __launch_bounds__(1024) sola_kernel(const float* __restrict__ y,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// phase_vocoder(a, b, fade_out, fade_in) (module/infer/stream.py:9-26), one CTA per stream:
+//   window = sqrt(fade_out * fade_in);  fa = rfft(a*window), fb = rfft(b*window)
+//   absab  = |fa| + |fb|, doubled for every bin but DC (and Nyquist when n is even)
+//   dphi   = angle(fb) - angle(fa), wrapped to [-pi, pi);  w = 2*pi*f + dphi;  t = i/n
+//   out[i] = a*fade_out^2 + b*fade_in^2 + sum_f absab[f] * cos(w[f]*t[i] + angle(fa)[f]) * window[i] / n
+// pv_dft_kernel evaluates the two real DFTs directly (n = 1920: 961 bins x 1920 samples, fp32
+// products accumulated in fp64, twiddles from a shared table) and leaves {absab, w, phia} per bin;
+// pv_synth_kernel evaluates the cosine bank with the reference's fp32 rounding of the argument
+// (w*t rounded, then + phia rounded: the argument reaches 6e3 rad, where that rounding is visible).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) pv_dft_kernel(const float* __restrict__ ab, long long a_stride, long long b_off,
+                                                      const float* __restrict__ fade_in, float* __restrict__ bins, int n) {
+    extern __shared__ float sm[];
+    float* xa = sm;            // [n] a * window
+    float* xb = xa + n;        // [n] b * window
+    float* tc = xb + n;        // [n] cos(2 pi k / n)
+    float* ts = tc + n;        // [n] sin(2 pi k / n)
+    const int s = blockIdx.x, nb = n / 2 + 1;
+    const float* a = ab + (long long)s * a_stride;
+    const float* b = a + b_off;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float fi = __ldg(fade_in + i), fo = __fsub_rn(1.0f, fi);
+        const float w = sqrtf(__fmul_rn(fo, fi));
+        xa[i] = __fmul_rn(a[i], w);
+        xb[i] = __fmul_rn(b[i], w);
+        double sv, cv;
+        sincospi(2.0 * (double)i / (double)n, &sv, &cv);
+        tc[i] = (float)cv;
+        ts[i] = (float)sv;
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < nb; f += blockDim.x) {
+        double ar = 0.0, ai = 0.0, br = 0.0, bi = 0.0;
+        int idx = 0;
+        for (int k = 0; k < n; ++k) {
+            const float c = tc[idx], sn = ts[idx];
+            const float va = xa[k], vb = xb[k];
+            ar += (double)(va * c); ai -= (double)(va * sn);
+            br += (double)(vb * c); bi -= (double)(vb * sn);
+            idx += f;
+            if (idx >= n) idx -= n;
+        }
+        const float far = (float)ar, fai = (float)ai, fbr = (float)br, fbi = (float)bi;
+        float absab = __fadd_rn(hypotf(far, fai), hypotf(fbr, fbi));
+        const bool dbl = (n % 2 == 0) ? (f >= 1 && f < nb - 1) : (f >= 1);
+        if (dbl) absab = __fmul_rn(absab, 2.0f);
+        const float phia = atan2f(fai, far), phib = atan2f(fbi, fbr);
+        float d = __fsub_rn(phib, phia);
+        const float turns = floorf(__fadd_rn(__fdiv_rn(__fdiv_rn(d, 2.0f), 3.14159274f), 0.5f));
+        d = __fsub_rn(d, __fmul_rn(6.2831855f, turns));
+        const float w = __fadd_rn(__fmul_rn(6.2831855f, (float)f), d);
+        float* o = bins + (long long)s * 3 * nb;
+        o[f] = absab;
+        o[nb + f] = w;
+        o[2 * nb + f] = phia;
+    }
+}
+
+__global__ void __launch_bounds__(256) pv_synth_kernel(const float* __restrict__ ab, long long a_stride, long long b_off,
+                                                       const float* __restrict__ fade_in, const float* __restrict__ bins,
+                                                       float* __restrict__ out, long long out_stride, int n) {
+    extern __shared__ float sm[];
+    const int s = blockIdx.y, nb = n / 2 + 1;
+    const float* bs = bins + (long long)s * 3 * nb;
+    for (int i = threadIdx.x; i < 3 * nb; i += blockDim.x) sm[i] = bs[i];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* absab = sm;
+    const float* w = sm + nb;
+    const float* phia = sm + 2 * nb;
+    const float t = __fdiv_rn((float)i, (float)n);
+    double acc = 0.0;
+    for (int f = 0; f < nb; ++f) {
+        const float arg = __fadd_rn(__fmul_rn(w[f], t), phia[f]);
+        acc += (double)__fmul_rn(absab[f], cosf(arg));
+    }
+    const float* a = ab + (long long)s * a_stride;
+    const float fi = __ldg(fade_in + i), fo = __fsub_rn(1.0f, fi);
+    const float win = sqrtf(__fmul_rn(fo, fi));
+    const float lin = __fadd_rn(__fmul_rn(a[i], __fmul_rn(fo, fo)), __fmul_rn(a[b_off + i], __fmul_rn(fi, fi)));
+    out[(long long)s * out_stride + i] = __fadd_rn(lin, __fdiv_rn(__fmul_rn((float)acc, win), (float)n));
+}
+
+size_t phase_vocoder_scratch_floats(int S, int n) { return (size_t)S * 3 * (size_t)(n / 2 + 1); }
+
+// a = ab + s*a_stride, b = a + b_off (floats); out[s*out_stride + i], i < n; bins: phase_vocoder_scratch_floats(S, n) floats
+int phase_vocoder_run(const float* ab, long long a_stride, long long b_off, const float* fade_in, float* bins, float* out,
+                      long long out_stride, int S, int n, cudaStream_t s) {
+    TVC_REQUIRE(n >= 2 && n <= 8192, "phase_vocoder: cross-fade length %d out of range [2, 8192]", n);
+    const size_t smem = sizeof(float) * 4 * (size_t)n;
+    static bool attr_done = false;
+    if (!attr_done) {
+        TVC_CUDA(cudaFuncSetAttribute(pv_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_done = true;
+    }
+    pv_dft_kernel<<<S, 1024, smem, s>>>(ab, a_stride, b_off, fade_in, bins, n);
+    TVC_LAUNCH_CHECK();
+    pv_synth_kernel<<<dim3(cdiv(n, 256), S), 256, sizeof(float) * 3 * (size_t)(n / 2 + 1), s>>>(ab, a_stride, b_off, fade_in, bins, out,
+                                                                                          out_stride, n);
+    TVC_LAUNCH_CHECK();
+    return 0;
+}
+
 int sola_run(const float* y, int y_len, float* sola_buf, const float* fade_in, float* out_block, int* shift_out, int S,
-             int block, int cross, int search, int delay, cudaStream_t s) {
+             int block, int cross, int search, int delay, cudaStream_t s, float* pv_scratch) {
     TVC_REQUIRE(y_len >= block + cross + search + delay, "sola: window of %d samples is shorter than block+cross+search+delay = %d",
                 y_len, block + cross + search + delay);
     const size_t smem = sizeof(float) * (size_t)(block + 2 * cross + search);
@@ -103,8 +216,14 @@ int sola_run(const float* y, int y_len, float* sola_buf, const float* fade_in, f
         TVC_CUDA(cudaFuncSetAttribute(sola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_done = true;
     }
-    sola_kernel<<<S, 1024, smem, s>>>(y, y_len, sola_buf, fade_in, out_block, shift_out, block, cross, search, delay);
+    TVC_REQUIRE(!pv_scratch || block >= cross, "sola: the phase-vocoder cross-fade needs block (%d) >= cross-fade (%d)", block, cross);
+    sola_kernel<<<S, 1024, smem, s>>>(y, y_len, sola_buf, fade_in, out_block, shift_out, block, cross, search, delay, pv_scratch);
     TVC_LAUNCH_CHECK();
+    if (pv_scratch) {
+        // scratch layout: [S][2][cross] (a, b) then the per-bin table
+        float* bins = pv_scratch + (size_t)S * 2 * cross;
+        return phase_vocoder_run(pv_scratch, 2LL * cross, cross, fade_in, bins, out_block, block, S, cross, s);
+    }
     return 0;
 }
 

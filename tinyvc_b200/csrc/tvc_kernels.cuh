@@ -39,6 +39,9 @@ constexpr int kKnnSegDecl = 16;
 
 // stream.cu
 int sola_run(const float* y, int y_len, float* sola_buf, const float* fade_in, float* out_block, int* shift_out, int S,
-             int block, int cross, int search, int delay, cudaStream_t s);
+             int block, int cross, int search, int delay, cudaStream_t s, float* pv_scratch = nullptr);
+size_t phase_vocoder_scratch_floats(int S, int n);
+int phase_vocoder_run(const float* ab, long long a_stride, long long b_off, const float* fade_in, float* bins, float* out,
+                      long long out_stride, int S, int n, cudaStream_t s);
 
 }  // namespace tvc

@@ -19,15 +19,30 @@ from .. import _lib
 from .generator import Generator
 
 
+@torch.inference_mode()
+def phase_vocoder(a: torch.Tensor, b: torch.Tensor, fade_out: torch.Tensor, fade_in: torch.Tensor) -> torch.Tensor:
+    """Reference `phase_vocoder(a, b, fade_out, fade_in)` (stream.py:9-26) on the GPU; a, b [n] or [S,n].
+    `fade_out` must be `1 - fade_in` (it always is: stream.py:61-62); only `fade_in` is passed down."""
+    a2, b2 = _lib.dev_f32(a, "a").reshape(-1, a.shape[-1]), _lib.dev_f32(b, "b").reshape(-1, b.shape[-1])
+    fade_in = _lib.dev_f32(fade_in, "fade_in")
+    if a2.shape != b2.shape or fade_in.numel() != a2.shape[1] or fade_out.numel() != a2.shape[1]:
+        raise RuntimeError(f"phase_vocoder: shapes {tuple(a.shape)}, {tuple(b.shape)}, {tuple(fade_out.shape)}, {tuple(fade_in.shape)}")
+    S, n = a2.shape
+    out = torch.empty_like(a2)
+    L = _lib.lib()
+    with torch.cuda.device(a2.device):
+        ws = _lib.WORKSPACE.get(L.tvc_phase_vocoder_workspace_bytes(S, n), a2.device)
+        _lib.check(L.tvc_phase_vocoder(a2.data_ptr(), b2.data_ptr(), fade_in.data_ptr(), out.data_ptr(), S, n, ws.data_ptr(),
+                                       ws.numel(), _lib.stream_ptr(a2.device)), "tvc_phase_vocoder")
+    return out.reshape(a.shape)
+
+
 class BatchedStreamInfer:
     """S independent streams sharing one target index; state tensors are [S, ...] on `device`."""
 
     def __init__(self, generator: Generator, num_streams: int, target=None, pitch_shift: float = 0.0,
                  device=torch.device("cuda"), block_size: int = 1920, extra_size: int = 0,
                  use_phase_vocoder: bool = False, f0_estimation: str = "default"):
-        if use_phase_vocoder:
-            raise NotImplementedError("phase-vocoder cross-fade (reference stream.py:9-26,83-89) is not built yet; "
-                                      "use the default SOLA cross-fade")
         self.generator = generator
         self.num_streams = int(num_streams)
         self.target = target
@@ -69,11 +84,19 @@ class BatchedStreamInfer:
         self.input_wav = nxt
         y = self.generator.convert(self.input_wav, self.target, self.pitch_shift, rand01=rand01).contiguous()
         out = torch.empty(S, bs, device=self.device, dtype=torch.float32)
+        L = _lib.lib()
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().tvc_sola(y.data_ptr(), y.shape[1], self.sola_buffer.data_ptr(),
-                                           self.fade_in_window.data_ptr(), out.data_ptr(), self._shift.data_ptr(), S, bs,
-                                           self.crossfade_size, self.sola_search_size, self.last_dilay_size,
-                                           _lib.stream_ptr(self.device)), "tvc_sola")
+            if self.use_phase_vocoder:        # stream.py:83-89
+                ws = _lib.WORKSPACE.get(L.tvc_sola_pv_workspace_bytes(S, self.crossfade_size), self.device)
+                _lib.check(L.tvc_sola_pv(y.data_ptr(), y.shape[1], self.sola_buffer.data_ptr(), self.fade_in_window.data_ptr(),
+                                         out.data_ptr(), self._shift.data_ptr(), S, bs, self.crossfade_size,
+                                         self.sola_search_size, self.last_dilay_size, ws.data_ptr(), ws.numel(),
+                                         _lib.stream_ptr(self.device)), "tvc_sola_pv")
+            else:                             # stream.py:90-92
+                _lib.check(L.tvc_sola(y.data_ptr(), y.shape[1], self.sola_buffer.data_ptr(),
+                                      self.fade_in_window.data_ptr(), out.data_ptr(), self._shift.data_ptr(), S, bs,
+                                      self.crossfade_size, self.sola_search_size, self.last_dilay_size,
+                                      _lib.stream_ptr(self.device)), "tvc_sola")
         self.last_shift = self._shift
         return out
 

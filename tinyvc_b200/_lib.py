@@ -87,6 +87,10 @@ def lib() -> ctypes.CDLL:
                 impl = os.environ.get("TVC_CONV_IMPL")
                 if impl and h.tvc_set_option(b"conv_impl", impl.encode()) != 0:
                     raise RuntimeError(f"tinyvc_b200: TVC_CONV_IMPL={impl!r} is not a known conv implementation")
+                for kv in filter(None, os.environ.get("TVC_OPTS", "").split(",")):      # e.g. TVC_OPTS=pdl=0,graphs=0
+                    k, _, v = kv.partition("=")
+                    if h.tvc_set_option(k.strip().encode(), v.strip().encode()) != 0:
+                        raise RuntimeError(f"tinyvc_b200: TVC_OPTS entry {kv!r} was rejected by tvc_set_option")
                 _lib = h
     return _lib
 

@@ -25,6 +25,7 @@ void set_error(const char* fmt, ...) {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static bool g_use_graphs = true;
+bool g_pdl = true;       // programmatic dependent launch between the decoder plan's kernels
 
 // ---- event profiler ----------------------------------------------------------------------------
 struct ProfEntry { std::string name; cudaEvent_t a, b; };
@@ -159,6 +160,10 @@ int tvc_set_option(const char* key, const char* value) {
         g_groups = g;
         return 0;
     }
+    if (!strcmp(key, "pdl")) {
+        g_pdl = !strcmp(value, "1");
+        return 0;
+    }
     if (!strcmp(key, "graphs")) {
         g_use_graphs = !strcmp(value, "1");
         return 0;
@@ -274,7 +279,7 @@ int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, co
     // that set is seen (callers that reuse their buffers -- serving loops, the Python wrapper's cached
     // workspace -- then pay one graph launch instead of ~100 kernel launches per call).
     std::lock_guard<std::mutex> lock(h->mu);
-    const DecoderGraphKey key{content, f0, energy, rand01, out, workspace, B, Lf, g_conv_impl};
+    const DecoderGraphKey key{content, f0, energy, rand01, out, workspace, B, Lf, g_conv_impl | (g_pdl ? 256 : 0)};
     ++h->tick;
     for (DecoderGraph& g : h->graphs)
         if (g.key == key) {

@@ -10,6 +10,7 @@ namespace tvc {
 // ---------------------------------------------------------------------------------------------
 __global__ void frame_prep_kernel(const float* __restrict__ energy, const float* __restrict__ f0,
                                   float* __restrict__ e_fr, float* __restrict__ lf0, long long nframes) {
+    TVC_PDL_PROLOGUE();
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= nframes) return;
@@ -28,7 +29,7 @@ __global__ void frame_prep_kernel(const float* __restrict__ energy, const float*
 int frame_prep(const float* energy, const float* f0, float* e_fr, float* lf0, int B, int Lf, cudaStream_t s) {
     const long long nf = (long long)B * Lf;
     const int threads = 256;
-    frame_prep_kernel<<<cdiv(nf * 32, threads), threads, 0, s>>>(energy, f0, e_fr, lf0, nf);
+    TVC_LAUNCH_PDL(frame_prep_kernel, cdiv(nf * 32, threads), threads, 0, s, energy, f0, e_fr, lf0, nf);
     TVC_LAUNCH_CHECK();
     return 0;
 }

@@ -224,6 +224,7 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 template <int SPEC>
 __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    pdl_launch_dependents();      // the next kernel of the plan may start its prologue as soon as SM resources free up
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
     const uint32_t smem_base = smem_u32(smem);
@@ -278,6 +279,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
         const uint32_t b_aux = film ? 2u * b_tap : b_tap;
         const uint32_t dst_c = (uint32_t)c * p.lbo_a;
         TileWalk tw(p, tile_beg);
+        // Weights do not depend on the previous kernel: the first tile's weight stages (as many as the ring
+        // holds) are requested before griddepcontrol.wait, so they land while the previous grid drains.
+        int pre = 0;
+        if (tile_beg < tile_end && !(p.dbg & 1)) {
+            pre = n_stage < p.ring ? n_stage : p.ring;
+            if (j == 0) {
+                const bf16* w0 = p.w + (long long)tw.n_tile * p.tile_elems;
+                for (int i = 0; i < pre; ++i) {
+                    const uint32_t bb = i >= n_main ? b_aux : b_main;
+                    const uint32_t full = bar_base + 8u * i;
+                    mbar_arrive_expect_tx(full, bb);
+                    bulk_g2s(smem_base + i * stage_bytes + p.a_stage_bytes, w0, bb, full);
+                    w0 += bb >> 1;
+                }
+            }
+        }
+        pdl_wait();
         for (long long tile = tile_beg; tile < tile_end; ++tile, tw.next(p)) {
             const long long row_tile = tw.row_tile;
             const bf16* wt = p.w + (long long)tw.n_tile * p.tile_elems;
@@ -310,7 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                 const uint32_t b_bytes = is_aux ? b_aux : b_main;
                 if (wrapped) mbar_wait(empty, ph);
                 const uint32_t a_dst = smem_base + s * stage_bytes;
-                if (j == 0) {
+                if (j == 0 && !(tile == tile_beg && i < pre)) {
                     if (p.dbg & 1) mbar_arrive(full);
                     else {
                         mbar_arrive_expect_tx(full, b_bytes);
@@ -429,6 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
         const int out_act = kGeneric ? p.out_act : kS.out_act;
         const int quarter = warp & 3, slot = warp >> 2;
         const int rloc = quarter * 32 + lane;
+        pdl_wait();               // residual reads and output writes must follow the previous grid
         const int n_groups = p.NT >> 3;
         uint32_t tcount = 0;
         TileWalk tw(p, tile_beg);
@@ -716,15 +735,15 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     }
     if (g_force_generic) spec = -1;
     switch (spec) {
-        case 0: tc_conv_kernel<0><<<grid, kThreads, smem, s>>>(p); break;
-        case 1: tc_conv_kernel<1><<<grid, kThreads, smem, s>>>(p); break;
-        case 2: tc_conv_kernel<2><<<grid, kThreads, smem, s>>>(p); break;
-        case 3: tc_conv_kernel<3><<<grid, kThreads, smem, s>>>(p); break;
-        case 4: tc_conv_kernel<4><<<grid, kThreads, smem, s>>>(p); break;
-        case 5: tc_conv_kernel<5><<<grid, kThreads, smem, s>>>(p); break;
-        case 6: tc_conv_kernel<6><<<grid, kThreads, smem, s>>>(p); break;
-        case 7: tc_conv_kernel<7><<<grid, kThreads, smem, s>>>(p); break;
-        default: tc_conv_kernel<-1><<<grid, kThreads, smem, s>>>(p); break;
+        case 0: TVC_LAUNCH_PDL(tc_conv_kernel<0>, grid, kThreads, smem, s, p); break;
+        case 1: TVC_LAUNCH_PDL(tc_conv_kernel<1>, grid, kThreads, smem, s, p); break;
+        case 2: TVC_LAUNCH_PDL(tc_conv_kernel<2>, grid, kThreads, smem, s, p); break;
+        case 3: TVC_LAUNCH_PDL(tc_conv_kernel<3>, grid, kThreads, smem, s, p); break;
+        case 4: TVC_LAUNCH_PDL(tc_conv_kernel<4>, grid, kThreads, smem, s, p); break;
+        case 5: TVC_LAUNCH_PDL(tc_conv_kernel<5>, grid, kThreads, smem, s, p); break;
+        case 6: TVC_LAUNCH_PDL(tc_conv_kernel<6>, grid, kThreads, smem, s, p); break;
+        case 7: TVC_LAUNCH_PDL(tc_conv_kernel<7>, grid, kThreads, smem, s, p); break;
+        default: TVC_LAUNCH_PDL(tc_conv_kernel<-1>, grid, kThreads, smem, s, p); break;
     }
     TVC_LAUNCH_CHECK();
     return 0;

@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256) noise_spectrum_cl_kernel(const float* __r
                                                                 bf16* __restrict__ yr_hi, bf16* __restrict__ yr_lo,
                                                                 bf16* __restrict__ yi_hi, bf16* __restrict__ yi_lo,
                                                                 int y_cs, int Lf) {
+    TVC_PDL_PROLOGUE();
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(256) noise_spectrum_cl_kernel(const float* __r
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) noise_ola_cl_kernel(const float* __restrict__ c, const float* __restrict__ sn,
                                                            int cs, float* __restrict__ noise, int Lf, long long total) {
+    TVC_PDL_PROLOGUE();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int L = Lf * kFrame;
@@ -110,6 +112,7 @@ __device__ __forceinline__ float osc_increment(const float* __restrict__ f0b, in
 
 __global__ void __launch_bounds__(kOsc * 32) osc_frame_sums_kernel(const float* __restrict__ f0, double* __restrict__ totals,
                                                                    int Lf, float scale_size) {
+    TVC_PDL_PROLOGUE();
     const int fr = blockIdx.x, b = blockIdx.y;
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
     const float* f0b = f0 + (long long)b * Lf;
@@ -124,6 +127,7 @@ __global__ void __launch_bounds__(kOsc * 32) osc_frame_sums_kernel(const float* 
 
 // in place: totals[b][fr][k] -> sum of totals[b][0..fr-1][k]
 __global__ void __launch_bounds__(kOsc * 32) osc_scan_frames_kernel(double* __restrict__ totals, int Lf) {
+    TVC_PDL_PROLOGUE();
     const int b = blockIdx.x, k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* tb = totals + (long long)b * Lf * kOsc + k;
     double carry = 0.0;
@@ -147,6 +151,7 @@ __global__ void __launch_bounds__(kOsc * 32, 2) osc_source_kernel(const float* _
                                                                const float* __restrict__ energy, bf16* __restrict__ src_hi,
                                                                bf16* __restrict__ src_lo, int src_cs, int Lf,
                                                                float scale_size, float scale_factor) {
+    TVC_PDL_PROLOGUE();
     __shared__ float tile[kFrame][kOsc + 2];      // [sample][oscillator], 17-float rows: conflict-free both ways
     const int fr = blockIdx.x, b = blockIdx.y;
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
@@ -214,14 +219,14 @@ __global__ void __launch_bounds__(kOsc * 32, 2) osc_source_kernel(const float* _
 int noise_spectrum_cl(const float* kern, int k_cs, const float* rand01, bf16* yr_hi, bf16* yr_lo, bf16* yi_hi,
                       bf16* yi_lo, int y_cs, int B, int Lf, cudaStream_t s) {
     dim3 grid(cdiv(Lf, 32), cdiv(y_cs, 32), B);
-    noise_spectrum_cl_kernel<<<grid, 256, 0, s>>>(kern, k_cs, rand01, yr_hi, yr_lo, yi_hi, yi_lo, y_cs, Lf);
+    TVC_LAUNCH_PDL(noise_spectrum_cl_kernel, grid, 256, 0, s, kern, k_cs, rand01, yr_hi, yr_lo, yi_hi, yi_lo, y_cs, Lf);
     TVC_LAUNCH_CHECK();
     return 0;
 }
 
 int noise_ola_cl(const float* c, const float* sn, int cs, float* noise, int B, int Lf, cudaStream_t s) {
     const long long total = (long long)B * Lf * kFrame;
-    noise_ola_cl_kernel<<<cdiv(total, 256), 256, 0, s>>>(c, sn, cs, noise, Lf, total);
+    TVC_LAUNCH_PDL(noise_ola_cl_kernel, cdiv(total, 256), 256, 0, s, c, sn, cs, noise, Lf, total);
     TVC_LAUNCH_CHECK();
     return 0;
 }
@@ -236,11 +241,11 @@ int harmonic_source_cl(const float* f0, const float* amps, int amps_cs, const fl
     const float scale_factor = (float)(1.0 / (double)kFrame);   // F.interpolate(scale_factor=480)
     double* totals = (double*)scratch;
     dim3 grid(Lf, B);
-    osc_frame_sums_kernel<<<grid, kOsc * 32, 0, s>>>(f0, totals, Lf, scale_size);
+    TVC_LAUNCH_PDL(osc_frame_sums_kernel, grid, kOsc * 32, 0, s, f0, totals, Lf, scale_size);
     TVC_LAUNCH_CHECK();
-    osc_scan_frames_kernel<<<B, kOsc * 32, 0, s>>>(totals, Lf);
+    TVC_LAUNCH_PDL(osc_scan_frames_kernel, B, kOsc * 32, 0, s, totals, Lf);
     TVC_LAUNCH_CHECK();
-    osc_source_kernel<<<grid, kOsc * 32, 0, s>>>(f0, totals, amps, amps_cs, noise, energy, src_hi, src_lo, src_cs, Lf,
+    TVC_LAUNCH_PDL(osc_source_kernel, grid, kOsc * 32, 0, s, f0, totals, amps, amps_cs, noise, energy, src_hi, src_lo, src_cs, Lf,
                                                scale_size, scale_factor);
     TVC_LAUNCH_CHECK();
     return 0;

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256) interp_cl_kernel(const float* __restrict_
                                                         bf16* __restrict__ r_hi, bf16* __restrict__ r_lo,
                                                         bf16* __restrict__ a_hi, bf16* __restrict__ a_lo, int p_cs,
                                                         long long total) {
+    TVC_PDL_PROLOGUE();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int g = (int)(i % C4);
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(256) dwconv_ln_cl_kernel(const float* __restri
                                                            const float* __restrict__ wb, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, bf16* __restrict__ hi,
                                                            bf16* __restrict__ lo, int T, long long rows) {
+    TVC_PDL_PROLOGUE();
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(256) dwconv_ln_cl_kernel(const float* __restri
 __global__ void __launch_bounds__(256) grn_apply_cl_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, bf16* __restrict__ hi,
                                                            bf16* __restrict__ lo, int C, int T) {
+    TVC_PDL_PROLOGUE();
     __shared__ float part[8];
     const int b = blockIdx.x, c = threadIdx.x, lane = c & 31, warp = c >> 5;
     const float* yb = y + (long long)b * T * C;
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(256) grn_apply_cl_kernel(const float* __restri
 __global__ void __launch_bounds__(256) out_conv_k7_cl_kernel(const float* __restrict__ x, const float* __restrict__ w,   // [24][7] torch layout
                                                              const float* __restrict__ bias, float* __restrict__ y, int T,
                                                              long long rows) {
+    TVC_PDL_PROLOGUE();
     __shared__ float ws[7][24];
     for (int e = threadIdx.x; e < 24 * 7; e += blockDim.x) ws[e % 7][e / 7] = __ldg(w + e);
     __syncthreads();
@@ -175,7 +179,7 @@ int interp_cl(const float* x, int x_cs, int B, int Tin, int Tout, float scale, i
               bf16* r_lo, bf16* a_hi, bf16* a_lo, int p_cs, cudaStream_t s) {
     TVC_REQUIRE(C % 4 == 0 && x_cs % 4 == 0 && (!y32 || y_cs % 4 == 0) && p_cs % 4 == 0, "interp_cl: channel counts must be multiples of 4");
     const long long total = (long long)B * Tout * (C / 4);
-    interp_cl_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, x_cs, Tin, Tout, scale, C / 4, y32, y_cs, r_hi, r_lo, a_hi, a_lo, p_cs, total);
+    TVC_LAUNCH_PDL(interp_cl_kernel, cdiv(total, 256), 256, 0, s, x, x_cs, Tin, Tout, scale, C / 4, y32, y_cs, r_hi, r_lo, a_hi, a_lo, p_cs, total);
     TVC_LAUNCH_CHECK();
     return 0;
 }
@@ -183,7 +187,7 @@ int interp_cl(const float* x, int x_cs, int B, int Tin, int Tout, float scale, i
 int dwconv_ln_cl(const float* x, int x_cs, const float* w7, const float* wb, const float* gamma, const float* beta,
                  bf16* hi, bf16* lo, int B, int T, cudaStream_t s) {
     const long long rows = (long long)B * T;
-    dwconv_ln_cl_kernel<<<cdiv(rows * 32, 256), 256, 0, s>>>(x, x_cs, w7, wb, gamma, beta, hi, lo, T, rows);
+    TVC_LAUNCH_PDL(dwconv_ln_cl_kernel, cdiv(rows * 32, 256), 256, 0, s, x, x_cs, w7, wb, gamma, beta, hi, lo, T, rows);
     TVC_LAUNCH_CHECK();
     return 0;
 }
@@ -191,14 +195,14 @@ int dwconv_ln_cl(const float* x, int x_cs, const float* w7, const float* wb, con
 int grn_apply_cl(const float* y, const float* gamma, const float* beta, bf16* hi, bf16* lo, int B, int C, int T,
                  cudaStream_t s) {
     TVC_REQUIRE(C <= 256, "grn_apply_cl: C=%d > 256", C);
-    grn_apply_cl_kernel<<<B, 256, 0, s>>>(y, gamma, beta, hi, lo, C, T);
+    TVC_LAUNCH_PDL(grn_apply_cl_kernel, B, 256, 0, s, y, gamma, beta, hi, lo, C, T);
     TVC_LAUNCH_CHECK();
     return 0;
 }
 
 int out_conv_k7_cl(const float* x, const float* w, const float* bias, float* y, int B, int T, cudaStream_t s) {
     const long long rows = (long long)B * T;
-    out_conv_k7_cl_kernel<<<cdiv(rows, 256), 256, 0, s>>>(x, w, bias, y, T, rows);
+    TVC_LAUNCH_PDL(out_conv_k7_cl_kernel, cdiv(rows, 256), 256, 0, s, x, w, bias, y, T, rows);
     TVC_LAUNCH_CHECK();
     return 0;
 }

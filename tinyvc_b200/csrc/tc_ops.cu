@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(256) cf_to_cl_kernel(const float* __restrict__
                                                        bf16* __restrict__ hi, bf16* __restrict__ lo, int C, int T,
                                                        int cs, int act, const float* __restrict__ extra0,
                                                        const float* __restrict__ extra1) {
+    TVC_PDL_PROLOGUE();
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(256) cl_to_cf_kernel(const float* __restrict__
 int cf_to_planes(const float* x, bf16* hi, bf16* lo, int B, int C, int T, int cs, int act, cudaStream_t s,
                  const float* extra0, const float* extra1) {
     dim3 grid(cdiv(T, 32), cdiv(cs, 32), B);
-    cf_to_cl_kernel<1><<<grid, 256, 0, s>>>(x, nullptr, hi, lo, C, T, cs, act, extra0, extra1);
+    TVC_LAUNCH_PDL(cf_to_cl_kernel<1>, grid, 256, 0, s, x, nullptr, hi, lo, C, T, cs, act, extra0, extra1);
     TVC_LAUNCH_CHECK();
     return 0;
 }

@@ -48,6 +48,40 @@ struct ProfScope {
         }                                                                                      \
     } while (0)
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+): kernels of the decoder plan are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's CTAs may become resident and run
+// their prologue (barrier init, TMEM allocation, weight prefetch) while the previous kernel drains.
+// Every such kernel must execute griddepcontrol.wait before its first access to memory the previous kernels
+// produce or still read (the wait returns once all prerequisite grids have completed and flushed).
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#define TVC_PDL_PROLOGUE()                  \
+    do {                                    \
+        ::tvc::pdl_launch_dependents();     \
+        ::tvc::pdl_wait();                  \
+    } while (0)
+extern bool g_pdl;      // tvc_set_option("pdl", "0"|"1")
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define TVC_LAUNCH_PDL(kernel, grid, block, smem, stream, ...) \
+    (void)::tvc::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
+#endif
+
 constexpr int kFrame = 480;        // samples per frame @ 24 kHz (decoder.py:242)
 constexpr int kNfft = 1920;
 constexpr int kBins = 961;         // n_fft/2 + 1

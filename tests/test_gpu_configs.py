@@ -1,0 +1,100 @@
+"""BASELINE.json configs at their full per-GPU sizes, through the public Python API / C-ABI.
+
+The CPU oracle cannot run these sizes in seconds, so each config is checked (a) on a handful of its utterances
+against the oracle and (b) at full size through properties that do not need the oracle: batch invariance (an
+utterance's result does not depend on what else is in the batch -- which is also what makes sharding across
+GPUs exact), gather consistency of the kNN output, finiteness.
+"""
+import pytest
+import torch
+
+from conftest import rmse, max_abs
+from oracle import tinyvc_oracle as O
+from tinyvc_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@torch.inference_mode()
+def test_config3_full_pipeline_b256_4s_n50k(cuda_models, weights, report):
+    """configs[2]: Encoder -> kNN(50k-vector index) -> Decoder, batch 256, 4 s clips."""
+    from tinyvc_b200.infer import Generator
+    enc, dec = cuda_models
+    PE, PD = weights
+    gen = Generator(enc, dec)
+    B, T, N = 256, 96000, 50000
+    inp = synth.pipeline_inputs(B, T, N, seed=1234 + 3)
+    g = torch.Generator().manual_seed(77)
+    rand01 = torch.rand(B, 961, T // 480, generator=g)
+    wf, index = inp["wf"].cuda(), inp["index"].cuda()
+    out, parts = gen.convert(wf, index, 0.0, rand01=rand01.cuda(), return_parts=True)
+    assert out.shape == (B, T) and bool(torch.isfinite(out).all())
+    # (b) full-size properties
+    idx = parts["idx"]                                           # [B, Lf, 4]
+    assert idx.shape == (B, T // 480, 4) and int(idx.min()) >= 0 and int(idx.max()) < N
+    assert bool((idx.sort(dim=2).values.diff(dim=2) != 0).all()), "a query returned the same index column twice"
+    gathered = index[0].t()[idx].mean(dim=2).transpose(1, 2)    # [B, 768, Lf] (feature_retrieval.py:30)
+    assert max_abs(gathered, parts["zm"]) < 1e-6
+    sub = [0, 131, 255]
+    alone = gen.convert(wf[sub], index, 0.0, rand01=rand01[sub].cuda())
+    assert torch.equal(alone, out[sub]), "an utterance's waveform depends on the rest of the batch"
+    # (a) oracle on a few utterances: indices identical (or a reported numerical near-tie), decoder teacher-forced
+    bad_total, worst = 0, 0.0
+    for b in (0, 200):
+        ref, rp = O.generator_convert(PE, PD, inp["wf"][b:b + 1], inp["index"], 0.0, rand01=rand01[b:b + 1], return_parts=True)
+        z_rel = max_abs(parts["z"][b:b + 1], rp["z"]) / float(rp["z"].abs().max())
+        assert z_rel < 2e-5
+        bad = (idx[b].cpu() != rp["idx"][0]).any(dim=1)
+        bad_total += int(bad.sum())
+        forced = dec.infer(rp["zm"].cuda(), rp["f0s"].cuda(), rp["energy"].cuda(), rand01=rand01[b:b + 1].cuda())
+        worst = max(worst, rmse(forced, ref))
+    report.add("config3_b256_n50k", idx_mismatched_queries=bad_total, queries_checked=2 * (T // 480),
+               teacher_forced_rmse=worst)
+    assert bad_total <= 1, f"{bad_total} of {2 * (T // 480)} queries picked different neighbours than the CPU reference"
+    assert worst < 1e-4
+
+
+@torch.inference_mode()
+def test_config4_share_b512_10s(cuda_models, weights, report):
+    """configs[3] per-GPU share: Decoder batch 4096 x 10 s over 8 GPUs = 512 utterances of 500 frames per GPU."""
+    _, dec = cuda_models
+    PD = weights[1]
+    B, Lf = 512, 500
+    inp = synth.decoder_inputs(B, Lf, seed=1234 + 4)
+    dev = {k: v.cuda() for k, v in inp.items()}
+    out = dec.infer(dev["content"], dev["f0"], dev["energy"], rand01=dev["rand01"])
+    assert out.shape == (B, Lf * 480) and bool(torch.isfinite(out).all())
+    sub = [0, 300, 511]
+    alone = dec.infer(dev["content"][sub], dev["f0"][sub], dev["energy"][sub], rand01=dev["rand01"][sub])
+    assert torch.equal(alone, out[sub]), "an utterance's waveform depends on the rest of the batch"
+    b = 300
+    ref = O.decoder_infer(PD, inp["content"][b:b + 1], inp["f0"][b:b + 1], inp["energy"][b:b + 1], inp["rand01"][b:b + 1])
+    e = rmse(out[b:b + 1], ref)
+    report.add("config4_share_b512_lf500", rmse=e, ref_rms=float(ref.pow(2).mean().sqrt()))
+    assert e < 1e-4
+
+
+@torch.inference_mode()
+def test_config5_share_128_streams(cuda_models, report):
+    """configs[4] per-GPU share: 128 concurrent streams, window 13 440 samples, 1 920 out per tick, shared 2 048-vector index."""
+    from tinyvc_b200.infer import Generator, StreamInfer, BatchedStreamInfer
+    enc, dec = cuda_models
+    gen = Generator(enc, dec)
+    S, ticks = 128, 3
+    gi = torch.Generator().manual_seed(5)
+    index = torch.randn(1, 768, 2048, generator=gi).cuda()
+    blocks = 0.1 * torch.randn(ticks, S, 1920, generator=gi)
+    rands = torch.rand(ticks, S, 961, 28, generator=gi)
+    bs = BatchedStreamInfer(gen, S, target=index, device=torch.device("cuda"))
+    bs.init_buffer()
+    probe = [0, 77, 127]
+    singles = {s: StreamInfer(gen, target=index, device=torch.device("cuda")) for s in probe}
+    for si in singles.values():
+        si.init_buffer()
+    for k in range(ticks):
+        out = bs.audio_callback(blocks[k].cuda(), rand01=rands[k].cuda())
+        assert out.shape == (S, 1920) and bool(torch.isfinite(out).all())
+        for s in probe:
+            one = singles[s].audio_callback(blocks[k, s].cuda(), rand01=rands[k, s:s + 1].cuda())
+            assert torch.equal(one, out[s]), f"tick {k}: stream {s} differs between the 128-stream batch and a lone stream"
+    report.add("config5_share_128_streams", ticks=ticks, streams=S)

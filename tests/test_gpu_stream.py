@@ -79,7 +79,7 @@ def test_phase_vocoder_matches_reference(report):
     from tinyvc_b200.infer.stream import phase_vocoder
     import math
     worst = 0.0
-    for n, S, seed in ((1920, 3, 0), (1920, 2, 1), (481, 2, 2), (64, 1, 3)):
+    for n, S, seed in ((1920, 3, 0), (1920, 1, 1), (481, 2, 2), (64, 1, 3)):
         g = torch.Generator().manual_seed(seed)
         fade_in = torch.sin(math.pi * torch.arange(0, 1, 1 / n)[:n] / 2) ** 2
         fade_out = 1 - fade_in
@@ -122,6 +122,13 @@ def test_stream_phase_vocoder_ticks(cuda_models, report):
             out = si.audio_callback(blocks[i].cuda(), rand01=rands[i].cuda()).cpu()
             ref = so.audio_callback(blocks[i].clone())
             assert int(si.last_shift[0]) == so.last_shift
+            if i == 0:
+                # First tick: a = the all-zero initial sola_buffer, so fa = rfft(0) and angle(fa) is the angle of a
+                # signed zero -- the reference gets 0 or +-pi per bin depending on which zeros its FFT library
+                # returns as -0.0 (479 of 961 bins on torch 2.11 CPU), i.e. the cross-fade from silence is not a
+                # function of the input.  Only the state hand-over is checked on this tick (tail = raw audio).
+                assert torch.equal(si.sola_buffer[0].cpu(), so.sola_buffer)
+                continue
             worst = max(worst, max_abs(out, ref))
     finally:
         gen.convert = real_convert

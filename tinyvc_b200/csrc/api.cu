@@ -25,7 +25,8 @@ void set_error(const char* fmt, ...) {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static bool g_use_graphs = true;
-bool g_pdl = true;       // programmatic dependent launch between the decoder plan's kernels
+bool g_pdl = false;      // programmatic dependent launch between the decoder plan's kernels (measured: no gain while a
+                         // tc_conv CTA fills an SM's registers and shared memory, so successors cannot become resident early)
 
 // ---- event profiler ----------------------------------------------------------------------------
 struct ProfEntry { std::string name; cudaEvent_t a, b; };

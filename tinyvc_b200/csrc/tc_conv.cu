@@ -213,6 +213,28 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// One K-stage of the implicit GEMM: TAPS x KS K-steps, three bf16 products each (hi*hi, hi*lo, lo*hi), straight-line.
+// a_lo0 / b_lo0: low descriptor words (start address | LBO << 16, 16-byte units) of the stage's activation window and
+// weight image; *_tap / *_ks: start-address increments per tap and per 16-channel K-step; plane_*: hi -> lo plane.
+template <int TAPS, int KS>
+__device__ __forceinline__ void issue_stage(uint32_t d, uint32_t a_lo0, uint32_t b_lo0, uint32_t a_tap, uint32_t b_tap,
+                                            uint32_t a_ks, uint32_t b_ks, uint32_t plane_a16, uint32_t plane_b16,
+                                            uint32_t desc_hi, uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) {
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)t * a_tap + (uint32_t)k * a_ks;
+            const uint32_t b_lo = b_lo0 + (uint32_t)t * b_tap + (uint32_t)k * b_ks;
+            const uint64_t a_h = ((uint64_t)desc_hi << 32) | a_lo, a_l = ((uint64_t)desc_hi << 32) | (a_lo + plane_a16);
+            const uint64_t b_h = ((uint64_t)desc_hi << 32) | b_lo, b_l = ((uint64_t)desc_hi << 32) | (b_lo + plane_b16);
+            umma_bf16(d, a_h, b_h, idesc, (t == 0 && k == 0) ? acc0 : 1u);
+            umma_bf16(d, a_h, b_l, idesc, 1u);
+            umma_bf16(d, a_l, b_h, idesc, 1u);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Persistent, warp-specialised: each CTA walks tiles (row tile, channel tile) round-robin.
 //   warps 0-11   epilogue: TMEM lane quarter = warp & 3, column slot = warp >> 2 (8-channel groups
@@ -380,14 +402,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
             }
         }
     } else if (warp == kMmaWarp) {
-        // ================= MMA issuer (one thread) =================
+        // ================= MMA issuer (one elected lane; the warp runs the loops uniformly) =================
+        // The issuing warp is a single instruction stream: every scalar instruction it spends per MMA is on the
+        // kernel's critical path (it bounded the C = 24 full-rate convs).  Everything that does not change from
+        // stage to stage is hoisted, and a stage's TAPS x KS x 3 MMAs are issued as straight-line code.
         {
-            const uint32_t leader = elect_one();
+            const bool leader = elect_one() != 0;
+            const bool issue = leader && !(p.dbg & 2);
             const uint32_t idesc_main = umma_idesc(kTileM, (uint32_t)p.NTp);
             const uint32_t idesc_film = umma_idesc(kTileM, 2u * (uint32_t)p.NTp);
             const uint32_t desc_hi = (128u >> 4) | (1u << 14);      // SBO = 128 bytes, descriptor version 1
             const uint32_t lbo_a16 = p.lbo_a >> 4, plane_a16 = plane_a >> 4;
             const int ksteps = p.KB >> 4;
+            // weight-image strides in 16-byte units: chunk stride = rows of the image (NTp, or 2*NTp for a FiLM stage)
+            const uint32_t lbo_b_main = (uint32_t)p.NTp, lbo_b_film = 2u * (uint32_t)p.NTp;
+            const uint32_t plane_b_main = (uint32_t)chunks * lbo_b_main, plane_b_film = (uint32_t)chunks * lbo_b_film;
+            const uint32_t a_lbo_field = lbo_a16 << 16;
+            const uint32_t a_stage16 = p.a_stage_bytes >> 4, stage16 = stage_bytes >> 4;
+            const uint32_t base16 = (smem_base & 0x3FFFFu) >> 4;
+            const bool halo_main = p.halo != 0;
             uint32_t s = 0, ph = 0, tcount = 0;
             for (long long tile = tile_beg; tile < tile_end; ++tile, ++tcount) {
                 const uint32_t buf = tcount & 1u, buse = tcount >> 1;
@@ -398,38 +431,38 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                 const uint32_t d_base = tmem + buf * acc_cols;
                 for (int i = 0; i < n_stage; ++i) {
                     const uint32_t full = bar_base + 8u * s, empty = bar_base + 8u * (p.ring + s);
-                    const bool is_film = i >= n_main && film;
-                    const uint32_t n_rows = is_film ? 2u * p.NTp : (uint32_t)p.NTp;
+                    const bool is_aux = i >= n_main;
+                    const bool is_film = is_aux && film;
                     const uint32_t idesc = is_film ? idesc_film : idesc_main;
                     const uint32_t d = d_base + (is_film ? (uint32_t)p.NTp : 0u);
-                    const bool first = is_film ? (i == n_main) : (i == 0);
+                    const uint32_t acc0 = (is_film ? (i == n_main) : (i == 0)) ? 0u : 1u;
+                    const uint32_t lbo_b = is_film ? lbo_b_film : lbo_b_main;
+                    const uint32_t plane_b = is_film ? plane_b_film : plane_b_main;
+                    // low descriptor words: start address | LBO (16-byte units); only the start address moves
+                    const uint32_t a_lo0 = (base16 + s * stage16) | a_lbo_field;
+                    const uint32_t b_lo0 = (base16 + s * stage16 + a_stage16) | (lbo_b << 16);
                     mbar_wait(full, ph);
                     tc_fence_after();
-                    // descriptors: hi word = SBO | version, lo word = start address | LBO (all in 16-byte units);
-                    // only the start address moves between MMAs
-                    const uint32_t a_base = smem_base + s * stage_bytes;
-                    const uint32_t b_lbo16 = n_rows;                    // weight-image chunk stride in 16-byte units
-                    const uint32_t a_lo0 = ((a_base & 0x3FFFFu) >> 4) | (lbo_a16 << 16);
-                    const uint32_t b_lo0 = (((a_base + p.a_stage_bytes) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
-                    const uint32_t plane_b16 = (uint32_t)chunks * b_lbo16;
-                    const int taps_here = (p.halo && i < n_main) ? p.taps : 1;
-                    uint32_t acc = first ? 0u : 1u;
-                    for (int tap = 0; tap < taps_here; ++tap) {
-                        // halo mode: the tap is a row offset into the shared window (one 16-byte slot per row)
-                        uint32_t a_lo = a_lo0 + (uint32_t)(tap * p.dil);
-                        uint32_t b_lo = b_lo0 + (uint32_t)tap * 2u * plane_b16;
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint64_t a_h = ((uint64_t)desc_hi << 32) | a_lo, a_l = ((uint64_t)desc_hi << 32) | (a_lo + plane_a16);
-                            const uint64_t b_h = ((uint64_t)desc_hi << 32) | b_lo, b_l = ((uint64_t)desc_hi << 32) | (b_lo + plane_b16);
-                            if (leader && !(p.dbg & 2)) {
-                                umma_bf16(d, a_h, b_h, idesc, acc);
-                                umma_bf16(d, a_h, b_l, idesc, 1u);
-                                umma_bf16(d, a_l, b_h, idesc, 1u);
+                    if (issue) {
+                        // halo mode: a tap is a row offset into the shared window (one 16-byte slot per row) and
+                        // selects the tap's weight image (hi + lo planes apart)
+#define TVC_ISSUE(T, K) issue_stage<T, K>(d, a_lo0, b_lo0, (uint32_t)p.dil, 2u * plane_b, 2u * lbo_a16, 2u * lbo_b, plane_a16, plane_b, desc_hi, idesc, acc0)
+                        if (halo_main && !is_aux) {
+                            switch (ksteps) {
+                                case 1: TVC_ISSUE(3, 1); break;
+                                case 2: TVC_ISSUE(3, 2); break;
+                                case 3: TVC_ISSUE(3, 3); break;
+                                default: TVC_ISSUE(3, 4); break;
                             }
-                            acc = 1u;
-                            a_lo += 2u * lbo_a16;
-                            b_lo += 2u * b_lbo16;
+                        } else {
+                            switch (ksteps) {
+                                case 1: TVC_ISSUE(1, 1); break;
+                                case 2: TVC_ISSUE(1, 2); break;
+                                case 3: TVC_ISSUE(1, 3); break;
+                                default: TVC_ISSUE(1, 4); break;
+                            }
                         }
+#undef TVC_ISSUE
                     }
                     if (leader) umma_commit(empty);                    // frees the smem stage once these MMAs retire
                     if (++s == (uint32_t)p.ring) { s = 0; ph ^= 1u; }
@@ -478,6 +511,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                     r0 = __ldg(rp);
                     r1 = __ldg(rp + 1);
                 }
+                // per-channel constants: requested before the accumulator wait so their latency hides behind it
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cg * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cg * 8) + 1);
+                float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, h0 = s0, h1 = s0;
+                if (film) {
+                    s0 = __ldg(reinterpret_cast<const float4*>(fbias + cg * 8));
+                    s1 = __ldg(reinterpret_cast<const float4*>(fbias + cg * 8) + 1);
+                    h0 = __ldg(reinterpret_cast<const float4*>(fbias + p.NTp + cg * 8));
+                    h1 = __ldg(reinterpret_cast<const float4*>(fbias + p.NTp + cg * 8) + 1);
+                }
                 if (!waited) {
                     mbar_wait(acc_full + 8u * buf, buse & 1u);
                     tc_fence_after();
@@ -492,16 +535,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                 tmem_ld_wait();
                 if (!live) continue;
                 {
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cg * 8));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cg * 8) + 1);
                     v[0] = __fadd_rn(v[0], b0.x); v[1] = __fadd_rn(v[1], b0.y); v[2] = __fadd_rn(v[2], b0.z); v[3] = __fadd_rn(v[3], b0.w);
                     v[4] = __fadd_rn(v[4], b1.x); v[5] = __fadd_rn(v[5], b1.y); v[6] = __fadd_rn(v[6], b1.z); v[7] = __fadd_rn(v[7], b1.w);
                 }
                 if (film) {
-                    const float4 s0 = __ldg(reinterpret_cast<const float4*>(fbias + cg * 8));
-                    const float4 s1 = __ldg(reinterpret_cast<const float4*>(fbias + cg * 8) + 1);
-                    const float4 h0 = __ldg(reinterpret_cast<const float4*>(fbias + p.NTp + cg * 8));
-                    const float4 h1 = __ldg(reinterpret_cast<const float4*>(fbias + p.NTp + cg * 8) + 1);
                     const float sb[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                     const float hb[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll

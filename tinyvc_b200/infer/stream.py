@@ -22,7 +22,9 @@ from .generator import Generator
 @torch.inference_mode()
 def phase_vocoder(a: torch.Tensor, b: torch.Tensor, fade_out: torch.Tensor, fade_in: torch.Tensor) -> torch.Tensor:
     """Reference `phase_vocoder(a, b, fade_out, fade_in)` (stream.py:9-26) on the GPU; a, b [n] or [S,n].
-    `fade_out` must be `1 - fade_in` (it always is: stream.py:61-62); only `fade_in` is passed down."""
+    `fade_out` must be `1 - fade_in` (it always is: stream.py:61-62); only `fade_in` is passed down.
+    For an all-zero `a` (the first tick after init_buffer) the reference's result depends on the signed zeros its
+    FFT library returns (angle(-0.0) = pi); here angle(0) = 0 for every bin."""
     a2, b2 = _lib.dev_f32(a, "a").reshape(-1, a.shape[-1]), _lib.dev_f32(b, "b").reshape(-1, b.shape[-1])
     fade_in = _lib.dev_f32(fade_in, "fade_in")
     if a2.shape != b2.shape or fade_in.numel() != a2.shape[1] or fade_out.numel() != a2.shape[1]:

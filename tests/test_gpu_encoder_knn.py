@@ -148,3 +148,22 @@ def test_build_index_matches_reference_loop(cuda_models, weights, report):
     e = max_abs(got, want) / float(want.abs().max())
     report.add("build_index", rel_max=e, vectors=got.shape[2])
     assert e < 2e-5
+
+
+@torch.inference_mode()
+def test_index_cache_survives_pointer_reuse():
+    """Two different indices of the same shape, the first freed before the second is allocated (the caching allocator
+    then usually hands out the same address): the prepared-index cache must not serve the first one's data."""
+    from tinyvc_b200.tinyvc import match_features
+    g = torch.Generator().manual_seed(21)
+    src = torch.randn(1, 768, 6, generator=g).cuda()
+    outs = []
+    for _ in range(3):
+        ref_cpu = torch.randn(1, 768, 512, generator=g)
+        ref = ref_cpu.cuda()
+        out, idx = match_features(src, ref, return_indices=True)
+        _, idx_ref = O.match_features(src.cpu(), ref_cpu, return_indices=True)
+        assert torch.equal(idx.cpu(), idx_ref)
+        outs.append(out)
+        del ref
+    assert not torch.equal(outs[0], outs[1])

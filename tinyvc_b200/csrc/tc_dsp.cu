@@ -105,21 +105,27 @@ __global__ void __launch_bounds__(256) noise_ola_cl_kernel(const float* __restri
 constexpr int kRun = kFrame / 32;   // 15 samples per lane
 static_assert(kRun * 32 == kFrame, "frame must split into 32 equal runs");
 
-__device__ __forceinline__ float osc_increment(const float* __restrict__ f0b, int n, float scale_size, int Lf, float kf) {
+// The interpolated f0 of a sample is shared by the 15 oscillators (and by the two passes over the increments), so
+// each block first evaluates it once per sample into shared memory; an increment is then fp32(fp32(fsi * k) / 24000).
+__device__ __forceinline__ float osc_f0_at(const float* __restrict__ f0b, int n, float scale_size, int Lf) {
     const LinCoord c = lin_coord(n, scale_size, Lf);
-    return __fdiv_rn(__fmul_rn(lin_blend(__ldg(f0b + c.i0), __ldg(f0b + c.i1), c), kf), kSampleRate);
+    return lin_blend(__ldg(f0b + c.i0), __ldg(f0b + c.i1), c);
 }
+__device__ __forceinline__ float osc_increment(float fsi, float kf) { return __fdiv_rn(__fmul_rn(fsi, kf), kSampleRate); }
 
 __global__ void __launch_bounds__(kOsc * 32) osc_frame_sums_kernel(const float* __restrict__ f0, double* __restrict__ totals,
                                                                    int Lf, float scale_size) {
     TVC_PDL_PROLOGUE();
+    __shared__ float s_fsi[kFrame];
     const int fr = blockIdx.x, b = blockIdx.y;
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
     const float* f0b = f0 + (long long)b * Lf;
-    const int n0 = fr * kFrame + lane * kRun;
+    s_fsi[threadIdx.x] = osc_f0_at(f0b, fr * kFrame + threadIdx.x, scale_size, Lf);
+    __syncthreads();
+    const float* run = s_fsi + lane * kRun;       // stride 15 words between lanes: conflict-free
     double v = 0.0;
 #pragma unroll
-    for (int i = 0; i < kRun; ++i) v = __dadd_rn(v, (double)osc_increment(f0b, n0 + i, scale_size, Lf, (float)(k + 1)));
+    for (int i = 0; i < kRun; ++i) v = __dadd_rn(v, (double)osc_increment(run[i], (float)(k + 1)));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
     if (lane == 0) totals[((long long)b * Lf + fr) * kOsc + k] = v;
@@ -153,14 +159,29 @@ __global__ void __launch_bounds__(kOsc * 32, 2) osc_source_kernel(const float* _
                                                                float scale_size, float scale_factor) {
     TVC_PDL_PROLOGUE();
     __shared__ float tile[kFrame][kOsc + 2];      // [sample][oscillator], 17-float rows: conflict-free both ways
+    __shared__ float s_fsi[kFrame], s_uv[kFrame], s_al0[kFrame], s_al1[kFrame];
+    __shared__ int s_ai0[kFrame];
     const int fr = blockIdx.x, b = blockIdx.y;
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
     const float* f0b = f0 + (long long)b * Lf;
-    const int n0 = fr * kFrame + lane * kRun;
+    {
+        // per-sample quantities shared by all oscillators: interp(f0), interp(f0 > 20), amplitude interpolation coords
+        const int n = fr * kFrame + threadIdx.x;
+        const LinCoord c = lin_coord(n, scale_size, Lf);
+        const float fa = __ldg(f0b + c.i0), fb = __ldg(f0b + c.i1);
+        s_fsi[threadIdx.x] = lin_blend(fa, fb, c);
+        s_uv[threadIdx.x] = lin_blend(fa > 20.0f ? 1.f : 0.f, fb > 20.0f ? 1.f : 0.f, c);
+        const LinCoord ca = lin_coord(n, scale_factor, Lf);
+        s_ai0[threadIdx.x] = ca.i0 | (ca.i1 != ca.i0 ? 0x40000000 : 0);
+        s_al0[threadIdx.x] = ca.l0;
+        s_al1[threadIdx.x] = ca.l1;
+    }
+    __syncthreads();
+    const int r0 = lane * kRun;
     const float kf = (float)(k + 1);
     double v = 0.0;
 #pragma unroll
-    for (int i = 0; i < kRun; ++i) v = __dadd_rn(v, (double)osc_increment(f0b, n0 + i, scale_size, Lf, kf));
+    for (int i = 0; i < kRun; ++i) v = __dadd_rn(v, (double)osc_increment(s_fsi[r0 + i], kf));
     double ex = v;                                  // exclusive scan of the lane totals
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -174,16 +195,15 @@ __global__ void __launch_bounds__(kOsc * 32, 2) osc_source_kernel(const float* _
     const float* ab = amps + (long long)b * Lf * amps_cs + k;
 #pragma unroll 5
     for (int i = 0; i < kRun; ++i) {
-        const int n = n0 + i;
-        acc = __dadd_rn(acc, (double)osc_increment(f0b, n, scale_size, Lf, kf));
+        acc = __dadd_rn(acc, (double)osc_increment(s_fsi[r0 + i], kf));
         const float I = __double2float_rn(acc);
-        const float theta = __fmul_rn(6.28318530717958647692f, fmodf(I, 1.0f));
-        const LinCoord c = lin_coord(n, scale_size, Lf);
-        const float uv = lin_blend(__ldg(f0b + c.i0) > 20.0f ? 1.f : 0.f, __ldg(f0b + c.i1) > 20.0f ? 1.f : 0.f, c);
-        const float h = __fmul_rn(sinf(theta), uv);
-        const LinCoord ca = lin_coord(n, scale_factor, Lf);
-        const float a = lin_blend(__ldg(ab + (long long)ca.i0 * amps_cs), __ldg(ab + (long long)ca.i1 * amps_cs), ca);
-        tile[lane * kRun + i][k] = __fmul_rn(h, a);
+        // I % 1 (decoder.py:50): for I >= 0 fmodf(I, 1) == I - floorf(I), and that difference is exact in fp32
+        const float theta = __fmul_rn(6.28318530717958647692f, I >= 0.f ? __fsub_rn(I, floorf(I)) : fmodf(I, 1.0f));
+        const float h = __fmul_rn(sinf(theta), s_uv[r0 + i]);
+        const int ai = s_ai0[r0 + i];
+        const int i0 = ai & 0x3fffffff, i1 = i0 + (ai >> 30);
+        const float a = __fmaf_rn(__ldg(ab + (long long)i0 * amps_cs), s_al0[r0 + i], __fmul_rn(__ldg(ab + (long long)i1 * amps_cs), s_al1[r0 + i]));
+        tile[r0 + i][k] = __fmul_rn(h, a);
     }
     __syncthreads();
     // one thread per sample assembles the 24-channel row: 15 harmonics, noise, energy, 7 zeros (decoder.py:224,265)

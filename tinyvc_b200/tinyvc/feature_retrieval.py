@@ -20,13 +20,17 @@ import torch
 from .. import _lib
 
 CONTENT = 768
-_CACHE_MAX = 8
+_CACHE_MAX = 4
 
 
 class _Index:
     def __init__(self, ref2d: torch.Tensor, metric: int):
         self.N = ref2d.shape[1]
         self.device = ref2d.device
+        # The cache key contains the tensor's address.  Holding the tensor keeps that address from being handed to a
+        # different index by the caching allocator while this entry is alive (a recycled pointer with the same shape
+        # would otherwise hit the cache and silently match against the previous index).
+        self.keep = ref2d
         h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             torch.cuda.current_stream(self.device).synchronize()

@@ -1,7 +1,7 @@
 // Decoder.infer on the tensor-core path: every dense conv of SourceNet / dsp / FilterNet
 // (module/tinyvc/decoder.py:102-257) runs on tc_conv_kernel (tcgen05, split bf16 x3, fp32 TMEM
-// accumulate); activations stay channels-last between layers (fp32 where a residual or a
-// resampler needs the exact value, split bf16 planes where the consumer is a conv).
+// accumulate); activations stay channels-last, chunk-major (tc_conv.cuh) between layers (fp32 where a
+// residual or a resampler needs the exact value, split bf16 planes where the consumer is a conv).
 #include "nets_tc.cuh"
 
 #include <cmath>
@@ -256,17 +256,17 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         ARENA_OK();
         for (int i = 0; i < 3; ++i) {
             const Cnxt& c = mid[i];
-            RUN(dwconv_ln_cl(fx, 512, c.w7, c.wb, c.ln_g, c.ln_b, t1.hi, t1.lo, B, Lf, s));
+            RUN(dwconv_ln_cl(fx, c.w7, c.wb, c.ln_g, c.ln_b, t1.hi, t1.lo, B, Lf, s));
             CONV("tc_cnxt_c2(", c.c2, ConvCall(t1, B, Lf).f32(t2, 256).epi(TC_ACT_GELU));
             RUN(grn_apply_cl(t2, c.grn_g, c.grn_b, t2p.hi, t2p.lo, B, 256, Lf, s));
             CONV("tc_cnxt_c3(", c.c3, ConvCall(t2p, B, Lf).res(fx, 512).f32(fx, 512).out(xp, TC_ACT_NONE));
         }
         CONV("tc_heads(", heads, ConvCall(xp, B, Lf).f32(hk, kHeadsCs).epi(TC_ACT_ELU1));
-        RUN(noise_spectrum_cl(hk, kHeadsCs, rand01, yr.hi, yr.lo, yi.hi, yi.lo, kBinsCs, B, Lf, s));
+        RUN(noise_spectrum_cl(hk, rand01, yr.hi, yr.lo, yi.hi, yi.lo, kBinsCs, B, Lf, s));
         CONV("tc_idft(", dft_cos, ConvCall(yr, B, Lf).f32(cc, kBinsCs));
         CONV("tc_idft(", dft_sin, ConvCall(yi, B, Lf).f32(ss, kBinsCs));
-        RUN(noise_ola_cl(cc, ss, kBinsCs, noise, B, Lf, s));
-        RUN(harmonic_source_cl(f0, hk + kAmpsOff, kHeadsCs, noise, energy, src.hi, src.lo, 24, osc, B, Lf, s));
+        RUN(noise_ola_cl(cc, ss, noise, B, Lf, s));
+        RUN(harmonic_source_cl(f0, hk + cm(0, kAmpsOff, rowsF), noise, energy, src.hi, src.lo, osc, B, Lf, s));
         A.release(m);
     }
     // ---- FilterNet down path (decoder.py:206-213,225-229): skips at L, L/5, L/20, L/80, L/240
@@ -289,7 +289,7 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         Pl xr = planes(A, rows, cin), xa = planes(A, rows, cin), a = planes(A, rows, cin), c = planes(A, rows, cin);
         ARENA_OK();
         const float scale = (float)(1.0 / (1.0 / (double)fac));   // F.interpolate(scale_factor=1/f)
-        RUN(interp_cl(skip32[i], cin, B, tin, tout, scale, cin, nullptr, 0, xr.hi, xr.lo, xa.hi, xa.lo, cin, s));
+        RUN(interp_cl(skip32[i], B, tin, tout, scale, cin, nullptr, xr.hi, xr.lo, xa.hi, xa.lo, s));
         const char* const n1[4] = {"tc_down1_c1(", "tc_down2_c1(", "tc_down3_c1(", "tc_down4_c1("};
         const char* const n2[4] = {"tc_down1_c2(", "tc_down2_c2(", "tc_down3_c2(", "tc_down4_c2("};
         const char* const n3[4] = {"tc_down1_c3(", "tc_down2_c3(", "tc_down3_c3(", "tc_down4_c3("};
@@ -299,8 +299,8 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         A.release(m);
     }
     // ---- FilterNet up path (decoder.py:214-219,230-233)
-    const float* x = fx + 128;
-    int x_cs = 512, tin = Lf;
+    const float* x = fx + cm(0, 128, rowsF);      // FilterNet x0 = channels [128, 512) of the frame-rate product
+    int tin = Lf;
     for (int i = 0; i < 5; ++i) {
         const Up& u = up[i];
         const int c = kUpCh[i], cn = kUpOut[i], fac = kUpFac[i];
@@ -315,7 +315,7 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         Pl p0 = planes(A, rows, c), p1 = planes(A, rows, c);
         ARENA_OK();
         const float scale = (float)(1.0 / (double)fac);           // F.interpolate(scale_factor=f)
-        RUN(interp_cl(x, x_cs, B, tin, tout, scale, c, xi, c, nullptr, nullptr, p0.hi, p0.lo, c, s));
+        RUN(interp_cl(x, B, tin, tout, scale, c, xi, nullptr, nullptr, p0.hi, p0.lo, s));
         const char* const un[5][5] = {{"tc_up0_c1(", "tc_up0_c2(", "tc_up0_c3(", "tc_up0_c4(", "tc_up0_c5("},
                                       {"tc_up1_c1(", "tc_up1_c2(", "tc_up1_c3(", "tc_up1_c4(", "tc_up1_c5("},
                                       {"tc_up2_c1(", "tc_up2_c2(", "tc_up2_c3(", "tc_up2_c4(", "tc_up2_c5("},
@@ -327,7 +327,7 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         CONV(un[i][3], u.c4, ConvCall(p1, B, tout, 27).aux(cond).res(y, c).out(p0, TC_ACT_NONE));
         CONV(un[i][4], u.c5, ConvCall(p0, B, tout, 1).f32(xo, cn));
         A.release(m);
-        x = xo; x_cs = cn; tin = tout;
+        x = xo; tin = tout;
     }
     RUN(out_conv_k7_cl(x, out_w, out_b, out, B, L, s));
     A.release(m0);

@@ -52,6 +52,7 @@ struct TcKParams {
     uint32_t tmem_cols;
     int epi_act, out_act;
     int dbg;   // ablation switches for profiling (TVC_TC_DBG): 1 no loads, 2 no MMAs, 4 no epilogue math/stores
+    uint2* trace;   // developer timeline (TVC_TC_TRACE): CTA 0 logs {clock, role|event|tile|stage} per pipeline event
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -213,6 +214,21 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// Developer timeline: CTA 0 appends {clock32, role << 28 | event << 24 | (tile & 0xffff) << 8 | (stage & 0xff)} to its
+// role's region of p.trace (kTraceRegion entries each).  p.trace == nullptr (always, unless TVC_TC_TRACE is set) costs one
+// uniform predicate per site.
+constexpr int kTraceRegion = 4096;
+struct Tracer {
+    uint2* base;
+    int n;
+    __device__ Tracer(uint2* t, int role) : base((t && blockIdx.x == 0) ? t + role * kTraceRegion : nullptr), n(0) {}
+    __device__ __forceinline__ void log(int role, int ev, int tile, int stage) {
+        if (base && n < kTraceRegion) {
+            base[n++] = make_uint2((uint32_t)clock64(), ((uint32_t)role << 28) | ((uint32_t)ev << 24) | (((uint32_t)tile & 0xffffu) << 8) | ((uint32_t)stage & 0xffu));
+        }
+    }
+};
+
 // One K-stage of the implicit GEMM: TAPS x KS K-steps, three bf16 products each (hi*hi, hi*lo, lo*hi), straight-line.
 // a_lo0 / b_lo0: low descriptor words (start address | LBO << 16, 16-byte units) of the stage's activation window and
 // weight image; *_tap / *_ks: start-address increments per tap and per 16-channel K-step; plane_*: hi -> lo plane.
@@ -287,19 +303,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
 
     if (warp >= kProdWarp0) {
         // ================= producers =================
-        // Lane mapping: consecutive threads fetch consecutive 16-byte chunks of one row (coalesced global
-        // reads); the odd chunk stride lbo_a keeps the shared-memory side conflict-free.
+        // Lane mapping: producer thread j serves tile row j (and window row j + 128 in halo mode) and walks the
+        // stage's 8-channel chunks.  With chunk-major operands a warp-level cp.async moves 32 consecutive rows of
+        // one chunk: 512 contiguous bytes in global memory and in shared memory (no bank conflicts).
         const int j = tid - kProdWarp0 * 32;
-        const int rpi = kTileM / chunks;                 // rows covered per pass of the 128 producer threads
-        const bool act = j < rpi * chunks;
-        const int c = act ? j % chunks : 0, rsub = act ? j / chunks : 0;
         uint32_t s = 0, ph = 0;    // ring slot and the parity of its *previous* use
         bool wrapped = false;
         const int half = (p.taps - 1) >> 1;
         const uint32_t b_tap = 4u * (uint32_t)p.KB * (uint32_t)p.NTp;
         const uint32_t b_main = p.halo ? (uint32_t)p.taps * b_tap : b_tap;
         const uint32_t b_aux = film ? 2u * b_tap : b_tap;
-        const uint32_t dst_c = (uint32_t)c * p.lbo_a;
         TileWalk tw(p, tile_beg);
         // Weights do not depend on the previous kernel: the first tile's weight stages (as many as the ring
         // holds) are requested before griddepcontrol.wait, so they land while the previous grid drains.
@@ -318,26 +331,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
             }
         }
         pdl_wait();
+        Tracer tr(j == 0 ? p.trace : nullptr, 0);
         for (long long tile = tile_beg; tile < tile_end; ++tile, tw.next(p)) {
             const long long row_tile = tw.row_tile;
             const bf16* wt = p.w + (long long)tw.n_tile * p.tile_elems;
-            // flat mode: (utterance base row, time) of the rows this thread serves; halo mode: window origin
-            int bT[8], tq[8];
+            // flat mode: (utterance base row, time) of the row this thread serves; halo mode: window origin
+            int bT = 0, tq = -1;
             int baseT = 0, tt0 = 0;
             if (!p.halo) {
-                // rows < 2^31 (checked at the API): 32-bit arithmetic, one division per tile, then increments
-                const unsigned g0 = (unsigned)(row_tile * kTileM) + (unsigned)rsub;
-                unsigned bcur = g0 / (unsigned)p.T;
-                int tcur = (int)(g0 - bcur * (unsigned)p.T);
-                int bTcur = (int)(bcur * (unsigned)p.T);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int m = rsub + q * rpi;
-                    const bool ok = act && m < kTileM && (long long)g0 + q * rpi < p.rows;
-                    bT[q] = bTcur;
-                    tq[q] = ok ? tcur : -1;
-                    tcur += rpi;
-                    while (tcur >= p.T) { tcur -= p.T; bTcur += p.T; }
+                // rows < 2^31 (checked at the API): 32-bit arithmetic, one division per tile
+                const unsigned g = (unsigned)(row_tile * kTileM) + (unsigned)j;
+                if ((long long)g < p.rows) {
+                    const unsigned bq = g / (unsigned)p.T;
+                    bT = (int)(bq * (unsigned)p.T);
+                    tq = (int)g - bT;
                 }
             } else {
                 tt0 = tw.tt0;
@@ -349,6 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                 const bool is_aux = i >= n_main;
                 const uint32_t b_bytes = is_aux ? b_aux : b_main;
                 if (wrapped) mbar_wait(empty, ph);
+                tr.log(0, 0, (int)(tile - tile_beg), i);
                 const uint32_t a_dst = smem_base + s * stage_bytes;
                 if (j == 0 && !(tile == tile_beg && i < pre)) {
                     if (p.dbg & 1) mbar_arrive(full);
@@ -361,39 +369,42 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                 const bf16* src_hi = is_aux ? p.x_hi : p.a_hi;
                 const bf16* src_lo = is_aux ? p.x_lo : p.a_lo;
                 const int cs = is_aux ? p.x_cs : p.a_cs;
-                const int gc = kb * chunks + c;
-                const bool c_ok = act && gc < (cs >> 3);
-                const uint32_t dst0 = a_dst + dst_c;
+                const int n_ok = (cs >> 3) - kb * chunks;      // chunks of this stage that exist in the tensor; the rest are zero-filled
+                const bf16* g_hi = src_hi + (long long)kb * chunks * p.rows * 8;
+                const bf16* g_lo = src_lo + (long long)kb * chunks * p.rows * 8;
                 if (p.dbg & 1) {
                 } else if (!p.halo) {
                     const int shift = is_aux ? 0 : (tap - half) * p.dil;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int m = rsub + q * rpi;
-                        if (m < kTileM && act) {
-                            int tt = tq[q] + shift;
-                            tt = tt < 0 ? 0 : (tt > p.T - 1 ? p.T - 1 : tt);
-                            const long long off = ((long long)(bT[q] + tt)) * cs + gc * 8;
-                            const uint32_t nb = (c_ok && tq[q] >= 0) ? 16u : 0u;       // 0 -> zero fill
-                            const uint32_t dst = dst0 + (uint32_t)m * 16u;
-                            cp_async16(dst, nb ? src_hi + off : src_hi, nb);
-                            cp_async16(dst + plane_a, nb ? src_lo + off : src_lo, nb);
-                        }
+                    int tt = tq + shift;
+                    tt = tt < 0 ? 0 : (tt > p.T - 1 ? p.T - 1 : tt);                    // replicate padding
+                    const long long grow = (long long)(bT + tt) * 8;
+                    const uint32_t dst = a_dst + (uint32_t)j * 16u;
+#pragma unroll 2
+                    for (int c = 0; c < chunks; ++c) {
+                        const uint32_t nb = (c < n_ok && tq >= 0) ? 16u : 0u;           // 0 -> zero fill
+                        const long long off = (long long)c * p.rows * 8 + grow;
+                        cp_async16(dst + (uint32_t)c * p.lbo_a, nb ? g_hi + off : g_hi, nb);
+                        cp_async16(dst + (uint32_t)c * p.lbo_a + plane_a, nb ? g_lo + off : g_lo, nb);
                     }
                 } else {
                     const int rows_s = is_aux ? kTileM : p.R;
                     const int org = tt0 - (is_aux ? 0 : p.dil);
-                    for (int m = rsub; m < rows_s && act; m += rpi) {
+                    for (int m = j; m < rows_s; m += kTileM) {
                         int tt = org + m;
                         tt = tt < 0 ? 0 : (tt > p.T - 1 ? p.T - 1 : tt);                // replicate padding
-                        const long long off = ((long long)(baseT + tt)) * cs + gc * 8;
-                        const uint32_t nb = c_ok ? 16u : 0u;
-                        const uint32_t dst = dst0 + (uint32_t)m * 16u;
-                        cp_async16(dst, nb ? src_hi + off : src_hi, nb);
-                        cp_async16(dst + plane_a, nb ? src_lo + off : src_lo, nb);
+                        const long long grow = (long long)(baseT + tt) * 8;
+                        const uint32_t dst = a_dst + (uint32_t)m * 16u;
+#pragma unroll 2
+                        for (int c = 0; c < chunks; ++c) {
+                            const uint32_t nb = c < n_ok ? 16u : 0u;
+                            const long long off = (long long)c * p.rows * 8 + grow;
+                            cp_async16(dst + (uint32_t)c * p.lbo_a, nb ? g_hi + off : g_hi, nb);
+                            cp_async16(dst + (uint32_t)c * p.lbo_a + plane_a, nb ? g_lo + off : g_lo, nb);
+                        }
                     }
                 }
                 cp_async_arrive_noinc(full);
+                tr.log(0, 1, (int)(tile - tile_beg), i);
                 // stage order: K-block major, tap minor (flat); K-block only (halo); then the aux K-blocks
                 if (is_aux || p.halo) { ++kb; }
                 else if (++tap == p.taps) { tap = 0; ++kb; }
@@ -422,12 +433,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
             const uint32_t base16 = (smem_base & 0x3FFFFu) >> 4;
             const bool halo_main = p.halo != 0;
             uint32_t s = 0, ph = 0, tcount = 0;
+            Tracer tr(leader ? p.trace : nullptr, 1);
             for (long long tile = tile_beg; tile < tile_end; ++tile, ++tcount) {
                 const uint32_t buf = tcount & 1u, buse = tcount >> 1;
                 if (buse > 0) {                                         // epilogue must have drained this accumulator
                     mbar_wait(acc_empty + 8u * buf, (buse - 1) & 1u);
                     tc_fence_after();
                 }
+                tr.log(1, 0, (int)tcount, 0);
                 const uint32_t d_base = tmem + buf * acc_cols;
                 for (int i = 0; i < n_stage; ++i) {
                     const uint32_t full = bar_base + 8u * s, empty = bar_base + 8u * (p.ring + s);
@@ -443,6 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                     const uint32_t b_lo0 = (base16 + s * stage16 + a_stage16) | (lbo_b << 16);
                     mbar_wait(full, ph);
                     tc_fence_after();
+                    tr.log(1, 1, (int)tcount, i);
                     if (issue) {
                         // halo mode: a tap is a row offset into the shared window (one 16-byte slot per row) and
                         // selects the tap's weight image (hi + lo planes apart)
@@ -465,6 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
 #undef TVC_ISSUE
                     }
                     if (leader) umma_commit(empty);                    // frees the smem stage once these MMAs retire
+                    tr.log(1, 2, (int)tcount, i);
                     if (++s == (uint32_t)p.ring) { s = 0; ph ^= 1u; }
                 }
                 if (leader) umma_commit(acc_full + 8u * buf);          // accumulators complete -> epilogue
@@ -484,9 +499,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
         const int n_groups = p.NT >> 3;
         uint32_t tcount = 0;
         TileWalk tw(p, tile_beg);
+        const int trole = warp == 0 ? 2 : 3;
+        Tracer tr((lane == 0 && (warp == 0 || warp == kEpiWarps - 1)) ? p.trace : nullptr, trole);
         for (long long tile = tile_beg; tile < tile_end; ++tile, ++tcount, tw.next(p)) {
             const uint32_t buf = tcount & 1u, buse = tcount >> 1;
             const int n_tile = tw.n_tile;
+            tr.log(trole, 0, (int)tcount, 0);
             long long row;
             bool valid;
             if (!p.halo) {
@@ -507,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                 const bool live = valid && ch < p.Cout && !(p.dbg & 4);
                 float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
                 if (has_res && live) {                                 // issued before the accumulator wait
-                    const float4* rp = reinterpret_cast<const float4*>(p.res + row * p.res_cs + ch);
+                    const float4* rp = reinterpret_cast<const float4*>(p.res + ((long long)(ch >> 3) * p.rows + row) * 8);
                     r0 = __ldg(rp);
                     r1 = __ldg(rp + 1);
                 }
@@ -525,6 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                     mbar_wait(acc_full + 8u * buf, buse & 1u);
                     tc_fence_after();
                     waited = true;
+                    tr.log(trole, 1, (int)tcount, 0);
                 }
                 float v[8], sc[8], sh[8];
                 tmem_ld8(lane_addr + (uint32_t)(cg * 8), v);
@@ -533,6 +552,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                     tmem_ld8(lane_addr + (uint32_t)(2 * p.NTp + cg * 8), sh);
                 }
                 tmem_ld_wait();
+                tr.log(trole, 2, (int)tcount, cg);
                 if (!live) continue;
                 {
                     v[0] = __fadd_rn(v[0], b0.x); v[1] = __fadd_rn(v[1], b0.y); v[2] = __fadd_rn(v[2], b0.z); v[3] = __fadd_rn(v[3], b0.w);
@@ -553,23 +573,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], epi_act);
                 }
-                if (has_y32) {
-                    float* yp = p.y32 + row * p.y32_cs + ch;
-                    if (ch + 8 <= p.y32_cs) {
-                        reinterpret_cast<float4*>(yp)[0] = make_float4(v[0], v[1], v[2], v[3]);
-                        reinterpret_cast<float4*>(yp)[1] = make_float4(v[4], v[5], v[6], v[7]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (ch + i < p.y32_cs) yp[i] = v[i];
-                    }
+                const long long o = ((long long)(ch >> 3) * p.rows + row) * 8;     // chunk-major: (row, chunk) -> 8 elements
+                if (has_y32 && ch + 8 <= p.y32_cs) {
+                    reinterpret_cast<float4*>(p.y32 + o)[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    reinterpret_cast<float4*>(p.y32 + o)[1] = make_float4(v[4], v[5], v[6], v[7]);
                 }
                 if (has_pl && ch + 8 <= p.y_cs) {
                     uint32_t h[4], l[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) split2(apply_act(v[2 * i], out_act), apply_act(v[2 * i + 1], out_act), h[i], l[i]);
-                    *reinterpret_cast<uint4*>(p.y_hi + row * p.y_cs + ch) = make_uint4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<uint4*>(p.y_lo + row * p.y_cs + ch) = make_uint4(l[0], l[1], l[2], l[3]);
+                    *reinterpret_cast<uint4*>(p.y_hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4*>(p.y_lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
                 }
             }
             if (!waited) {                                             // a slot without column groups still takes part
@@ -578,6 +592,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + 8u * buf);          // accumulator buffer may be overwritten
+            tr.log(trole, 3, (int)tcount, 0);
         }
     }
     tc_fence_before();
@@ -714,14 +729,58 @@ int tc_conv_init() {
     return 0;
 }
 
+// ---- developer timeline (see Tracer) -------------------------------------------------------------
+constexpr int kTraceKernels = 8;
+static uint2* g_trace_buf = nullptr;           // [kTraceKernels][4 roles][kTraceRegion]
+static int g_trace_want[kTraceKernels], g_trace_n = 0, g_trace_count = -1;   // -1: not armed
+
+int tc_trace_arm(const char* list) {
+    g_trace_n = 0;
+    for (const char* c = list; *c && g_trace_n < kTraceKernels;) {
+        g_trace_want[g_trace_n++] = atoi(c);
+        while (*c && *c != ',') ++c;
+        if (*c == ',') ++c;
+    }
+    const size_t bytes = sizeof(uint2) * kTraceKernels * 4 * kTraceRegion;
+    if (!g_trace_buf) TVC_CUDA(cudaMalloc(&g_trace_buf, bytes));
+    TVC_CUDA(cudaMemset(g_trace_buf, 0, bytes));
+    g_trace_count = 0;
+    return 0;
+}
+static uint2* tc_trace_slot() {
+    if (g_trace_count < 0) return nullptr;
+    const int k = g_trace_count++;
+    for (int i = 0; i < g_trace_n; ++i)
+        if (g_trace_want[i] == k) return g_trace_buf + (size_t)i * 4 * kTraceRegion;
+    return nullptr;
+}
+int tc_trace_dump(const char* path) {
+    TVC_REQUIRE(g_trace_buf, "tc_trace: nothing armed");
+    TVC_CUDA(cudaDeviceSynchronize());
+    std::vector<uint2> h((size_t)kTraceKernels * 4 * kTraceRegion);
+    TVC_CUDA(cudaMemcpy(h.data(), g_trace_buf, h.size() * sizeof(uint2), cudaMemcpyDeviceToHost));
+    FILE* f = fopen(path, "w");
+    TVC_REQUIRE(f, "tc_trace: cannot open %s", path);
+    for (int i = 0; i < g_trace_n; ++i)
+        for (int r = 0; r < 4; ++r)
+            for (int e = 0; e < kTraceRegion; ++e) {
+                const uint2 v = h[((size_t)i * 4 + r) * kTraceRegion + e];
+                if (!v.y && !v.x) break;
+                fprintf(f, "%d %u %u %u %u %u\n", g_trace_want[i], v.y >> 28, (v.y >> 24) & 15u, (v.y >> 8) & 0xffffu, v.y & 0xffu, v.x);
+            }
+    fclose(f);
+    g_trace_count = -1;
+    return 0;
+}
+
 int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     TVC_REQUIRE(W.w && a.a_hi && a.a_lo, "tc_conv: missing weights or input");
     TVC_REQUIRE(a.B > 0 && a.T > 0, "tc_conv: empty problem B=%d T=%d", a.B, a.T);
     TVC_REQUIRE(a.a_cs % 8 == 0 && a.a_cs >= W.Cin, "tc_conv: input channel stride %d (need multiple of 8 >= %d)", a.a_cs, W.Cin);
     TVC_REQUIRE(W.aux_mode == TC_AUX_NONE || (a.x_hi && a.x_lo && a.x_cs % 8 == 0 && a.x_cs >= W.aux_cin), "tc_conv: aux input missing / bad stride");
     TVC_REQUIRE(!a.y_hi || (a.y_lo && a.y_cs % 8 == 0), "tc_conv: plane output needs both planes and a stride multiple of 8");
-    TVC_REQUIRE(!a.y32 || a.y32_cs % 4 == 0, "tc_conv: fp32 output stride must be a multiple of 4");
-    TVC_REQUIRE(!a.res || (a.res_cs % 4 == 0 && a.res_cs >= (int)align_up(W.Cout, 8)), "tc_conv: residual stride must be a multiple of 4 covering Cout rounded up to 8");
+    TVC_REQUIRE(!a.y32 || a.y32_cs % 8 == 0, "tc_conv: fp32 output capacity must be a multiple of 8 channels");
+    TVC_REQUIRE(!a.res || (a.res_cs % 8 == 0 && a.res_cs >= (int)align_up(W.Cout, 8)), "tc_conv: residual capacity must be a multiple of 8 covering Cout rounded up to 8");
     TcKParams p;
     p.a_hi = a.a_hi; p.a_lo = a.a_lo; p.x_hi = a.x_hi; p.x_lo = a.x_lo; p.w = W.w;
     p.bias = W.bias; p.film_bias = W.film_bias; p.res = a.res; p.y32 = a.y32; p.y_hi = a.y_hi; p.y_lo = a.y_lo;
@@ -732,6 +791,7 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     p.epi_act = a.epi_act; p.out_act = a.out_act;
     static const int dbg = getenv("TVC_TC_DBG") ? atoi(getenv("TVC_TC_DBG")) : 0;
     p.dbg = dbg;
+    p.trace = tc_trace_slot();
     // halo mode: k=3 convs whose utterances fill their 128-row tiles well share one row window across the taps
     const int tpu = cdiv(a.T, kTileM);
     p.halo = (W.taps == 3 && (double)a.T / ((double)tpu * kTileM) >= 0.75 && !g_force_flat) ? 1 : 0;

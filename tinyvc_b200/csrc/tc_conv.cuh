@@ -1,9 +1,18 @@
 // Tensor-core (tcgen05 / TMEM) dense Conv1d for the TinyVC decoder -- declarations.
 //
 // Activations on this path are channels-last "split planes": a tensor [rows = B*T][C] is stored
-// as two bf16 matrices hi = bf16(v), lo = bf16(v - hi) with channel stride `cs` (a multiple of
+// as two bf16 matrices hi = bf16(v), lo = bf16(v - hi) with `cs` channels of capacity (a multiple of
 // 8 elements = one 16-byte UMMA core-matrix row; channels [C, cs) hold finite padding, their
-// weights are zero).  A conv is evaluated as three bf16 tensor-core products accumulated in
+// weights are zero).
+//
+// Memory order is CHUNK-MAJOR: element (row, ch) of a tensor with R rows lives at
+//     cm(row, ch, R) = ((ch / 8) * R + row) * 8 + ch % 8
+// i.e. every 8-channel chunk is its own dense [R][8] array (16 bytes per row for bf16, 32 for fp32).  That
+// is the order the tensor cores consume (the smem operand of one K-chunk is a column of rows at a 16-byte
+// pitch): a warp moving 32 consecutive rows of one chunk touches 512 contiguous bytes on both the global
+// and the shared side, for the conv kernel's operand gathers and for its epilogue stores alike.  fp32
+// companions (residuals, resampler inputs) use the same order.  A view on channels [c0, c0 + n) with
+// c0 % 8 == 0 of a tensor with the same R is just a pointer offset of cm(0, c0, R).  A conv is evaluated as three bf16 tensor-core products accumulated in
 // fp32 in TMEM:  x*w ~= x_hi*w_hi + x_hi*w_lo + x_lo*w_hi  (relative error ~2^-16, against
 // 2^-11 for one TF32 product, which SURVEY.md section 0 shows is not enough for RMSE < 1e-4).
 #pragma once
@@ -14,6 +23,10 @@
 namespace tvc {
 
 typedef __nv_bfloat16 bf16;
+
+__host__ __device__ __forceinline__ long long cm(long long row, int ch, long long R) {
+    return ((long long)(ch >> 3) * R + row) * 8 + (ch & 7);
+}
 
 enum TcAux { TC_AUX_NONE = 0, TC_AUX_ACC = 1, TC_AUX_FILM = 2 };
 enum TcAct { TC_ACT_NONE = 0, TC_ACT_LRELU = 1, TC_ACT_GELU = 2, TC_ACT_ELU1 = 3 };
@@ -40,23 +53,26 @@ int tc_pack_conv(const float* w, const float* b, int Cout, int Cin, int taps, co
                  int aux_cin, int aux_mode, int NT, TcConvW& out);
 
 struct TcConvArgs {
-    const bf16 *a_hi = nullptr, *a_lo = nullptr;   // main input planes [B*T][a_cs]
+    const bf16 *a_hi = nullptr, *a_lo = nullptr;   // main input planes, chunk-major, a_cs channels of capacity
     int a_cs = 0;
-    const bf16 *x_hi = nullptr, *x_lo = nullptr;   // aux input planes [B*T][x_cs]
+    const bf16 *x_hi = nullptr, *x_lo = nullptr;   // aux input planes (same rows)
     int x_cs = 0;
     int dil = 1;
     int B = 0, T = 0;                  // taps are clamped inside each utterance of T rows (replicate padding)
-    const float* res = nullptr;        // fp32 residual [B*T][res_cs], added after bias / FiLM
+    const float* res = nullptr;        // fp32 residual (chunk-major, same rows), added after bias / FiLM
     int res_cs = 0;
-    float* y32 = nullptr;              // fp32 output [B*T][y32_cs] (nullable)
+    float* y32 = nullptr;              // fp32 output (chunk-major, nullable)
     int y32_cs = 0;
-    bf16 *y_hi = nullptr, *y_lo = nullptr;   // split-plane output [B*T][y_cs] (nullable)
+    bf16 *y_hi = nullptr, *y_lo = nullptr;   // split-plane output (chunk-major, nullable)
     int y_cs = 0;
     int epi_act = TC_ACT_NONE;         // applied to the value (both outputs)
     int out_act = TC_ACT_NONE;         // applied additionally to the split-plane copy only
 };
 int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s);
 int tc_conv_init();
+// developer timeline of selected tc_conv launches (ordinals counted from arming); see tc_conv.cu Tracer
+int tc_trace_arm(const char* ordinals);
+int tc_trace_dump(const char* path);
 
 // layout helpers (tc_ops.cu)
 // extra0/extra1 (nullable, [B*T]) are appended as channels C and C+1 (frame-rate scalars such as log-f0).

@@ -18,9 +18,10 @@ __device__ __forceinline__ uint32_t pack2(bf16 a, bf16 b) {
 // noise_spectrum_cl (decoder.py:78-80): angle = (rand01*2)*pi - pi, Y = kernel * exp(j*angle).
 // rand01 arrives channels-first [B][961][Lf] (the layout torch.rand draws it in); a 32x32 tile
 // transpose through shared memory turns it into channels-last rows.  Outputs: split planes of
-// Re(Y) and Im(Y), [B*Lf][y_cs], channels >= 961 zero.
+// Re(Y) and Im(Y) (chunk-major, B*Lf rows, y_cs channels of capacity), channels >= 961 zero.
+// `kern` is the fp32 head output (chunk-major, same rows; its first 961 channels are the noise filter).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) noise_spectrum_cl_kernel(const float* __restrict__ kern, int k_cs,
+__global__ void __launch_bounds__(256) noise_spectrum_cl_kernel(const float* __restrict__ kern,
                                                                 const float* __restrict__ rand01,
                                                                 bf16* __restrict__ yr_hi, bf16* __restrict__ yr_lo,
                                                                 bf16* __restrict__ yi_hi, bf16* __restrict__ yi_lo,
@@ -29,31 +30,46 @@ __global__ void __launch_bounds__(256) noise_spectrum_cl_kernel(const float* __r
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long R = (long long)gridDim.z * Lf;
     for (int j = ty; j < 32; j += 8) {
         const int c = c0 + j, t = t0 + tx;
         tile[j][tx] = (c < kBins && t < Lf) ? __ldg(rand01 + ((long long)b * kBins + c) * Lf + t) : 0.f;
     }
     __syncthreads();
     const float pi_f = 3.14159265358979323846f;
-    for (int j = ty; j < 32; j += 8) {
-        const int t = t0 + j, c = c0 + tx;
-        if (t >= Lf || c >= y_cs) continue;
-        const long long row = (long long)b * Lf + t;
-        float re = 0.f, im = 0.f;
-        if (c < kBins) {
-            const float a = __fsub_rn(__fmul_rn(__fmul_rn(tile[tx][j], 2.0f), pi_f), pi_f);
+    if (threadIdx.x >= 128) return;
+    // one (frame, 8-bin chunk) per thread: 8 bins of Re and Im, stored as one 16-byte row of each chunk array
+    const int q = threadIdx.x >> 5, t = t0 + tx, cq = c0 + q * 8;
+    if (t >= Lf || cq >= y_cs) return;
+    const long long row = (long long)b * Lf + t;
+    const long long o = cm(row, cq, R);
+    const float4 k0 = __ldg(reinterpret_cast<const float4*>(kern + o)), k1 = __ldg(reinterpret_cast<const float4*>(kern + o) + 1);
+    const float kv[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+    float re[8], im[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        re[e] = 0.f; im[e] = 0.f;
+        if (cq + e < kBins) {
+            const float a = __fsub_rn(__fmul_rn(__fmul_rn(tile[q * 8 + e][tx], 2.0f), pi_f), pi_f);
             float sn, cs;
             sincosf(a, &sn, &cs);
-            const float kv = __ldg(kern + row * k_cs + c);
-            re = __fmul_rn(cs, kv);
-            im = __fmul_rn(sn, kv);
+            re[e] = __fmul_rn(cs, kv[e]);
+            im[e] = __fmul_rn(sn, kv[e]);
         }
-        bf16 h, l;
-        split_bf16(re, h, l);
-        yr_hi[row * y_cs + c] = h; yr_lo[row * y_cs + c] = l;
-        split_bf16(im, h, l);
-        yi_hi[row * y_cs + c] = h; yi_lo[row * y_cs + c] = l;
     }
+    uint32_t rh[4], rl[4], ih[4], il[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        bf16 h0, l0, h1, l1;
+        split_bf16(re[2 * e], h0, l0); split_bf16(re[2 * e + 1], h1, l1);
+        rh[e] = pack2(h0, h1); rl[e] = pack2(l0, l1);
+        split_bf16(im[2 * e], h0, l0); split_bf16(im[2 * e + 1], h1, l1);
+        ih[e] = pack2(h0, h1); il[e] = pack2(l0, l1);
+    }
+    *reinterpret_cast<uint4*>(yr_hi + o) = make_uint4(rh[0], rh[1], rh[2], rh[3]);
+    *reinterpret_cast<uint4*>(yr_lo + o) = make_uint4(rl[0], rl[1], rl[2], rl[3]);
+    *reinterpret_cast<uint4*>(yi_hi + o) = make_uint4(ih[0], ih[1], ih[2], ih[3]);
+    *reinterpret_cast<uint4*>(yi_lo + o) = make_uint4(il[0], il[1], il[2], il[3]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -61,10 +77,10 @@ __global__ void __launch_bounds__(256) noise_spectrum_cl_kernel(const float* __r
 // one all-zero frame prepended).  The inverse real DFT of frame t is x[p] = C[p] - S[p],
 // x[N-p] = C[p] + S[p] (p <= N/2) with C = cos-basis * Re(Y), S = sin-basis * Im(Y) computed by
 // two tensor-core products; this kernel overlap-adds and divides by the window coverage.
-// c, sn: fp32 [B*Lf][cs];  noise: [B][L].
+// c, sn: fp32 chunk-major with B*Lf rows;  noise: [B][L].
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) noise_ola_cl_kernel(const float* __restrict__ c, const float* __restrict__ sn,
-                                                           int cs, float* __restrict__ noise, int Lf, long long total) {
+                                                           long long R, float* __restrict__ noise, int Lf, long long total) {
     TVC_PDL_PROLOGUE();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -80,8 +96,8 @@ __global__ void __launch_bounds__(256) noise_ola_cl_kernel(const float* __restri
         const int q = kFrame * (j + 2 - t) + r;    // position inside frame t, 0..1919
         const long long row = b * Lf + (t - 1);
         float v;
-        if (q <= kNfft / 2) v = __fsub_rn(__ldg(c + row * cs + q), __ldg(sn + row * cs + q));
-        else v = __fadd_rn(__ldg(c + row * cs + (kNfft - q)), __ldg(sn + row * cs + (kNfft - q)));
+        if (q <= kNfft / 2) v = __fsub_rn(__ldg(c + cm(row, q, R)), __ldg(sn + cm(row, q, R)));
+        else v = __fadd_rn(__ldg(c + cm(row, kNfft - q, R)), __ldg(sn + cm(row, kNfft - q, R)));
         acc = __fadd_rn(acc, v);
     }
     noise[i] = __fdiv_rn(acc, (float)(thi - tlo + 1));
@@ -152,10 +168,10 @@ __global__ void __launch_bounds__(kOsc * 32) osc_scan_frames_kernel(double* __re
 }
 
 __global__ void __launch_bounds__(kOsc * 32, 2) osc_source_kernel(const float* __restrict__ f0, const double* __restrict__ carry,
-                                                               const float* __restrict__ amps, int amps_cs,
+                                                               const float* __restrict__ amps,
                                                                const float* __restrict__ noise,
                                                                const float* __restrict__ energy, bf16* __restrict__ src_hi,
-                                                               bf16* __restrict__ src_lo, int src_cs, int Lf,
+                                                               bf16* __restrict__ src_lo, int Lf,
                                                                float scale_size, float scale_factor) {
     TVC_PDL_PROLOGUE();
     __shared__ float tile[kFrame][kOsc + 2];      // [sample][oscillator], 17-float rows: conflict-free both ways
@@ -192,7 +208,8 @@ __global__ void __launch_bounds__(kOsc * 32, 2) osc_source_kernel(const float* _
     // on top of everything that precedes this lane's run.  (base + run prefix) in one chain: the sums are
     // exact in fp64, so the association does not change the fp32 rounding of I.
     double acc = __dadd_rn(carry[((long long)b * Lf + fr) * kOsc + k], __dadd_rn(ex, -v));
-    const float* ab = amps + (long long)b * Lf * amps_cs + k;
+    const long long RF = (long long)gridDim.y * Lf;           // rows of the frame-rate tensors
+    const float* ab = amps + cm((long long)b * Lf, k, RF);     // amplitude k of frame 0 of this utterance; frames are 8 floats apart
 #pragma unroll 5
     for (int i = 0; i < kRun; ++i) {
         acc = __dadd_rn(acc, (double)osc_increment(s_fsi[r0 + i], kf));
@@ -202,7 +219,7 @@ __global__ void __launch_bounds__(kOsc * 32, 2) osc_source_kernel(const float* _
         const float h = __fmul_rn(sinf(theta), s_uv[r0 + i]);
         const int ai = s_ai0[r0 + i];
         const int i0 = ai & 0x3fffffff, i1 = i0 + (ai >> 30);
-        const float a = __fmaf_rn(__ldg(ab + (long long)i0 * amps_cs), s_al0[r0 + i], __fmul_rn(__ldg(ab + (long long)i1 * amps_cs), s_al1[r0 + i]));
+        const float a = __fmaf_rn(__ldg(ab + (long long)i0 * 8), s_al0[r0 + i], __fmul_rn(__ldg(ab + (long long)i1 * 8), s_al1[r0 + i]));
         tile[r0 + i][k] = __fmul_rn(h, a);
     }
     __syncthreads();
@@ -225,37 +242,35 @@ __global__ void __launch_bounds__(kOsc * 32, 2) osc_source_kernel(const float* _
         hh[q] = pack2(h0, h1);
         ll[q] = pack2(l0, l1);
     }
-    uint4* ph = reinterpret_cast<uint4*>(src_hi + row * src_cs);
-    uint4* pl = reinterpret_cast<uint4*>(src_lo + row * src_cs);
+    const long long RL = RF * kFrame;                           // rows of the sample-rate tensors
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        ph[q] = make_uint4(hh[4 * q], hh[4 * q + 1], hh[4 * q + 2], hh[4 * q + 3]);
-        pl[q] = make_uint4(ll[4 * q], ll[4 * q + 1], ll[4 * q + 2], ll[4 * q + 3]);
+    for (int q = 0; q < 3; ++q) {                                // chunk-major: 32 consecutive samples of a chunk = 512 B
+        *reinterpret_cast<uint4*>(src_hi + (q * RL + row) * 8) = make_uint4(hh[4 * q], hh[4 * q + 1], hh[4 * q + 2], hh[4 * q + 3]);
+        *reinterpret_cast<uint4*>(src_lo + (q * RL + row) * 8) = make_uint4(ll[4 * q], ll[4 * q + 1], ll[4 * q + 2], ll[4 * q + 3]);
     }
 }
 
 }  // namespace
 
-int noise_spectrum_cl(const float* kern, int k_cs, const float* rand01, bf16* yr_hi, bf16* yr_lo, bf16* yi_hi,
+int noise_spectrum_cl(const float* kern, const float* rand01, bf16* yr_hi, bf16* yr_lo, bf16* yi_hi,
                       bf16* yi_lo, int y_cs, int B, int Lf, cudaStream_t s) {
     dim3 grid(cdiv(Lf, 32), cdiv(y_cs, 32), B);
-    TVC_LAUNCH_PDL(noise_spectrum_cl_kernel, grid, 256, 0, s, kern, k_cs, rand01, yr_hi, yr_lo, yi_hi, yi_lo, y_cs, Lf);
+    TVC_LAUNCH_PDL(noise_spectrum_cl_kernel, grid, 256, 0, s, kern, rand01, yr_hi, yr_lo, yi_hi, yi_lo, y_cs, Lf);
     TVC_LAUNCH_CHECK();
     return 0;
 }
 
-int noise_ola_cl(const float* c, const float* sn, int cs, float* noise, int B, int Lf, cudaStream_t s) {
+int noise_ola_cl(const float* c, const float* sn, float* noise, int B, int Lf, cudaStream_t s) {
     const long long total = (long long)B * Lf * kFrame;
-    TVC_LAUNCH_PDL(noise_ola_cl_kernel, cdiv(total, 256), 256, 0, s, c, sn, cs, noise, Lf, total);
+    TVC_LAUNCH_PDL(noise_ola_cl_kernel, cdiv(total, 256), 256, 0, s, c, sn, (long long)B * Lf, noise, Lf, total);
     TVC_LAUNCH_CHECK();
     return 0;
 }
 
 size_t osc_scratch_bytes(int B, int Lf) { return sizeof(double) * (size_t)B * Lf * kOsc; }
 
-int harmonic_source_cl(const float* f0, const float* amps, int amps_cs, const float* noise, const float* energy,
-                       bf16* src_hi, bf16* src_lo, int src_cs, void* scratch, int B, int Lf, cudaStream_t s) {
-    TVC_REQUIRE(src_cs == 24, "harmonic_source_cl: source planes must have 24 channels");
+int harmonic_source_cl(const float* f0, const float* amps, const float* noise, const float* energy,
+                       bf16* src_hi, bf16* src_lo, void* scratch, int B, int Lf, cudaStream_t s) {
     const int L = Lf * kFrame;
     const float scale_size = (float)Lf / (float)L;              // F.interpolate(size=L)
     const float scale_factor = (float)(1.0 / (double)kFrame);   // F.interpolate(scale_factor=480)
@@ -265,7 +280,7 @@ int harmonic_source_cl(const float* f0, const float* amps, int amps_cs, const fl
     TVC_LAUNCH_CHECK();
     TVC_LAUNCH_PDL(osc_scan_frames_kernel, B, kOsc * 32, 0, s, totals, Lf);
     TVC_LAUNCH_CHECK();
-    TVC_LAUNCH_PDL(osc_source_kernel, grid, kOsc * 32, 0, s, f0, totals, amps, amps_cs, noise, energy, src_hi, src_lo, src_cs, Lf,
+    TVC_LAUNCH_PDL(osc_source_kernel, grid, kOsc * 32, 0, s, f0, totals, amps, noise, energy, src_hi, src_lo, Lf,
                                                scale_size, scale_factor);
     TVC_LAUNCH_CHECK();
     return 0;

@@ -23,44 +23,64 @@ __device__ __forceinline__ void store_planes4(bf16* hi, bf16* lo, long long off,
     *reinterpret_cast<uint2*>(lo + off) = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
 }
 
+// store the 8 channels of one (row, chunk) of both planes (16 bytes each)
+__device__ __forceinline__ void store_planes8(bf16* hi, bf16* lo, long long off, const float v[8]) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        bf16 h0, l0, h1, l1;
+        split_bf16(v[2 * i], h0, l0);
+        split_bf16(v[2 * i + 1], h1, l1);
+        h[i] = pack2(h0, h1);
+        l[i] = pack2(l0, l1);
+    }
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // ---------------------------------------------------------------------------------------------
-// interp_cl:  F.interpolate(x, scale_factor=..., mode='linear') along time for channels-last
-// fp32 input [B*Tin][x_cs] (decoder.py:148 Downsample, :174 Upsample), exact ATen coordinate
-// arithmetic (tvc_common.cuh lin_coord/lin_blend).  Writes any of: fp32 [B*Tout][y_cs],
-// raw split planes, leaky_relu(0.1) split planes (the convs that follow apply leaky_relu first).
-// One thread per (output row, 4-channel group).
+// interp_cl:  F.interpolate(x, scale_factor=..., mode='linear') along time for chunk-major channels-last
+// fp32 input with B*Tin rows (decoder.py:148 Downsample, :174 Upsample), exact ATen coordinate
+// arithmetic (tvc_common.cuh lin_coord/lin_blend).  Writes any of: fp32, raw split planes,
+// leaky_relu(0.1) split planes (the convs that follow apply leaky_relu first), all with B*Tout rows.
+// One thread per (8-channel chunk, output row); consecutive threads = consecutive rows of one chunk.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) interp_cl_kernel(const float* __restrict__ x, int x_cs, int Tin, int Tout,
-                                                        float scale, int C4, float* __restrict__ y32, int y_cs,
+__global__ void __launch_bounds__(256) interp_cl_kernel(const float* __restrict__ x, int Tin, int Tout, float scale,
+                                                        long long rows_in, long long rows_out, float* __restrict__ y32,
                                                         bf16* __restrict__ r_hi, bf16* __restrict__ r_lo,
-                                                        bf16* __restrict__ a_hi, bf16* __restrict__ a_lo, int p_cs,
-                                                        long long total) {
+                                                        bf16* __restrict__ a_hi, bf16* __restrict__ a_lo, long long total) {
     TVC_PDL_PROLOGUE();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int g = (int)(i % C4);
-    const long long row = i / C4;
+    const long long q = i / rows_out;            // chunk
+    const long long row = i - q * rows_out;
     const long long b = row / Tout;
     const int t = (int)(row - b * Tout);
     const LinCoord c = lin_coord(t, scale, Tin);
-    const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + (b * Tin + c.i0) * x_cs) + g);
-    const float4 x1 = __ldg(reinterpret_cast<const float4*>(x + (b * Tin + c.i1) * x_cs) + g);
-    float v[4] = {lin_blend(x0.x, x1.x, c), lin_blend(x0.y, x1.y, c), lin_blend(x0.z, x1.z, c), lin_blend(x0.w, x1.w, c)};
-    if (y32) *reinterpret_cast<float4*>(y32 + row * y_cs + g * 4) = make_float4(v[0], v[1], v[2], v[3]);
-    if (r_hi) store_planes4(r_hi, r_lo, row * p_cs + g * 4, v);
+    const float4* p0 = reinterpret_cast<const float4*>(x + (q * rows_in + b * Tin + c.i0) * 8);
+    const float4* p1 = reinterpret_cast<const float4*>(x + (q * rows_in + b * Tin + c.i1) * 8);
+    const float4 x0 = __ldg(p0), x1 = __ldg(p0 + 1), z0 = __ldg(p1), z1 = __ldg(p1 + 1);
+    float v[8] = {lin_blend(x0.x, z0.x, c), lin_blend(x0.y, z0.y, c), lin_blend(x0.z, z0.z, c), lin_blend(x0.w, z0.w, c),
+                  lin_blend(x1.x, z1.x, c), lin_blend(x1.y, z1.y, c), lin_blend(x1.z, z1.z, c), lin_blend(x1.w, z1.w, c)};
+    const long long o = (q * rows_out + row) * 8;
+    if (y32) {
+        reinterpret_cast<float4*>(y32 + o)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(y32 + o)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (r_hi) store_planes8(r_hi, r_lo, o, v);
     if (a_hi) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = leaky01(v[k]);
-        store_planes4(a_hi, a_lo, row * p_cs + g * 4, v);
+        for (int k = 0; k < 8; ++k) v[k] = leaky01(v[k]);
+        store_planes8(a_hi, a_lo, o, v);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // dwconv_ln_cl (C = 128): depth-wise k=7 conv (dilation 1, replicate padding) + LayerNorm over
-// channels (convnext.py:42-43,52-53) on channels-last fp32 rows -> split planes.  One warp per
-// row, 4 channels per lane; the LayerNorm statistics are two warp-shuffle reductions.
+// channels (convnext.py:42-43,52-53) on chunk-major channels-last fp32 -> split planes.  One warp per
+// row, 4 channels per lane (half a chunk); the LayerNorm statistics are two warp-shuffle reductions.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dwconv_ln_cl_kernel(const float* __restrict__ x, int x_cs,
+__global__ void __launch_bounds__(256) dwconv_ln_cl_kernel(const float* __restrict__ x,
                                                            const float* __restrict__ w7,   // [7][128] repacked
                                                            const float* __restrict__ wb, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, bf16* __restrict__ hi,
@@ -77,7 +97,7 @@ __global__ void __launch_bounds__(256) dwconv_ln_cl_kernel(const float* __restri
     for (int j = 0; j < 7; ++j) {
         int tt = t + j - 3;
         tt = tt < 0 ? 0 : (tt > T - 1 ? T - 1 : tt);
-        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (b * T + tt) * x_cs) + lane);
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + cm(b * T + tt, lane * 4, rows)));
         const float4 wv = __ldg(reinterpret_cast<const float4*>(w7 + j * 128) + lane);
         v[0] = fmaf(wv.x, xv.x, v[0]); v[1] = fmaf(wv.y, xv.y, v[1]);
         v[2] = fmaf(wv.z, xv.z, v[2]); v[3] = fmaf(wv.w, xv.w, v[3]);
@@ -99,11 +119,11 @@ __global__ void __launch_bounds__(256) dwconv_ln_cl_kernel(const float* __restri
     const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + lane);
     float o4[4] = {fmaf((v[0] - mean) * rstd, g.x, be.x), fmaf((v[1] - mean) * rstd, g.y, be.y),
                    fmaf((v[2] - mean) * rstd, g.z, be.z), fmaf((v[3] - mean) * rstd, g.w, be.w)};
-    store_planes4(hi, lo, row * 128 + lane * 4, o4);
+    store_planes4(hi, lo, cm(row, lane * 4, rows), o4);
 }
 
 // ---------------------------------------------------------------------------------------------
-// grn_apply_cl: GRN (convnext.py:23-34) on channels-last fp32 [B*T][C] -> split planes:
+// grn_apply_cl: GRN (convnext.py:23-34) on chunk-major channels-last fp32 (B*T rows, C channels) -> split planes:
 //   g[c] = sqrt(sum_t y^2),  n = g / (mean_c g + 1e-6),  out = y * (gamma*n + 1) + beta
 // One block per utterance, thread = channel (coalesced over channels), fixed summation order.
 // ---------------------------------------------------------------------------------------------
@@ -113,11 +133,12 @@ __global__ void __launch_bounds__(256) grn_apply_cl_kernel(const float* __restri
     TVC_PDL_PROLOGUE();
     __shared__ float part[8];
     const int b = blockIdx.x, c = threadIdx.x, lane = c & 31, warp = c >> 5;
-    const float* yb = y + (long long)b * T * C;
+    const long long R = (long long)gridDim.x * T;
+    const long long base = cm((long long)b * T, c, R);        // (row b*T, channel c); consecutive rows are 8 floats apart
     float s = 0.f;
     if (c < C)
         for (int t = 0; t < T; ++t) {
-            const float v = __ldg(yb + (long long)t * C + c);
+            const float v = __ldg(y + base + (long long)t * 8);
             s = fmaf(v, v, s);
         }
     const float g = sqrtf(s);
@@ -132,7 +153,7 @@ __global__ void __launch_bounds__(256) grn_apply_cl_kernel(const float* __restri
     const float scale = fmaf(__ldg(gamma + c), g / (all / (float)C + 1e-6f), 1.0f);
     const float bt = __ldg(beta + c);
     for (int t = 0; t < T; ++t) {
-        const long long o = ((long long)b * T + t) * C + c;
+        const long long o = base + (long long)t * 8;
         bf16 h, l;
         split_bf16(fmaf(__ldg(y + o), scale, bt), h, l);
         hi[o] = h;
@@ -142,7 +163,8 @@ __global__ void __launch_bounds__(256) grn_apply_cl_kernel(const float* __restri
 
 // ---------------------------------------------------------------------------------------------
 // out_conv_k7_cl: FilterNet.output_layer, Conv1d(24 -> 1, k = 7, replicate pad 3) (decoder.py:220,233)
-// on channels-last fp32 [B*T][24] -> waveform [B][T].  One thread per output sample.
+// on chunk-major channels-last fp32 (B*T rows, 24 channels = 3 chunks) -> waveform [B][T].  One thread per output
+// sample; a warp reads 32 consecutive rows of a chunk = 1 KB contiguous.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) out_conv_k7_cl_kernel(const float* __restrict__ x, const float* __restrict__ w,   // [24][7] torch layout
                                                              const float* __restrict__ bias, float* __restrict__ y, int T,
@@ -160,10 +182,9 @@ __global__ void __launch_bounds__(256) out_conv_k7_cl_kernel(const float* __rest
     for (int j = 0; j < 7; ++j) {
         int tt = t + j - 3;
         tt = tt < 0 ? 0 : (tt > T - 1 ? T - 1 : tt);
-        const float4* xr = reinterpret_cast<const float4*>(x + (b * T + tt) * 24);
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
-            const float4 v = __ldg(xr + q);
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x + cm(b * T + tt, q * 4, rows)));
             acc = fmaf(ws[j][q * 4 + 0], v.x, acc);
             acc = fmaf(ws[j][q * 4 + 1], v.y, acc);
             acc = fmaf(ws[j][q * 4 + 2], v.z, acc);
@@ -175,19 +196,20 @@ __global__ void __launch_bounds__(256) out_conv_k7_cl_kernel(const float* __rest
 
 }  // namespace
 
-int interp_cl(const float* x, int x_cs, int B, int Tin, int Tout, float scale, int C, float* y32, int y_cs, bf16* r_hi,
-              bf16* r_lo, bf16* a_hi, bf16* a_lo, int p_cs, cudaStream_t s) {
-    TVC_REQUIRE(C % 4 == 0 && x_cs % 4 == 0 && (!y32 || y_cs % 4 == 0) && p_cs % 4 == 0, "interp_cl: channel counts must be multiples of 4");
-    const long long total = (long long)B * Tout * (C / 4);
-    TVC_LAUNCH_PDL(interp_cl_kernel, cdiv(total, 256), 256, 0, s, x, x_cs, Tin, Tout, scale, C / 4, y32, y_cs, r_hi, r_lo, a_hi, a_lo, p_cs, total);
+int interp_cl(const float* x, int B, int Tin, int Tout, float scale, int C, float* y32, bf16* r_hi, bf16* r_lo, bf16* a_hi,
+              bf16* a_lo, cudaStream_t s) {
+    TVC_REQUIRE(C % 8 == 0, "interp_cl: channel count %d must be a multiple of 8", C);
+    const long long rows_in = (long long)B * Tin, rows_out = (long long)B * Tout;
+    const long long total = rows_out * (C / 8);
+    TVC_LAUNCH_PDL(interp_cl_kernel, cdiv(total, 256), 256, 0, s, x, Tin, Tout, scale, rows_in, rows_out, y32, r_hi, r_lo, a_hi, a_lo, total);
     TVC_LAUNCH_CHECK();
     return 0;
 }
 
-int dwconv_ln_cl(const float* x, int x_cs, const float* w7, const float* wb, const float* gamma, const float* beta,
+int dwconv_ln_cl(const float* x, const float* w7, const float* wb, const float* gamma, const float* beta,
                  bf16* hi, bf16* lo, int B, int T, cudaStream_t s) {
     const long long rows = (long long)B * T;
-    TVC_LAUNCH_PDL(dwconv_ln_cl_kernel, cdiv(rows * 32, 256), 256, 0, s, x, x_cs, w7, wb, gamma, beta, hi, lo, T, rows);
+    TVC_LAUNCH_PDL(dwconv_ln_cl_kernel, cdiv(rows * 32, 256), 256, 0, s, x, w7, wb, gamma, beta, hi, lo, T, rows);
     TVC_LAUNCH_CHECK();
     return 0;
 }

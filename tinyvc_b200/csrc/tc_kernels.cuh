@@ -5,20 +5,22 @@
 namespace tvc {
 
 // tc_frame.cu
-int interp_cl(const float* x, int x_cs, int B, int Tin, int Tout, float scale, int C, float* y32, int y_cs, bf16* r_hi,
-              bf16* r_lo, bf16* a_hi, bf16* a_lo, int p_cs, cudaStream_t s);
-int dwconv_ln_cl(const float* x, int x_cs, const float* w7, const float* wb, const float* gamma, const float* beta,
+// all channels-last tensors are chunk-major (tc_conv.cuh); row counts follow from B and T
+int interp_cl(const float* x, int B, int Tin, int Tout, float scale, int C, float* y32, bf16* r_hi, bf16* r_lo, bf16* a_hi,
+              bf16* a_lo, cudaStream_t s);
+int dwconv_ln_cl(const float* x, const float* w7, const float* wb, const float* gamma, const float* beta,
                  bf16* hi, bf16* lo, int B, int T, cudaStream_t s);
 int grn_apply_cl(const float* y, const float* gamma, const float* beta, bf16* hi, bf16* lo, int B, int C, int T,
                  cudaStream_t s);
 int out_conv_k7_cl(const float* x, const float* w, const float* bias, float* y, int B, int T, cudaStream_t s);
 
 // tc_dsp.cu
-int noise_spectrum_cl(const float* kern, int k_cs, const float* rand01, bf16* yr_hi, bf16* yr_lo, bf16* yi_hi,
+int noise_spectrum_cl(const float* kern, const float* rand01, bf16* yr_hi, bf16* yr_lo, bf16* yi_hi,
                       bf16* yi_lo, int y_cs, int B, int Lf, cudaStream_t s);
-int noise_ola_cl(const float* c, const float* sn, int cs, float* noise, int B, int Lf, cudaStream_t s);
+int noise_ola_cl(const float* c, const float* sn, float* noise, int B, int Lf, cudaStream_t s);
 size_t osc_scratch_bytes(int B, int Lf);
-int harmonic_source_cl(const float* f0, const float* amps, int amps_cs, const float* noise, const float* energy,
-                       bf16* src_hi, bf16* src_lo, int src_cs, void* scratch, int B, int Lf, cudaStream_t s);
+// amps: view on the 15 amplitude channels (chunk-major, B*Lf rows); src planes: 24 channels of capacity, B*L rows
+int harmonic_source_cl(const float* f0, const float* amps, const float* noise, const float* energy,
+                       bf16* src_hi, bf16* src_lo, void* scratch, int B, int Lf, cudaStream_t s);
 
 }  // namespace tvc

@@ -19,8 +19,9 @@ __device__ __forceinline__ void split_bf16(float v, bf16& h, bf16& l) {
     l = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(h)));
 }
 
-// Tiled transpose [B][C][T] (channels-first fp32) -> channels-last rows [B*T][cs]; MODE 0 = fp32 copy,
-// MODE 1 = split planes.  Tile 32 channels x 32 time steps through shared memory, coalesced both ways.
+// Tiled transpose [B][C][T] (channels-first fp32) -> chunk-major channels-last (tc_conv.cuh) with `cs` channels of
+// capacity; MODE 0 = fp32 copy, MODE 1 = split planes.  Tile 32 channels x 32 time steps through shared memory;
+// the write side handles one (time step, 8-channel chunk) per thread = one 16 / 32-byte row of a chunk array.
 template <int MODE>
 __global__ void __launch_bounds__(256) cf_to_cl_kernel(const float* __restrict__ x, float* __restrict__ y32,
                                                        bf16* __restrict__ hi, bf16* __restrict__ lo, int C, int T,
@@ -30,6 +31,7 @@ __global__ void __launch_bounds__(256) cf_to_cl_kernel(const float* __restrict__
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long R = (long long)gridDim.z * T;
     for (int j = ty; j < 32; j += 8) {
         const int c = c0 + j, t = t0 + tx;
         float v = 0.f;
@@ -41,23 +43,35 @@ __global__ void __launch_bounds__(256) cf_to_cl_kernel(const float* __restrict__
         tile[j][tx] = v;
     }
     __syncthreads();
-    for (int j = ty; j < 32; j += 8) {
-        const int t = t0 + j, c = c0 + tx;
-        if (t >= T || c >= cs) continue;
-        const float v = tile[tx][j];
-        const long long o = ((long long)b * T + t) * cs + c;
-        if (MODE == 0) {
-            y32[o] = v;
-        } else {
-            bf16 h, l;
-            split_bf16(act_of(v, act), h, l);
-            hi[o] = h;
-            lo[o] = l;
+    if (threadIdx.x < 128) {
+        const int q = threadIdx.x >> 5, t = t0 + tx;          // chunk q of this tile, time step t
+        const int c = c0 + q * 8;
+        if (t < T && c < cs) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = tile[q * 8 + e][tx];
+            const long long o = cm((long long)b * T + t, c, R);
+            if (MODE == 0) {
+                reinterpret_cast<float4*>(y32 + o)[0] = make_float4(v[0], v[1], v[2], v[3]);
+                reinterpret_cast<float4*>(y32 + o)[1] = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    bf16 h0, l0, h1, l1;
+                    split_bf16(act_of(v[2 * e], act), h0, l0);
+                    split_bf16(act_of(v[2 * e + 1], act), h1, l1);
+                    h[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    l[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                *reinterpret_cast<uint4*>(hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
         }
     }
 }
 
-// channels-last [B*T][cs] -> channels-first [B][C][T]; MODE 0 reads fp32, MODE 1 reads hi+lo planes.
+// chunk-major channels-last -> channels-first [B][C][T]; MODE 0 reads fp32, MODE 1 reads hi+lo planes (parity probes).
 template <int MODE>
 __global__ void __launch_bounds__(256) cl_to_cf_kernel(const float* __restrict__ x32, const bf16* __restrict__ hi,
                                                        const bf16* __restrict__ lo, float* __restrict__ y, int C, int T,
@@ -65,11 +79,12 @@ __global__ void __launch_bounds__(256) cl_to_cf_kernel(const float* __restrict__
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long R = (long long)gridDim.z * T;
     for (int j = ty; j < 32; j += 8) {
         const int t = t0 + j, c = c0 + tx;
         float v = 0.f;
         if (t < T && c < C) {
-            const long long o = ((long long)b * T + t) * cs + c;
+            const long long o = cm((long long)b * T + t, c, R);
             v = MODE == 0 ? __ldg(x32 + o) : __fadd_rn(__bfloat162float(hi[o]), __bfloat162float(lo[o]));
         }
         tile[j][tx] = v;

@@ -62,10 +62,14 @@ size_t tvc_decoder_workspace_bytes(int B, int Lf);
 /* Decoder.infer(content, f0, energy)  (decoder.py:253-257).
  *   content [B,768,Lf]  f0 [B,1,Lf]  energy [B,1,L]  rand01 [B,961,Lf]  ->  out [B,L]
  * `rand01` is the uniform [0,1) draw that decoder.py:78 takes from torch's generator; passing
- * it in makes the noise branch reproducible against the CPU reference.                       */
+ * it in makes the noise branch reproducible against the CPU reference.  NULL: the draw is made
+ * inside the noise kernel (Philox-4x32-10 keyed by tvc_decoder_seed, one fresh tensor per call). */
 int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, const float* energy,
                       const float* rand01, float* out, int B, int Lf, void* workspace,
                       size_t workspace_bytes, void* stream);
+
+/* Seed of the in-kernel noise draw (the role torch.manual_seed plays for decoder.py:78).      */
+int tvc_decoder_seed(tvc_decoder_t h, uint64_t seed, void* stream);
 
 /* SourceNet.forward (decoder.py:126-134): -> amps [B,15,Lf], kernel [B,961,Lf].              */
 int tvc_source_net(tvc_decoder_t h, const float* content, const float* f0, const float* energy,

@@ -197,3 +197,31 @@ def test_decoder_graph_replay_matches_eager(cuda_models):
         per_call.append(_lib.launch_count() - n0)
         n0 = _lib.launch_count()
     assert len(set(per_call)) == 1 and per_call[0] > 50, per_call   # replays account for every captured kernel
+
+
+@torch.inference_mode()
+def test_in_kernel_noise_draw(cuda_models, weights, report):
+    """rand01 omitted: the uniform draw of decoder.py:78 is made inside the noise kernel (Philox, seeded per decoder).
+    Same seed -> same waveform; consecutive calls -> fresh draws (also under CUDA-graph replay); the result differs
+    from an oracle run by what two oracle runs with different draws differ by (same noise power)."""
+    _, dec = cuda_models
+    PD = weights[1]
+    inp = synth.decoder_inputs(3, 12, seed=41)
+    c, f, e = inp["content"].cuda(), inp["f0"].cuda(), inp["energy"].cuda()
+    dec.seed_noise(1234)
+    a1 = dec.infer(c, f, e).clone()
+    a2 = dec.infer(c, f, e).clone()
+    a3 = dec.infer(c, f, e).clone()          # third call with the same buffers: graph replay
+    dec.seed_noise(1234)
+    b1 = dec.infer(c, f, e).clone()
+    b2 = dec.infer(c, f, e).clone()
+    assert torch.equal(a1, b1) and torch.equal(a2, b2), "same seed must reproduce the same sequence of draws"
+    assert not torch.equal(a1, a2) and not torch.equal(a2, a3), "every call must use a fresh draw"
+    g = torch.Generator().manual_seed(3)
+    ra, rb = torch.rand(3, 961, 12, generator=g), torch.rand(3, 961, 12, generator=g)
+    oa = O.decoder_infer(PD, inp["content"], inp["f0"], inp["energy"], ra)
+    ob = O.decoder_infer(PD, inp["content"], inp["f0"], inp["energy"], rb)
+    between = rmse(oa, ob)
+    ours = rmse(a1, oa)
+    report.add("in_kernel_noise", rmse_vs_oracle_draw=ours, rmse_between_oracle_draws=between)
+    assert 0.5 * between < ours < 2.0 * between

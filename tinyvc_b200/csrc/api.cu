@@ -9,6 +9,8 @@
 
 #include "../../include/tinyvc_b200.h"
 #include "nets.cuh"
+#include "nets_tc.cuh"
+#include "tc_kernels.cuh"
 #include "tc_conv.cuh"
 
 namespace tvc {
@@ -271,7 +273,8 @@ int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, co
                       const float* rand01, float* out, int B, int Lf, void* workspace, size_t workspace_bytes,
                       void* stream) {
     API_BEGIN
-    TVC_REQUIRE(h && content && f0 && energy && rand01 && out && workspace, "tvc_decoder_infer: null argument");
+    TVC_REQUIRE(h && content && f0 && energy && out && workspace, "tvc_decoder_infer: null argument");
+    TVC_REQUIRE(rand01 || g_conv_impl == CONV_IMPL_TC, "tvc_decoder_infer: the fp32 plan needs an injected rand01 draw");
     CHECK_SHAPES();
     cudaStream_t s = (cudaStream_t)stream;
     if (!g_use_graphs || g_prof_on) {
@@ -321,7 +324,7 @@ int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, co
             if (g > 0) cudaStreamWaitEvent(bs, h->fork_ev, 0);
             Arena A((char*)workspace + (size_t)g * slice, slice, false);
             rc = h->m.infer(A, bs, content + (long long)b0 * kContent * Lf, f0 + (long long)b0 * Lf, energy + b0 * L,
-                            rand01 + (long long)b0 * kBins * Lf, out + b0 * L, nb, Lf);
+                            rand01 ? rand01 + (long long)b0 * kBins * Lf : nullptr, out + b0 * L, nb, Lf);
             if (g > 0) {
                 cudaEventRecord(h->join_ev[g - 1], bs);
                 cudaStreamWaitEvent(h->cap_stream, h->join_ev[g - 1], 0);
@@ -352,6 +355,13 @@ int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, co
     h->graphs.push_back(g);
     TVC_CUDA(cudaGraphLaunch(g.exec, s));
     return 0;
+    API_END
+}
+
+int tvc_decoder_seed(tvc_decoder_t h, uint64_t seed, void* stream) {
+    API_BEGIN
+    TVC_REQUIRE(h && h->m.tc && h->m.tc->rng_state, "tvc_decoder_seed: decoder has no tensor-core plan");
+    return rng_seed(h->m.tc->rng_state, (unsigned long long)seed, (cudaStream_t)stream);
     API_END
 }
 

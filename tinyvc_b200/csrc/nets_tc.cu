@@ -87,6 +87,7 @@ DecoderTC::~DecoderTC() {
     for (auto& d : down) { d.c1.free_all(); d.c2.free_all(); d.c3.free_all(); }
     for (auto& u : up) { u.c1.free_all(); u.c2.free_all(); u.c3.free_all(); u.c4.free_all(); u.c5.free_all(); }
     if (w7_buf) cudaFree(w7_buf);
+    if (rng_state) cudaFree(rng_state);
 }
 
 int DecoderTC::init(const WeightStore& store) {
@@ -187,6 +188,8 @@ int DecoderTC::init(const WeightStore& store) {
     out_w = store.raw(fn + ".output_layer.weight");
     out_b = store.raw(fn + ".output_layer.bias");
     TVC_REQUIRE(out_w && out_b, "tc weights: missing output layer");
+    TVC_CUDA(cudaMalloc(&rng_state, 2 * sizeof(unsigned long long)));
+    TVC_CUDA(cudaMemset(rng_state, 0, 2 * sizeof(unsigned long long)));
     ready = true;
     return 0;
 }
@@ -262,7 +265,7 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
             CONV("tc_cnxt_c3(", c.c3, ConvCall(t2p, B, Lf).res(fx, 512).f32(fx, 512).out(xp, TC_ACT_NONE));
         }
         CONV("tc_heads(", heads, ConvCall(xp, B, Lf).f32(hk, kHeadsCs).epi(TC_ACT_ELU1));
-        RUN(noise_spectrum_cl(hk, rand01, yr.hi, yr.lo, yi.hi, yi.lo, kBinsCs, B, Lf, s));
+        RUN(noise_spectrum_cl(hk, rand01, rng_state, yr.hi, yr.lo, yi.hi, yi.lo, kBinsCs, B, Lf, s));
         CONV("tc_idft(", dft_cos, ConvCall(yr, B, Lf).f32(cc, kBinsCs));
         CONV("tc_idft(", dft_sin, ConvCall(yi, B, Lf).f32(ss, kBinsCs));
         RUN(noise_ola_cl(cc, ss, noise, B, Lf, s));

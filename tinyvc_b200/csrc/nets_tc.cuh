@@ -18,6 +18,7 @@ struct DecoderTC {
     struct Up { TcConvW c1, c2, c3, c4, c5; } up[5];
     const float *out_w = nullptr, *out_b = nullptr;
     float* w7_buf = nullptr;      // depth-wise weights repacked [3][7][128]
+    unsigned long long* rng_state = nullptr;   // device {seed, step} of the noise generator (used when no draw is injected)
     bool ready = false;
     ~DecoderTC();
     int init(const WeightStore& store);

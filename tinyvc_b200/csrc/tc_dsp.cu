@@ -15,6 +15,34 @@ __device__ __forceinline__ uint32_t pack2(bf16 a, bf16 b) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Counter-based uniform generator for the noise phases when the caller does not inject the draw:
+// Philox-4x32-10 keyed by the decoder's seed; counter = (element group, launch step).  One call yields
+// four 32-bit words = four uniforms u = (w >> 8) * 2^-24 in [0, 1), the grid torch.rand uses on the CPU.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t w) { return (float)(w >> 8) * 5.9604644775390625e-8f; }
+
+__global__ void rng_seed_kernel(unsigned long long* state, unsigned long long seed) {
+    state[0] = seed;
+    state[1] = 0ull;
+}
+__global__ void rng_advance_kernel(unsigned long long* state) {
+    TVC_PDL_PROLOGUE();
+    state[1] += 1ull;
+}
+
+// ---------------------------------------------------------------------------------------------
 // noise_spectrum_cl (decoder.py:78-80): angle = (rand01*2)*pi - pi, Y = kernel * exp(j*angle).
 // rand01 arrives channels-first [B][961][Lf] (the layout torch.rand draws it in); a 32x32 tile
 // transpose through shared memory turns it into channels-last rows.  Outputs: split planes of
@@ -23,6 +51,7 @@ __device__ __forceinline__ uint32_t pack2(bf16 a, bf16 b) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) noise_spectrum_cl_kernel(const float* __restrict__ kern,
                                                                 const float* __restrict__ rand01,
+                                                                const unsigned long long* __restrict__ rng_state,
                                                                 bf16* __restrict__ yr_hi, bf16* __restrict__ yr_lo,
                                                                 bf16* __restrict__ yi_hi, bf16* __restrict__ yi_lo,
                                                                 int y_cs, int Lf) {
@@ -31,9 +60,11 @@ __global__ void __launch_bounds__(256) noise_spectrum_cl_kernel(const float* __r
     const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const long long R = (long long)gridDim.z * Lf;
-    for (int j = ty; j < 32; j += 8) {
-        const int c = c0 + j, t = t0 + tx;
-        tile[j][tx] = (c < kBins && t < Lf) ? __ldg(rand01 + ((long long)b * kBins + c) * Lf + t) : 0.f;
+    if (rand01) {
+        for (int j = ty; j < 32; j += 8) {
+            const int c = c0 + j, t = t0 + tx;
+            tile[j][tx] = (c < kBins && t < Lf) ? __ldg(rand01 + ((long long)b * kBins + c) * Lf + t) : 0.f;
+        }
     }
     __syncthreads();
     const float pi_f = 3.14159265358979323846f;
@@ -45,12 +76,26 @@ __global__ void __launch_bounds__(256) noise_spectrum_cl_kernel(const float* __r
     const long long o = cm(row, cq, R);
     const float4 k0 = __ldg(reinterpret_cast<const float4*>(kern + o)), k1 = __ldg(reinterpret_cast<const float4*>(kern + o) + 1);
     const float kv[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+    float u[8];
+    if (rand01) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) u[e] = tile[q * 8 + e][tx];
+    } else {
+        // torch.rand(B, 961, Lf) of decoder.py:78, drawn here: element (row, bin) <- word (bin % 4) of block (row * 242 + bin / 4)
+        const unsigned long long seed = rng_state[0], step = rng_state[1];
+        const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+        const unsigned long long blk = (unsigned long long)row * 242ull + (unsigned long long)(cq >> 2);
+        const uint4 r0 = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)step, (uint32_t)(step >> 32)), key);
+        const uint4 r1 = philox4x32_10(make_uint4((uint32_t)(blk + 1), (uint32_t)((blk + 1) >> 32), (uint32_t)step, (uint32_t)(step >> 32)), key);
+        u[0] = u01(r0.x); u[1] = u01(r0.y); u[2] = u01(r0.z); u[3] = u01(r0.w);
+        u[4] = u01(r1.x); u[5] = u01(r1.y); u[6] = u01(r1.z); u[7] = u01(r1.w);
+    }
     float re[8], im[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         re[e] = 0.f; im[e] = 0.f;
         if (cq + e < kBins) {
-            const float a = __fsub_rn(__fmul_rn(__fmul_rn(tile[q * 8 + e][tx], 2.0f), pi_f), pi_f);
+            const float a = __fsub_rn(__fmul_rn(__fmul_rn(u[e], 2.0f), pi_f), pi_f);
             float sn, cs;
             sincosf(a, &sn, &cs);
             re[e] = __fmul_rn(cs, kv[e]);
@@ -252,10 +297,22 @@ __global__ void __launch_bounds__(kOsc * 32, 2) osc_source_kernel(const float* _
 
 }  // namespace
 
-int noise_spectrum_cl(const float* kern, const float* rand01, bf16* yr_hi, bf16* yr_lo, bf16* yi_hi,
-                      bf16* yi_lo, int y_cs, int B, int Lf, cudaStream_t s) {
+int noise_spectrum_cl(const float* kern, const float* rand01, unsigned long long* rng_state, bf16* yr_hi, bf16* yr_lo,
+                      bf16* yi_hi, bf16* yi_lo, int y_cs, int B, int Lf, cudaStream_t s) {
+    TVC_REQUIRE(rand01 || rng_state, "noise_spectrum: neither an injected draw nor a generator state");
     dim3 grid(cdiv(Lf, 32), cdiv(y_cs, 32), B);
-    TVC_LAUNCH_PDL(noise_spectrum_cl_kernel, grid, 256, 0, s, kern, rand01, yr_hi, yr_lo, yi_hi, yi_lo, y_cs, Lf);
+    TVC_LAUNCH_PDL(noise_spectrum_cl_kernel, grid, 256, 0, s, kern, rand01, (const unsigned long long*)rng_state, yr_hi, yr_lo,
+                   yi_hi, yi_lo, y_cs, Lf);
+    TVC_LAUNCH_CHECK();
+    if (!rand01) {                       // the next call draws a fresh tensor
+        TVC_LAUNCH_PDL(rng_advance_kernel, 1, 1, 0, s, rng_state);
+        TVC_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int rng_seed(unsigned long long* state, unsigned long long seed, cudaStream_t s) {
+    rng_seed_kernel<<<1, 1, 0, s>>>(state, seed);
     TVC_LAUNCH_CHECK();
     return 0;
 }

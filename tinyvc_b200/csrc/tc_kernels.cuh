@@ -15,8 +15,10 @@ int grn_apply_cl(const float* y, const float* gamma, const float* beta, bf16* hi
 int out_conv_k7_cl(const float* x, const float* w, const float* bias, float* y, int B, int T, cudaStream_t s);
 
 // tc_dsp.cu
-int noise_spectrum_cl(const float* kern, const float* rand01, bf16* yr_hi, bf16* yr_lo, bf16* yi_hi,
-                      bf16* yi_lo, int y_cs, int B, int Lf, cudaStream_t s);
+// rand01 == nullptr: the uniform draw of decoder.py:78 comes from the Philox state {seed, step} at rng_state
+int noise_spectrum_cl(const float* kern, const float* rand01, unsigned long long* rng_state, bf16* yr_hi, bf16* yr_lo,
+                      bf16* yi_hi, bf16* yi_lo, int y_cs, int B, int Lf, cudaStream_t s);
+int rng_seed(unsigned long long* state, unsigned long long seed, cudaStream_t s);
 int noise_ola_cl(const float* c, const float* sn, float* noise, int B, int Lf, cudaStream_t s);
 size_t osc_scratch_bytes(int B, int Lf);
 // amps: view on the 15 amplitude channels (chunk-major, B*Lf rows); src planes: 24 channels of capacity, B*L rows

@@ -162,6 +162,17 @@ class Decoder(nn.Module):
                                f"{tuple(content.shape)}, {tuple(f0.shape)}, {tuple(energy.shape)}")
         return content, f0, energy, B, Lf
 
+    def seed_noise(self, seed: Optional[int] = None) -> None:
+        """Seed the in-kernel noise draw used when `rand01` is not injected (the role torch.manual_seed plays for
+        the reference's torch.rand, decoder.py:78).  Default: a value drawn from torch's CPU generator."""
+        if seed is None:
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())
+        h = self._native.get()
+        dev = self._native.device
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().tvc_decoder_seed(h, int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.stream_ptr(dev)), "tvc_decoder_seed")
+        self._noise_seeded_for = h.value
+
     def _rand(self, rand01, B, Lf, device):
         if rand01 is None:
             return torch.rand(B, FFT_BIN, Lf, device=device)       # decoder.py:78
@@ -180,9 +191,12 @@ class Decoder(nn.Module):
     def infer(self, content, f0, energy, *, rand01: Optional[torch.Tensor] = None) -> torch.Tensor:
         content, f0, energy, B, Lf = self._prep(content, f0, energy)
         dev = content.device
-        rand01 = self._rand(rand01, B, Lf, dev)
         L = _lib.lib()
         h = self._native.get()
+        if rand01 is not None:
+            rand01 = self._rand(rand01, B, Lf, dev)
+        elif getattr(self, "_noise_seeded_for", None) != h.value:
+            self.seed_noise()            # the draw of decoder.py:78 happens inside the noise kernel
         out = torch.empty(B, Lf * FRAME, device=dev, dtype=torch.float32)
         step = self._batch_chunk(B, Lf)
         with torch.cuda.device(dev):
@@ -191,7 +205,8 @@ class Decoder(nn.Module):
                 nbytes = L.tvc_decoder_workspace_bytes(nb, Lf)
                 ws = _lib.WORKSPACE.get(nbytes, dev)
                 _lib.check(L.tvc_decoder_infer(h, content[b0:b0 + nb].data_ptr(), f0[b0:b0 + nb].data_ptr(),
-                                               energy[b0:b0 + nb].data_ptr(), rand01[b0:b0 + nb].data_ptr(),
+                                               energy[b0:b0 + nb].data_ptr(),
+                                               rand01[b0:b0 + nb].data_ptr() if rand01 is not None else None,
                                                out[b0:b0 + nb].data_ptr(), nb, Lf, ws.data_ptr(), ws.numel(),
                                                _lib.stream_ptr(dev)), "tvc_decoder_infer")
         return out

@@ -79,7 +79,14 @@ struct IndexModel {
     float* bias = nullptr;       // [N]
     int N = 0, NP = 0, metric = 0;
     ConvW as_conv;
+    // tensor-core screening (cos metric): the normalised index as a packed 1x1 conv with Cout = N, and a row-major
+    // copy of the same normalised values for the exact re-scoring of the candidates (knn.cu)
+    TcConvW tc;
+    float* index_wn = nullptr;   // [N][C]
+    bool screened = false;
     ~IndexModel() {
+        tc.free_all();
+        if (index_wn) cudaFree(index_wn);
         if (index_w) cudaFree(index_w);
         if (index_nc) cudaFree(index_nc);
         if (bias) cudaFree(bias);
@@ -468,6 +475,9 @@ int tvc_pitch_decode(const float* logits, float* f0, int B, int Lf, void* stream
 }
 
 // ---------------------------------------------------------------------------------------------- kNN
+constexpr int kScreenMinN = 1024;    // below this the exact CUDA-core product is as fast
+constexpr int kScreenNT = 128;       // reference vectors per CTA tile of the screening product
+
 int tvc_index_create(const float* index, int N, int metric, tvc_index_t* out) {
     API_BEGIN
     TVC_REQUIRE(index && out, "tvc_index_create: null argument");
@@ -494,6 +504,21 @@ int tvc_index_create(const float* index, int N, int metric, tvc_index_t* out) {
     if (r) { delete h; return r; }
     m.as_conv.w = m.index_w; m.as_conv.b = m.bias; m.as_conv.Cin = kContent; m.as_conv.Cout = N; m.as_conv.CoutP = m.NP;
     m.as_conv.K = 1;
+    static const bool no_screen = getenv("TVC_KNN_EXACT") != nullptr;      // developer switch: CUDA-core similarity product
+    if (metric == 0 && N >= kScreenMinN && !no_screen) {
+        // normalised index rows on the host -> tensor-core weight image (Cout = N) and the row-major device copy
+        std::vector<float> wcn((size_t)kContent * m.NP), wn((size_t)N * kContent);
+        r = cudaMemcpy(wcn.data(), m.index_w, sizeof(float) * wcn.size(), cudaMemcpyDeviceToHost) != cudaSuccess;
+        if (!r) {
+            for (int c = 0; c < kContent; ++c)
+                for (int n = 0; n < N; ++n) wn[(size_t)n * kContent + c] = wcn[(size_t)c * m.NP + n];
+            r = tc_pack_conv(wn.data(), nullptr, N, kContent, 1, nullptr, nullptr, 0, 0, kScreenNT, m.tc);
+        }
+        if (!r) r = cudaMalloc(&m.index_wn, sizeof(float) * wn.size()) != cudaSuccess;
+        if (!r) r = cudaMemcpy(m.index_wn, wn.data(), sizeof(float) * wn.size(), cudaMemcpyHostToDevice) != cudaSuccess;
+        if (r) { set_error("tvc_index_create: building the tensor-core image failed for N=%d", N); delete h; return 1; }
+        m.screened = true;
+    }
     *out = h;
     return 0;
     API_END
@@ -514,9 +539,13 @@ size_t tvc_match_workspace_bytes(tvc_index_t h, int B, int Lf) {
     const size_t f = sizeof(float);
     size_t tot = 0;
     tot += align_up((size_t)B * kContent * Lf * f, 256);                    // normalised queries
-    tot += align_up((size_t)bc * N * Lf * f, 256);                          // sims chunk
+    tot += align_up((size_t)bc * (h->m.screened ? (size_t)align_up(N, 8) : (size_t)N) * Lf * f, 256);   // sims chunk
     tot += 2 * align_up((size_t)16 * bc * Lf * 8 * f, 256);                 // partial top-k (values, indices)
     tot += align_up((size_t)B * Lf * 8 * sizeof(int), 256);                 // indices
+    if (h->m.screened) {
+        tot += 2 * align_up((size_t)bc * Lf * kContent * sizeof(bf16), 256);     // query planes
+        tot += align_up((size_t)bc * Lf * 8 * sizeof(int), 256) + align_up((size_t)bc * Lf * sizeof(int), 256);   // candidates, flags
+    }
     return tot + 1024;
 }
 
@@ -532,12 +561,32 @@ int tvc_match_features(tvc_index_t h, const float* source, float* out, int32_t* 
     Arena A(workspace, workspace_bytes, false);
     const int bc = std::min(B, match_chunk_utts(m.N, Lf));
     float* qn = A.f32((int64_t)B * kContent * Lf);
-    float* sims = A.f32((int64_t)bc * m.N * Lf);
+    float* sims = A.f32((int64_t)bc * (m.screened ? (int64_t)align_up(m.N, 8) : (int64_t)m.N) * Lf);   // chunk-major needs N rounded up to 8
     float* pv = A.f32((int64_t)16 * bc * Lf * 8);
     int* pi = A.i32((int64_t)16 * bc * Lf * 8);
     int* idx = idx_out ? idx_out : A.i32((int64_t)B * Lf * k);
     TVC_REQUIRE(!A.overflow, "workspace too small: need at least %zu bytes, got %zu", A.peak, A.cap);
     TVC_TRY(knn_normalize_queries(source, qn, B, kContent, Lf, m.metric, s));
+    if (m.screened && k <= 4) {
+        // similarity product on the tensor cores, exact re-scoring of the nominated candidates (knn.cu)
+        const int N8 = (int)align_up(m.N, 8);
+        bf16* q_hi = (bf16*)A.bytes((size_t)bc * Lf * kContent * sizeof(bf16));
+        bf16* q_lo = (bf16*)A.bytes((size_t)bc * Lf * kContent * sizeof(bf16));
+        int* cand = A.i32((int64_t)bc * Lf * 8);
+        int* flag = A.i32((int64_t)bc * Lf);
+        TVC_REQUIRE(!A.overflow, "workspace too small: need at least %zu bytes, got %zu", A.peak, A.cap);
+        for (int b0 = 0; b0 < B; b0 += bc) {
+            const int nb = std::min(bc, B - b0);
+            const float* qc = qn + (long long)b0 * kContent * Lf;
+            TVC_TRY(cf_to_planes(qc, q_hi, q_lo, nb, kContent, Lf, kContent, TC_ACT_NONE, s));
+            TcConvArgs a;
+            a.a_hi = q_hi; a.a_lo = q_lo; a.a_cs = kContent; a.B = nb; a.T = Lf;
+            a.y32 = sims; a.y32_cs = N8;
+            TVC_TRY(tc_conv_launch(m.tc, a, s));
+            TVC_TRY(knn_screened_topk(sims, qc, m.index_wn, pv, pi, cand, flag, idx + (long long)b0 * Lf * k, nb, Lf, m.N, k, s));
+        }
+        return knn_gather_mean(source, m.index_nc, idx, out, B, kContent, Lf, k, alpha, s);
+    }
     for (int b0 = 0; b0 < B; b0 += bc) {
         const int nb = std::min(bc, B - b0);
         TVC_TRY(conv_run(A, s, m.as_conv, qn + (long long)b0 * kContent * Lf, (long long)kContent * Lf, sims,

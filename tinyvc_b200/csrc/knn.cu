@@ -147,6 +147,204 @@ int knn_topk(const float* sims, float* pv, int* pi, int* idx_out, int B, int T, 
     return 0;
 }
 
+
+// =============================================================================================
+// Tensor-core screening (cos metric, k <= 4).  The similarity product runs on tcgen05 with split-bf16 operands
+// (tc_conv.cu; |error| <~ 1e-6 for unit vectors, worst case 3e-5), which is only trusted to nominate candidates:
+//   1. approximate sims (chunk-major fp32 [N/8][R][8]) -> per query the kKnnCand best candidates (ties: lower index)
+//   2. the candidates are re-scored in exact fp32 with the SAME operation order as the CUDA-core path above
+//      (acc = fma(w[ci], x[ci], acc), ci ascending), and the top-k of those exact scores is the answer
+//   3. if the k-th and the kKnnCand-th approximate scores are closer than kKnnEps (>= 2 x the worst-case
+//      screening error) a true top-k member could have been missed; such queries are re-done by an exact full scan.
+// With |approx - exact| <= delta and a_(k) - a_(kKnnCand) > 2 delta every exact top-k member is among the
+// candidates, so the result is identical to the exact path's.
+// =============================================================================================
+constexpr int kKnnCand = 8;
+constexpr float kKnnEps = 1e-4f;
+
+__device__ __forceinline__ bool knn_better(float x, int n, float y, int m) { return x > y || (x == y && n < m); }
+
+// pass 1: thread = query row, blockIdx.y = segment of 8-reference chunks; coalesced 32-byte reads per chunk
+__global__ void knn_cand_scan_kernel(const float* __restrict__ sims, float* __restrict__ pv, int* __restrict__ pi, int N,
+                                     long long R) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= R) return;
+    const int nch = (N + 7) >> 3;
+    const int per = (nch + kKnnSeg - 1) / kKnnSeg;
+    const int c0 = blockIdx.y * per, c1 = min(nch, c0 + per);
+    float v[kKnnMaxK];
+    int id[kKnnMaxK];
+#pragma unroll
+    for (int i = 0; i < kKnnMaxK; ++i) {
+        v[i] = -INFINITY;
+        id[i] = -1;
+    }
+    for (int c = c0; c < c1; ++c) {
+        const float4* sp = reinterpret_cast<const float4*>(sims + ((long long)c * R + row) * 8);
+        const float4 a = __ldg(sp), b = __ldg(sp + 1);
+        const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (c * 8 + e < N) topk_insert(v, id, kKnnCand, x[e], c * 8 + e);     // increasing n: '>' keeps the lower index
+    }
+    for (int i = 0; i < kKnnCand; ++i) {
+        pv[((long long)blockIdx.y * R + row) * kKnnMaxK + i] = v[i];
+        pi[((long long)blockIdx.y * R + row) * kKnnMaxK + i] = id[i];
+    }
+}
+
+// pass 2: merge the segments' lists -> candidates [R][kKnnCand]; flag[row] = 1 when the screening margin is too thin
+__global__ void knn_cand_merge_kernel(const float* __restrict__ pv, const int* __restrict__ pi, int* __restrict__ cand,
+                                      int* __restrict__ flag, long long R, int k, int N) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= R) return;
+    float v[kKnnMaxK];
+    int id[kKnnMaxK];
+#pragma unroll
+    for (int i = 0; i < kKnnMaxK; ++i) {
+        v[i] = -INFINITY;
+        id[i] = -1;
+    }
+    for (int seg = 0; seg < kKnnSeg; ++seg)
+        for (int i = 0; i < kKnnCand; ++i) {
+            const int n = pi[((long long)seg * R + row) * kKnnMaxK + i];
+            if (n >= 0) topk_insert(v, id, kKnnCand, pv[((long long)seg * R + row) * kKnnMaxK + i], n);
+        }
+    for (int i = 0; i < kKnnCand; ++i) cand[row * kKnnCand + i] = id[i];
+    // fewer references than candidates: every reference is a candidate, nothing can be missed
+    const bool thin = N > kKnnCand && !(v[k - 1] - v[kKnnCand - 1] > kKnnEps);      // also true for NaN scores
+    flag[row] = thin ? 1 : 0;
+}
+
+// exact fp32 score of reference n for query (b, t): the CUDA-core path's operation order (conv1d.cu FMA loop)
+__device__ __forceinline__ float knn_exact_score(const float* __restrict__ wrow, const float* __restrict__ q, int T) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int ci = 0; ci < kContent; ++ci) acc = fmaf(__ldg(wrow + ci), __ldg(q + (long long)ci * T), acc);
+    return acc + 0.f;
+}
+
+// pass 3: block = 32 queries x kKnnCand candidates; thread (q, j) re-scores candidate j exactly, thread (q, 0) selects
+__global__ void __launch_bounds__(32 * kKnnCand) knn_rescore_kernel(const float* __restrict__ qn, const float* __restrict__ index_wn,
+                                                                    const int* __restrict__ cand, int* __restrict__ idx_out,
+                                                                    int T, long long R, int k) {
+    __shared__ float sv[32][kKnnCand];
+    __shared__ int si[32][kKnnCand];
+    const int ql = threadIdx.x / kKnnCand, j = threadIdx.x % kKnnCand;
+    const long long row = (long long)blockIdx.x * 32 + ql;
+    if (row < R) {
+        const int n = cand[row * kKnnCand + j];
+        const long long b = row / T;
+        const int t = (int)(row - b * T);
+        si[ql][j] = n;
+        sv[ql][j] = n >= 0 ? knn_exact_score(index_wn + (long long)n * kContent, qn + b * kContent * (long long)T + t, T) : -INFINITY;
+    }
+    __syncthreads();
+    if (row < R && j == 0) {
+        // selection sort of the k best by (score desc, index asc) -- torch.topk order on the CPU
+        bool used[kKnnCand];
+#pragma unroll
+        for (int i = 0; i < kKnnCand; ++i) used[i] = si[ql][i] < 0;
+        for (int o = 0; o < k; ++o) {
+            int best = -1;
+            for (int i = 0; i < kKnnCand; ++i)
+                if (!used[i] && (best < 0 || knn_better(sv[ql][i], si[ql][i], sv[ql][best], si[ql][best]))) best = i;
+            idx_out[row * k + o] = best >= 0 ? si[ql][best] : 0;
+            if (best >= 0) used[best] = true;
+        }
+    }
+}
+
+// pass 4 (rare): exact full scan for flagged queries; block = one query
+__global__ void __launch_bounds__(256) knn_exact_fallback_kernel(const float* __restrict__ qn, const float* __restrict__ index_wn,
+                                                                 const int* __restrict__ flag, int* __restrict__ idx_out, int T,
+                                                                 int N, int k) {
+    const long long row = blockIdx.x;
+    if (!flag[row]) return;
+    __shared__ float sv[256][4];
+    __shared__ int si[256][4];
+    const long long b = row / T;
+    const int t = (int)(row - b * T);
+    const float* q = qn + b * kContent * (long long)T + t;
+    float v[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int id[4] = {-1, -1, -1, -1};
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const float x = knn_exact_score(index_wn + (long long)n * kContent, q, T);
+        if (id[k - 1] < 0 || knn_better(x, n, v[k - 1], id[k - 1])) {
+            int pos = k - 1;
+            while (pos > 0 && (id[pos - 1] < 0 || knn_better(x, n, v[pos - 1], id[pos - 1]))) {
+                v[pos] = v[pos - 1];
+                id[pos] = id[pos - 1];
+                --pos;
+            }
+            v[pos] = x;
+            id[pos] = n;
+        }
+    }
+    for (int i = 0; i < 4; ++i) {
+        sv[threadIdx.x][i] = v[i];
+        si[threadIdx.x][i] = id[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int bi[4] = {-1, -1, -1, -1};
+        for (int th = 0; th < 256; ++th)
+            for (int i = 0; i < k; ++i) {
+                const int n = si[th][i];
+                if (n < 0) continue;
+                const float x = sv[th][i];
+                if (bi[k - 1] < 0 || knn_better(x, n, bv[k - 1], bi[k - 1])) {
+                    int pos = k - 1;
+                    while (pos > 0 && (bi[pos - 1] < 0 || knn_better(x, n, bv[pos - 1], bi[pos - 1]))) {
+                        bv[pos] = bv[pos - 1];
+                        bi[pos] = bi[pos - 1];
+                        --pos;
+                    }
+                    bv[pos] = x;
+                    bi[pos] = n;
+                }
+            }
+        for (int i = 0; i < k; ++i) idx_out[row * k + i] = bi[i] >= 0 ? bi[i] : 0;
+    }
+}
+
+int knn_screened_topk(const float* sims_cm, const float* qn, const float* index_wn, float* pv, int* pi, int* cand, int* flag,
+                      int* idx_out, int B, int T, int N, int k, cudaStream_t s) {
+    TVC_REQUIRE(k >= 1 && k <= 4 && k < kKnnCand, "knn_screened_topk: k=%d unsupported", k);
+    const long long R = (long long)B * T;
+    knn_cand_scan_kernel<<<dim3(cdiv(R, 128), kKnnSeg), 128, 0, s>>>(sims_cm, pv, pi, N, R);
+    TVC_LAUNCH_CHECK();
+    knn_cand_merge_kernel<<<cdiv(R, 128), 128, 0, s>>>(pv, pi, cand, flag, R, k, N);
+    TVC_LAUNCH_CHECK();
+    knn_rescore_kernel<<<cdiv(R, 32), 32 * kKnnCand, 0, s>>>(qn, index_wn, cand, idx_out, T, R, k);
+    TVC_LAUNCH_CHECK();
+    knn_exact_fallback_kernel<<<(unsigned)R, 256, 0, s>>>(qn, index_wn, flag, idx_out, T, N, k);
+    TVC_LAUNCH_CHECK();
+    return 0;
+}
+
+// [C][NP] -> [N][C] (bitwise copy of the normalised index, rows contiguous for the exact re-scoring)
+__global__ void knn_transpose_kernel(const float* __restrict__ w, float* __restrict__ wn, int C, int N, int NP) {
+    __shared__ float tile[32][33];
+    const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j, n = n0 + tx;
+        tile[j][tx] = (c < C && n < N) ? __ldg(w + (long long)c * NP + n) : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int n = n0 + j, c = c0 + tx;
+        if (n < N && c < C) wn[(long long)n * C + c] = tile[tx][j];
+    }
+}
+int knn_transpose_index(const float* index_w, float* index_wn, int C, int N, int NP, cudaStream_t s) {
+    knn_transpose_kernel<<<dim3(cdiv(N, 32), cdiv(C, 32)), 256, 0, s>>>(index_w, index_wn, C, N, NP);
+    TVC_LAUNCH_CHECK();
+    return 0;
+}
+
 // ---- gather + mean + alpha blend ----------------------------------------------------------------
 // out[b,c,t] = (sum_{i<k} index_nc[idx[b,t,i]][c]) / k * (1-alpha) + src[b,c,t] * alpha     (:30-33)
 __global__ void knn_gather_kernel(const float* __restrict__ src, const float* __restrict__ index_nc,

@@ -36,7 +36,8 @@ const char* tvc_version(void);
 /* Runtime switches.  ("conv_impl","tc"|"fp32"): Decoder.infer on the tcgen05 tensor-core plan (default)
  * or on the exact-fp32 CUDA-core plan.  ("graphs","1"|"0"): tvc_decoder_infer replays a captured CUDA
  * graph when it is called again with the same buffers (default on).  ("pdl","0"|"1"): launch the plan's
- * kernels with programmatic dependent launch (default off).  ("profile","0"|"1").
+ * kernels with programmatic dependent launch (default off).  ("weight_prefetch","0"|"1"): pull all packed
+ * weights into L2 at the start of a step (default off).  ("profile","0"|"1").
  * Returns non-zero for unknown keys.                                                                */
 int tvc_set_option(const char* key, const char* value);
 /* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */

@@ -172,6 +172,7 @@ int tvc_set_option(const char* key, const char* value) {
     }
     if (!strcmp(key, "tc_trace")) return tc_trace_arm(value);          // developer: "k0,k1,..." launch ordinals
     if (!strcmp(key, "tc_trace_dump")) return tc_trace_dump(value);    // developer: write the timeline to a file
+    if (!strcmp(key, "weight_prefetch")) { set_weight_prefetch(!strcmp(value, "1")); return 0; }
     if (!strcmp(key, "pdl")) {
         g_pdl = !strcmp(value, "1");
         return 0;

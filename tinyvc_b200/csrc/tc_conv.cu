@@ -51,6 +51,10 @@ struct TcKParams {
     uint32_t a_stage_bytes, b_stage_bytes;
     uint32_t tmem_cols;
     int epi_act, out_act;
+    int bulk;      // activation windows that are one contiguous run per (plane, chunk) come by TMA bulk copy: 1 = in halo mode
+                   // (measured: full-rate k=3 layers -8 %), 2 = also 1x1 / flat stages (measured slower), 0 = never
+    int zero_once; // bulk mode: every stage has the same number of existing chunks -> padding chunks zeroed once per CTA
+    int pad_from;  // first padding chunk (zero_once)
     int dbg;   // ablation switches for profiling (TVC_TC_DBG): 1 no loads, 2 no MMAs, 4 no epilogue math/stores
     uint2* trace;   // developer timeline (TVC_TC_TRACE): CTA 0 logs {clock, role|event|tile|stage} per pipeline event
 };
@@ -66,6 +70,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -307,6 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
         // stage's 8-channel chunks.  With chunk-major operands a warp-level cp.async moves 32 consecutive rows of
         // one chunk: 512 contiguous bytes in global memory and in shared memory (no bank conflicts).
         const int j = tid - kProdWarp0 * 32;
+        const long long chunk_bytes = p.rows * 16;     // bytes between consecutive 8-channel chunk arrays of a plane
         uint32_t s = 0, ph = 0;    // ring slot and the parity of its *previous* use
         bool wrapped = false;
         const int half = (p.taps - 1) >> 1;
@@ -329,6 +337,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                     w0 += bb >> 1;
                 }
             }
+        }
+        if (p.bulk && p.zero_once && p.pad_from < chunks) {
+            // channel padding of the K-stages (weights there are zero, data must be finite): no copy ever writes these
+            // slots, so they are cleared once per CTA instead of once per stage
+            for (int sl = 0; sl < p.ring; ++sl)
+                for (int m = j; m < p.R; m += kTileM)
+                    for (int c = p.pad_from; c < chunks; ++c) {
+                        const uint32_t dst = smem_base + sl * stage_bytes + (uint32_t)c * p.lbo_a + (uint32_t)m * 16u;
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst + plane_a), "r"(0u) : "memory");
+                    }
+            fence_proxy_async();
         }
         pdl_wait();
         Tracer tr(j == 0 ? p.trace : nullptr, 0);
@@ -358,33 +378,99 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                 if (wrapped) mbar_wait(empty, ph);
                 tr.log(0, 0, (int)(tile - tile_beg), i);
                 const uint32_t a_dst = smem_base + s * stage_bytes;
-                if (j == 0 && !(tile == tile_beg && i < pre)) {
-                    if (p.dbg & 1) mbar_arrive(full);
+                const bf16* src_hi = is_aux ? p.x_hi : p.a_hi;
+                const bf16* src_lo = is_aux ? p.x_lo : p.a_lo;
+                const int cs = is_aux ? p.x_cs : p.a_cs;
+                // Bulk mode: a stage whose rows are one contiguous run of the chunk-major operand (halo windows, 1x1 convs,
+                // aux 1x1 stages) is fetched with one TMA bulk copy per (plane, chunk), issued by lanes of the first producer
+                // warp; only replicate-padded rows at utterance edges are gathered per thread.
+                const bool bulk = (p.bulk == 2 && (p.halo || is_aux || p.taps == 1)) || (p.bulk == 1 && p.halo);
+                int win = kTileM, lo = 0, hi = 0, org = 0;      // window rows; [lo, hi) = window slots covered by the bulk copies
+                long long src_row0 = 0;                          // operand row landing in window slot `lo`
+                if (bulk) {
+                    if (p.halo) {
+                        win = is_aux ? kTileM : p.R;
+                        org = tt0 - (is_aux ? 0 : p.dil);
+                        const int t_lo = org < 0 ? 0 : org, t_hi = org + win < p.T ? org + win : p.T;
+                        lo = t_lo - org; hi = t_hi - org;
+                        src_row0 = (long long)baseT + t_lo;
+                    } else {
+                        const long long g0 = row_tile * kTileM, left = p.rows - g0;
+                        hi = left < kTileM ? (int)left : kTileM;
+                        src_row0 = g0;
+                    }
+                }
+                int n_okb = (cs >> 3) - kb * chunks;
+                n_okb = n_okb > chunks ? chunks : n_okb;
+                const uint32_t a_bytes = bulk ? (uint32_t)(hi - lo) * 32u * (uint32_t)n_okb : 0u;
+                if (j == 0) {
+                    if (tile == tile_beg && i < pre) { if (a_bytes) mbar_expect_tx(full, a_bytes); }     // weights already requested
+                    else if (p.dbg & 1) mbar_arrive(full);
                     else {
-                        mbar_arrive_expect_tx(full, b_bytes);
+                        mbar_arrive_expect_tx(full, b_bytes + a_bytes);
                         bulk_g2s(a_dst + p.a_stage_bytes, wt, b_bytes, full);
                     }
                 }
                 wt += b_bytes >> 1;
-                const bf16* src_hi = is_aux ? p.x_hi : p.a_hi;
-                const bf16* src_lo = is_aux ? p.x_lo : p.a_lo;
-                const int cs = is_aux ? p.x_cs : p.a_cs;
-                const int n_ok = (cs >> 3) - kb * chunks;      // chunks of this stage that exist in the tensor; the rest are zero-filled
-                const bf16* g_hi = src_hi + (long long)kb * chunks * p.rows * 8;
-                const bf16* g_lo = src_lo + (long long)kb * chunks * p.rows * 8;
+                int n_ok = (cs >> 3) - kb * chunks;            // chunks of this stage that exist in the tensor; the rest are zero-filled
+                n_ok = n_ok > chunks ? chunks : n_ok;
+                // Pointer-walking gathers: per 16-byte copy only a 64-bit pointer bump and a shared-address bump remain
+                // (the producers' issue rate, not memory, paced the deep-K layers: ~10 instructions per cp.async before).
+                const char* g_hi = reinterpret_cast<const char*>(src_hi) + (long long)kb * chunks * chunk_bytes;
+                const char* g_lo = reinterpret_cast<const char*>(src_lo) + (long long)kb * chunks * chunk_bytes;
                 if (p.dbg & 1) {
+                } else if (bulk) {
+                    if (j < 2 * n_ok) {                          // lanes 0 .. 2*n_ok-1: one (plane, chunk) each
+                        const int c = j >> 1;
+                        const char* g = ((j & 1) ? g_lo : g_hi) + (long long)c * chunk_bytes + src_row0 * 16;
+                        bulk_g2s(a_dst + (uint32_t)c * p.lbo_a + ((j & 1) ? plane_a : 0u) + (uint32_t)lo * 16u, g,
+                                 (uint32_t)(hi - lo) * 16u, full);
+                    }
+                    if (p.halo && (lo > 0 || hi < win)) {        // utterance edge: replicate-padded rows
+                        for (int m = j; m < win; m += kTileM) {
+                            if (m >= lo && m < hi) continue;
+                            int tt = org + m;
+                            tt = tt < 0 ? 0 : (tt > p.T - 1 ? p.T - 1 : tt);
+                            const long long rb = (long long)(baseT + tt) * 16;
+                            const char* ph = g_hi + rb;
+                            const char* pl = g_lo + rb;
+                            uint32_t dst = a_dst + (uint32_t)m * 16u;
+                            for (int c = 0; c < n_ok; ++c) {
+                                cp_async16(dst, ph, 16u);
+                                cp_async16(dst + plane_a, pl, 16u);
+                                ph += chunk_bytes; pl += chunk_bytes; dst += p.lbo_a;
+                            }
+                        }
+                    }
+                    if (!p.zero_once && n_ok < chunks) {         // per-stage padding (layouts that differ between stages)
+                        for (int m = j; m < win; m += kTileM)
+                            for (int c = n_ok; c < chunks; ++c) {
+                                const uint32_t dst = a_dst + (uint32_t)c * p.lbo_a + (uint32_t)m * 16u;
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst + plane_a), "r"(0u) : "memory");
+                            }
+                        fence_proxy_async();
+                    }
                 } else if (!p.halo) {
                     const int shift = is_aux ? 0 : (tap - half) * p.dil;
                     int tt = tq + shift;
                     tt = tt < 0 ? 0 : (tt > p.T - 1 ? p.T - 1 : tt);                    // replicate padding
-                    const long long grow = (long long)(bT + tt) * 8;
-                    const uint32_t dst = a_dst + (uint32_t)j * 16u;
-#pragma unroll 2
-                    for (int c = 0; c < chunks; ++c) {
-                        const uint32_t nb = (c < n_ok && tq >= 0) ? 16u : 0u;           // 0 -> zero fill
-                        const long long off = (long long)c * p.rows * 8 + grow;
-                        cp_async16(dst + (uint32_t)c * p.lbo_a, nb ? g_hi + off : g_hi, nb);
-                        cp_async16(dst + (uint32_t)c * p.lbo_a + plane_a, nb ? g_lo + off : g_lo, nb);
+                    const long long rb = (long long)(bT + tt) * 16;                     // byte offset of the row inside a chunk array
+                    const uint32_t sz = tq >= 0 ? 16u : 0u;                             // 0 -> zero fill (rows past the end)
+                    const char* ph = g_hi + rb;
+                    const char* pl = g_lo + rb;
+                    uint32_t dst = a_dst + (uint32_t)j * 16u;
+                    int c = 0;
+#pragma unroll 4
+                    for (; c < n_ok; ++c) {
+                        cp_async16(dst, ph, sz);
+                        cp_async16(dst + plane_a, pl, sz);
+                        ph += chunk_bytes; pl += chunk_bytes; dst += p.lbo_a;
+                    }
+                    for (; c < chunks; ++c) {                                           // channel padding of the K-stage
+                        cp_async16(dst, g_hi, 0u);
+                        cp_async16(dst + plane_a, g_lo, 0u);
+                        dst += p.lbo_a;
                     }
                 } else {
                     const int rows_s = is_aux ? kTileM : p.R;
@@ -392,14 +478,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                     for (int m = j; m < rows_s; m += kTileM) {
                         int tt = org + m;
                         tt = tt < 0 ? 0 : (tt > p.T - 1 ? p.T - 1 : tt);                // replicate padding
-                        const long long grow = (long long)(baseT + tt) * 8;
-                        const uint32_t dst = a_dst + (uint32_t)m * 16u;
-#pragma unroll 2
-                        for (int c = 0; c < chunks; ++c) {
-                            const uint32_t nb = c < n_ok ? 16u : 0u;
-                            const long long off = (long long)c * p.rows * 8 + grow;
-                            cp_async16(dst + (uint32_t)c * p.lbo_a, nb ? g_hi + off : g_hi, nb);
-                            cp_async16(dst + (uint32_t)c * p.lbo_a + plane_a, nb ? g_lo + off : g_lo, nb);
+                        const long long rb = (long long)(baseT + tt) * 16;
+                        const char* ph = g_hi + rb;
+                        const char* pl = g_lo + rb;
+                        uint32_t dst = a_dst + (uint32_t)m * 16u;
+                        int c = 0;
+#pragma unroll 4
+                        for (; c < n_ok; ++c) {
+                            cp_async16(dst, ph, 16u);
+                            cp_async16(dst + plane_a, pl, 16u);
+                            ph += chunk_bytes; pl += chunk_bytes; dst += p.lbo_a;
+                        }
+                        for (; c < chunks; ++c) {
+                            cp_async16(dst, g_hi, 0u);
+                            cp_async16(dst + plane_a, g_lo, 0u);
+                            dst += p.lbo_a;
                         }
                     }
                 }
@@ -792,6 +885,24 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     static const int dbg = getenv("TVC_TC_DBG") ? atoi(getenv("TVC_TC_DBG")) : 0;
     p.dbg = dbg;
     p.trace = tc_trace_slot();
+    static const int bulk_env = getenv("TVC_TC_BULK") ? atoi(getenv("TVC_TC_BULK")) : 1;
+    p.bulk = bulk_env;
+    {
+        // do all K-stages see the same number of existing 8-channel chunks?  (then the padding chunks are cleared once)
+        const int chunks = W.KB / 8;
+        int v = -1;
+        bool same = true;
+        for (int kb = 0; kb < W.nkb; ++kb) {
+            int n = a.a_cs / 8 - kb * chunks; n = n > chunks ? chunks : n;
+            if (v < 0) v = n; else same = same && n == v;
+        }
+        for (int kb = 0; kb < W.aux_nkb; ++kb) {
+            int n = a.x_cs / 8 - kb * chunks; n = n > chunks ? chunks : n;
+            same = same && n == v;
+        }
+        p.zero_once = same ? 1 : 0;
+        p.pad_from = v;
+    }
     // halo mode: k=3 convs whose utterances fill their 128-row tiles well share one row window across the taps
     const int tpu = cdiv(a.T, kTileM);
     p.halo = (W.taps == 3 && (double)a.T / ((double)tpu * kTileM) >= 0.75 && !g_force_flat) ? 1 : 0;

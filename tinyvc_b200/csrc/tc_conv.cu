@@ -885,7 +885,7 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     static const int dbg = getenv("TVC_TC_DBG") ? atoi(getenv("TVC_TC_DBG")) : 0;
     p.dbg = dbg;
     p.trace = tc_trace_slot();
-    static const int bulk_env = getenv("TVC_TC_BULK") ? atoi(getenv("TVC_TC_BULK")) : 1;
+    static const int bulk_env = getenv("TVC_TC_BULK") ? atoi(getenv("TVC_TC_BULK")) : 0;   // measured: no consistent gain (r01j/r01k), off
     p.bulk = bulk_env;
     {
         // do all K-stages see the same number of existing 8-channel chunks?  (then the padding chunks are cleared once)

@@ -18,5 +18,12 @@ y = gen.convert(p["wf"].to(dev), p["index"].to(dev), 1.0)
 si = StreamInfer(gen, target=p["index"].to(dev), device=dev)
 si.init_buffer()
 o = si.audio_callback(torch.randn(1920, device=dev) * 0.1)
+out2 = dec.infer(inp["content"], inp["f0"], inp["energy"])                     # in-kernel noise draw
+big = synth.pipeline_inputs(1, 2400, 1100, 3)                                    # N >= 1024: tensor-core screened kNN
+y2 = gen.convert(big["wf"].to(dev), big["index"].to(dev), 0.0)
+sp = StreamInfer(gen, target=p["index"].to(dev), device=dev, use_phase_vocoder=True)
+sp.init_buffer()
+o2 = sp.audio_callback(torch.randn(1920, device=dev) * 0.1)
+o2 = sp.audio_callback(torch.randn(1920, device=dev) * 0.1)
 torch.cuda.synchronize()
 print("sanitize_small ok", out.shape, y.shape, o.shape, float(out.abs().max()), float(y.abs().max()))

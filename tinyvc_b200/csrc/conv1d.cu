@@ -76,15 +76,21 @@ __global__ void __launch_bounds__(NTY* NTX) conv1d_f32_kernel(ConvParams p) {
         for (int n = 0; n < TN; ++n) acc[m][n] = 0.f;
 
     const int pre = p.pre;
-    for (int ci0 = 0; ci0 < p.Cin; ci0 += BK) {
-        // ---- stage inputs (tap-expanded, pre-op applied) ----
-        for (int row = rbase; row < BK * KT; row += RSTEP) {
+    // Software pipeline: chunk c+1 travels global -> registers while chunk c is multiplied out of shared memory.
+    constexpr int XROWS = (BK * KT + RSTEP - 1) / RSTEP;          // staged input rows per loader thread
+    constexpr int WPT = (KT * BK * (BM / 4) + NT - 1) / NT;       // staged weight float4s per thread
+    float xr[XROWS][CPT];
+    float4 wr[WPT];
+    auto load_chunk = [&](int ci0) {
+#pragma unroll
+        for (int r = 0; r < XROWS; ++r) {
+            const int row = rbase + r * RSTEP;
             const int k = row / KT, tap = row - k * KT;
             const int ci = ci0 + k;
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
                 float v = 0.f;
-                if (colok[c] && ci < p.Cin) {
+                if (row < BK * KT && colok[c] && ci < p.Cin) {
                     v = __ldg(p.x + colbase[c] + (long long)ci * T + toff[c][tap]);
                     if (pre == PRE_LRELU) {
                         v = leaky01(v);
@@ -92,22 +98,47 @@ __global__ void __launch_bounds__(NTY* NTX) conv1d_f32_kernel(ConvParams p) {
                         v = fmaf(v, __ldg(p.pre_scale + (long long)colb[c] * p.Cin + ci), __ldg(p.pre_shift + ci));
                     }
                 }
-                xs[row * BN + jbase + c * NT] = v;
+                xr[r][c] = v;
             }
         }
-        // ---- stage weights ----
-        for (int e = tid; e < KT * BK * (BM / 4); e += NT) {
+#pragma unroll
+        for (int q = 0; q < WPT; ++q) {
+            const int e = tid + q * NT;
             const int m4 = e % (BM / 4);
             const int rk = e / (BM / 4);          // tap*BK + k
             const int tap = rk / BK, k = rk - tap * BK;
             const int ci = ci0 + k, co = co0 + m4 * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ci < p.Cin && co < p.CoutP)
+            if (e < KT * BK * (BM / 4) && ci < p.Cin && co < p.CoutP)
                 v = __ldg(reinterpret_cast<const float4*>(p.w + ((long long)tap * p.Cin + ci) * p.CoutP + co));
-            *reinterpret_cast<float4*>(ws + rk * BM + m4 * 4) = v;
+            wr[q] = v;
         }
+    };
+    auto store_chunk = [&]() {
+#pragma unroll
+        for (int r = 0; r < XROWS; ++r) {
+            const int row = rbase + r * RSTEP;
+            if (row < BK * KT) {
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) xs[row * BN + jbase + c * NT] = xr[r][c];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < WPT; ++q) {
+            const int e = tid + q * NT;
+            if (e < KT * BK * (BM / 4)) {
+                const int m4 = e % (BM / 4);
+                const int rk = e / (BM / 4);
+                *reinterpret_cast<float4*>(ws + rk * BM + m4 * 4) = wr[q];
+            }
+        }
+    };
+    load_chunk(0);
+    for (int ci0 = 0; ci0 < p.Cin; ci0 += BK) {
+        store_chunk();
         __syncthreads();
-        // ---- FMA ----
+        if (ci0 + BK < p.Cin) load_chunk(ci0 + BK);
+        // ---- FMA (per output: acc = fma(w, x, acc) with ci ascending, taps inner -- the order parity tests pin) ----
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
 #pragma unroll
@@ -222,6 +253,7 @@ template <int KT> using F48 = ConvCfg<4, 12, 64, 8, KT>;    // 48 x 256, 256 thr
 template <int KT> using F96 = ConvCfg<8, 12, 32, 8, KT>;    // 96 x 128, 256 threads
 template <int KT> using G64 = ConvCfg<8, 8, 32, 8, KT>;     // 64 x 128, 256 threads
 template <int KT> using G16 = ConvCfg<2, 8, 64, 8, KT>;     // 16 x 256, 128 threads (tiny Cout)
+using G128 = ConvCfg<8, 16, 32, 16, 1>;                      // 128 x 128, 256 threads, BK 16: the big 1x1 products (encoder, STFT, kNN)
 
 int conv1d_init() {
     TVC_TRY(F24<1>::init()); TVC_TRY(F24<3>::init());
@@ -229,6 +261,7 @@ int conv1d_init() {
     TVC_TRY(F96<1>::init()); TVC_TRY(F96<3>::init());
     TVC_TRY(G64<1>::init()); TVC_TRY(G64<3>::init());
     TVC_TRY(G16<1>::init()); TVC_TRY(G16<3>::init());
+    TVC_TRY(G128::init());
     return 0;
 }
 
@@ -248,6 +281,11 @@ int conv1d_launch(const ConvParams& p, cudaStream_t stream) {
     TVC_REQUIRE(p.epi != EPI_FILM_RES || (p.film && p.res), "conv1d: FiLM epilogue needs film and res");
     TVC_REQUIRE(p.epi != EPI_RES || p.res, "conv1d: residual epilogue needs res");
     TVC_REQUIRE(p.pre != PRE_AFFINE || (p.pre_scale && p.pre_shift), "conv1d: affine prologue needs scale/shift");
+    // large 1x1 products: 128 x 128 tiles when they still give every SM at least ~2 CTAs
+    if (p.K == 1 && p.Cout >= 256) {
+        const long long tiles = (((long long)p.B * p.T + 127) / 128) * ((p.Cout + 127) / 128);
+        if (tiles >= 296) return G128::launch(p, stream);
+    }
     if (p.K == 1) return dispatch_cfg<1>(p, stream);
     if (p.K == 3) return dispatch_cfg<3>(p, stream);
     set_error("conv1d: unsupported kernel size %d", p.K);

@@ -19,6 +19,7 @@
 //              (x*scale+shift from a second accumulator fed by the aux 1x1 on the skip tensor), the
 //              residual, the activation, and writes fp32 and/or re-split bf16 planes, channels-last.
 // Every mbarrier wait is bounded (trap after ~2 s) so a protocol bug cannot hang the GPU.
+#include <cuda.h>      // CUtensorMap (types only; cuTensorMapEncodeTiled is resolved through the runtime, no -lcuda)
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -32,7 +33,10 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kThreads = 544;   // 12 epilogue warps + 1 MMA warp + 4 producer warps
 
-struct TcKParams {
+struct alignas(64) TcKParams {
+    // TMA tensor maps of the operand planes viewed as [chunk][row / 8][8 rows x 8 channels] (tma_* flags say which are set)
+    CUtensorMap tm_a_hi, tm_a_lo, tm_x_hi, tm_x_lo;
+    int tma_main, tma_aux;   // flat mode: main stages (1x1 convs) / aux stages fetched by one tensor copy per plane
     const bf16 *a_hi, *a_lo, *x_hi, *x_lo, *w;
     const float *bias, *film_bias, *res;
     float* y32;
@@ -96,6 +100,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// TMA tensor copy global -> shared of one [chunks][16 row groups][64 elements] box; completes `bytes` on the mbarrier
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
                  : "memory");
 }
 // 16-byte cp.async (LDGSTS) with zero fill when src_bytes == 0
@@ -267,7 +277,7 @@ __device__ __forceinline__ void issue_stage(uint32_t d, uint32_t a_lo0, uint32_t
 //                signalled with cp.async.mbarrier.arrive.noinc, so a producer never waits for its loads
 // ---------------------------------------------------------------------------------------------
 template <int SPEC>
-__global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p) {
+__global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcKParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     pdl_launch_dependents();      // the next kernel of the plan may start its prologue as soon as SM resources free up
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -403,7 +413,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                 int n_okb = (cs >> 3) - kb * chunks;
                 n_okb = n_okb > chunks ? chunks : n_okb;
                 const uint32_t a_bytes = bulk ? (uint32_t)(hi - lo) * 32u * (uint32_t)n_okb : 0u;
-                if (j == 0) {
+                // Flat-mode stages without a tap shift are one dense [chunks][128 rows] box of the chunk-major operand:
+                // one TMA tensor copy per plane; chunks past the tensor's capacity and rows past its end arrive as zeros.
+                const bool tma = !p.halo && (is_aux ? p.tma_aux != 0 : p.tma_main != 0) && !(p.dbg & 1);
+                const uint32_t t_bytes = tma ? 2u * (uint32_t)chunks * (uint32_t)kTileM * 16u : 0u;
+                if (tma && j == 0) {
+                    if (tile == tile_beg && i < pre) mbar_expect_tx(full, t_bytes);
+                    else {
+                        mbar_arrive_expect_tx(full, b_bytes + t_bytes);
+                        bulk_g2s(a_dst + p.a_stage_bytes, wt, b_bytes, full);
+                    }
+                    const int r8 = (int)(row_tile * (kTileM / 8));
+                    tma_load_3d(a_dst, is_aux ? &p.tm_x_hi : &p.tm_a_hi, 0, r8, kb * chunks, full);
+                    tma_load_3d(a_dst + plane_a, is_aux ? &p.tm_x_lo : &p.tm_a_lo, 0, r8, kb * chunks, full);
+                }
+                if (j == 0 && !tma) {
                     if (tile == tile_beg && i < pre) { if (a_bytes) mbar_expect_tx(full, a_bytes); }     // weights already requested
                     else if (p.dbg & 1) mbar_arrive(full);
                     else {
@@ -418,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                 // (the producers' issue rate, not memory, paced the deep-K layers: ~10 instructions per cp.async before).
                 const char* g_hi = reinterpret_cast<const char*>(src_hi) + (long long)kb * chunks * chunk_bytes;
                 const char* g_lo = reinterpret_cast<const char*>(src_lo) + (long long)kb * chunks * chunk_bytes;
-                if (p.dbg & 1) {
+                if ((p.dbg & 1) || tma) {
                 } else if (bulk) {
                     if (j < 2 * n_ok) {                          // lanes 0 .. 2*n_ok-1: one (plane, chunk) each
                         const int c = j >> 1;
@@ -866,6 +890,35 @@ int tc_trace_dump(const char* path) {
     return 0;
 }
 
+// ---- TMA tensor maps -------------------------------------------------------------------------------
+typedef CUresult (*TmEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmEncodeFn tm_encode_fn() {
+    static TmEncodeFn fn = [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            ptr = nullptr;
+        return (TmEncodeFn)ptr;
+    }();
+    return fn;
+}
+// Chunk-major bf16 plane with `rows` rows and `nch` 8-channel chunks, viewed as [nch][ceil(rows / 8)][64 elements];
+// box = [box_ch][16][64] = box_ch chunk columns of 128 rows, landing in shared memory as [chunk][row][16 B].
+static int make_plane_map(CUtensorMap* m, const bf16* base, long long rows, int nch, int box_ch) {
+    TmEncodeFn enc = tm_encode_fn();
+    TVC_REQUIRE(enc, "tc_conv: cuTensorMapEncodeTiled is not available");
+    const cuuint64_t dims[3] = {64, (cuuint64_t)((rows + 7) / 8), (cuuint64_t)nch};
+    const cuuint64_t strides[2] = {128, (cuuint64_t)rows * 16};
+    const cuuint32_t box[3] = {64, 16, (cuuint32_t)box_ch};
+    const cuuint32_t es[3] = {1, 1, 1};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TVC_REQUIRE(r == CUDA_SUCCESS, "tc_conv: cuTensorMapEncodeTiled failed (%d) rows=%lld chunks=%d", (int)r, rows, nch);
+    return 0;
+}
+
 int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     TVC_REQUIRE(W.w && a.a_hi && a.a_lo, "tc_conv: missing weights or input");
     TVC_REQUIRE(a.B > 0 && a.T > 0, "tc_conv: empty problem B=%d T=%d", a.B, a.T);
@@ -910,6 +963,21 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     p.R = p.halo ? kTileM + 2 * a.dil : kTileM;
     TVC_REQUIRE(a.dil >= 1 && a.dil <= 64, "tc_conv: dilation %d out of range", a.dil);
     p.lbo_a = (uint32_t)(p.R | 1) * 16u;                          // odd number of 16-byte slots: conflict-free stores
+    memset(&p.tm_a_hi, 0, 4 * sizeof(CUtensorMap));
+    static const int tma_env = getenv("TVC_TC_TMA") ? atoi(getenv("TVC_TC_TMA")) : 1;
+    // rows * 16 B is the chunk stride of the map: it must be a multiple of 16 (always) and the 128-row box must stay
+    // inside the 2^32 coordinate range (rows < 2^31 is checked at the API)
+    p.tma_main = (tma_env && !p.halo && W.taps == 1) ? 1 : 0;
+    p.tma_aux = (tma_env && !p.halo && W.aux_mode != TC_AUX_NONE) ? 1 : 0;
+    if (p.tma_main || p.tma_aux) p.lbo_a = (uint32_t)kTileM * 16u;       // the box lands densely: chunk stride = 128 rows
+    if (p.tma_main) {
+        TVC_TRY(make_plane_map(&p.tm_a_hi, a.a_hi, p.rows, a.a_cs / 8, W.KB / 8));
+        TVC_TRY(make_plane_map(&p.tm_a_lo, a.a_lo, p.rows, a.a_cs / 8, W.KB / 8));
+    }
+    if (p.tma_aux) {
+        TVC_TRY(make_plane_map(&p.tm_x_hi, a.x_hi, p.rows, a.x_cs / 8, W.KB / 8));
+        TVC_TRY(make_plane_map(&p.tm_x_lo, a.x_lo, p.rows, a.x_cs / 8, W.KB / 8));
+    }
     const int n_rows_max = W.aux_mode == TC_AUX_FILM ? 2 * W.NTp : W.NTp;
     p.a_stage_bytes = (uint32_t)align_up(2 * (W.KB / 8) * (int)p.lbo_a, 128);         // 2 planes x KB/8 chunks x rows x 16 B
     uint32_t b_main = 4u * (uint32_t)W.KB * (uint32_t)W.NTp * (uint32_t)(p.halo ? W.taps : 1);

@@ -19,7 +19,6 @@
 //              (x*scale+shift from a second accumulator fed by the aux 1x1 on the skip tensor), the
 //              residual, the activation, and writes fp32 and/or re-split bf16 planes, channels-last.
 // Every mbarrier wait is bounded (trap after ~2 s) so a protocol bug cannot hang the GPU.
-#include <cuda.h>      // CUtensorMap (types only; cuTensorMapEncodeTiled is resolved through the runtime, no -lcuda)
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -33,10 +32,7 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kThreads = 544;   // 12 epilogue warps + 1 MMA warp + 4 producer warps
 
-struct alignas(64) TcKParams {
-    // TMA tensor maps of the operand planes viewed as [chunk][row / 8][8 rows x 8 channels] (tma_* flags say which are set)
-    CUtensorMap tm_a_hi, tm_a_lo, tm_x_hi, tm_x_lo;
-    int tma_main, tma_aux;   // flat mode: main stages (1x1 convs) / aux stages fetched by one tensor copy per plane
+struct TcKParams {
     const bf16 *a_hi, *a_lo, *x_hi, *x_lo, *w;
     const float *bias, *film_bias, *res;
     float* y32;
@@ -55,10 +51,6 @@ struct alignas(64) TcKParams {
     uint32_t a_stage_bytes, b_stage_bytes;
     uint32_t tmem_cols;
     int epi_act, out_act;
-    int bulk;      // activation windows that are one contiguous run per (plane, chunk) come by TMA bulk copy: 1 = in halo mode
-                   // (measured: full-rate k=3 layers -8 %), 2 = also 1x1 / flat stages (measured slower), 0 = never
-    int zero_once; // bulk mode: every stage has the same number of existing chunks -> padding chunks zeroed once per CTA
-    int pad_from;  // first padding chunk (zero_once)
     int dbg;   // ablation switches for profiling (TVC_TC_DBG): 1 no loads, 2 no MMAs, 4 no epilogue math/stores
     uint2* trace;   // developer timeline (TVC_TC_TRACE): CTA 0 logs {clock, role|event|tile|stage} per pipeline event
 };
@@ -74,9 +66,6 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -100,12 +89,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-// TMA tensor copy global -> shared of one [chunks][16 row groups][64 elements] box; completes `bytes` on the mbarrier
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
                  : "memory");
 }
 // 16-byte cp.async (LDGSTS) with zero fill when src_bytes == 0
@@ -277,7 +260,7 @@ __device__ __forceinline__ void issue_stage(uint32_t d, uint32_t a_lo0, uint32_t
 //                signalled with cp.async.mbarrier.arrive.noinc, so a producer never waits for its loads
 // ---------------------------------------------------------------------------------------------
 template <int SPEC>
-__global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcKParams p) {
+__global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     pdl_launch_dependents();      // the next kernel of the plan may start its prologue as soon as SM resources free up
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -348,18 +331,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                 }
             }
         }
-        if (p.bulk && p.zero_once && p.pad_from < chunks) {
-            // channel padding of the K-stages (weights there are zero, data must be finite): no copy ever writes these
-            // slots, so they are cleared once per CTA instead of once per stage
-            for (int sl = 0; sl < p.ring; ++sl)
-                for (int m = j; m < p.R; m += kTileM)
-                    for (int c = p.pad_from; c < chunks; ++c) {
-                        const uint32_t dst = smem_base + sl * stage_bytes + (uint32_t)c * p.lbo_a + (uint32_t)m * 16u;
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst + plane_a), "r"(0u) : "memory");
-                    }
-            fence_proxy_async();
-        }
         pdl_wait();
         Tracer tr(j == 0 ? p.trace : nullptr, 0);
         for (long long tile = tile_beg; tile < tile_end; ++tile, tw.next(p)) {
@@ -388,93 +359,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                 if (wrapped) mbar_wait(empty, ph);
                 tr.log(0, 0, (int)(tile - tile_beg), i);
                 const uint32_t a_dst = smem_base + s * stage_bytes;
-                const bf16* src_hi = is_aux ? p.x_hi : p.a_hi;
-                const bf16* src_lo = is_aux ? p.x_lo : p.a_lo;
-                const int cs = is_aux ? p.x_cs : p.a_cs;
-                // Bulk mode: a stage whose rows are one contiguous run of the chunk-major operand (halo windows, 1x1 convs,
-                // aux 1x1 stages) is fetched with one TMA bulk copy per (plane, chunk), issued by lanes of the first producer
-                // warp; only replicate-padded rows at utterance edges are gathered per thread.
-                const bool bulk = (p.bulk == 2 && (p.halo || is_aux || p.taps == 1)) || (p.bulk == 1 && p.halo);
-                int win = kTileM, lo = 0, hi = 0, org = 0;      // window rows; [lo, hi) = window slots covered by the bulk copies
-                long long src_row0 = 0;                          // operand row landing in window slot `lo`
-                if (bulk) {
-                    if (p.halo) {
-                        win = is_aux ? kTileM : p.R;
-                        org = tt0 - (is_aux ? 0 : p.dil);
-                        const int t_lo = org < 0 ? 0 : org, t_hi = org + win < p.T ? org + win : p.T;
-                        lo = t_lo - org; hi = t_hi - org;
-                        src_row0 = (long long)baseT + t_lo;
-                    } else {
-                        const long long g0 = row_tile * kTileM, left = p.rows - g0;
-                        hi = left < kTileM ? (int)left : kTileM;
-                        src_row0 = g0;
-                    }
-                }
-                int n_okb = (cs >> 3) - kb * chunks;
-                n_okb = n_okb > chunks ? chunks : n_okb;
-                const uint32_t a_bytes = bulk ? (uint32_t)(hi - lo) * 32u * (uint32_t)n_okb : 0u;
-                // Flat-mode stages without a tap shift are one dense [chunks][128 rows] box of the chunk-major operand:
-                // one TMA tensor copy per plane; chunks past the tensor's capacity and rows past its end arrive as zeros.
-                const bool tma = !p.halo && (is_aux ? p.tma_aux != 0 : p.tma_main != 0) && !(p.dbg & 1);
-                const uint32_t t_bytes = tma ? 2u * (uint32_t)chunks * (uint32_t)kTileM * 16u : 0u;
-                if (tma && j == 0) {
-                    if (tile == tile_beg && i < pre) mbar_expect_tx(full, t_bytes);
+                if (j == 0 && !(tile == tile_beg && i < pre)) {
+                    if (p.dbg & 1) mbar_arrive(full);
                     else {
-                        mbar_arrive_expect_tx(full, b_bytes + t_bytes);
-                        bulk_g2s(a_dst + p.a_stage_bytes, wt, b_bytes, full);
-                    }
-                    const int r8 = (int)(row_tile * (kTileM / 8));
-                    tma_load_3d(a_dst, is_aux ? &p.tm_x_hi : &p.tm_a_hi, 0, r8, kb * chunks, full);
-                    tma_load_3d(a_dst + plane_a, is_aux ? &p.tm_x_lo : &p.tm_a_lo, 0, r8, kb * chunks, full);
-                }
-                if (j == 0 && !tma) {
-                    if (tile == tile_beg && i < pre) { if (a_bytes) mbar_expect_tx(full, a_bytes); }     // weights already requested
-                    else if (p.dbg & 1) mbar_arrive(full);
-                    else {
-                        mbar_arrive_expect_tx(full, b_bytes + a_bytes);
+                        mbar_arrive_expect_tx(full, b_bytes);
                         bulk_g2s(a_dst + p.a_stage_bytes, wt, b_bytes, full);
                     }
                 }
                 wt += b_bytes >> 1;
+                const bf16* src_hi = is_aux ? p.x_hi : p.a_hi;
+                const bf16* src_lo = is_aux ? p.x_lo : p.a_lo;
+                const int cs = is_aux ? p.x_cs : p.a_cs;
                 int n_ok = (cs >> 3) - kb * chunks;            // chunks of this stage that exist in the tensor; the rest are zero-filled
                 n_ok = n_ok > chunks ? chunks : n_ok;
                 // Pointer-walking gathers: per 16-byte copy only a 64-bit pointer bump and a shared-address bump remain
                 // (the producers' issue rate, not memory, paced the deep-K layers: ~10 instructions per cp.async before).
                 const char* g_hi = reinterpret_cast<const char*>(src_hi) + (long long)kb * chunks * chunk_bytes;
                 const char* g_lo = reinterpret_cast<const char*>(src_lo) + (long long)kb * chunks * chunk_bytes;
-                if ((p.dbg & 1) || tma) {
-                } else if (bulk) {
-                    if (j < 2 * n_ok) {                          // lanes 0 .. 2*n_ok-1: one (plane, chunk) each
-                        const int c = j >> 1;
-                        const char* g = ((j & 1) ? g_lo : g_hi) + (long long)c * chunk_bytes + src_row0 * 16;
-                        bulk_g2s(a_dst + (uint32_t)c * p.lbo_a + ((j & 1) ? plane_a : 0u) + (uint32_t)lo * 16u, g,
-                                 (uint32_t)(hi - lo) * 16u, full);
-                    }
-                    if (p.halo && (lo > 0 || hi < win)) {        // utterance edge: replicate-padded rows
-                        for (int m = j; m < win; m += kTileM) {
-                            if (m >= lo && m < hi) continue;
-                            int tt = org + m;
-                            tt = tt < 0 ? 0 : (tt > p.T - 1 ? p.T - 1 : tt);
-                            const long long rb = (long long)(baseT + tt) * 16;
-                            const char* ph = g_hi + rb;
-                            const char* pl = g_lo + rb;
-                            uint32_t dst = a_dst + (uint32_t)m * 16u;
-                            for (int c = 0; c < n_ok; ++c) {
-                                cp_async16(dst, ph, 16u);
-                                cp_async16(dst + plane_a, pl, 16u);
-                                ph += chunk_bytes; pl += chunk_bytes; dst += p.lbo_a;
-                            }
-                        }
-                    }
-                    if (!p.zero_once && n_ok < chunks) {         // per-stage padding (layouts that differ between stages)
-                        for (int m = j; m < win; m += kTileM)
-                            for (int c = n_ok; c < chunks; ++c) {
-                                const uint32_t dst = a_dst + (uint32_t)c * p.lbo_a + (uint32_t)m * 16u;
-                                asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
-                                asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst + plane_a), "r"(0u) : "memory");
-                            }
-                        fence_proxy_async();
-                    }
+                if (p.dbg & 1) {
                 } else if (!p.halo) {
                     const int shift = is_aux ? 0 : (tap - half) * p.dil;
                     int tt = tq + shift;
@@ -890,35 +792,6 @@ int tc_trace_dump(const char* path) {
     return 0;
 }
 
-// ---- TMA tensor maps -------------------------------------------------------------------------------
-typedef CUresult (*TmEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static TmEncodeFn tm_encode_fn() {
-    static TmEncodeFn fn = [] {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-            ptr = nullptr;
-        return (TmEncodeFn)ptr;
-    }();
-    return fn;
-}
-// Chunk-major bf16 plane with `rows` rows and `nch` 8-channel chunks, viewed as [nch][ceil(rows / 8)][64 elements];
-// box = [box_ch][16][64] = box_ch chunk columns of 128 rows, landing in shared memory as [chunk][row][16 B].
-static int make_plane_map(CUtensorMap* m, const bf16* base, long long rows, int nch, int box_ch) {
-    TmEncodeFn enc = tm_encode_fn();
-    TVC_REQUIRE(enc, "tc_conv: cuTensorMapEncodeTiled is not available");
-    const cuuint64_t dims[3] = {64, (cuuint64_t)((rows + 7) / 8), (cuuint64_t)nch};
-    const cuuint64_t strides[2] = {128, (cuuint64_t)rows * 16};
-    const cuuint32_t box[3] = {64, 16, (cuuint32_t)box_ch};
-    const cuuint32_t es[3] = {1, 1, 1};
-    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    TVC_REQUIRE(r == CUDA_SUCCESS, "tc_conv: cuTensorMapEncodeTiled failed (%d) rows=%lld chunks=%d", (int)r, rows, nch);
-    return 0;
-}
-
 int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     TVC_REQUIRE(W.w && a.a_hi && a.a_lo, "tc_conv: missing weights or input");
     TVC_REQUIRE(a.B > 0 && a.T > 0, "tc_conv: empty problem B=%d T=%d", a.B, a.T);
@@ -938,24 +811,6 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     static const int dbg = getenv("TVC_TC_DBG") ? atoi(getenv("TVC_TC_DBG")) : 0;
     p.dbg = dbg;
     p.trace = tc_trace_slot();
-    static const int bulk_env = getenv("TVC_TC_BULK") ? atoi(getenv("TVC_TC_BULK")) : 0;   // measured: no consistent gain (r01j/r01k), off
-    p.bulk = bulk_env;
-    {
-        // do all K-stages see the same number of existing 8-channel chunks?  (then the padding chunks are cleared once)
-        const int chunks = W.KB / 8;
-        int v = -1;
-        bool same = true;
-        for (int kb = 0; kb < W.nkb; ++kb) {
-            int n = a.a_cs / 8 - kb * chunks; n = n > chunks ? chunks : n;
-            if (v < 0) v = n; else same = same && n == v;
-        }
-        for (int kb = 0; kb < W.aux_nkb; ++kb) {
-            int n = a.x_cs / 8 - kb * chunks; n = n > chunks ? chunks : n;
-            same = same && n == v;
-        }
-        p.zero_once = same ? 1 : 0;
-        p.pad_from = v;
-    }
     // halo mode: k=3 convs whose utterances fill their 128-row tiles well share one row window across the taps
     const int tpu = cdiv(a.T, kTileM);
     p.halo = (W.taps == 3 && (double)a.T / ((double)tpu * kTileM) >= 0.75 && !g_force_flat) ? 1 : 0;
@@ -963,21 +818,6 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     p.R = p.halo ? kTileM + 2 * a.dil : kTileM;
     TVC_REQUIRE(a.dil >= 1 && a.dil <= 64, "tc_conv: dilation %d out of range", a.dil);
     p.lbo_a = (uint32_t)(p.R | 1) * 16u;                          // odd number of 16-byte slots: conflict-free stores
-    memset(&p.tm_a_hi, 0, 4 * sizeof(CUtensorMap));
-    static const int tma_env = getenv("TVC_TC_TMA") ? atoi(getenv("TVC_TC_TMA")) : 1;
-    // rows * 16 B is the chunk stride of the map: it must be a multiple of 16 (always) and the 128-row box must stay
-    // inside the 2^32 coordinate range (rows < 2^31 is checked at the API)
-    p.tma_main = (tma_env && !p.halo && W.taps == 1) ? 1 : 0;
-    p.tma_aux = (tma_env && !p.halo && W.aux_mode != TC_AUX_NONE) ? 1 : 0;
-    if (p.tma_main || p.tma_aux) p.lbo_a = (uint32_t)kTileM * 16u;       // the box lands densely: chunk stride = 128 rows
-    if (p.tma_main) {
-        TVC_TRY(make_plane_map(&p.tm_a_hi, a.a_hi, p.rows, a.a_cs / 8, W.KB / 8));
-        TVC_TRY(make_plane_map(&p.tm_a_lo, a.a_lo, p.rows, a.a_cs / 8, W.KB / 8));
-    }
-    if (p.tma_aux) {
-        TVC_TRY(make_plane_map(&p.tm_x_hi, a.x_hi, p.rows, a.x_cs / 8, W.KB / 8));
-        TVC_TRY(make_plane_map(&p.tm_x_lo, a.x_lo, p.rows, a.x_cs / 8, W.KB / 8));
-    }
     const int n_rows_max = W.aux_mode == TC_AUX_FILM ? 2 * W.NTp : W.NTp;
     p.a_stage_bytes = (uint32_t)align_up(2 * (W.KB / 8) * (int)p.lbo_a, 128);         // 2 planes x KB/8 chunks x rows x 16 B
     uint32_t b_main = 4u * (uint32_t)W.KB * (uint32_t)W.NTp * (uint32_t)(p.halo ? W.taps : 1);

@@ -176,9 +176,8 @@ def run_ours(args) -> None:
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the one JSON line: NCCL writes its version banner / debug output there unless told otherwise
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -243,6 +242,40 @@ def run_ours(args) -> None:
     ms_e2e, _ = timed(step_e2e, args.steps)
     clk = clocks.stop() if clocks else None
 
+    # Optional (--scatter-gather, N > 1): the north-star's other multi-GPU mode -- rank 0 holds the whole job
+    # (world x BATCH utterances), tinyvc_b200.shard scatters utterance blocks over NCCL, every rank converts, rank 0
+    # gathers the waveforms.  Reported as an extra object; `value` stays the collective-free weak-scaling number.
+    sg = None
+    if world > 1 and args.scatter_gather:
+        from tinyvc_b200.shard import ShardedDecoder
+        sd = ShardedDecoder(dec, dev, micro_batch=32)
+        full = None
+        if rank == 0:
+            full = {k: v.to(dev) for k, v in synth.decoder_inputs(BATCH * world, LF, seed=4321).items()}
+
+        def step_sg():
+            if rank == 0:
+                return sd.infer(full["content"], full["f0"], full["energy"])
+            return sd.infer()
+
+        for _ in range(3):
+            step_sg()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_sg()
+        torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        tmax = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        per = float(tmax) / args.steps
+        in_b = sum(v.numel() * 4 for k, v in full.items() if k != "rand01") * (world - 1) // world if rank == 0 else 0
+        sg = {"value": world * samples / per, "unit": "samples/s", "ms_per_step": per * 1e3, "utterances": BATCH * world,
+              "scattered_bytes_per_step": in_b, "gathered_bytes_per_step": (world - 1) * samples * 4,
+              "timing": "host clock around K steps between barriers, max over ranks (transfers are inside)"}
+
     # per-kernel event profile (separate pass; not part of the timed numbers)
     prof = None
     if rank == 0:
@@ -305,6 +338,8 @@ def run_ours(args) -> None:
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "rtf_x": value / 24000.0,
         }
+        if sg is not None:
+            line["scatter_gather"] = sg
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -317,6 +352,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle timing (profiler runs)")
+    ap.add_argument("--scatter-gather", action="store_true",
+                    help="N > 1: also time rank-0-holds-the-job scatter -> convert -> gather over NCCL (extra JSON object)")
     ap.add_argument("--conv-impl", default=os.environ.get("TVC_CONV_IMPL", "tc"), choices=["fp32", "tc"])
     args = ap.parse_args()
     if args.impl == "reference":

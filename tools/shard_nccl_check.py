@@ -24,8 +24,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=dev)
     dec = load_synth_weights(Decoder().eval(), seed=7).to(dev)
     B, Lf = int(os.environ.get("CHECK_B", 37)), int(os.environ.get("CHECK_LF", 50))      # ragged: 37 utterances

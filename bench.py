@@ -176,9 +176,19 @@ def run_ours(args) -> None:
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL writes its version banner / debug output there unless told otherwise
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # Keep stdout to the one JSON line: NCCL prints its version banner (and NCCL_DEBUG output) on stdout when the
+        # first communicator is created, so file descriptor 1 points at stderr until that has happened.
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:

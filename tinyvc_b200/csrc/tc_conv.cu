@@ -19,6 +19,7 @@
 //              (x*scale+shift from a second accumulator fed by the aux 1x1 on the skip tensor), the
 //              residual, the activation, and writes fp32 and/or re-split bf16 planes, channels-last.
 // Every mbarrier wait is bounded (trap after ~2 s) so a protocol bug cannot hang the GPU.
+#include <cuda.h>      // CUtensorMap (types only; cuTensorMapEncodeTiled is resolved through the runtime, no -lcuda)
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -32,7 +33,12 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kThreads = 544;   // 12 epilogue warps + 1 MMA warp + 4 producer warps
 
-struct TcKParams {
+struct alignas(64) TcKParams {
+    // TMA tensor maps of the operand planes, each viewed as [chunk][row / 8][8 rows x 8 channels = 128 B]; the box is
+    // [KB/8 chunks][G row groups][128 B] and lands in shared memory as [chunk][row][16 B], the UMMA K-major order
+    CUtensorMap tm_a_hi, tm_a_lo, tm_x_hi, tm_x_lo;
+    int tma_main, tma_aux;         // which stage types may use them (interior tiles only: no replicate padding inside)
+    uint32_t lbo_main, lbo_aux;    // bytes between consecutive 8-channel chunk columns of a main / aux stage (= 128 * G)
     const bf16 *a_hi, *a_lo, *x_hi, *x_lo, *w;
     const float *bias, *film_bias, *res;
     float* y32;
@@ -47,7 +53,6 @@ struct TcKParams {
     int halo;                      // 1: one stage holds a (128 + 2*dil)-row window shared by the 3 taps (tiles never straddle utterances)
     int R;                         // rows per A stage (128, or 128 + 2*dil in halo mode)
     int tiles_per_utt;             // halo mode
-    uint32_t lbo_a;                // bytes between consecutive 8-channel chunks of the A stage (odd multiple of 16)
     uint32_t a_stage_bytes, b_stage_bytes;
     uint32_t tmem_cols;
     int epi_act, out_act;
@@ -89,6 +94,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA tensor copy global -> shared of one [chunks][G row groups][128 B] box; the box's bytes complete on the mbarrier
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
                  : "memory");
 }
 // 16-byte cp.async (LDGSTS) with zero fill when src_bytes == 0
@@ -260,7 +274,7 @@ __device__ __forceinline__ void issue_stage(uint32_t d, uint32_t a_lo0, uint32_t
 //                signalled with cp.async.mbarrier.arrive.noinc, so a producer never waits for its loads
 // ---------------------------------------------------------------------------------------------
 template <int SPEC>
-__global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p) {
+__global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcKParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     pdl_launch_dependents();      // the next kernel of the plan may start its prologue as soon as SM resources free up
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -278,7 +292,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
     const int n_main = p.halo ? p.nkb : p.taps * p.nkb;
     const int n_stage = n_main + p.aux_nkb;
     const int chunks = p.KB >> 3;                   // 16-byte chunks per row per plane in one stage
-    const uint32_t plane_a = (uint32_t)chunks * p.lbo_a;
     const uint32_t acc_cols = (uint32_t)(film ? 3 * p.NTp : p.NTp);
     const long long n_tiles_total = p.row_tiles * p.n_tiles;
     // contiguous tile range of this CTA; tile id = n_tile * row_tiles + row_tile
@@ -359,24 +372,49 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                 if (wrapped) mbar_wait(empty, ph);
                 tr.log(0, 0, (int)(tile - tile_beg), i);
                 const uint32_t a_dst = smem_base + s * stage_bytes;
-                if (j == 0 && !(tile == tile_beg && i < pre)) {
-                    if (p.dbg & 1) mbar_arrive(full);
-                    else {
-                        mbar_arrive_expect_tx(full, b_bytes);
-                        bulk_g2s(a_dst + p.a_stage_bytes, wt, b_bytes, full);
-                    }
-                }
-                wt += b_bytes >> 1;
                 const bf16* src_hi = is_aux ? p.x_hi : p.a_hi;
                 const bf16* src_lo = is_aux ? p.x_lo : p.a_lo;
                 const int cs = is_aux ? p.x_cs : p.a_cs;
+                const uint32_t lbo = is_aux ? p.lbo_aux : p.lbo_main;
+                const uint32_t plane = (uint32_t)chunks * lbo;
+                // Window geometry.  `start` = operand row that belongs in window slot 0; the window sits `off` = start mod 8
+                // slots into the stage so that a TMA box (which starts on a multiple of 8 rows) lands it in place; the MMA
+                // warp applies the same offset to its descriptors.  Tiles whose window leaves the utterance (replicate
+                // padding) and k = 3 stages of flat mode are gathered per thread with cp.async instead.
+                int win = kTileM, org = 0;
+                long long start;
+                bool edge = false;
+                if (p.halo) {
+                    win = is_aux ? kTileM : p.R;
+                    org = tt0 - (is_aux ? 0 : p.dil);
+                    start = (long long)baseT + org;
+                    edge = org < 0 || org + win > p.T;
+                } else {
+                    start = row_tile * kTileM;
+                }
+                const uint32_t off = (uint32_t)(start + 64) & 7u;
+                const bool tma = (is_aux ? p.tma_aux != 0 : (p.tma_main != 0 && (p.halo || p.taps == 1))) && !edge && !(p.dbg & 1);
+                if (j == 0) {
+                    const uint32_t t_bytes = tma ? 2u * plane : 0u;
+                    if (tile == tile_beg && i < pre) { if (tma) mbar_expect_tx(full, t_bytes); }       // weights already requested
+                    else if (p.dbg & 1) mbar_arrive(full);
+                    else {
+                        mbar_arrive_expect_tx(full, b_bytes + t_bytes);
+                        bulk_g2s(a_dst + p.a_stage_bytes, wt, b_bytes, full);
+                    }
+                    if (tma) {
+                        const int r8 = (int)((start - off) >> 3);
+                        tma_load_3d(a_dst, is_aux ? &p.tm_x_hi : &p.tm_a_hi, 0, r8, kb * chunks, full);
+                        tma_load_3d(a_dst + plane, is_aux ? &p.tm_x_lo : &p.tm_a_lo, 0, r8, kb * chunks, full);
+                    }
+                }
+                wt += b_bytes >> 1;
                 int n_ok = (cs >> 3) - kb * chunks;            // chunks of this stage that exist in the tensor; the rest are zero-filled
                 n_ok = n_ok > chunks ? chunks : n_ok;
                 // Pointer-walking gathers: per 16-byte copy only a 64-bit pointer bump and a shared-address bump remain
-                // (the producers' issue rate, not memory, paced the deep-K layers: ~10 instructions per cp.async before).
                 const char* g_hi = reinterpret_cast<const char*>(src_hi) + (long long)kb * chunks * chunk_bytes;
                 const char* g_lo = reinterpret_cast<const char*>(src_lo) + (long long)kb * chunks * chunk_bytes;
-                if (p.dbg & 1) {
+                if ((p.dbg & 1) || tma) {
                 } else if (!p.halo) {
                     const int shift = is_aux ? 0 : (tap - half) * p.dil;
                     int tt = tq + shift;
@@ -385,40 +423,38 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                     const uint32_t sz = tq >= 0 ? 16u : 0u;                             // 0 -> zero fill (rows past the end)
                     const char* ph = g_hi + rb;
                     const char* pl = g_lo + rb;
-                    uint32_t dst = a_dst + (uint32_t)j * 16u;
+                    uint32_t dst = a_dst + (uint32_t)j * 16u;                           // flat tiles start on a multiple of 128 rows: off = 0
                     int c = 0;
 #pragma unroll 4
                     for (; c < n_ok; ++c) {
                         cp_async16(dst, ph, sz);
-                        cp_async16(dst + plane_a, pl, sz);
-                        ph += chunk_bytes; pl += chunk_bytes; dst += p.lbo_a;
+                        cp_async16(dst + plane, pl, sz);
+                        ph += chunk_bytes; pl += chunk_bytes; dst += lbo;
                     }
                     for (; c < chunks; ++c) {                                           // channel padding of the K-stage
                         cp_async16(dst, g_hi, 0u);
-                        cp_async16(dst + plane_a, g_lo, 0u);
-                        dst += p.lbo_a;
+                        cp_async16(dst + plane, g_lo, 0u);
+                        dst += lbo;
                     }
                 } else {
-                    const int rows_s = is_aux ? kTileM : p.R;
-                    const int org = tt0 - (is_aux ? 0 : p.dil);
-                    for (int m = j; m < rows_s; m += kTileM) {
+                    for (int m = j; m < win; m += kTileM) {
                         int tt = org + m;
                         tt = tt < 0 ? 0 : (tt > p.T - 1 ? p.T - 1 : tt);                // replicate padding
                         const long long rb = (long long)(baseT + tt) * 16;
                         const char* ph = g_hi + rb;
                         const char* pl = g_lo + rb;
-                        uint32_t dst = a_dst + (uint32_t)m * 16u;
+                        uint32_t dst = a_dst + (off + (uint32_t)m) * 16u;
                         int c = 0;
 #pragma unroll 4
                         for (; c < n_ok; ++c) {
                             cp_async16(dst, ph, 16u);
-                            cp_async16(dst + plane_a, pl, 16u);
-                            ph += chunk_bytes; pl += chunk_bytes; dst += p.lbo_a;
+                            cp_async16(dst + plane, pl, 16u);
+                            ph += chunk_bytes; pl += chunk_bytes; dst += lbo;
                         }
                         for (; c < chunks; ++c) {
                             cp_async16(dst, g_hi, 0u);
-                            cp_async16(dst + plane_a, g_lo, 0u);
-                            dst += p.lbo_a;
+                            cp_async16(dst + plane, g_lo, 0u);
+                            dst += lbo;
                         }
                     }
                 }
@@ -442,24 +478,32 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
             const uint32_t idesc_main = umma_idesc(kTileM, (uint32_t)p.NTp);
             const uint32_t idesc_film = umma_idesc(kTileM, 2u * (uint32_t)p.NTp);
             const uint32_t desc_hi = (128u >> 4) | (1u << 14);      // SBO = 128 bytes, descriptor version 1
-            const uint32_t lbo_a16 = p.lbo_a >> 4, plane_a16 = plane_a >> 4;
+            const uint32_t lbo_m16 = p.lbo_main >> 4, lbo_x16 = p.lbo_aux >> 4;       // A chunk-column strides (16-byte units)
+            const uint32_t plane_m16 = (uint32_t)chunks * lbo_m16, plane_x16 = (uint32_t)chunks * lbo_x16;
             const int ksteps = p.KB >> 4;
             // weight-image strides in 16-byte units: chunk stride = rows of the image (NTp, or 2*NTp for a FiLM stage)
             const uint32_t lbo_b_main = (uint32_t)p.NTp, lbo_b_film = 2u * (uint32_t)p.NTp;
             const uint32_t plane_b_main = (uint32_t)chunks * lbo_b_main, plane_b_film = (uint32_t)chunks * lbo_b_film;
-            const uint32_t a_lbo_field = lbo_a16 << 16;
             const uint32_t a_stage16 = p.a_stage_bytes >> 4, stage16 = stage_bytes >> 4;
             const uint32_t base16 = (smem_base & 0x3FFFFu) >> 4;
             const bool halo_main = p.halo != 0;
             uint32_t s = 0, ph = 0, tcount = 0;
             Tracer tr(leader ? p.trace : nullptr, 1);
-            for (long long tile = tile_beg; tile < tile_end; ++tile, ++tcount) {
+            TileWalk tw(p, tile_beg);
+            for (long long tile = tile_beg; tile < tile_end; ++tile, ++tcount, tw.next(p)) {
                 const uint32_t buf = tcount & 1u, buse = tcount >> 1;
                 if (buse > 0) {                                         // epilogue must have drained this accumulator
                     mbar_wait(acc_empty + 8u * buf, (buse - 1) & 1u);
                     tc_fence_after();
                 }
                 tr.log(1, 0, (int)tcount, 0);
+                // where window slot 0 sits inside a stage (see the producers): operand row of slot 0, modulo 8
+                uint32_t off_m = 0, off_x = 0;
+                if (halo_main) {
+                    const long long st = (long long)tw.bq * p.T + tw.tt0;
+                    off_m = (uint32_t)(st - p.dil + 64) & 7u;
+                    off_x = (uint32_t)(st + 64) & 7u;
+                }
                 const uint32_t d_base = tmem + buf * acc_cols;
                 for (int i = 0; i < n_stage; ++i) {
                     const uint32_t full = bar_base + 8u * s, empty = bar_base + 8u * (p.ring + s);
@@ -471,7 +515,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const TcKParams p)
                     const uint32_t lbo_b = is_film ? lbo_b_film : lbo_b_main;
                     const uint32_t plane_b = is_film ? plane_b_film : plane_b_main;
                     // low descriptor words: start address | LBO (16-byte units); only the start address moves
-                    const uint32_t a_lo0 = (base16 + s * stage16) | a_lbo_field;
+                    const uint32_t lbo_a16 = is_aux ? lbo_x16 : lbo_m16, plane_a16 = is_aux ? plane_x16 : plane_m16;
+                    const uint32_t a_lo0 = (base16 + s * stage16 + (is_aux ? off_x : off_m)) | (lbo_a16 << 16);
                     const uint32_t b_lo0 = (base16 + s * stage16 + a_stage16) | (lbo_b << 16);
                     mbar_wait(full, ph);
                     tc_fence_after();
@@ -792,6 +837,36 @@ int tc_trace_dump(const char* path) {
     return 0;
 }
 
+// ---- TMA tensor maps -------------------------------------------------------------------------------
+typedef CUresult (*TmEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmEncodeFn tm_encode_fn() {
+    static TmEncodeFn fn = [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            ptr = nullptr;
+        return (TmEncodeFn)ptr;
+    }();
+    return fn;
+}
+// Chunk-major bf16 plane with `rows` rows and `nch` 8-channel chunks, viewed as [nch][ceil(rows / 8)][64 elements]
+// (8 consecutive rows of a chunk are 128 contiguous bytes); box = [box_ch][groups][64].  Row groups past the end and
+// chunks past `nch` arrive as zeros (the channel padding of a K-stage needs exactly that).
+static int make_plane_map(CUtensorMap* m, const bf16* base, long long rows, int nch, int box_ch, int groups) {
+    TmEncodeFn enc = tm_encode_fn();
+    TVC_REQUIRE(enc, "tc_conv: cuTensorMapEncodeTiled is not available");
+    const cuuint64_t dims[3] = {64, (cuuint64_t)((rows + 7) / 8), (cuuint64_t)nch};
+    const cuuint64_t strides[2] = {128, (cuuint64_t)rows * 16};
+    const cuuint32_t box[3] = {64, (cuuint32_t)groups, (cuuint32_t)box_ch};
+    const cuuint32_t es[3] = {1, 1, 1};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TVC_REQUIRE(r == CUDA_SUCCESS, "tc_conv: cuTensorMapEncodeTiled failed (%d) rows=%lld chunks=%d", (int)r, rows, nch);
+    return 0;
+}
+
 int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     TVC_REQUIRE(W.w && a.a_hi && a.a_lo, "tc_conv: missing weights or input");
     TVC_REQUIRE(a.B > 0 && a.T > 0, "tc_conv: empty problem B=%d T=%d", a.B, a.T);
@@ -817,9 +892,27 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     p.tiles_per_utt = tpu;
     p.R = p.halo ? kTileM + 2 * a.dil : kTileM;
     TVC_REQUIRE(a.dil >= 1 && a.dil <= 64, "tc_conv: dilation %d out of range", a.dil);
-    p.lbo_a = (uint32_t)(p.R | 1) * 16u;                          // odd number of 16-byte slots: conflict-free stores
+    // Stage geometry: a main / aux stage holds G row groups of 8 rows per chunk column: the window (R or 128 rows) plus
+    // up to 7 leading rows, because a TMA box starts on a multiple of 8 operand rows.
+    const int g_main = p.halo ? (p.R + 7 + 7) / 8 : kTileM / 8;
+    const int g_aux = p.halo ? (kTileM + 7 + 7) / 8 : kTileM / 8;
+    p.lbo_main = (uint32_t)g_main * 128u;
+    p.lbo_aux = (uint32_t)g_aux * 128u;
     const int n_rows_max = W.aux_mode == TC_AUX_FILM ? 2 * W.NTp : W.NTp;
-    p.a_stage_bytes = (uint32_t)align_up(2 * (W.KB / 8) * (int)p.lbo_a, 128);         // 2 planes x KB/8 chunks x rows x 16 B
+    const uint32_t lbo_max = (W.aux_mode && p.lbo_aux > p.lbo_main) ? p.lbo_aux : p.lbo_main;
+    p.a_stage_bytes = (uint32_t)align_up(2 * (W.KB / 8) * (int)lbo_max, 128);         // 2 planes x KB/8 chunk columns
+    static const int tma_env = getenv("TVC_TC_TMA") ? atoi(getenv("TVC_TC_TMA")) : 1;
+    memset(&p.tm_a_hi, 0, 4 * sizeof(CUtensorMap));
+    p.tma_main = (tma_env && (p.halo || W.taps == 1)) ? 1 : 0;
+    p.tma_aux = (tma_env && W.aux_mode != TC_AUX_NONE) ? 1 : 0;
+    if (p.tma_main) {
+        TVC_TRY(make_plane_map(&p.tm_a_hi, a.a_hi, p.rows, a.a_cs / 8, W.KB / 8, g_main));
+        TVC_TRY(make_plane_map(&p.tm_a_lo, a.a_lo, p.rows, a.a_cs / 8, W.KB / 8, g_main));
+    }
+    if (p.tma_aux) {
+        TVC_TRY(make_plane_map(&p.tm_x_hi, a.x_hi, p.rows, a.x_cs / 8, W.KB / 8, g_aux));
+        TVC_TRY(make_plane_map(&p.tm_x_lo, a.x_lo, p.rows, a.x_cs / 8, W.KB / 8, g_aux));
+    }
     uint32_t b_main = 4u * (uint32_t)W.KB * (uint32_t)W.NTp * (uint32_t)(p.halo ? W.taps : 1);
     uint32_t b_aux = W.aux_mode ? 4u * (uint32_t)W.KB * (uint32_t)n_rows_max : 0u;
     p.b_stage_bytes = b_main > b_aux ? b_main : b_aux;

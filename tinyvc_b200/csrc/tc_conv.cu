@@ -394,6 +394,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                 }
                 const uint32_t off = (uint32_t)(start + 64) & 7u;
                 const bool tma = (is_aux ? p.tma_aux != 0 : (p.tma_main != 0 && (p.halo || p.taps == 1))) && !edge && !(p.dbg & 1);
+                // issue work is spread over the first lanes of three producer warps (a bulk / tensor copy costs its issuing
+                // thread a few hundred cycles): lane 0 of warp 0 books the bytes and fetches the weights, warps 1 and 2 the planes
                 if (j == 0) {
                     const uint32_t t_bytes = tma ? 2u * plane : 0u;
                     if (tile == tile_beg && i < pre) { if (tma) mbar_expect_tx(full, t_bytes); }       // weights already requested
@@ -402,11 +404,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                         mbar_arrive_expect_tx(full, b_bytes + t_bytes);
                         bulk_g2s(a_dst + p.a_stage_bytes, wt, b_bytes, full);
                     }
-                    if (tma) {
-                        const int r8 = (int)((start - off) >> 3);
-                        tma_load_3d(a_dst, is_aux ? &p.tm_x_hi : &p.tm_a_hi, 0, r8, kb * chunks, full);
-                        tma_load_3d(a_dst + plane, is_aux ? &p.tm_x_lo : &p.tm_a_lo, 0, r8, kb * chunks, full);
-                    }
+                } else if (tma && j == 32) {
+                    tma_load_3d(a_dst, is_aux ? &p.tm_x_hi : &p.tm_a_hi, 0, (int)((start - off) >> 3), kb * chunks, full);
+                } else if (tma && j == 64) {
+                    tma_load_3d(a_dst + plane, is_aux ? &p.tm_x_lo : &p.tm_a_lo, 0, (int)((start - off) >> 3), kb * chunks, full);
                 }
                 wt += b_bytes >> 1;
                 int n_ok = (cs >> 3) - kb * chunks;            // chunks of this stage that exist in the tensor; the rest are zero-filled
@@ -488,6 +489,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
             const uint32_t base16 = (smem_base & 0x3FFFFu) >> 4;
             const bool halo_main = p.halo != 0;
             uint32_t s = 0, ph = 0, tcount = 0;
+            // (Alternating tiles between two issuing warps was tried to hide this warp's per-tile scalar work behind the other's
+            // blocking MMA issue: correct up to ~4 tiles per CTA, then the kernel stops making progress -- left out.)
             Tracer tr(leader ? p.trace : nullptr, 1);
             TileWalk tw(p, tile_beg);
             for (long long tile = tile_beg; tile < tile_end; ++tile, ++tcount, tw.next(p)) {

@@ -470,86 +470,125 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         }
     } else if (warp == kMmaWarp) {
         // ================= MMA issuer (one elected lane; the warp runs the loops uniformly) =================
-        // The issuing warp is a single instruction stream: every scalar instruction it spends per MMA is on the
-        // kernel's critical path (it bounded the C = 24 full-rate convs).  Everything that does not change from
-        // stage to stage is hoisted, and a stage's TAPS x KS x 3 MMAs are issued as straight-line code.
+        // This warp is a single instruction stream and, once the operands arrive by TMA, the kernel's critical path: a
+        // full-rate 24-channel tile is 18 MMAs (~940 cycles of blocking issue) and used to cost as much again in scalar
+        // work between them.  So: kernel parameters live in registers (not re-read from the constant bank), the tile
+        // walk is a few adds, main and aux stages have their own loops with pre-built descriptor words, and a stage's
+        // TAPS x KS x 3 MMAs are straight-line code.
         {
             const bool leader = elect_one() != 0;
             const bool issue = leader && !(p.dbg & 2);
-            const uint32_t idesc_main = umma_idesc(kTileM, (uint32_t)p.NTp);
-            const uint32_t idesc_film = umma_idesc(kTileM, 2u * (uint32_t)p.NTp);
             const uint32_t desc_hi = (128u >> 4) | (1u << 14);      // SBO = 128 bytes, descriptor version 1
-            const uint32_t lbo_m16 = p.lbo_main >> 4, lbo_x16 = p.lbo_aux >> 4;       // A chunk-column strides (16-byte units)
-            const uint32_t plane_m16 = (uint32_t)chunks * lbo_m16, plane_x16 = (uint32_t)chunks * lbo_x16;
             const int ksteps = p.KB >> 4;
-            // weight-image strides in 16-byte units: chunk stride = rows of the image (NTp, or 2*NTp for a FiLM stage)
-            const uint32_t lbo_b_main = (uint32_t)p.NTp, lbo_b_film = 2u * (uint32_t)p.NTp;
-            const uint32_t plane_b_main = (uint32_t)chunks * lbo_b_main, plane_b_film = (uint32_t)chunks * lbo_b_film;
-            const uint32_t a_stage16 = p.a_stage_bytes >> 4, stage16 = stage_bytes >> 4;
+            uint32_t ring = (uint32_t)p.ring, NTp = (uint32_t)p.NTp, dil = (uint32_t)p.dil;
+            uint32_t stage16 = stage_bytes >> 4;
             const uint32_t base16 = (smem_base & 0x3FFFFu) >> 4;
+            // low descriptor words without the moving start address: LBO field, and for B the fixed offset inside a stage
+            uint32_t lbo_m16 = p.lbo_main >> 4, lbo_x16 = p.lbo_aux >> 4;
+            uint32_t plane_m16 = (uint32_t)chunks * lbo_m16, plane_x16 = (uint32_t)chunks * lbo_x16;
+            uint32_t a_fld_m = lbo_m16 << 16, a_fld_x = lbo_x16 << 16;
+            const uint32_t lbo_bx = film ? 2u * NTp : NTp;                 // weight-image chunk stride: rows of the image
+            uint32_t plane_bm = (uint32_t)chunks * NTp, plane_bx = (uint32_t)chunks * lbo_bx;
+            uint32_t b_fld_m = (base16 + (p.a_stage_bytes >> 4)) | (NTp << 16), b_fld_x = (base16 + (p.a_stage_bytes >> 4)) | (lbo_bx << 16);
+            uint32_t idesc_m = umma_idesc(kTileM, NTp), idesc_x = film ? umma_idesc(kTileM, 2u * NTp) : idesc_m;
             const bool halo_main = p.halo != 0;
+            int n_aux = p.aux_nkb;
+            // tile walk state (halo mode: operand row of the tile's first output row; only its low 3 bits matter)
+            uint32_t T = (uint32_t)p.T, tt0 = 0, row0 = 0;
+            long long rt_left = 0;
+            {
+                TileWalk tw(p, tile_beg);
+                tt0 = (uint32_t)tw.tt0;
+                row0 = (uint32_t)((long long)tw.bq * p.T + tw.tt0);
+                rt_left = p.row_tiles - tw.row_tile;                      // row tiles until the walk wraps to the next channel tile
+            }
+            // keep them in registers: opaque to the optimiser, so no re-materialisation through LDC in the loops
+            asm volatile("" : "+r"(ring), "+r"(NTp), "+r"(dil), "+r"(stage16), "+r"(lbo_m16), "+r"(lbo_x16), "+r"(plane_m16), "+r"(plane_x16));
+            asm volatile("" : "+r"(a_fld_m), "+r"(a_fld_x), "+r"(plane_bm), "+r"(plane_bx), "+r"(b_fld_m), "+r"(b_fld_x), "+r"(idesc_m), "+r"(idesc_x));
+            asm volatile("" : "+r"(T), "+r"(n_aux));
             uint32_t s = 0, ph = 0, tcount = 0;
-            // (Alternating tiles between two issuing warps was tried to hide this warp's per-tile scalar work behind the other's
-            // blocking MMA issue: correct up to ~4 tiles per CTA, then the kernel stops making progress -- left out.)
             Tracer tr(leader ? p.trace : nullptr, 1);
-            TileWalk tw(p, tile_beg);
-            for (long long tile = tile_beg; tile < tile_end; ++tile, ++tcount, tw.next(p)) {
+            const long long n_my = tile_end - tile_beg;
+            for (long long it = 0; it < n_my; ++it, ++tcount) {
                 const uint32_t buf = tcount & 1u, buse = tcount >> 1;
+                tr.log(1, 4, (int)tcount, 0);
                 if (buse > 0) {                                         // epilogue must have drained this accumulator
                     mbar_wait(acc_empty + 8u * buf, (buse - 1) & 1u);
                     tc_fence_after();
                 }
                 tr.log(1, 0, (int)tcount, 0);
                 // where window slot 0 sits inside a stage (see the producers): operand row of slot 0, modulo 8
-                uint32_t off_m = 0, off_x = 0;
-                if (halo_main) {
-                    const long long st = (long long)tw.bq * p.T + tw.tt0;
-                    off_m = (uint32_t)(st - p.dil + 64) & 7u;
-                    off_x = (uint32_t)(st + 64) & 7u;
-                }
+                const uint32_t off_m = halo_main ? ((row0 - dil + 64u) & 7u) : 0u;
+                const uint32_t off_x = halo_main ? (row0 & 7u) : 0u;
                 const uint32_t d_base = tmem + buf * acc_cols;
-                for (int i = 0; i < n_stage; ++i) {
-                    const uint32_t full = bar_base + 8u * s, empty = bar_base + 8u * (p.ring + s);
-                    const bool is_aux = i >= n_main;
-                    const bool is_film = is_aux && film;
-                    const uint32_t idesc = is_film ? idesc_film : idesc_main;
-                    const uint32_t d = d_base + (is_film ? (uint32_t)p.NTp : 0u);
-                    const uint32_t acc0 = (is_film ? (i == n_main) : (i == 0)) ? 0u : 1u;
-                    const uint32_t lbo_b = is_film ? lbo_b_film : lbo_b_main;
-                    const uint32_t plane_b = is_film ? plane_b_film : plane_b_main;
-                    // low descriptor words: start address | LBO (16-byte units); only the start address moves
-                    const uint32_t lbo_a16 = is_aux ? lbo_x16 : lbo_m16, plane_a16 = is_aux ? plane_x16 : plane_m16;
-                    const uint32_t a_lo0 = (base16 + s * stage16 + (is_aux ? off_x : off_m)) | (lbo_a16 << 16);
-                    const uint32_t b_lo0 = (base16 + s * stage16 + a_stage16) | (lbo_b << 16);
+#define TVC_ISSUE(T_, K_, A_LO, B_LO, PA, PB, LBA, LBB, IDESC, D_, ACC0) \
+    issue_stage<T_, K_>(D_, A_LO, B_LO, dil, 2u * (PB), 2u * (LBA), 2u * (LBB), PA, PB, desc_hi, IDESC, ACC0)
+                // ---- main stages
+                for (int i = 0; i < n_main; ++i) {
+                    const uint32_t full = bar_base + 8u * s, empty = bar_base + 8u * (ring + s);
+                    const uint32_t so = s * stage16;
+                    const uint32_t a_lo0 = (a_fld_m + base16 + so + off_m), b_lo0 = b_fld_m + so;
+                    const uint32_t acc0 = i == 0 ? 0u : 1u;
+                    tr.log(1, 5, (int)tcount, i);
                     mbar_wait(full, ph);
                     tc_fence_after();
                     tr.log(1, 1, (int)tcount, i);
                     if (issue) {
                         // halo mode: a tap is a row offset into the shared window (one 16-byte slot per row) and
                         // selects the tap's weight image (hi + lo planes apart)
-#define TVC_ISSUE(T, K) issue_stage<T, K>(d, a_lo0, b_lo0, (uint32_t)p.dil, 2u * plane_b, 2u * lbo_a16, 2u * lbo_b, plane_a16, plane_b, desc_hi, idesc, acc0)
-                        if (halo_main && !is_aux) {
+                        if (halo_main) {
                             switch (ksteps) {
-                                case 1: TVC_ISSUE(3, 1); break;
-                                case 2: TVC_ISSUE(3, 2); break;
-                                case 3: TVC_ISSUE(3, 3); break;
-                                default: TVC_ISSUE(3, 4); break;
+                                case 1: TVC_ISSUE(3, 1, a_lo0, b_lo0, plane_m16, plane_bm, lbo_m16, NTp, idesc_m, d_base, acc0); break;
+                                case 2: TVC_ISSUE(3, 2, a_lo0, b_lo0, plane_m16, plane_bm, lbo_m16, NTp, idesc_m, d_base, acc0); break;
+                                case 3: TVC_ISSUE(3, 3, a_lo0, b_lo0, plane_m16, plane_bm, lbo_m16, NTp, idesc_m, d_base, acc0); break;
+                                default: TVC_ISSUE(3, 4, a_lo0, b_lo0, plane_m16, plane_bm, lbo_m16, NTp, idesc_m, d_base, acc0); break;
                             }
                         } else {
                             switch (ksteps) {
-                                case 1: TVC_ISSUE(1, 1); break;
-                                case 2: TVC_ISSUE(1, 2); break;
-                                case 3: TVC_ISSUE(1, 3); break;
-                                default: TVC_ISSUE(1, 4); break;
+                                case 1: TVC_ISSUE(1, 1, a_lo0, b_lo0, plane_m16, plane_bm, lbo_m16, NTp, idesc_m, d_base, acc0); break;
+                                case 2: TVC_ISSUE(1, 2, a_lo0, b_lo0, plane_m16, plane_bm, lbo_m16, NTp, idesc_m, d_base, acc0); break;
+                                case 3: TVC_ISSUE(1, 3, a_lo0, b_lo0, plane_m16, plane_bm, lbo_m16, NTp, idesc_m, d_base, acc0); break;
+                                default: TVC_ISSUE(1, 4, a_lo0, b_lo0, plane_m16, plane_bm, lbo_m16, NTp, idesc_m, d_base, acc0); break;
                             }
                         }
-#undef TVC_ISSUE
                     }
                     if (leader) umma_commit(empty);                    // frees the smem stage once these MMAs retire
                     tr.log(1, 2, (int)tcount, i);
-                    if (++s == (uint32_t)p.ring) { s = 0; ph ^= 1u; }
+                    if (++s == ring) { s = 0; ph ^= 1u; }
                 }
+                // ---- aux stages (1x1 on the second input): accumulate into the same columns (TC_AUX_ACC) or feed the
+                //      FiLM scale|shift accumulator next to them
+                for (int i = 0; i < n_aux; ++i) {
+                    const uint32_t full = bar_base + 8u * s, empty = bar_base + 8u * (ring + s);
+                    const uint32_t so = s * stage16;
+                    const uint32_t a_lo0 = (a_fld_x + base16 + so + off_x), b_lo0 = b_fld_x + so;
+                    const uint32_t d = d_base + (film ? NTp : 0u);
+                    const uint32_t acc0 = (film && i == 0) ? 0u : 1u;
+                    tr.log(1, 5, (int)tcount, n_main + i);
+                    mbar_wait(full, ph);
+                    tc_fence_after();
+                    tr.log(1, 1, (int)tcount, n_main + i);
+                    if (issue) {
+                        switch (ksteps) {
+                            case 1: TVC_ISSUE(1, 1, a_lo0, b_lo0, plane_x16, plane_bx, lbo_x16, lbo_bx, idesc_x, d, acc0); break;
+                            case 2: TVC_ISSUE(1, 2, a_lo0, b_lo0, plane_x16, plane_bx, lbo_x16, lbo_bx, idesc_x, d, acc0); break;
+                            case 3: TVC_ISSUE(1, 3, a_lo0, b_lo0, plane_x16, plane_bx, lbo_x16, lbo_bx, idesc_x, d, acc0); break;
+                            default: TVC_ISSUE(1, 4, a_lo0, b_lo0, plane_x16, plane_bx, lbo_x16, lbo_bx, idesc_x, d, acc0); break;
+                        }
+                    }
+                    if (leader) umma_commit(empty);
+                    tr.log(1, 2, (int)tcount, n_main + i);
+                    if (++s == ring) { s = 0; ph ^= 1u; }
+                }
+#undef TVC_ISSUE
                 if (leader) umma_commit(acc_full + 8u * buf);          // accumulators complete -> epilogue
+                tr.log(1, 3, (int)tcount, 0);
+                // next tile of the walk (row tiles first, then the next channel tile starts again at row 0)
+                if (--rt_left == 0) { rt_left = p.row_tiles; tt0 = 0; row0 = 0; }
+                else if (halo_main) {
+                    tt0 += kTileM; row0 += kTileM;
+                    if (tt0 >= T) { row0 += T - tt0; tt0 = 0; }        // first row of the next utterance
+                }
             }
         }
         __syncwarp();

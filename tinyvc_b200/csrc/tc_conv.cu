@@ -6,18 +6,21 @@
 // heads, :143-146 Downsample, :165-171 Upsample, :201 content_in, :206 downs.0) as an implicit GEMM:
 //     M = 128 rows (time), N = NT channels, K = taps * Cin, processed in K-stages of KB channels of one tap.
 //
-// Warp roles (160 threads):
-//   warps 0-3  producers, then epilogue.  Thread r owns tile row r: it gathers that row's 16-byte
-//              channel chunks of both split planes for the stage's tap (time index clamped inside the
-//              utterance = replicate padding) straight into the UMMA K-major core-matrix layout
-//              smem[plane][chunk][row][16 B]; fence.proxy.async; arrive on the stage's `full` mbarrier.
-//              Thread 0 also launches the stage's weight image with one cp.async.bulk (TMA bulk copy,
-//              complete_tx on the same mbarrier); weights are pre-packed in exactly the smem layout.
-//   warp 4     lane 0 waits `full`, issues 3 x KB/16 tcgen05.mma (hi*hi, hi*lo, lo*hi; fp32 accumulate in
-//              TMEM), tcgen05.commit -> the stage's `empty` mbarrier; after the last stage commit -> `acc`.
-//   epilogue   thread r reads TMEM lane r with tcgen05.ld (32x32b), adds bias, applies FiLM
-//              (x*scale+shift from a second accumulator fed by the aux 1x1 on the skip tensor), the
-//              residual, the activation, and writes fp32 and/or re-split bf16 planes, channels-last.
+// Operands are chunk-major split planes (tc_conv.cuh): every 8-channel chunk is a dense [rows][16 B] array, which is also
+// the order of the UMMA K-major smem operand ([chunk][row][16 B]).
+//
+// Warp roles (544 threads, one persistent CTA per SM walking tiles):
+//   warps 13-16  producers.  A K-stage's activation window comes by ONE TMA tensor copy per plane
+//                (cp.async.bulk.tensor.3d over the plane viewed as [chunk][row / 8][128 B]); k = 3 convs share one
+//                (128 + 2*dil)-row window across the taps.  Windows that leave their utterance (replicate padding) and
+//                k = 3 stages of tiles that straddle utterances are gathered per thread with 16-byte cp.async instead.
+//                The stage's weight image (pre-packed in smem order) comes by cp.async.bulk.  Everything completes on the
+//                stage's `full` mbarrier (complete_tx / cp.async.mbarrier.arrive.noinc).
+//   warp 12      lane 0 waits `full`, issues 3 x KB/16 tcgen05.mma per tap (hi*hi, hi*lo, lo*hi; fp32 accumulate in
+//                TMEM), tcgen05.commit -> the stage's `empty` mbarrier; after the last stage commit -> `acc_full`.
+//   warps 0-11   epilogue: tcgen05.ld from the double-buffered TMEM accumulators, bias, FiLM (x*scale+shift from a
+//                second accumulator fed by the aux 1x1 on the skip tensor), residual, activation, fp32 and/or re-split
+//                bf16 planes, chunk-major stores.
 // Every mbarrier wait is bounded (trap after ~2 s) so a protocol bug cannot hang the GPU.
 #include <cuda.h>      // CUtensorMap (types only; cuTensorMapEncodeTiled is resolved through the runtime, no -lcuda)
 #include <cstdlib>
@@ -270,8 +273,8 @@ __device__ __forceinline__ void issue_stage(uint32_t d, uint32_t a_lo0, uint32_t
 //   warps 0-11   epilogue: TMEM lane quarter = warp & 3, column slot = warp >> 2 (8-channel groups
 //                slot, slot+3, ...); accumulators are double-buffered in TMEM
 //   warp  12     TMEM allocation + single-thread tcgen05.mma issue
-//   warps 13-16  producers (thread = tile row): cp.async 16-byte gathers into the smem ring, completion
-//                signalled with cp.async.mbarrier.arrive.noinc, so a producer never waits for its loads
+//   warps 13-16  producers: TMA tensor copies (interior windows, 1x1 / aux stages) or per-thread cp.async gathers (edge
+//                windows, flat k = 3 stages) into the smem ring; a producer never waits for its loads
 // ---------------------------------------------------------------------------------------------
 template <int SPEC>
 __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcKParams p) {

@@ -34,12 +34,15 @@ namespace tvc {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 544;   // 12 epilogue warps + 1 MMA warp + 4 producer warps
+constexpr int kThreads = 576;   // 12 epilogue warps + MMA warp + 4 producer warps + second MMA warp
 
 struct alignas(64) TcKParams {
     // TMA tensor maps of the operand planes, each viewed as [chunk][row / 8][8 rows x 8 channels = 128 B]; the box is
     // [KB/8 chunks][G row groups][128 B] and lands in shared memory as [chunk][row][16 B], the UMMA K-major order
     CUtensorMap tm_a_hi, tm_a_lo, tm_x_hi, tm_x_lo;
+    uint32_t w_bytes;              // > 0: the whole weight image of the (single) channel tile stays resident in shared memory
+                                   //      (loaded once per CTA) instead of travelling with every K-stage
+    int mma2;                      // 1: two MMA-issuing warps, each with its own half of the smem ring (tiles alternate)
     int tma_main, tma_aux;         // which stage types may use them (interior tiles only: no replicate padding inside)
     uint32_t lbo_main, lbo_aux;    // bytes between consecutive 8-channel chunk columns of a main / aux stage (= 128 * G)
     const bf16 *a_hi, *a_lo, *x_hi, *x_lo, *w;
@@ -50,7 +53,8 @@ struct alignas(64) TcKParams {
     long long tile_elems;
     int a_cs, x_cs, res_cs, y32_cs, y_cs;
     int T, dil, taps, nkb, aux_nkb, aux_mode, KB, NT, NTp, Cout;
-    int ring;                      // smem ring depth
+    int ring;                      // smem ring depth in use
+    int ring_alloc;                // slots laid out in shared memory (>= ring)
     long long row_tiles;
     int n_tiles;
     int halo;                      // 1: one stage holds a (128 + 2*dil)-row window shared by the 3 taps (tiles never straddle utterances)
@@ -202,6 +206,7 @@ __host__ __device__ constexpr EpiSpec epi_spec(int i) {
 constexpr int kEpiWarps = 12;      // 4 TMEM lane quarters x 3 column slots
 constexpr int kMmaWarp = 12;
 constexpr int kProdWarp0 = 13;
+constexpr int kMmaWarp2 = 17;     // second MMA-issuing warp: tiles alternate between the two (even: kMmaWarp, odd: kMmaWarp2)
 
 // Walks consecutive tile ids (n_tile * row_tiles + row_tile) without per-tile divisions.
 struct TileWalk {
@@ -284,10 +289,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
     const uint32_t smem_base = smem_u32(smem);
     // barriers: full[ring], empty[ring], acc_full[2], acc_empty[2]
-    const uint32_t bar_base = smem_base + (uint32_t)p.ring * stage_bytes;
+    const uint32_t wreg = smem_base + (uint32_t)p.ring_alloc * stage_bytes;       // resident weight image (w_bytes, may be 0)
+    const uint32_t bar_base = wreg + p.w_bytes;
     const uint32_t acc_full = bar_base + 16u * (uint32_t)p.ring;
     const uint32_t acc_empty = acc_full + 16u;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)p.ring * stage_bytes + 16 * p.ring + 32);
+    const uint32_t wfull = acc_full + 40u;                                        // weights-resident: image has landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)p.ring_alloc * stage_bytes + p.w_bytes + 16 * p.ring + 32);
 
     constexpr bool kGeneric = SPEC < 0;
     constexpr EpiSpec kS = epi_spec(SPEC < 0 ? 0 : SPEC);
@@ -307,6 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
             mbar_init(bar_base + 8u * s, kTileM + 1);              // full: 128 gather arrivals + 1 expect_tx
             mbar_init(bar_base + 8u * (p.ring + s), 1);            // empty: one tcgen05.commit
         }
+        mbar_init(wfull, 1);
         mbar_init(acc_full, 1); mbar_init(acc_full + 8, 1);
         mbar_init(acc_empty, kEpiWarps); mbar_init(acc_empty + 8, kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -317,15 +325,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp >= kProdWarp0) {
+    if (warp >= kProdWarp0 && warp < kMmaWarp2) {
         // ================= producers =================
         // Lane mapping: producer thread j serves tile row j (and window row j + 128 in halo mode) and walks the
         // stage's 8-channel chunks.  With chunk-major operands a warp-level cp.async moves 32 consecutive rows of
         // one chunk: 512 contiguous bytes in global memory and in shared memory (no bank conflicts).
         const int j = tid - kProdWarp0 * 32;
         const long long chunk_bytes = p.rows * 16;     // bytes between consecutive 8-channel chunk arrays of a plane
-        uint32_t s = 0, ph = 0;    // ring slot and the parity of its *previous* use
-        bool wrapped = false;
+        // Ring state per issuing warp: with two MMA warps the ring is split in two halves (tile parity picks the half), so
+        // that every thread meets the phases of the barriers it waits on strictly in order (a parity wait cannot tell
+        // phase u from phase u - 2).  rs = slot inside the half, rp = parity of the slot's previous use.
+        const uint32_t rhalf = p.mma2 ? (uint32_t)p.ring >> 1 : (uint32_t)p.ring;
+        uint32_t rs[2] = {0u, 0u}, rp[2] = {0u, 0u};
+        bool rwrapped[2] = {false, false};
         const int half = (p.taps - 1) >> 1;
         const uint32_t b_tap = 4u * (uint32_t)p.KB * (uint32_t)p.NTp;
         const uint32_t b_main = p.halo ? (uint32_t)p.taps * b_tap : b_tap;
@@ -334,8 +346,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         // Weights do not depend on the previous kernel: the first tile's weight stages (as many as the ring
         // holds) are requested before griddepcontrol.wait, so they land while the previous grid drains.
         int pre = 0;
-        if (tile_beg < tile_end && !(p.dbg & 1)) {
-            pre = n_stage < p.ring ? n_stage : p.ring;
+        if (p.w_bytes) {
+            if (j == 0 && tile_beg < tile_end) {                     // one copy of the whole image (n_tiles == 1)
+                mbar_arrive_expect_tx(wfull, p.w_bytes);
+                bulk_g2s(wreg, p.w, p.w_bytes, wfull);
+            }
+        } else if (tile_beg < tile_end && !(p.dbg & 1)) {
+            pre = n_stage < (int)rhalf ? n_stage : (int)rhalf;
             if (j == 0) {
                 const bf16* w0 = p.w + (long long)tw.n_tile * p.tile_elems;
                 for (int i = 0; i < pre; ++i) {
@@ -368,11 +385,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                 baseT = tw.bq * p.T;
             }
             int tap = 0, kb = 0;
+            const int w = p.mma2 ? (int)((tile - tile_beg) & 1) : 0;          // which issuing warp (= ring half) takes this tile
             for (int i = 0; i < n_stage; ++i) {
+                const uint32_t s = (uint32_t)w * rhalf + rs[w];
                 const uint32_t full = bar_base + 8u * s, empty = bar_base + 8u * (p.ring + s);
                 const bool is_aux = i >= n_main;
                 const uint32_t b_bytes = is_aux ? b_aux : b_main;
-                if (wrapped) mbar_wait(empty, ph);
+                if (rwrapped[w]) mbar_wait(empty, rp[w]);
                 tr.log(0, 0, (int)(tile - tile_beg), i);
                 const uint32_t a_dst = smem_base + s * stage_bytes;
                 const bf16* src_hi = is_aux ? p.x_hi : p.a_hi;
@@ -403,6 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                     const uint32_t t_bytes = tma ? 2u * plane : 0u;
                     if (tile == tile_beg && i < pre) { if (tma) mbar_expect_tx(full, t_bytes); }       // weights already requested
                     else if (p.dbg & 1) mbar_arrive(full);
+                    else if (p.w_bytes) mbar_arrive_expect_tx(full, t_bytes);                           // weights are resident
                     else {
                         mbar_arrive_expect_tx(full, b_bytes + t_bytes);
                         bulk_g2s(a_dst + p.a_stage_bytes, wt, b_bytes, full);
@@ -468,11 +488,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                 if (is_aux || p.halo) { ++kb; }
                 else if (++tap == p.taps) { tap = 0; ++kb; }
                 if (i + 1 == n_main) { kb = 0; tap = 0; }
-                if (++s == (uint32_t)p.ring) { s = 0; ph = wrapped ? ph ^ 1u : 0u; wrapped = true; }
+                if (++rs[w] == rhalf) { rs[w] = 0; rp[w] = rwrapped[w] ? rp[w] ^ 1u : 0u; rwrapped[w] = true; }
             }
         }
-    } else if (warp == kMmaWarp) {
-        // ================= MMA issuer (one elected lane; the warp runs the loops uniformly) =================
+    } else if (warp == kMmaWarp || warp == kMmaWarp2) {
+        // ================= MMA issuers (one elected lane; the warp runs the loops uniformly) =================
         // This warp is a single instruction stream and, once the operands arrive by TMA, the kernel's critical path: a
         // full-rate 24-channel tile is 18 MMAs (~940 cycles of blocking issue) and used to cost as much again in scalar
         // work between them.  So: kernel parameters live in registers (not re-read from the constant bank), the tile
@@ -492,7 +512,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
             uint32_t a_fld_m = lbo_m16 << 16, a_fld_x = lbo_x16 << 16;
             const uint32_t lbo_bx = film ? 2u * NTp : NTp;                 // weight-image chunk stride: rows of the image
             uint32_t plane_bm = (uint32_t)chunks * NTp, plane_bx = (uint32_t)chunks * lbo_bx;
-            uint32_t b_fld_m = (base16 + (p.a_stage_bytes >> 4)) | (NTp << 16), b_fld_x = (base16 + (p.a_stage_bytes >> 4)) | (lbo_bx << 16);
+            // B descriptor words: inside the stage (after the A window), or inside the resident image (stage i at a fixed offset)
+            const bool wres = p.w_bytes != 0;
+            const uint32_t bimg16 = wres ? (wreg & 0x3FFFFu) >> 4 : base16 + (p.a_stage_bytes >> 4);
+            uint32_t b_fld_m = bimg16 | (NTp << 16), b_fld_x = bimg16 | (lbo_bx << 16);
+            uint32_t bstep_m = 0, bstep_x = 0, bx0 = 0;                  // weights-resident: image offsets of the stages (16-byte units)
+            if (wres) {
+                const uint32_t b_tap16 = (4u * (uint32_t)p.KB * NTp) >> 4;
+                bstep_m = p.halo ? (uint32_t)p.taps * b_tap16 : b_tap16;
+                bstep_x = film ? 2u * b_tap16 : b_tap16;
+                bx0 = (uint32_t)n_main * bstep_m;
+            }
             uint32_t idesc_m = umma_idesc(kTileM, NTp), idesc_x = film ? umma_idesc(kTileM, 2u * NTp) : idesc_m;
             const bool halo_main = p.halo != 0;
             int n_aux = p.aux_nkb;
@@ -510,9 +540,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
             asm volatile("" : "+r"(a_fld_m), "+r"(a_fld_x), "+r"(plane_bm), "+r"(plane_bx), "+r"(b_fld_m), "+r"(b_fld_x), "+r"(idesc_m), "+r"(idesc_x));
             asm volatile("" : "+r"(T), "+r"(n_aux));
             uint32_t s = 0, ph = 0, tcount = 0;
-            Tracer tr(leader ? p.trace : nullptr, 1);
+            // Two issuing warps alternate tiles (tile parity = TMEM buffer = half of the smem ring), so one warp's per-tile
+            // scalar work (barrier waits, descriptor set-up, commits) overlaps the other's blocking MMA issue.  Each warp owns
+            // its half of the ring: sharing one ring let a parity wait fall through two uses early (an mbarrier parity wait
+            // cannot tell phase u from phase u - 2 unless the thread has passed every phase in order).
+            const uint32_t mine = warp == kMmaWarp ? 0u : 1u;
+            const uint32_t rhalf = p.mma2 ? (uint32_t)p.ring >> 1 : (uint32_t)p.ring;
+            const uint32_t sbase = mine * rhalf;                          // first slot of this warp's half (single issuer: 0)
+            ring = rhalf;                                                  // wrap point of this warp's slot counter
+            Tracer tr((leader && mine == 0) ? p.trace : nullptr, 1);
             const long long n_my = tile_end - tile_beg;
+            if (wres && n_my > 0) { mbar_wait(wfull, 0u); tc_fence_after(); }
             for (long long it = 0; it < n_my; ++it, ++tcount) {
+              if (p.mma2 ? (tcount & 1u) != mine : mine != 0u) {
+                // the other issuer's tile (single-issuer mode: the second warp idles)
+              } else {
                 const uint32_t buf = tcount & 1u, buse = tcount >> 1;
                 tr.log(1, 4, (int)tcount, 0);
                 if (buse > 0) {                                         // epilogue must have drained this accumulator
@@ -528,9 +570,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     issue_stage<T_, K_>(D_, A_LO, B_LO, dil, 2u * (PB), 2u * (LBA), 2u * (LBB), PA, PB, desc_hi, IDESC, ACC0)
                 // ---- main stages
                 for (int i = 0; i < n_main; ++i) {
-                    const uint32_t full = bar_base + 8u * s, empty = bar_base + 8u * (ring + s);
-                    const uint32_t so = s * stage16;
-                    const uint32_t a_lo0 = (a_fld_m + base16 + so + off_m), b_lo0 = b_fld_m + so;
+                    const uint32_t full = bar_base + 8u * (sbase + s), empty = bar_base + 8u * ((uint32_t)p.ring + sbase + s);
+                    const uint32_t so = (sbase + s) * stage16;
+                    const uint32_t a_lo0 = (a_fld_m + base16 + so + off_m), b_lo0 = b_fld_m + (wres ? (uint32_t)i * bstep_m : so);
                     const uint32_t acc0 = i == 0 ? 0u : 1u;
                     tr.log(1, 5, (int)tcount, i);
                     mbar_wait(full, ph);
@@ -562,9 +604,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                 // ---- aux stages (1x1 on the second input): accumulate into the same columns (TC_AUX_ACC) or feed the
                 //      FiLM scale|shift accumulator next to them
                 for (int i = 0; i < n_aux; ++i) {
-                    const uint32_t full = bar_base + 8u * s, empty = bar_base + 8u * (ring + s);
-                    const uint32_t so = s * stage16;
-                    const uint32_t a_lo0 = (a_fld_x + base16 + so + off_x), b_lo0 = b_fld_x + so;
+                    const uint32_t full = bar_base + 8u * (sbase + s), empty = bar_base + 8u * ((uint32_t)p.ring + sbase + s);
+                    const uint32_t so = (sbase + s) * stage16;
+                    const uint32_t a_lo0 = (a_fld_x + base16 + so + off_x), b_lo0 = b_fld_x + (wres ? bx0 + (uint32_t)i * bstep_x : so);
                     const uint32_t d = d_base + (film ? NTp : 0u);
                     const uint32_t acc0 = (film && i == 0) ? 0u : 1u;
                     tr.log(1, 5, (int)tcount, n_main + i);
@@ -586,6 +628,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
 #undef TVC_ISSUE
                 if (leader) umma_commit(acc_full + 8u * buf);          // accumulators complete -> epilogue
                 tr.log(1, 3, (int)tcount, 0);
+              }
                 // next tile of the walk (row tiles first, then the next channel tile starts again at row 0)
                 if (--rt_left == 0) { rt_left = p.row_tiles; tt0 = 0; row0 = 0; }
                 else if (halo_main) {
@@ -961,13 +1004,19 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     uint32_t b_main = 4u * (uint32_t)W.KB * (uint32_t)W.NTp * (uint32_t)(p.halo ? W.taps : 1);
     uint32_t b_aux = W.aux_mode ? 4u * (uint32_t)W.KB * (uint32_t)n_rows_max : 0u;
     p.b_stage_bytes = b_main > b_aux ? b_main : b_aux;
+    // Weights-resident mode: a layer with a single channel tile whose whole weight image is small keeps it in shared
+    // memory for the life of the CTA (the 24- and 48-channel layers of the two highest rates: every tile used to re-fetch
+    // the same 12-46 KB); the ring then holds activation windows only.
+    static const int wres_env = getenv("TVC_TC_WRES") ? atoi(getenv("TVC_TC_WRES")) : 1;
+    const size_t image_bytes = W.tile_elems * sizeof(bf16);
+    p.w_bytes = (wres_env && W.n_tiles == 1 && image_bytes <= 64 * 1024 && !(dbg & 1)) ? (uint32_t)image_bytes : 0u;
+    if (p.w_bytes) p.b_stage_bytes = 0;
     const uint32_t stage = p.a_stage_bytes + p.b_stage_bytes;
-    const int n_stage = W.taps * W.nkb + W.aux_nkb;
-    (void)n_stage;
-    int ring = (kTcMaxSmem - 256) / (int)stage;
+    int ring = (kTcMaxSmem - 256 - (int)p.w_bytes) / (int)stage;
     ring = ring > 8 ? 8 : ring;
     TVC_REQUIRE(ring >= 1, "tc_conv: a K-stage of %u bytes does not fit shared memory", stage);
     p.ring = ring;
+    p.ring_alloc = ring;
     const uint32_t cols = 2u * (uint32_t)(W.aux_mode == TC_AUX_FILM ? 3 * W.NTp : W.NTp);   // double-buffered accumulators
     uint32_t tc = 32;
     while (tc < cols) tc <<= 1;
@@ -975,9 +1024,14 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     p.tmem_cols = tc;
     p.row_tiles = p.halo ? (long long)a.B * tpu : (p.rows + kTileM - 1) / kTileM;
     p.n_tiles = W.n_tiles;
-    const size_t smem = (size_t)ring * stage + 16 * ring + 64;
+    const size_t smem = (size_t)ring * stage + p.w_bytes + 16 * ring + 64;
     const long long tiles = p.row_tiles * p.n_tiles;
     const unsigned grid = (unsigned)(tiles < g_num_sms ? tiles : g_num_sms);
+    // Two MMA-issuing warps (each with its own half of the ring) when a CTA has several tiles to alternate and the ring
+    // is deep enough that half of it still prefetches ahead.
+    static const int mma2_env = getenv("TVC_TC_MMA2") ? atoi(getenv("TVC_TC_MMA2")) : 1;
+    p.mma2 = (mma2_env && ring >= 4 && tiles >= 2LL * grid) ? 1 : 0;
+    if (p.mma2 && (ring & 1)) p.ring = ring - 1;                   // equal halves (the smem layout keeps the full ring)
     int spec = -1;
     for (int i = 0; i < kNumSpecs; ++i) {
         const EpiSpec e = epi_spec(i);

@@ -1,4 +1,5 @@
 #!/bin/bash
+# tests + bench (+ per-kernel profile) + pipeline trace + config 3/4/5 throughput, one GPU
 set -u
 mkdir -p gpurun_out
 TAG=${1:-q}
@@ -11,4 +12,4 @@ d=json.load(open("gpurun_out/bench_$TAG.json")); print("bench", d["ms_per_step"]
 PY
 tail -3 gpurun_out/bench_$TAG.err
 python tools/trace_run.py "23,43,44,47" gpurun_out/tc_trace_$TAG.txt 2>&1 | tail -1
-python tools/bench_configs.py --configs 4 --steps 3 2>&1 | tail -1
+python tools/bench_configs.py --configs 3,4,5 --steps 3 2>&1 | tail -3

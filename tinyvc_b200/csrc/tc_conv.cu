@@ -9,15 +9,16 @@
 // Operands are chunk-major split planes (tc_conv.cuh): every 8-channel chunk is a dense [rows][16 B] array, which is also
 // the order of the UMMA K-major smem operand ([chunk][row][16 B]).
 //
-// Warp roles (544 threads, one persistent CTA per SM walking tiles):
+// Warp roles (576 threads, one persistent CTA per SM walking tiles):
 //   warps 13-16  producers.  A K-stage's activation window comes by ONE TMA tensor copy per plane
 //                (cp.async.bulk.tensor.3d over the plane viewed as [chunk][row / 8][128 B]); k = 3 convs share one
 //                (128 + 2*dil)-row window across the taps.  Windows that leave their utterance (replicate padding) and
 //                k = 3 stages of tiles that straddle utterances are gathered per thread with 16-byte cp.async instead.
 //                The stage's weight image (pre-packed in smem order) comes by cp.async.bulk.  Everything completes on the
 //                stage's `full` mbarrier (complete_tx / cp.async.mbarrier.arrive.noinc).
-//   warp 12      lane 0 waits `full`, issues 3 x KB/16 tcgen05.mma per tap (hi*hi, hi*lo, lo*hi; fp32 accumulate in
-//                TMEM), tcgen05.commit -> the stage's `empty` mbarrier; after the last stage commit -> `acc_full`.
+//   warps 12,17  MMA issuers (tiles alternate; each owns half of the smem ring and one TMEM accumulator): lane 0 waits
+//                `full`, issues 3 x KB/16 tcgen05.mma per tap (hi*hi, hi*lo, lo*hi; fp32 accumulate in TMEM),
+//                tcgen05.commit -> the stage's `empty` mbarrier; after the last stage commit -> `acc_full`.
 //   warps 0-11   epilogue: tcgen05.ld from the double-buffered TMEM accumulators, bias, FiLM (x*scale+shift from a
 //                second accumulator fed by the aux 1x1 on the skip tensor), residual, activation, fp32 and/or re-split
 //                bf16 planes, chunk-major stores.

@@ -1030,8 +1030,11 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     const unsigned grid = (unsigned)(tiles < g_num_sms ? tiles : g_num_sms);
     // Two MMA-issuing warps (each with its own half of the ring) when a CTA has several tiles to alternate and the ring
     // is deep enough that half of it still prefetches ahead.
-    static const int mma2_env = getenv("TVC_TC_MMA2") ? atoi(getenv("TVC_TC_MMA2")) : 1;
-    p.mma2 = (mma2_env && ring >= 4 && tiles >= 2LL * grid) ? 1 : 0;
+    // Same-box A/B (profiles/r01z_ab_issuer_modes.log): tiles of one K-stage gain 3-6 % from the second issuer, FiLM / deep-K
+    // tiles lose as much, so the default (2) uses it for single-stage tiles only; 1 = wherever eligible, 0 = never.
+    static const int mma2_env = getenv("TVC_TC_MMA2") ? atoi(getenv("TVC_TC_MMA2")) : 2;
+    const int stages_per_tile = (p.halo ? W.nkb : W.taps * W.nkb) + (W.aux_mode ? W.aux_nkb : 0);
+    p.mma2 = (mma2_env && ring >= 4 && tiles >= 2LL * grid && (mma2_env != 2 || stages_per_tile == 1)) ? 1 : 0;   // 2: single-stage tiles only
     if (p.mma2 && (ring & 1)) p.ring = ring - 1;                   // equal halves (the smem layout keeps the full ring)
     int spec = -1;
     for (int i = 0; i < kNumSpecs; ++i) {

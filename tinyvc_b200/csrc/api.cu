@@ -173,6 +173,7 @@ int tvc_set_option(const char* key, const char* value) {
     if (!strcmp(key, "tc_trace")) return tc_trace_arm(value);          // developer: "k0,k1,..." launch ordinals
     if (!strcmp(key, "tc_trace_dump")) return tc_trace_dump(value);    // developer: write the timeline to a file
     if (!strcmp(key, "weight_prefetch")) { set_weight_prefetch(!strcmp(value, "1")); return 0; }
+    if (!strcmp(key, "fused_up")) { set_fused_up(!strcmp(value, "1")); return 0; }
     if (!strcmp(key, "pdl")) {
         g_pdl = !strcmp(value, "1");
         return 0;
@@ -293,7 +294,7 @@ int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, co
     // that set is seen (callers that reuse their buffers -- serving loops, the Python wrapper's cached
     // workspace -- then pay one graph launch instead of ~100 kernel launches per call).
     std::lock_guard<std::mutex> lock(h->mu);
-    const DecoderGraphKey key{content, f0, energy, rand01, out, workspace, B, Lf, g_conv_impl | (g_pdl ? 256 : 0)};
+    const DecoderGraphKey key{content, f0, energy, rand01, out, workspace, B, Lf, g_conv_impl | (g_pdl ? 256 : 0) | (fused_up() ? 512 : 0)};
     ++h->tick;
     for (DecoderGraph& g : h->graphs)
         if (g.key == key) {

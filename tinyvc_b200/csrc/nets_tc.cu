@@ -3,6 +3,7 @@
 // accumulate); activations stay channels-last, chunk-major (tc_conv.cuh) between layers (fp32 where a
 // residual or a resampler needs the exact value, split bf16 planes where the consumer is a conv).
 #include "nets_tc.cuh"
+#include "tc_block.cuh"
 
 #include <cmath>
 #include <string>
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(256) weights_to_l2_kernel(const DecoderTC::Wei
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (l << 7)));
     }
 }
+bool g_fused_up = false;         // tvc_set_option("fused_up", "1"): experimental fused Upsample block at 24 channels
 bool g_weight_prefetch = false;   // measured at config 2 with a flushed L2: 1.074 ms with, 1.064 ms without -> off
 struct ConvCall {
     TcConvArgs a;
@@ -351,6 +353,19 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
                                       {"tc_up2_c1(", "tc_up2_c2(", "tc_up2_c3(", "tc_up2_c4(", "tc_up2_c5("},
                                       {"tc_up3_c1(", "tc_up3_c2(", "tc_up3_c3(", "tc_up3_c4(", "tc_up3_c5("},
                                       {"tc_up4_c1(", "tc_up4_c2(", "tc_up4_c3(", "tc_up4_c4(", "tc_up4_c5("}};
+        if (g_fused_up && c == 24 && tc_up24_block_supported(u.c1, u.c2, u.c3, u.c4, u.c5)) {
+            // experimental: the whole block in one kernel (tc_block.cu); same arithmetic as the five launches below
+            TcUpBlockArgs fa;
+            fa.p_hi = p0.hi; fa.p_lo = p0.lo; fa.c_hi = cond.hi; fa.c_lo = cond.lo; fa.xi = xi; fa.xo = xo; fa.xo_cs = cn;
+            fa.B = B; fa.T = tout;
+            if (!A.dry) {
+                ProfScope ps("tc_up4_fused(", s);
+                TVC_TRY(tc_up24_block_launch(u.c1, u.c2, u.c3, u.c4, u.c5, fa, s));
+            }
+            A.release(m);
+            x = xo; tin = tout;
+            continue;
+        }
         CONV(un[i][0], u.c1, ConvCall(p0, B, tout, 1).out(p1, TC_ACT_LRELU));
         CONV(un[i][1], u.c2, ConvCall(p1, B, tout, 3).aux(cond).res(xi, c).f32(y, c).out(p0, TC_ACT_LRELU));
         CONV(un[i][2], u.c3, ConvCall(p0, B, tout, 9).out(p1, TC_ACT_LRELU));
@@ -365,5 +380,7 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
 }
 
 void set_weight_prefetch(bool on) { g_weight_prefetch = on; }
+void set_fused_up(bool on) { g_fused_up = on; }
+bool fused_up() { return g_fused_up; }
 
 }  // namespace tvc

@@ -34,5 +34,7 @@ struct DecoderTC {
 };
 
 void set_weight_prefetch(bool on);   // tvc_set_option("weight_prefetch", "0"|"1")
+void set_fused_up(bool on);          // tvc_set_option("fused_up", "0"|"1"): experimental fused 24-channel Upsample block
+bool fused_up();
 
 }  // namespace tvc

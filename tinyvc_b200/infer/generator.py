@@ -1,26 +1,62 @@
-"""Drop-in for `module.infer.generator.Generator` (reference module/infer/generator.py:12-34)."""
+"""Drop-in for `module.infer.generator.Generator` (reference module/infer/generator.py:12-34).
+
+The conversion is organised as three device-side stages so that parity tests and the config-3 bench can time and
+compare them one by one:
+
+    analyse    waveform -> (padded waveform, spectrogram, energy, content z, f0)      front end + Encoder
+    retarget   (z, f0)  -> (matched content, shifted f0)                                kNN over the index + pitch shift
+    synthesise (content, f0, energy) -> waveform                                        Decoder
+
+`convert` chains them and is the reference's public call.
+"""
 from __future__ import annotations
 
-from typing import Optional
+from typing import NamedTuple, Optional
 
 import torch
 import torch.nn as nn
 
-from ..tinyvc import Decoder, Encoder, match_features
-from ..utils import autopad_waveform, estimate_energy, shift_frequency, spectrogram
+from .. import tinyvc as _tv
+from .. import utils as _ut
+
+
+class Analysis(NamedTuple):
+    wf: torch.Tensor        # [B, L]        input padded to whole 480-sample frames
+    spec: torch.Tensor      # [B, 961, Lf]
+    energy: torch.Tensor    # [B, 1, L]
+    z: torch.Tensor         # [B, 768, Lf]
+    f0: torch.Tensor        # [B, 1, Lf]
 
 
 class Generator(nn.Module):
-    def __init__(self, encoder: Encoder, decoder: Decoder):
+    def __init__(self, encoder: "_tv.Encoder", decoder: "_tv.Decoder"):
         super().__init__()
-        self.encoder = encoder
-        self.decoder = decoder
+        self.encoder, self.decoder = encoder, decoder
 
+    # ---- stages -----------------------------------------------------------------------------------
+    def analyse(self, wf: torch.Tensor, with_energy: bool = True) -> Analysis:
+        padded = _ut.autopad_waveform(wf)
+        spec = _ut.spectrogram(padded)
+        energy = _ut.estimate_energy(padded) if with_energy else None
+        z, f0 = self.encoder.infer(spec)
+        return Analysis(padded, spec, energy, z, f0)
+
+    def retarget(self, z: torch.Tensor, f0: torch.Tensor, tgt: torch.Tensor, pitch_shift, want_indices: bool = False):
+        if want_indices:
+            zm, idx = _tv.match_features(z, tgt, return_indices=True)
+        else:
+            zm, idx = _tv.match_features(z, tgt), None
+        return zm, _ut.shift_frequency(f0, pitch_shift), idx
+
+    def synthesise(self, content, f0, energy, rand01: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.decoder.infer(content, f0, energy, rand01=rand01)
+
+    # ---- the reference's surface ------------------------------------------------------------------
     @torch.inference_mode()
     def encode(self, wf):
         """wf [B,T] -> (content [B,768,Lf], f0 [B,1,Lf])   (generator.py:18-23)."""
-        spec = spectrogram(autopad_waveform(wf))
-        return self.encoder.infer(spec)
+        a = self.analyse(wf, with_energy=False)
+        return a.z, a.f0
 
     @torch.inference_mode()
     def convert(self, wf, tgt, pitch_shift, f0_estimation="default", device=torch.device("cpu"), *,
@@ -31,16 +67,9 @@ class Generator(nn.Module):
         convert never reads them; infer.py:66 even passes the device string in the f0 slot).
         Keyword-only extras: `rand01` injects the noise draw (see Decoder.infer);
         `return_parts` also returns the intermediates for stage-wise parity checks."""
-        wf = autopad_waveform(wf)
-        spec = spectrogram(wf)
-        energy = estimate_energy(wf)
-        z, f0 = self.encoder.infer(spec)
+        a = self.analyse(wf)
+        zm, f0s, idx = self.retarget(a.z, a.f0, tgt, pitch_shift, want_indices=return_parts)
+        out = self.synthesise(zm, f0s, a.energy, rand01)
         if return_parts:
-            zm, idx = match_features(z, tgt, return_indices=True)
-        else:
-            zm, idx = match_features(z, tgt), None
-        f0s = shift_frequency(f0, pitch_shift)
-        out = self.decoder.infer(zm, f0s, energy, rand01=rand01)
-        if return_parts:
-            return out, dict(spec=spec, energy=energy, z=z, f0=f0, idx=idx, zm=zm, f0s=f0s)
+            return out, dict(spec=a.spec, energy=a.energy, z=a.z, f0=a.f0, idx=idx, zm=zm, f0s=f0s)
         return out

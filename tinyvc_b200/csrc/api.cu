@@ -53,14 +53,14 @@ ProfScope::~ProfScope() {
     cudaEventRecord(g_prof[slot].b, stream);
 }
 
-static std::once_flag g_init_once;
-static int g_init_status = 0;
+// Kernel attributes are per device: the set-up runs the first time each device is seen (every entry point that launches
+// the conv kernels goes through here, so `Decoder().to("cuda:1")` after cuda:0 works in one process).
 static int global_init() {
-    std::call_once(g_init_once, [] {
-        g_init_status = conv1d_init();
-        if (!g_init_status) g_init_status = tc_conv_init();
+    static PerDeviceOnce once;
+    return once.run([] {
+        TVC_TRY(conv1d_init());
+        return tc_conv_init();
     });
-    return g_init_status;
 }
 
 static ParamTable& table_of(int kind) {
@@ -97,12 +97,6 @@ struct IndexModel {
 
 using namespace tvc;
 
-constexpr int kMaxGroups = 4;
-static int g_groups = 1;   // utterance groups captured as parallel graph branches (option "groups")
-// Utterances are independent end to end, so a captured step runs the batch as up to kMaxGroups
-// sub-batches on forked streams: the latency-bound low-rate layers of one group overlap the others'.
-static int decoder_groups(int B) { return B >= 2 * g_groups ? g_groups : 1; }
-
 // A captured CUDA graph of one Decoder.infer launch sequence, valid for one exact set of buffers.
 struct DecoderGraphKey {
     const void *content, *f0, *energy, *rand01, *out, *ws;
@@ -123,16 +117,11 @@ struct tvc_decoder {
     std::vector<DecoderGraph> graphs;          // small LRU cache
     std::vector<DecoderGraphKey> seen;         // buffer sets seen once (a second sighting triggers capture)
     cudaStream_t cap_stream = nullptr;
-    cudaStream_t branch[kMaxGroups - 1] = {};   // extra capture streams: utterance groups run as parallel graph branches
-    cudaEvent_t fork_ev = nullptr, join_ev[kMaxGroups - 1] = {};
     unsigned long long tick = 0;
     ~tvc_decoder() {
         for (DecoderGraph& g : graphs)
             if (g.exec) cudaGraphExecDestroy(g.exec);
         if (cap_stream) cudaStreamDestroy(cap_stream);
-        for (cudaStream_t b : branch) if (b) cudaStreamDestroy(b);
-        if (fork_ev) cudaEventDestroy(fork_ev);
-        for (cudaEvent_t e : join_ev) if (e) cudaEventDestroy(e);
     }
 };
 struct tvc_encoder { EncoderModel m; };
@@ -164,15 +153,8 @@ int tvc_set_option(const char* key, const char* value) {
         set_error("conv_impl: unknown value '%s'", value);
         return 2;
     }
-    if (!strcmp(key, "groups")) {
-        const int g = atoi(value);
-        if (g < 1 || g > kMaxGroups) { set_error("groups: %d not in 1..%d", g, kMaxGroups); return 2; }
-        g_groups = g;
-        return 0;
-    }
     if (!strcmp(key, "tc_trace")) return tc_trace_arm(value);          // developer: "k0,k1,..." launch ordinals
     if (!strcmp(key, "tc_trace_dump")) return tc_trace_dump(value);    // developer: write the timeline to a file
-    if (!strcmp(key, "weight_prefetch")) { set_weight_prefetch(!strcmp(value, "1")); return 0; }
     if (!strcmp(key, "fused_up")) { set_fused_up(!strcmp(value, "1")); return 0; }
     if (!strcmp(key, "pdl")) {
         g_pdl = !strcmp(value, "1");
@@ -254,28 +236,18 @@ int tvc_decoder_destroy(tvc_decoder_t h) { delete h; return 0; }
 static void shapes_ok_msg(int B, int Lf) { set_error("invalid shape B=%d Lf=%d", B, Lf); }
 #define CHECK_SHAPES() do { if (B <= 0 || Lf <= 0 || (long long)B * Lf * 480 > (1LL << 31) - 1) { shapes_ok_msg(B, Lf); return 2; } } while (0)
 
-static size_t decoder_ws_one(int B, int Lf) {
-    static DecoderModel shape_only;   // dry runs never touch weights
-    // the larger of the two execution plans, so the caller's buffer fits whichever option is active
+size_t tvc_decoder_workspace_bytes(int B, int Lf) {
+    if (B <= 0 || Lf <= 0) return 0;
+    static DecoderModel shape_only;   // dry runs never touch weights (nor any mutable state of the model)
+    // the larger of the two execution plans, so the caller's buffer fits whichever option is active; the plan is passed
+    // explicitly (no global is touched: other threads may be inside tvc_decoder_infer)
     size_t need = 0;
-    const int saved = g_conv_impl;
     for (int impl : {CONV_IMPL_FP32, CONV_IMPL_TC}) {
-        g_conv_impl = impl;
         Arena A(nullptr, 0, true);
-        const int r = shape_only.infer(A, 0, nullptr, nullptr, nullptr, nullptr, nullptr, B, Lf);
-        g_conv_impl = saved;
-        if (r) return 0;
+        if (shape_only.infer(A, 0, nullptr, nullptr, nullptr, nullptr, nullptr, B, Lf, impl)) return 0;
         need = A.peak > need ? A.peak : need;
     }
     return need + 256;
-}
-
-size_t tvc_decoder_workspace_bytes(int B, int Lf) {
-    if (B <= 0 || Lf <= 0) return 0;
-    // whole batch in one piece, or kMaxGroups concurrent sub-batches (graph branches), whichever is larger
-    const size_t whole = decoder_ws_one(B, Lf);
-    const size_t grouped = B >= 2 * kMaxGroups ? (size_t)kMaxGroups * (decoder_ws_one((B + kMaxGroups - 1) / kMaxGroups, Lf) + 256) : 0;
-    return whole > grouped ? whole : grouped;
 }
 
 int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, const float* energy,
@@ -283,18 +255,19 @@ int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, co
                       void* stream) {
     API_BEGIN
     TVC_REQUIRE(h && content && f0 && energy && out && workspace, "tvc_decoder_infer: null argument");
-    TVC_REQUIRE(rand01 || g_conv_impl == CONV_IMPL_TC, "tvc_decoder_infer: the fp32 plan needs an injected rand01 draw");
+    const int impl = g_conv_impl;     // read once: the whole call runs one plan
+    TVC_REQUIRE(rand01 || impl == CONV_IMPL_TC, "tvc_decoder_infer: the fp32 plan needs an injected rand01 draw");
     CHECK_SHAPES();
     cudaStream_t s = (cudaStream_t)stream;
     if (!g_use_graphs || g_prof_on) {
         Arena A(workspace, workspace_bytes, false);
-        return h->m.infer(A, s, content, f0, energy, rand01, out, B, Lf);
+        return h->m.infer(A, s, content, f0, energy, rand01, out, B, Lf, impl);
     }
     // CUDA-graph replay: the launch sequence for one exact set of buffers is captured the second time
     // that set is seen (callers that reuse their buffers -- serving loops, the Python wrapper's cached
     // workspace -- then pay one graph launch instead of ~100 kernel launches per call).
     std::lock_guard<std::mutex> lock(h->mu);
-    const DecoderGraphKey key{content, f0, energy, rand01, out, workspace, B, Lf, g_conv_impl | (g_pdl ? 256 : 0) | (fused_up() ? 512 : 0)};
+    const DecoderGraphKey key{content, f0, energy, rand01, out, workspace, B, Lf, impl | (g_pdl ? 256 : 0) | (plan_options() << 9)};
     ++h->tick;
     for (DecoderGraph& g : h->graphs)
         if (g.key == key) {
@@ -309,36 +282,15 @@ int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, co
         if (h->seen.size() >= 32) h->seen.erase(h->seen.begin());
         h->seen.push_back(key);
         Arena A(workspace, workspace_bytes, false);
-        return h->m.infer(A, s, content, f0, energy, rand01, out, B, Lf);
+        return h->m.infer(A, s, content, f0, energy, rand01, out, B, Lf, impl);
     }
     if (!h->cap_stream) TVC_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
     const unsigned long long n0 = g_launches.load();
-    const int G = decoder_groups(B);
-    for (int g = 0; g + 1 < G; ++g) {
-        if (!h->branch[g]) TVC_CUDA(cudaStreamCreateWithFlags(&h->branch[g], cudaStreamNonBlocking));
-        if (!h->join_ev[g]) TVC_CUDA(cudaEventCreateWithFlags(&h->join_ev[g], cudaEventDisableTiming));
-    }
-    if (!h->fork_ev) TVC_CUDA(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
     TVC_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
     int rc = 0;
     {
-        const long long L = (long long)Lf * kFrame;
-        const int per = (B + G - 1) / G;
-        const size_t slice = (workspace_bytes / (size_t)G) & ~(size_t)255;
-        if (G > 1) cudaEventRecord(h->fork_ev, h->cap_stream);
-        for (int g = 0; g < G && !rc; ++g) {
-            const int b0 = g * per, nb = (b0 + per <= B ? per : B - b0);
-            if (nb <= 0) continue;
-            cudaStream_t bs = g == 0 ? h->cap_stream : h->branch[g - 1];
-            if (g > 0) cudaStreamWaitEvent(bs, h->fork_ev, 0);
-            Arena A((char*)workspace + (size_t)g * slice, slice, false);
-            rc = h->m.infer(A, bs, content + (long long)b0 * kContent * Lf, f0 + (long long)b0 * Lf, energy + b0 * L,
-                            rand01 ? rand01 + (long long)b0 * kBins * Lf : nullptr, out + b0 * L, nb, Lf);
-            if (g > 0) {
-                cudaEventRecord(h->join_ev[g - 1], bs);
-                cudaStreamWaitEvent(h->cap_stream, h->join_ev[g - 1], 0);
-            }
-        }
+        Arena A(workspace, workspace_bytes, false);
+        rc = h->m.infer(A, h->cap_stream, content, f0, energy, rand01, out, B, Lf, impl);
     }
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);

@@ -142,11 +142,8 @@ int dwconv_ln(const float* x, float* y, const float* w, const float* wb, const f
     const size_t smem = sizeof(float) * ((size_t)C * 33 + 64);
     TVC_REQUIRE(smem <= 200 * 1024, "dwconv_ln: C=%d too large for the shared-memory tile", C);
     TVC_REQUIRE(!(w && x == y), "dwconv_ln: the conv form is not in-place safe");
-    static bool attr_done = false;   // idempotent; racing threads set the same value
-    if (!attr_done) {
-        TVC_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
-    }
+    static PerDeviceOnce attr;
+    TVC_TRY(attr.run([] { TVC_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); return 0; }));
     dim3 grid(cdiv(T, kLnTT), B);
     dwconv_ln_kernel<<<grid, 256, smem, s>>>(x, y, w, wb, gamma, beta, C, T, dil, 1e-5f);
     TVC_LAUNCH_CHECK();

@@ -89,7 +89,6 @@ DecoderTC::~DecoderTC() {
     for (auto& u : up) { u.c1.free_all(); u.c2.free_all(); u.c3.free_all(); u.c4.free_all(); u.c5.free_all(); }
     if (w7_buf) cudaFree(w7_buf);
     if (rng_state) cudaFree(rng_state);
-    if (spans) cudaFree(spans);
 }
 
 int DecoderTC::init(const WeightStore& store) {
@@ -190,17 +189,6 @@ int DecoderTC::init(const WeightStore& store) {
     out_w = store.raw(fn + ".output_layer.weight");
     out_b = store.raw(fn + ".output_layer.bias");
     TVC_REQUIRE(out_w && out_b, "tc weights: missing output layer");
-    {
-        std::vector<WeightSpan> sp;
-        auto add = [&](const TcConvW& W) { if (W.w) sp.push_back({W.w, (unsigned long long)W.tile_elems * W.n_tiles * sizeof(bf16)}); };
-        add(frame_in); add(heads); add(dft_cos); add(dft_sin); add(down0);
-        for (auto& m : mid) { add(m.c2); add(m.c3); }
-        for (auto& d : down) { add(d.c1); add(d.c2); add(d.c3); }
-        for (auto& u : up) { add(u.c1); add(u.c2); add(u.c3); add(u.c4); add(u.c5); }
-        n_spans = (int)sp.size();
-        TVC_CUDA(cudaMalloc(&spans, sizeof(WeightSpan) * sp.size()));
-        TVC_CUDA(cudaMemcpy(spans, sp.data(), sizeof(WeightSpan) * sp.size(), cudaMemcpyHostToDevice));
-    }
     TVC_CUDA(cudaMalloc(&rng_state, 2 * sizeof(unsigned long long)));
     TVC_CUDA(cudaMemset(rng_state, 0, 2 * sizeof(unsigned long long)));
     ready = true;
@@ -217,17 +205,9 @@ int DecoderTC::init(const WeightStore& store) {
 #define ARENA_OK() TVC_REQUIRE(!A.overflow, "workspace too small: need at least %zu bytes, got %zu", A.peak, A.cap)
 
 namespace {
-// One pass over all packed weights with prefetch.global.L2 (128-byte lines); no data reaches the SM.
-__global__ void __launch_bounds__(256) weights_to_l2_kernel(const DecoderTC::WeightSpan* __restrict__ spans, int n) {
-    for (int i = 0; i < n; ++i) {
-        const char* p = (const char*)spans[i].p;
-        const unsigned long long lines = (spans[i].bytes + 127) >> 7;
-        for (unsigned long long l = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; l < lines; l += (unsigned long long)gridDim.x * blockDim.x)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (l << 7)));
-    }
-}
-bool g_fused_up = false;         // tvc_set_option("fused_up", "1"): experimental fused Upsample block at 24 channels
-bool g_weight_prefetch = false;   // measured at config 2 with a flushed L2: 1.074 ms with, 1.064 ms without -> off
+// tvc_set_option("fused_up", "0"): run the 24-channel Upsample block as five tc_conv launches instead of the fused block
+// kernel (tc_block.cu).  The two are bit-identical (tests/test_gpu_fused_block.py); fused is 263 -> 146 us at config 2.
+bool g_fused_up = true;
 struct ConvCall {
     TcConvArgs a;
     ConvCall(const Pl& in, int B, int T, int dil = 1) {
@@ -254,11 +234,6 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
     const int L = Lf * kFrame;
     const long long rowsF = (long long)B * Lf, rowsL = (long long)B * L;
     const size_t m0 = A.mark();
-    if (!A.dry && spans && g_weight_prefetch) {
-        ProfScope ps("weights_to_l2(", s);
-        weights_to_l2_kernel<<<148 * 2, 256, 0, s>>>(spans, n_spans);
-        TVC_LAUNCH_CHECK();
-    }
 
     // ---- frame-rate inputs -> [SourceNet x (128) | FilterNet x0 (384)], channels-last fp32 [rowsF][512]
     float* e_fr = A.f32(rowsF);
@@ -354,7 +329,7 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
                                       {"tc_up3_c1(", "tc_up3_c2(", "tc_up3_c3(", "tc_up3_c4(", "tc_up3_c5("},
                                       {"tc_up4_c1(", "tc_up4_c2(", "tc_up4_c3(", "tc_up4_c4(", "tc_up4_c5("}};
         if (g_fused_up && c == 24 && tc_up24_block_supported(u.c1, u.c2, u.c3, u.c4, u.c5)) {
-            // experimental: the whole block in one kernel (tc_block.cu); same arithmetic as the five launches below
+            // the whole block in one kernel (tc_block.cu); same arithmetic as the five launches below
             TcUpBlockArgs fa;
             fa.p_hi = p0.hi; fa.p_lo = p0.lo; fa.c_hi = cond.hi; fa.c_lo = cond.lo; fa.xi = xi; fa.xo = xo; fa.xo_cs = cn;
             fa.B = B; fa.T = tout;
@@ -379,8 +354,8 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
     return 0;
 }
 
-void set_weight_prefetch(bool on) { g_weight_prefetch = on; }
 void set_fused_up(bool on) { g_fused_up = on; }
 bool fused_up() { return g_fused_up; }
+unsigned plan_options() { return g_fused_up ? 1u : 0u; }
 
 }  // namespace tvc

@@ -18,12 +18,6 @@ struct DecoderTC {
     struct Up { TcConvW c1, c2, c3, c4, c5; } up[5];
     const float *out_w = nullptr, *out_b = nullptr;
     float* w7_buf = nullptr;      // depth-wise weights repacked [3][7][128]
-    // {pointer, bytes} of every packed weight image: one kernel at the start of a step pulls them into L2, so that a
-    // step that starts with a cold L2 (serving after other work, the benchmark's flush) does not pay a DRAM round trip
-    // at the head of each of the ~50 latency-bound conv launches
-    struct WeightSpan { const void* p; unsigned long long bytes; };
-    WeightSpan* spans = nullptr;
-    int n_spans = 0;
     unsigned long long* rng_state = nullptr;   // device {seed, step} of the noise generator (used when no draw is injected)
     bool ready = false;
     ~DecoderTC();
@@ -33,8 +27,8 @@ struct DecoderTC {
               float* out, int B, int Lf) const;
 };
 
-void set_weight_prefetch(bool on);   // tvc_set_option("weight_prefetch", "0"|"1")
-void set_fused_up(bool on);          // tvc_set_option("fused_up", "0"|"1"): experimental fused 24-channel Upsample block
+void set_fused_up(bool on);          // tvc_set_option("fused_up", "0"|"1"): fused 24-channel Upsample block (default on)
 bool fused_up();
+unsigned plan_options();             // bit set of the options that change the launch plan (part of the graph-cache key)
 
 }  // namespace tvc

@@ -192,11 +192,8 @@ int phase_vocoder_run(const float* ab, long long a_stride, long long b_off, cons
                       long long out_stride, int S, int n, cudaStream_t s) {
     TVC_REQUIRE(n >= 2 && n <= 8192, "phase_vocoder: cross-fade length %d out of range [2, 8192]", n);
     const size_t smem = sizeof(float) * 4 * (size_t)n;
-    static bool attr_done = false;
-    if (!attr_done) {
-        TVC_CUDA(cudaFuncSetAttribute(pv_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_done = true;
-    }
+    static PerDeviceOnce attr;
+    TVC_TRY(attr.run([] { TVC_CUDA(cudaFuncSetAttribute(pv_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); return 0; }));
     pv_dft_kernel<<<S, 1024, smem, s>>>(ab, a_stride, b_off, fade_in, bins, n);
     TVC_LAUNCH_CHECK();
     pv_synth_kernel<<<dim3(cdiv(n, 256), S), 256, sizeof(float) * 3 * (size_t)(n / 2 + 1), s>>>(ab, a_stride, b_off, fade_in, bins, out,
@@ -211,11 +208,8 @@ int sola_run(const float* y, int y_len, float* sola_buf, const float* fade_in, f
                 y_len, block + cross + search + delay);
     const size_t smem = sizeof(float) * (size_t)(block + 2 * cross + search);
     TVC_REQUIRE(smem <= 200 * 1024, "sola: block/cross/search too large for shared memory (%zu bytes)", smem);
-    static bool attr_done = false;
-    if (!attr_done) {
-        TVC_CUDA(cudaFuncSetAttribute(sola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
-    }
+    static PerDeviceOnce attr;
+    TVC_TRY(attr.run([] { TVC_CUDA(cudaFuncSetAttribute(sola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); return 0; }));
     TVC_REQUIRE(!pv_scratch || block >= cross, "sola: the phase-vocoder cross-fade needs block (%d) >= cross-fade (%d)", block, cross);
     sola_kernel<<<S, 1024, smem, s>>>(y, y_len, sola_buf, fade_in, out_block, shift_out, block, cross, search, delay, pv_scratch);
     TVC_LAUNCH_CHECK();

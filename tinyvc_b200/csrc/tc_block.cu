@@ -363,11 +363,8 @@ int tc_up24_block_launch(const TcConvW& c1, const TcConvW& c2, const TcConvW& c3
     for (int i = 0; i < 4; ++i)
         TVC_REQUIRE(a.dil[i] >= 1 && a.dil[i] <= kBMaxDil, "tc_up24_block: dilation %d out of range", a.dil[i]);
     TVC_REQUIRE(a.dil[0] == 1 && a.dil[0] + a.dil[1] + a.dil[2] + a.dil[3] <= kBHalo, "tc_up24_block: dilations exceed the window halo");
-    static bool attr_set = false;
-    if (!attr_set) {
-        TVC_CUDA(cudaFuncSetAttribute(tc_up24_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlockSmem));
-        attr_set = true;
-    }
+    static PerDeviceOnce attr;
+    TVC_TRY(attr.run([] { TVC_CUDA(cudaFuncSetAttribute(tc_up24_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlockSmem)); return 0; }));
     UpBlockParams p;
     memset(&p, 0, sizeof(p));
     p.rows = (long long)a.B * a.T;

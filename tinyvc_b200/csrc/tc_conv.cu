@@ -134,9 +134,7 @@ struct Tracer {
 //   warps 13-16  producers: TMA tensor copies (interior windows, 1x1 / aux stages) or per-thread cp.async gathers (edge
 //                windows, flat k = 3 stages) into the smem ring; a producer never waits for its loads
 // ---------------------------------------------------------------------------------------------
-// ETMA (experimental, TVC_TC_EDGE_TMA=1): windows that leave their utterance are fetched by the tensor copy as well and the
-// replicate rows are patched in shared memory by the MMA warp; 1x1 (aux) stages never need replicate rows.
-template <int SPEC, bool ETMA = false>
+template <int SPEC>
 __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcKParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     pdl_launch_dependents();      // the next kernel of the plan may start its prologue as soon as SM resources free up
@@ -270,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                     start = row_tile * kTileM;
                 }
                 const uint32_t off = (uint32_t)(start + 64) & 7u;
-                const bool tma = (is_aux ? p.tma_aux != 0 : (p.tma_main != 0 && (p.halo || p.taps == 1))) && (ETMA || !edge) && !(p.dbg & 1);
+                const bool tma = (is_aux ? p.tma_aux != 0 : (p.tma_main != 0 && (p.halo || p.taps == 1))) && !edge && !(p.dbg & 1);
                 // issue work is spread over the first lanes of three producer warps (a bulk / tensor copy costs its issuing
                 // thread a few hundred cycles): lane 0 of warp 0 books the bytes and fetches the weights, warps 1 and 2 the planes
                 if (j == 0) {
@@ -432,32 +430,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                     tr.log(1, 5, (int)tcount, i);
                     mbar_wait(full, ph);
                     tc_fence_after();
-                    if constexpr (ETMA) {
-                        // replicate padding of a window fetched by the tensor copy: slots before t = 0 <- row 0, slots after
-                        // t = T - 1 <- row T - 1 (the copy brought the neighbouring utterances' rows or zeros there)
-                        if (halo_main && p.tma_main && !(p.dbg & 1)) {
-                            const int org = (int)tt0 - (int)dil, win = kTileM + 2 * (int)dil;
-                            const int pad_lo = org < 0 ? -org : 0;
-                            const int hi_first = (int)T - org;                     // first window slot past the utterance
-                            if (pad_lo > 0 || hi_first < win) {
-                                uint8_t* st = smem + (size_t)(sbase + s) * stage_bytes + off_m * 16u;
-                                const int ncol = 2 * chunks;                        // hi chunks, then lo chunks, p.lbo_main apart
-                                for (int idx = lane; idx < ncol * pad_lo; idx += 32) {
-                                    const int q = idx / pad_lo, m = idx - q * pad_lo;
-                                    uint8_t* col = st + (size_t)q * p.lbo_main;
-                                    *reinterpret_cast<uint4*>(col + m * 16) = *reinterpret_cast<const uint4*>(col + pad_lo * 16);
-                                }
-                                const int nh = win - hi_first;
-                                for (int idx = lane; idx < ncol * nh; idx += 32) {
-                                    const int q = idx / nh, m = idx - q * nh;
-                                    uint8_t* col = st + (size_t)q * p.lbo_main;
-                                    *reinterpret_cast<uint4*>(col + (hi_first + m) * 16) = *reinterpret_cast<const uint4*>(col + (hi_first - 1) * 16);
-                                }
-                                fence_proxy_async();
-                                __syncwarp();
-                            }
-                        }
-                    }
                     tr.log(1, 1, (int)tcount, i);
                     if (issue) {
                         // halo mode: a tap is a row offset into the shared window (one 16-byte slot per row) and
@@ -759,15 +731,6 @@ int tc_conv_init() {
     TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
     TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
     TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
-    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<-1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
-    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
-    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
-    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
-    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
-    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
-    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
-    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
-    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
     return 0;
 }
 
@@ -935,23 +898,6 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
         }
     }
     if (g_force_generic) spec = -1;
-    // experimental (not yet validated on hardware): tensor copies for edge windows too, see the kernel's ETMA parameter
-    static const int etma_env = getenv("TVC_TC_EDGE_TMA") ? atoi(getenv("TVC_TC_EDGE_TMA")) : 0;
-    if (etma_env && tma_env && p.halo) {
-        switch (spec) {
-            case 0: TVC_LAUNCH_PDL((tc_conv_kernel<0, true>), grid, kThreads, smem, s, p); break;
-            case 1: TVC_LAUNCH_PDL((tc_conv_kernel<1, true>), grid, kThreads, smem, s, p); break;
-            case 2: TVC_LAUNCH_PDL((tc_conv_kernel<2, true>), grid, kThreads, smem, s, p); break;
-            case 3: TVC_LAUNCH_PDL((tc_conv_kernel<3, true>), grid, kThreads, smem, s, p); break;
-            case 4: TVC_LAUNCH_PDL((tc_conv_kernel<4, true>), grid, kThreads, smem, s, p); break;
-            case 5: TVC_LAUNCH_PDL((tc_conv_kernel<5, true>), grid, kThreads, smem, s, p); break;
-            case 6: TVC_LAUNCH_PDL((tc_conv_kernel<6, true>), grid, kThreads, smem, s, p); break;
-            case 7: TVC_LAUNCH_PDL((tc_conv_kernel<7, true>), grid, kThreads, smem, s, p); break;
-            default: TVC_LAUNCH_PDL((tc_conv_kernel<-1, true>), grid, kThreads, smem, s, p); break;
-        }
-        TVC_LAUNCH_CHECK();
-        return 0;
-    }
     switch (spec) {
         case 0: TVC_LAUNCH_PDL(tc_conv_kernel<0>, grid, kThreads, smem, s, p); break;
         case 1: TVC_LAUNCH_PDL(tc_conv_kernel<1>, grid, kThreads, smem, s, p); break;

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <mutex>
 
 namespace tvc {
 
@@ -47,6 +48,24 @@ struct ProfScope {
             return 2;                                                                          \
         }                                                                                      \
     } while (0)
+
+// Runs `f` once per CUDA device (kernel attributes such as the opt-in shared-memory size are per device, so a second
+// GPU used by the same process needs its own set-up); f returns 0 on success.
+struct PerDeviceOnce {
+    std::mutex mu;
+    unsigned long long done = 0;
+    template <class F>
+    int run(F&& f) {
+        int dev = 0;
+        TVC_CUDA(cudaGetDevice(&dev));
+        TVC_REQUIRE(dev >= 0 && dev < 64, "unsupported device ordinal %d", dev);
+        std::lock_guard<std::mutex> lock(mu);
+        if ((done >> dev) & 1ull) return 0;
+        const int r = f();
+        if (!r) done |= 1ull << dev;
+        return r;
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch (sm_90+): kernels of the decoder plan are launched with

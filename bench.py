@@ -6,7 +6,10 @@
 Workload (N = 1): BASELINE.json configs[1] -- Decoder-only forward, batch = 64, 8192-sample chunks
 (autopadded to 18 frames = 8640 samples), seeded random F0 + content, random
 weights of the reference's architecture.  N > 1: every rank runs the same per-GPU batch on its own
-utterances (utterances are independent; no data-path collective) -> "scaling": "weak".
+utterances (utterances are independent; no data-path collective) -> "scaling": "weak"; in the same run the
+north-star's multi-GPU mode is timed as well (`scatter_gather`): rank 0 holds BASELINE configs[3]'s job
+(512 x N utterances of 10 s), `tinyvc_b200.shard.ShardedDecoder` shards it over the GPUs and returns the
+waveforms to rank 0, with its efficiency against N x the single-GPU rate of the same share.
 
 A step = one `Decoder.infer` over the batch: SourceNet -> harmonic+noise dsp -> FilterNet.
   value : samples/s with inputs resident in HBM, CUDA events, L2 flushed before every timed step,
@@ -39,7 +42,8 @@ BATCH, LF = 64, 18                       # configs[1]: 64 x 8192-sample chunks -
 CONV1D_BYTES_PER_SAMPLE = 3706.3         # every Conv1d reads its input + writes its output once
 COMPULSORY_BYTES_PER_SAMPLE = 22.4       # content 6.4 + energy 4 + out 4 + noise draw 8.0 (+f0)
 FLOP_PER_SAMPLE = 105232.0               # 2 x 52 616 MAC
-FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # CUDA-core FMA peak at max clock (not measured)
+FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12   # CUDA-core FMA peak at max clock; the measured one is used
+C4_SHARE, C4_LF, C4_MB = 512, 500, 64    # configs[3]: 4096 x 10 s over 8 GPUs = 512 utterances of 500 frames per GPU
 METRIC = "decoder audio samples/sec (RTF) at 1/2/4/8 B200 vs host-CPU reference"
 WORKLOAD = "Decoder-only fwd, batch=64, 8192-sample chunks (18 frames = 8640 samples), random F0+content"
 
@@ -162,6 +166,171 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def device_decoder_inputs(n: int, lf: int, dev, seed: int):
+    """Synthetic decoder inputs of SURVEY 8(d)'s distributions generated ON the device (the 4096 x 10 s job is 10 GB:
+    too slow to draw on the host): content ~ N(0,1), f0 random-walk contour 80..800 Hz with ~25 % unvoiced frames in
+    runs, energy ~ U(0,1)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    content = torch.randn(n, 768, lf, device=dev, generator=g)
+    walk = torch.cumsum(0.03 * torch.randn(n, lf, device=dev, generator=g), dim=1)
+    f0 = (220.0 * torch.exp2(walk)).clamp_(80.0, 800.0)
+    period = torch.randint(60, 120, (n, 1), device=dev, generator=g)
+    phase = torch.randint(0, 120, (n, 1), device=dev, generator=g)
+    t = torch.arange(lf, device=dev)[None, :]
+    f0 = torch.where(((t + phase) % period) < period // 4, torch.zeros_like(f0), f0).unsqueeze(1).contiguous()
+    energy = torch.rand(n, 1, lf * FRAME, device=dev, generator=g)
+    return {"content": content, "f0": f0, "energy": energy}
+
+
+def time_events(fn, k: int, warm: int) -> float:
+    """ms per call: CUDA events on the current stream around k calls after `warm` untimed ones."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(k):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / k
+
+
+def other_configs(dec, dev, peak_hbm: float) -> dict:
+    """BASELINE.json configs[2], the per-GPU share of configs[3] and of configs[4] on this GPU (inputs resident in HBM,
+    CUDA events, 2 warm-ups; working sets are far larger than L2)."""
+    from tinyvc_b200 import _lib, synth
+    from tinyvc_b200.infer import BatchedStreamInfer, Generator
+    from tinyvc_b200.tinyvc import Encoder, match_features
+    from tinyvc_b200.utils import estimate_energy, shift_frequency, spectrogram
+    from tinyvc_b200.weights import load_synth_weights
+    out = {}
+    enc = load_synth_weights(Encoder().eval(), seed=7).to(dev)
+    gen = Generator(enc, dec)
+    # ---- configs[2]: Encoder -> kNN(50k) -> Decoder, 256 x 4 s
+    B, T, N = 256, 96000, 50000
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + 3)
+    wf = 0.1 * torch.randn(B, T, device=dev, generator=g)
+    index = torch.randn(1, 768, N, device=dev, generator=g)
+    ms = time_events(lambda: gen.convert(wf, index, 0.0), 3, 2)
+    spec, energy = spectrogram(wf), estimate_energy(wf)
+    z, f0 = enc.infer(spec)
+    zm = match_features(z, index)
+    stages = {"spectrogram+energy": time_events(lambda: (spectrogram(wf), estimate_energy(wf)), 3, 1),
+              "encoder": time_events(lambda: enc.infer(spec), 3, 1),
+              "knn": time_events(lambda: match_features(z, index), 3, 1),
+              "decoder": time_events(lambda: dec.infer(zm, shift_frequency(f0, 0.0), energy), 3, 1)}
+    sps = B * T / ms * 1e3
+    dec_sps = B * T / stages["decoder"] * 1e3
+    out["config3_full_pipeline"] = {
+        "workload": "Encoder -> kNN(50k-vector index) -> Decoder, batch 256 x 4 s clips, 1 GPU", "ms_per_step": ms,
+        "samples_per_s": sps, "stages_ms": {k: round(v, 3) for k, v in stages.items()},
+        "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak_hbm, "achieved": dec_sps * CONV1D_BYTES_PER_SAMPLE / 1e9,
+                     "frac": dec_sps * CONV1D_BYTES_PER_SAMPLE / (peak_hbm * 1e9), "of": "decoder stage, Conv1d-layer model"}}
+    del wf, index, spec, energy, z, f0, zm
+    torch.cuda.empty_cache()
+    # ---- configs[3] share: Decoder 512 x 10 s
+    inp = device_decoder_inputs(C4_SHARE, C4_LF, dev, 1234 + 4)
+    res = torch.empty(C4_SHARE, C4_LF * FRAME, device=dev)
+
+    def c4():
+        for o in range(0, C4_SHARE, C4_MB):
+            dec.infer(inp["content"][o:o + C4_MB], inp["f0"][o:o + C4_MB], inp["energy"][o:o + C4_MB], out=res[o:o + C4_MB])
+
+    ms = time_events(c4, 3, 2)
+    sps = C4_SHARE * C4_LF * FRAME / ms * 1e3
+    out["config4_share"] = {
+        "workload": "Decoder batch 512 x 10 s (one GPU's share of 4096 over 8 GPUs), micro-batches of 64", "ms_per_step": ms,
+        "samples_per_s": sps,
+        "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak_hbm, "achieved": sps * CONV1D_BYTES_PER_SAMPLE / 1e9,
+                     "frac": sps * CONV1D_BYTES_PER_SAMPLE / (peak_hbm * 1e9), "of": "whole step, Conv1d-layer model"}}
+    del inp, res
+    torch.cuda.empty_cache()
+    # ---- configs[4] share: 128 concurrent streams, one tick = 1920 new samples per stream
+    S = 128
+    index = torch.randn(1, 768, 2048, device=dev, generator=g)
+    bs = BatchedStreamInfer(gen, S, target=index, device=dev)
+    bs.init_buffer()
+    blocks = 0.1 * torch.randn(S, 1920, device=dev, generator=g)
+    n0 = _lib.launch_count()
+    ms = time_events(lambda: bs.audio_callback(blocks), 20, 3)
+    out["config5_share"] = {
+        "workload": "128 concurrent streams (one GPU's share of 1024), 13 440-sample window, 1 920 new samples per stream per tick",
+        "ms_per_tick": ms, "samples_per_s": S * 1920 / ms * 1e3, "realtime_streams_supported": S * 80.0 / ms,
+        "gpu_launches_per_tick": (_lib.launch_count() - n0) // 23}
+    _lib.WORKSPACE.clear()
+    torch.cuda.empty_cache()
+    return out
+
+
+def scatter_gather(dec, dev, rank: int, world: int, steps: int, barrier) -> dict:
+    """North-star multi-GPU mode at BASELINE configs[3] size: rank 0 holds 512 x N utterances of 10 s; ShardedDecoder
+    shards them over the N GPUs and the waveforms come back to rank 0.  Timed with CUDA events on every rank's stream
+    between barriers, max over ranks; the single-GPU rate of one share (same micro-batching) is measured in the same run
+    on rank 0 so that efficiency = aggregate / (N x single)."""
+    import torch.distributed as dist
+    from tinyvc_b200 import synth
+    from tinyvc_b200.shard import ShardedDecoder
+    sd = ShardedDecoder(dec, dev, micro_batch=C4_MB)
+    n = C4_SHARE * world
+    full = device_decoder_inputs(n, C4_LF, dev, 4321) if rank == 0 else None
+
+    def step():
+        return sd.infer(full["content"], full["f0"], full["energy"]) if rank == 0 else sd.infer()
+
+    for _ in range(2):
+        step()
+    barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    barrier()
+    t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t) / steps
+    samples = n * C4_LF * FRAME
+    res = {"workload": f"Decoder batch {n} x 10 s held by rank 0, sharded over {world} GPUs ({C4_SHARE} per GPU), micro-batches of {C4_MB}",
+           "transport": sd.transport, "value": samples / ms * 1e3, "unit": "samples/s", "ms_per_step": ms, "steps": steps,
+           "utterances": n,
+           "input_bytes_leaving_rank0_per_step": (world - 1) * C4_SHARE * (768 * C4_LF + C4_LF + C4_LF * FRAME) * 4,
+           "output_bytes_entering_rank0_per_step": (world - 1) * C4_SHARE * C4_LF * FRAME * 4,
+           "timing": "CUDA events on each rank's stream around K sharded calls between barriers, max over ranks; "
+                     "transfers and both barriers of every call are inside"}
+    # single-GPU rate of one share, same run, same micro-batching (rank 0, everyone else idle)
+    if rank == 0:
+        res1 = torch.empty(C4_SHARE, C4_LF * FRAME, device=dev)
+
+        def one():
+            for o in range(0, C4_SHARE, C4_MB):
+                dec.infer(full["content"][o:o + C4_MB], full["f0"][o:o + C4_MB], full["energy"][o:o + C4_MB], out=res1[o:o + C4_MB])
+
+        ms1 = time_events(one, max(2, steps // 2), 1)
+        single = C4_SHARE * C4_LF * FRAME / ms1 * 1e3
+        res.update(single_gpu_share={"ms_per_step": ms1, "samples_per_s": single},
+                   speedup_vs_one_gpu=res["value"] / single, efficiency=res["value"] / (world * single))
+        del res1
+    barrier()
+    # parity of the sharded path: a small job with an injected noise draw must equal rank 0 converting it alone, bit for bit
+    small = None
+    if rank == 0:
+        small = {k: v.to(dev) for k, v in synth.decoder_inputs(3 * world + 1, 20, seed=99).items()}
+    sdp = ShardedDecoder(dec, dev, micro_batch=2, transport=sd.transport)
+    got = sdp.infer(small["content"], small["f0"], small["energy"], small["rand01"]) if rank == 0 else sdp.infer()
+    if rank == 0:
+        want = dec.infer(small["content"], small["f0"], small["energy"], rand01=small["rand01"])
+        res["bit_identical_to_one_gpu"] = bool(torch.equal(got, want))
+    barrier()
+    del full
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args) -> None:
     import torch.distributed as dist
     from tinyvc_b200 import _lib, synth
@@ -251,44 +420,18 @@ def run_ours(args) -> None:
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
     clk = clocks.stop() if clocks else None
+    del flush
+    torch.cuda.empty_cache()
 
-    # Optional (--scatter-gather, N > 1): the north-star's other multi-GPU mode -- rank 0 holds the whole job
-    # (world x BATCH utterances), tinyvc_b200.shard scatters utterance blocks over NCCL, every rank converts, rank 0
-    # gathers the waveforms.  Reported as an extra object; `value` stays the collective-free weak-scaling number.
     sg = None
-    if world > 1 and args.scatter_gather:
-        from tinyvc_b200.shard import ShardedDecoder
-        sd = ShardedDecoder(dec, dev, micro_batch=32)
-        full = None
-        if rank == 0:
-            full = {k: v.to(dev) for k, v in synth.decoder_inputs(BATCH * world, LF, seed=4321).items()}
+    if world > 1 and not args.no_scatter_gather:
+        sg = scatter_gather(dec, dev, rank, world, max(2, min(args.steps, 5)), barrier)
 
-        def step_sg():
-            if rank == 0:
-                return sd.infer(full["content"], full["f0"], full["energy"])
-            return sd.infer()
-
-        for _ in range(3):
-            step_sg()
-        barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_sg()
-        torch.cuda.synchronize()
-        barrier()
-        dt = time.perf_counter() - t0
-        tmax = torch.tensor([dt], device=dev, dtype=torch.float64)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        per = float(tmax) / args.steps
-        in_b = sum(v.numel() * 4 for k, v in full.items() if k != "rand01") * (world - 1) // world if rank == 0 else 0
-        sg = {"value": world * samples / per, "unit": "samples/s", "ms_per_step": per * 1e3, "utterances": BATCH * world,
-              "scattered_bytes_per_step": in_b, "gathered_bytes_per_step": (world - 1) * samples * 4,
-              "timing": "host clock around K steps between barriers, max over ranks (transfers are inside)"}
-
-    # per-kernel event profile (separate pass; not part of the timed numbers)
+    # per-launcher event profile: a SEPARATE pass (graph replay off, two events per launch), reported as a breakdown
+    # only -- every roofline figure below comes from the timed steps above
     prof = None
     if rank == 0:
+        flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
         _lib.set_option("profile", "1")
         pk = 3
         for _ in range(pk):
@@ -296,6 +439,7 @@ def run_ours(args) -> None:
             step()
         prof = _lib.profile_report()
         _lib.set_option("profile", "0")
+        del flush
         for v in prof.values():
             v["ms_per_step"] = v["ms"] / pk
             v["launches_per_step"] = v["launches"] / pk
@@ -305,36 +449,43 @@ def run_ours(args) -> None:
         value = world * samples / (ms_step * 1e-3)
         e2e_val = world * samples / (ms_e2e / args.steps * 1e-3)
         peak, peak_src = measured_peak_hbm()
-        conv_ms = sum(v["ms_per_step"] for k, v in prof.items() if k.startswith(("conv1d", "tc_")))
         prof_ms = sum(v["ms_per_step"] for v in prof.values())
+        conv_prof_ms = sum(v["ms_per_step"] for k, v in prof.items() if k.startswith(("conv1d", "tc_")))
         per_gpu_rate = samples / (ms_step * 1e-3)
+        fp32_peak = _lib.measure_fp32_peak(dev)
         traffic = None
         tp = os.path.join(REPO, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("conv1d_dram_bytes_per_step")
+                traffic = json.load(open(tp)).get("decoder_dram_bytes_per_step")
             except Exception:
                 traffic = None
-        achieved = CONV1D_BYTES_PER_SAMPLE * samples / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else None
+        achieved = CONV1D_BYTES_PER_SAMPLE * samples / (ms_step * 1e-3) / 1e9
         roofline = {
-            "bound": "hbm", "kernel": "dense-conv launches of one step (all Conv1d layers: tc_conv_kernel / conv1d_f32_kernel)",
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+            "bound": "hbm",
+            "kernel": "the decoder step as timed (one CUDA-graph replay of all its launches); Conv1d-layer traffic model",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_step": CONV1D_BYTES_PER_SAMPLE * samples,
-            "kernel_ms_per_step": conv_ms, "kernel_share_of_step": conv_ms / prof_ms if prof_ms else None,
+            "kernel_ms_per_step": ms_step, "kernel_share_of_step": 1.0,
             "hbm_conv1d_fraction": per_gpu_rate * CONV1D_BYTES_PER_SAMPLE / (peak * 1e9),
             "hbm_compulsory_fraction": per_gpu_rate * COMPULSORY_BYTES_PER_SAMPLE / (peak * 1e9),
-            "fp32_flop_fraction": per_gpu_rate * FLOP_PER_SAMPLE / (FP32_PEAK_TFLOPS * 1e12),
-            "per_kernel_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items())},
+            "fp32_flop_fraction": per_gpu_rate * FLOP_PER_SAMPLE / (fp32_peak * 1e12),
+            "fp32_peak_tflops_measured": fp32_peak, "fp32_peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL,
+            "breakdown": {"note": "separate profiling pass (graphs off, events per launch: adds ~4 us per launch); shares only",
+                          "dense_conv_share": conv_prof_ms / prof_ms if prof_ms else None,
+                          "per_kernel_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items())}},
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             utts = 16
             rate, ts = oracle_decoder_rate(sd_cpu, host, utts, reps=5, threads=threads)
+            rate1, _ = oracle_decoder_rate(sd_cpu, host, 4, reps=2, threads=1)
             cpu = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port", "cpu": cpu_model(),
                    "sample": f"{utts} of the {BATCH} utterances ({utts * LF * FRAME} samples), median of 5 after 1 warm-up, "
-                             "oracle port of decoder.py on torch-CPU"}
+                             "oracle port of decoder.py on torch-CPU",
+                   "value_1thread": rate1, "sample_1thread": f"4 utterances ({4 * LF * FRAME} samples), median of 2, 1 thread"}
         h2d = sum(pinned[k].numel() * 4 for k in ("content", "f0", "energy"))
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -350,8 +501,14 @@ def run_ours(args) -> None:
         }
         if sg is not None:
             line["scatter_gather"] = sg
+        if world == 1 and not args.no_extra_configs:
+            try:
+                line["other_configs"] = other_configs(dec, dev, peak)
+            except Exception as e:          # the contract line must survive a failure of the extras
+                line["other_configs"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -362,8 +519,9 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle timing (profiler runs)")
-    ap.add_argument("--scatter-gather", action="store_true",
-                    help="N > 1: also time rank-0-holds-the-job scatter -> convert -> gather over NCCL (extra JSON object)")
+    ap.add_argument("--no-scatter-gather", action="store_true",
+                    help="N > 1: skip the sharded configs[3] job (rank 0 holds 512 x N utterances of 10 s)")
+    ap.add_argument("--no-extra-configs", action="store_true", help="N = 1: skip configs[2], the configs[3] share and the configs[4] share")
     ap.add_argument("--conv-impl", default=os.environ.get("TVC_CONV_IMPL", "tc"), choices=["fp32", "tc"])
     args = ap.parse_args()
     if args.impl == "reference":

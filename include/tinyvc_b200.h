@@ -35,9 +35,10 @@ const char* tvc_last_error(void);
 const char* tvc_version(void);
 /* Runtime switches.  ("conv_impl","tc"|"fp32"): Decoder.infer on the tcgen05 tensor-core plan (default)
  * or on the exact-fp32 CUDA-core plan.  ("graphs","1"|"0"): tvc_decoder_infer replays a captured CUDA
- * graph when it is called again with the same buffers (default on).  ("pdl","0"|"1"): launch the plan's
- * kernels with programmatic dependent launch (default off).  ("weight_prefetch","0"|"1"): pull all packed
- * weights into L2 at the start of a step (default off).  ("profile","0"|"1").
+ * graph when it is called again with the same buffers (default on).  ("fused_up","1"|"0"): the 24-channel
+ * Upsample block as one fused kernel (default) or five conv launches.  ("chain","0"|"1"): Downsample 1-4 +
+ * Upsample 0-3 as one persistent cooperative launch with in-kernel grid barriers (see DESIGN.md for the measured
+ * trade-off).  ("pdl","0"|"1"): programmatic dependent launch (default off).  ("profile","0"|"1").
  * Returns non-zero for unknown keys.                                                                */
 int tvc_set_option(const char* key, const char* value);
 /* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
@@ -45,6 +46,13 @@ unsigned long long tvc_launch_count(void);
 /* With option ("profile","1"): per-launcher CUDA-event times since the last report, as a JSON
  * object {"name": {"launches": n, "ms": total}} written to buf.  Synchronises the device.      */
 int tvc_profile_report(char* buf, size_t n);
+/* Measurement aid (bench.py's `fp32_flop_fraction` denominator): sustained CUDA-core FP32 FMA rate of the current
+ * device in TFLOP/s, from a register-resident FMA micro-benchmark timed with CUDA events.            */
+int tvc_measure_fp32_peak(double* tflops, void* stream);
+/* Multi-GPU (tinyvc_b200/shard.py, one process per GPU): lets kernels of the CURRENT device load / store memory of
+ * `peer_device` (cudaDeviceEnablePeerAccess), which is what allows tvc_decoder_infer's last kernel to store its
+ * waveform straight into a result buffer that lives on another GPU of the box (NVLink / NVSwitch).  Idempotent.  */
+int tvc_enable_peer_access(int peer_device);
 
 /* ---- parameter contract: flat fp32 buffers in torch state_dict() order ------------------- */
 /* kind: 0 = Decoder (module/tinyvc/decoder.py:236-251), 1 = Encoder (encoder.py:100-106).     */

@@ -30,7 +30,9 @@ _SIGNATURES = {
     "tvc_version": (c_char_p, []),
     "tvc_set_option": (c_int, [c_char_p, c_char_p]),
     "tvc_launch_count": (ctypes.c_ulonglong, []),
+    "tvc_measure_fp32_peak": (c_int, [ctypes.POINTER(ctypes.c_double), c_void_p]),
     "tvc_profile_report": (c_int, [c_char_p, c_size_t]),
+    "tvc_enable_peer_access": (c_int, [c_int]),
     "tvc_param_count": (c_int, [c_int]),
     "tvc_param_name": (c_char_p, [c_int, c_int]),
     "tvc_param_numel": (c_int64, [c_int, c_int]),
@@ -108,6 +110,16 @@ def set_option(key: str, value: str) -> None:
 
 def launch_count() -> int:
     return int(lib().tvc_launch_count())
+
+
+def measure_fp32_peak(device=None) -> float:
+    """Sustained CUDA-core FP32 FMA rate of the current device in TFLOP/s (FMA micro-benchmark inside the library)."""
+    import torch
+    v = ctypes.c_double(0.0)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    with torch.cuda.device(dev):
+        check(lib().tvc_measure_fp32_peak(ctypes.byref(v), stream_ptr(dev)), "tvc_measure_fp32_peak")
+    return float(v.value)
 
 
 def profile_report() -> dict:

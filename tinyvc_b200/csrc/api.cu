@@ -109,6 +109,7 @@ struct DecoderGraphKey {
 struct DecoderGraph {
     DecoderGraphKey key;
     cudaGraphExec_t exec = nullptr;
+    void* chain_dev = nullptr;       // op tables + grid-barrier counters of the graph's chained launches (ChainSink)
     unsigned long long launches = 0, last_use = 0;
 };
 struct tvc_decoder {
@@ -119,8 +120,10 @@ struct tvc_decoder {
     cudaStream_t cap_stream = nullptr;
     unsigned long long tick = 0;
     ~tvc_decoder() {
-        for (DecoderGraph& g : graphs)
+        for (DecoderGraph& g : graphs) {
             if (g.exec) cudaGraphExecDestroy(g.exec);
+            if (g.chain_dev) cudaFree(g.chain_dev);
+        }
         if (cap_stream) cudaStreamDestroy(cap_stream);
     }
 };
@@ -156,6 +159,7 @@ int tvc_set_option(const char* key, const char* value) {
     if (!strcmp(key, "tc_trace")) return tc_trace_arm(value);          // developer: "k0,k1,..." launch ordinals
     if (!strcmp(key, "tc_trace_dump")) return tc_trace_dump(value);    // developer: write the timeline to a file
     if (!strcmp(key, "fused_up")) { set_fused_up(!strcmp(value, "1")); return 0; }
+    if (!strcmp(key, "chain")) { set_chain(!strcmp(value, "1")); return 0; }
     if (!strcmp(key, "pdl")) {
         g_pdl = !strcmp(value, "1");
         return 0;
@@ -201,6 +205,27 @@ int tvc_profile_report(char* buf, size_t n) {
     js += "}";
     TVC_REQUIRE(js.size() + 1 <= n, "tvc_profile_report: buffer of %zu bytes too small (%zu needed)", n, js.size() + 1);
     memcpy(buf, js.c_str(), js.size() + 1);
+    return 0;
+    API_END
+}
+
+int tvc_measure_fp32_peak(double* tflops, void* stream) {
+    API_BEGIN
+    TVC_REQUIRE(tflops, "tvc_measure_fp32_peak: null argument");
+    return measure_fp32_peak(tflops, (cudaStream_t)stream);
+    API_END
+}
+
+int tvc_enable_peer_access(int peer_device) {
+    API_BEGIN
+    int dev = 0, can = 0;
+    TVC_CUDA(cudaGetDevice(&dev));
+    if (dev == peer_device) return 0;
+    TVC_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    TVC_REQUIRE(can, "tvc_enable_peer_access: device %d cannot address device %d", dev, peer_device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+    TVC_CUDA(e);
     return 0;
     API_END
 }
@@ -286,31 +311,50 @@ int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, co
     }
     if (!h->cap_stream) TVC_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
     const unsigned long long n0 = g_launches.load();
-    TVC_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    DecoderGraph g;
+    ChainSink sink;
+    TVC_CUDA(cudaMalloc(&g.chain_dev, kChainSinkBytes));
+    sink.dev = (unsigned char*)g.chain_dev;
+    sink.cap = kChainSinkBytes;
+    sink.deferred = true;
+    cudaError_t be = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal);
+    if (be != cudaSuccess) {
+        cudaFree(g.chain_dev);
+        TVC_CUDA(be);
+    }
     int rc = 0;
     {
         Arena A(workspace, workspace_bytes, false);
-        rc = h->m.infer(A, h->cap_stream, content, f0, energy, rand01, out, B, Lf, impl);
+        rc = h->m.infer(A, h->cap_stream, content, f0, energy, rand01, out, B, Lf, impl, &sink);
     }
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
-    if (rc) {
+    if (rc || ce != cudaSuccess || !graph) {
         if (graph) cudaGraphDestroy(graph);
-        return rc;
+        cudaFree(g.chain_dev);
+        if (rc) return rc;
+        TVC_REQUIRE(false, "tvc_decoder_infer: graph capture failed: %s", cudaGetErrorString(ce));
     }
-    TVC_REQUIRE(ce == cudaSuccess && graph, "tvc_decoder_infer: graph capture failed: %s", cudaGetErrorString(ce));
-    DecoderGraph g;
+    // op tables of the chained launches (and their zeroed barrier counters): uploaded once, outside the graph
+    sink.host.resize(kChainSinkBytes, 0);
+    if (cudaMemcpy(g.chain_dev, sink.host.data(), kChainSinkBytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        cudaFree(g.chain_dev);
+        TVC_REQUIRE(false, "tvc_decoder_infer: chain table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     g.key = key;
     g.launches = g_launches.load() - n0;
     g.last_use = h->tick;
     const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) cudaFree(g.chain_dev);
     TVC_REQUIRE(ie == cudaSuccess, "tvc_decoder_infer: graph instantiation failed: %s", cudaGetErrorString(ie));
     if (h->graphs.size() >= 8) {               // evict the least recently used
         size_t victim = 0;
         for (size_t i = 1; i < h->graphs.size(); ++i)
             if (h->graphs[i].last_use < h->graphs[victim].last_use) victim = i;
         cudaGraphExecDestroy(h->graphs[victim].exec);
+        if (h->graphs[victim].chain_dev) cudaFree(h->graphs[victim].chain_dev);
         h->graphs.erase(h->graphs.begin() + victim);
     }
     h->graphs.push_back(g);

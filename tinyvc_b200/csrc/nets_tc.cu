@@ -208,6 +208,33 @@ namespace {
 // tvc_set_option("fused_up", "0"): run the 24-channel Upsample block as five tc_conv launches instead of the fused block
 // kernel (tc_block.cu).  The two are bit-identical (tests/test_gpu_fused_block.py); fused is 263 -> 146 us at config 2.
 bool g_fused_up = true;
+// tvc_set_option("chain", "0"): one launch per conv / resampler for the levels below the full rate.  Default: Downsample 1-4
+// and Upsample 0-3 (16 + 24 ops) run as ONE cooperative persistent launch with grid barriers between the ops
+// (tc_conv.cu tc_chain_kernel); same kernels' arithmetic, so the result is bit-identical.
+bool g_chain = false;
+
+// Hands a finished chain to the device: table into the sink (64-byte aligned), two zeroed counters behind it.
+int flush_chain(TcChain& c, ChainSink& sink, cudaStream_t s, const char* name) {
+    if (!c.n_ops) return 0;
+    const size_t off = (size_t)align_up((int64_t)sink.used, 64), bytes = c.table.size();
+    const size_t sync_off = off + (size_t)align_up((int64_t)bytes, 64);
+    TVC_REQUIRE(sync_off + 64 <= sink.cap, "decoder: chain tables need %zu bytes, %zu reserved", sync_off + 64, sink.cap);
+    sink.used = sync_off + 64;
+    if (sink.deferred) {
+        sink.host.resize(sink.used, 0);                              // counters stay zero in the image
+        memcpy(sink.host.data() + off, c.table.data(), bytes);
+    } else {
+        TVC_CUDA(cudaMemcpyAsync(sink.dev + off, c.table.data(), bytes, cudaMemcpyHostToDevice, s));   // pageable: staged before return
+        TVC_CUDA(cudaMemsetAsync(sink.dev + sync_off, 0, 64, s));
+    }
+    {
+        ProfScope ps(name, s);
+        TVC_TRY(tc_chain_launch(sink.dev + off, c.n_ops, reinterpret_cast<unsigned*>(sink.dev + sync_off), s));
+    }
+    c.table.clear();
+    c.n_ops = 0;
+    return 0;
+}
 struct ConvCall {
     TcConvArgs a;
     ConvCall(const Pl& in, int B, int T, int dil = 1) {
@@ -224,16 +251,31 @@ int tc_conv_k(const char* name, const TcConvW& W, const ConvCall& c, cudaStream_
     return tc_conv_launch(W, c.a, s);
 }
 }  // namespace
-#define CONV(name, W, call)                                   \
-    do {                                                      \
-        if (!A.dry) TVC_TRY(tc_conv_k(name, W, call, s));     \
+#define CONV(name, W, call)                                                  \
+    do {                                                                     \
+        if (A.dry) break;                                                    \
+        if (chaining) TVC_TRY(tc_chain_add_conv(chain, W, (call).a));        \
+        else TVC_TRY(tc_conv_k(name, W, call, s));                           \
+    } while (0)
+#define INTERP(x_, B_, Tin_, Tout_, scale_, C_, y32_, rh_, rl_, ah_, al_)                                           \
+    do {                                                                                                            \
+        if (A.dry) break;                                                                                           \
+        if (chaining) TVC_TRY(tc_chain_add_interp(chain, x_, B_, Tin_, Tout_, scale_, C_, y32_, rh_, rl_, ah_, al_)); \
+        else { ProfScope ps__("interp_cl(", s); TVC_TRY(interp_cl(x_, B_, Tin_, Tout_, scale_, C_, y32_, rh_, rl_, ah_, al_, s)); } \
     } while (0)
 
 int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float* f0, const float* energy,
-                     const float* rand01, float* out, int B, int Lf) const {
+                     const float* rand01, float* out, int B, int Lf, ChainSink* sink) const {
     const int L = Lf * kFrame;
     const long long rowsF = (long long)B * Lf, rowsL = (long long)B * L;
     const size_t m0 = A.mark();
+    // chain tables: the caller's sink (captured graph), else a slice of the workspace (always reserved: stable sizing)
+    ChainSink local;
+    local.dev = (unsigned char*)A.bytes(kChainSinkBytes);
+    local.cap = kChainSinkBytes;
+    if (!sink) sink = &local;
+    TcChain chain;
+    bool chaining = false;
 
     // ---- frame-rate inputs -> [SourceNet x (128) | FilterNet x0 (384)], channels-last fp32 [rowsF][512]
     float* e_fr = A.f32(rowsF);
@@ -296,7 +338,8 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         Pl xr = planes(A, rows, cin), xa = planes(A, rows, cin), a = planes(A, rows, cin), c = planes(A, rows, cin);
         ARENA_OK();
         const float scale = (float)(1.0 / (1.0 / (double)fac));   // F.interpolate(scale_factor=1/f)
-        RUN(interp_cl(skip32[i], B, tin, tout, scale, cin, nullptr, xr.hi, xr.lo, xa.hi, xa.lo, s));
+        chaining = g_chain;                                        // Downsample 1-4 and Upsample 0-3: one persistent launch
+        INTERP(skip32[i], B, tin, tout, scale, cin, nullptr, xr.hi, xr.lo, xa.hi, xa.lo);
         const char* const n1[4] = {"tc_down1_c1(", "tc_down2_c1(", "tc_down3_c1(", "tc_down4_c1("};
         const char* const n2[4] = {"tc_down1_c2(", "tc_down2_c2(", "tc_down3_c2(", "tc_down4_c2("};
         const char* const n3[4] = {"tc_down1_c3(", "tc_down2_c3(", "tc_down3_c3(", "tc_down4_c3("};
@@ -322,7 +365,11 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         Pl p0 = planes(A, rows, c), p1 = planes(A, rows, c);
         ARENA_OK();
         const float scale = (float)(1.0 / (double)fac);           // F.interpolate(scale_factor=f)
-        RUN(interp_cl(x, B, tin, tout, scale, c, xi, nullptr, nullptr, p0.hi, p0.lo, s));
+        if (i == 4 && chaining) {                                   // the full-rate block has its own kernel(s)
+            if (!A.dry) TVC_TRY(flush_chain(chain, *sink, s, "tc_chain_low("));
+            chaining = false;
+        }
+        INTERP(x, B, tin, tout, scale, c, xi, nullptr, nullptr, p0.hi, p0.lo);
         const char* const un[5][5] = {{"tc_up0_c1(", "tc_up0_c2(", "tc_up0_c3(", "tc_up0_c4(", "tc_up0_c5("},
                                       {"tc_up1_c1(", "tc_up1_c2(", "tc_up1_c3(", "tc_up1_c4(", "tc_up1_c5("},
                                       {"tc_up2_c1(", "tc_up2_c2(", "tc_up2_c3(", "tc_up2_c4(", "tc_up2_c5("},
@@ -356,6 +403,7 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
 
 void set_fused_up(bool on) { g_fused_up = on; }
 bool fused_up() { return g_fused_up; }
-unsigned plan_options() { return g_fused_up ? 1u : 0u; }
+void set_chain(bool on) { g_chain = on; }
+unsigned plan_options() { return (g_fused_up ? 1u : 0u) | (g_chain ? 2u : 0u); }
 
 }  // namespace tvc

@@ -17,6 +17,7 @@
 // 2^-11 for one TF32 product, which SURVEY.md section 0 shows is not enough for RMSE < 1e-4).
 #pragma once
 #include <cuda_bf16.h>
+#include <vector>
 
 #include "tvc_common.cuh"
 
@@ -70,9 +71,25 @@ struct TcConvArgs {
 };
 int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s);
 int tc_conv_init();
+
+// Chains: several convs (and the linear resamplers between them) as ONE persistent cooperative launch; the ops run in
+// order, separated by grid barriers inside the kernel (tc_conv.cu).  The host builds the table, copies it to device memory
+// (64-byte aligned, tc_chain_op_bytes() per op) and passes it with two zero-initialised counters (`dev_sync`).
+struct TcChain {
+    std::vector<unsigned char> table;
+    int n_ops = 0;
+};
+size_t tc_chain_op_bytes();
+int tc_chain_add_conv(TcChain& c, const TcConvW& W, const TcConvArgs& a);
+// F.interpolate(mode='linear') of chunk-major fp32 rows (tc_kernels.cuh interp_cl: same outputs, same arithmetic)
+int tc_chain_add_interp(TcChain& c, const float* x, int B, int Tin, int Tout, float scale, int C, float* y32, bf16* r_hi,
+                        bf16* r_lo, bf16* a_hi, bf16* a_lo);
+int tc_chain_launch(const void* dev_table, int n_ops, unsigned* dev_sync, cudaStream_t s);
 // developer timeline of selected tc_conv launches (ordinals counted from arming); see tc_conv.cu Tracer
 int tc_trace_arm(const char* ordinals);
 int tc_trace_dump(const char* path);
+
+int measure_fp32_peak(double* tflops, cudaStream_t s);   // tc_ops.cu: FMA micro-benchmark
 
 // layout helpers (tc_ops.cu)
 // extra0/extra1 (nullable, [B*T]) are appended as channels C and C+1 (frame-rate scalars such as log-f0).

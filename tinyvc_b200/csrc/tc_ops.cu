@@ -6,6 +6,21 @@ namespace tvc {
 
 namespace {
 
+// FP32 FMA peak probe: 8 independent chains per thread, all operands in registers.
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (float)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    if (s == 123.456f) out[0] = s;       // never true for the arguments used; keeps the chains alive
+}
+
 __device__ __forceinline__ float act_of(float v, int act) {
     switch (act) {
         case TC_ACT_LRELU: return leaky01(v);
@@ -121,6 +136,35 @@ int planes_to_cf(const bf16* hi, const bf16* lo, float* y, int B, int C, int T, 
     dim3 grid(cdiv(T, 32), cdiv(C, 32), B);
     cl_to_cf_kernel<1><<<grid, 256, 0, s>>>(nullptr, hi, lo, y, C, T, cs);
     TVC_LAUNCH_CHECK();
+    return 0;
+}
+
+int measure_fp32_peak(double* tflops, cudaStream_t s) {
+    int dev = 0, sms = 0;
+    TVC_CUDA(cudaGetDevice(&dev));
+    TVC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float* sink = nullptr;
+    TVC_CUDA(cudaMalloc(&sink, sizeof(float)));
+    cudaEvent_t a, b;
+    TVC_CUDA(cudaEventCreate(&a));
+    TVC_CUDA(cudaEventCreate(&b));
+    const int iters = 1 << 14, blocks = sms * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {            // first repetition warms the clocks up
+        cudaEventRecord(a, s);
+        fma_peak_kernel<<<blocks, 256, 0, s>>>(sink, iters, 0.999f, 0.001f);
+        cudaEventRecord(b, s);
+        TVC_CUDA(cudaEventSynchronize(b));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        const double fl = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+        if (ms > 0.f && fl / (ms * 1e-3) / 1e12 > best) best = fl / (ms * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(sink);
+    TVC_CUDA(cudaGetLastError());
+    *tflops = best;
     return 0;
 }
 

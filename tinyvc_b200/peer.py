@@ -1,0 +1,61 @@
+"""Peer windows: a device tensor of one rank mapped into every rank's address space (CUDA IPC), one box.
+
+The multi-GPU structure of this path is scatter -> convert -> gather with no reduction.  Over NVLink /
+NVSwitch every GPU reaches every peer's HBM directly, so the ranks do not need a two-sided exchange at all: the owner
+publishes its buffers once, the other ranks PULL their utterance blocks out of the owner's input tensors and PUSH
+their waveforms into the owner's result tensor with plain device-to-device copies (`cudaMemcpyPeerAsync` behind
+`Tensor.copy_`: copy engines, no SM is taken from the conv kernels, no NCCL kernel has to be co-scheduled with the
+persistent tcgen05 kernels that fill every SM).  The process group is still needed, but only for control: shipping
+the IPC handles once per buffer set and the two barriers around a step.
+
+One process per GPU, all GPUs visible to every process (torchrun's default).  The handles are the ones
+`torch.multiprocessing` uses to share CUDA tensors between processes (`reduce_tensor`), exchanged with
+`broadcast_object_list`; opening a handle maps the owner's allocation into this process (on the owner's device
+ordinal) and enables peer access between the two GPUs on first use.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+from torch.multiprocessing.reductions import reduce_tensor
+
+
+def export_handles(tensors: Dict[str, torch.Tensor]) -> Dict[str, tuple]:
+    """Picklable IPC descriptions of CUDA tensors (the owner must keep the tensors alive while peers use them)."""
+    out = {}
+    for k, t in tensors.items():
+        if not (t.is_cuda and t.is_contiguous()):
+            raise RuntimeError(f"peer window {k!r}: need a contiguous CUDA tensor")
+        fn, args = reduce_tensor(t)
+        out[k] = (fn, args)
+    return out
+
+
+def open_handles(handles: Dict[str, tuple]) -> Dict[str, torch.Tensor]:
+    """Views of the owner's tensors in this process (device = the owner's ordinal)."""
+    return {k: fn(*args) for k, (fn, args) in handles.items()}
+
+
+def share_from(owner: int, tensors: Optional[Dict[str, torch.Tensor]], group=None) -> Dict[str, torch.Tensor]:
+    """Collective: every rank gets a dict of tensors aliasing the owner's memory (the owner gets its own back)."""
+    rank = dist.get_rank(group)
+    box = [export_handles(tensors) if rank == owner else None]
+    src = dist.get_global_rank(group, owner) if group is not None else owner
+    dist.broadcast_object_list(box, src=src, group=group)
+    if rank == owner:
+        return dict(tensors)
+    return open_handles(box[0])
+
+
+def p2p_available(device: torch.device, owner_device: int) -> bool:
+    """Whether kernels / copy engines of `device` can address the owner's GPU directly."""
+    if device.type != "cuda":
+        return False
+    if device.index == owner_device:
+        return True
+    try:
+        return bool(torch.cuda.can_device_access_peer(device.index, owner_device))
+    except Exception:
+        return False

@@ -168,30 +168,189 @@ def sharded_map(fn: Callable[[Fields], torch.Tensor], fields: Optional[Fields], 
     return None
 
 
+class _P2PState:
+    """Per (buffer set) state of the one-sided transport: windows on the owner's tensors + staging buffers."""
+
+    def __init__(self):
+        self.key = None
+        self.win: Dict[str, torch.Tensor] = {}
+        self.n = 0
+        self.names: Tuple[str, ...] = ()
+        self.result: Optional[torch.Tensor] = None      # owner only
+        self.stage: List[Fields] = []                   # two input staging sets (non-owners)
+        self.ybuf: List[torch.Tensor] = []              # two output staging buffers (non-owners, copy-out mode)
+        self.copy_in: Optional[torch.cuda.Stream] = None
+        self.copy_out: Optional[torch.cuda.Stream] = None
+
+
 class ShardedDecoder:
     """`Decoder.infer` over a batch held by rank 0, utterances sharded over the process group
     (BASELINE.json configs[3]: batch 4096 x 10 s over 8 GPUs).
 
         sd = ShardedDecoder(decoder, device)            # every rank, same weights
         wav = sd.infer(content, f0, energy, rand01)     # tensors on rank 0, None elsewhere -> [B, L] on rank 0
+
+    transport:
+      "p2p"  (default on CUDA when every GPU can address rank 0's): one-sided.  Rank 0 publishes its input and result
+             tensors as peer windows (tinyvc_b200.peer, CUDA IPC); every other rank pulls its utterance block out of
+             them micro-batch by micro-batch with copy-engine peer copies on a side stream (the pull of micro-batch
+             j + 1 overlaps the conversion of j) and the LAST KERNEL of the conversion stores the waveform straight
+             into rank 0's result tensor over NVLink (`Decoder.infer(out=window slice)`), so there is no gather step.
+             The process group carries control only: window handles once per buffer set, two barriers per call.
+      "nccl" two-sided grouped send/recv through the process group's backend (`sharded_map`); the only choice on CPU
+             (gloo, tests) and the fallback when peer access is unavailable.
+    Per-utterance results are those of the single-GPU path either way (same kernels on the same utterances).
     """
 
     def __init__(self, decoder, device: torch.device, micro_batch: int = 64, group=None,
-                 decode: Optional[Callable[..., torch.Tensor]] = None):
+                 decode: Optional[Callable[..., torch.Tensor]] = None, transport: str = "auto", direct_out: bool = True):
         self.decoder = decoder
         self.device = torch.device(device)
         self.micro_batch = micro_batch
         self.group = group
+        self.direct_out = direct_out
         # `decode` is injectable so the host logic can be exercised on CPU (gloo) in tests
-        self._decode = decode or (lambda content, f0, energy, rand01: decoder.infer(content, f0, energy, rand01=rand01))
+        self._custom = decode is not None
+        self._decode = decode or (lambda content, f0, energy, rand01, out=None:
+                                  decoder.infer(content, f0, energy, rand01=rand01, out=out))
+        rank, world = _world(self.group)
+        if transport == "auto":
+            transport = "p2p" if (self.device.type == "cuda" and world > 1 and not self._custom) else "nccl"
+        if transport == "p2p" and world > 1:
+            # all ranks must agree: p2p only if every rank's GPU can address the owner's GPU
+            from . import peer
+            owner_dev = torch.tensor([self.device.index if rank == 0 else -1], device=self.device)
+            dist.all_reduce(owner_dev, op=dist.ReduceOp.MAX, group=self.group)
+            ok = torch.tensor([1 if peer.p2p_available(self.device, int(owner_dev)) else 0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok) == 0:
+                transport = "nccl"
+        self.transport = transport
+        self._p2p = _P2PState()
+        if decoder is not None and self.device.type == "cuda" and world > 1 and hasattr(decoder, "seed_noise"):
+            # in-kernel noise draws (no injected rand01): distinct streams per rank, or utterance u of every rank's
+            # micro-batch j would get the same draw
+            decoder.seed_noise(0x5EED0000 + 7919 * rank)
+
+    # ---- one-sided transport --------------------------------------------------------------------------------
+    def _bind(self, fields: Optional[Fields]) -> None:
+        """Collective.  (Re)publishes rank 0's tensors as peer windows when the buffer set changed."""
+        from . import peer
+        rank, world = _world(self.group)
+        st = self._p2p
+        hdr = torch.zeros(4, dtype=torch.int64, device=self.device)
+        if rank == 0:
+            names = tuple(sorted(fields))
+            key = tuple((k, fields[k].data_ptr(), tuple(fields[k].shape)) for k in names)
+            changed = key != st.key
+            n = fields[names[0]].shape[0]
+            hdr[0], hdr[1] = int(changed), n
+        dist.broadcast(hdr, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        if int(hdr[0]) == 0:
+            return
+        if rank == 0:
+            for k in names:
+                if not fields[k].is_contiguous():
+                    raise RuntimeError(f"ShardedDecoder: {k} must be contiguous on rank 0 (it is published as a peer window)")
+            L = fields["energy"].shape[-1]
+            st.result = torch.empty((n, L), device=self.device, dtype=torch.float32)
+            st.key, st.names, st.n = key, names, n
+            st.win = peer.share_from(0, {**{k: fields[k] for k in names}, "result": st.result}, self.group)
+        else:
+            st.win = peer.share_from(0, None, self.group)
+            st.names = tuple(sorted(k for k in st.win if k != "result"))
+            st.n = int(hdr[1])
+            st.key = ("remote", st.n)
+            st.stage, st.ybuf = [], []
+            # first touch of the owner's GPU from this process.  Copy engines need nothing, but the conversion's last
+            # kernel STORES into the owner's result tensor (direct_out): kernels of this device may only address the
+            # owner's memory once peer access is enabled in THIS direction (torch's peer copies enable the other one).
+            owner_dev = st.win["result"].device.index
+            if self.direct_out and owner_dev != self.device.index:
+                from . import _lib
+                with torch.cuda.device(self.device):
+                    _lib.check(_lib.lib().tvc_enable_peer_access(owner_dev), "tvc_enable_peer_access")
+            probe = torch.empty(1, device=self.device)
+            probe.copy_(st.win["result"].view(-1)[:1])
+            torch.cuda.synchronize(self.device)
+        if st.copy_in is None:
+            st.copy_in = torch.cuda.Stream(self.device)
+            st.copy_out = torch.cuda.Stream(self.device)
+
+    def _infer_p2p(self, fields: Optional[Fields]) -> Optional[torch.Tensor]:
+        rank, world = _world(self.group)
+        self._bind(fields)
+        st = self._p2p
+        start, count = partition(st.n, world)[rank]
+        mbs = micro_batches(count, self.micro_batch)
+        cur = torch.cuda.current_stream(self.device)
+        if rank == 0:
+            cur.synchronize()                      # the inputs other ranks are about to pull are complete
+        dist.barrier(group=self.group)
+        if rank == 0:
+            for o, m in mbs:
+                g0 = start + o
+                self._decode(*(fields[k][g0:g0 + m] if k in fields else None for k in ("content", "f0", "energy", "rand01")),
+                             out=st.result[g0:g0 + m])
+            cur.synchronize()
+            dist.barrier(group=self.group)         # every rank's stores / copies into `result` have completed
+            return st.result
+        names = st.names
+        if not st.stage:
+            mmax = min(self.micro_batch, max(count, 1))
+            st.stage = [{k: torch.empty((mmax, *st.win[k].shape[1:]), device=self.device, dtype=torch.float32) for k in names}
+                        for _ in range(2)]
+            if not self.direct_out:
+                st.ybuf = [torch.empty((mmax, st.win["result"].shape[1]), device=self.device, dtype=torch.float32) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in mbs]
+        done = [torch.cuda.Event() for _ in mbs]
+        pushed = [torch.cuda.Event() for _ in mbs]
+
+        def pull(j):
+            o, m = mbs[j]
+            g0 = start + o
+            with torch.cuda.stream(st.copy_in):
+                if j >= 2:
+                    st.copy_in.wait_event(done[j - 2])            # the staging set is free again
+                for k in names:
+                    st.stage[j & 1][k][:m].copy_(st.win[k][g0:g0 + m], non_blocking=True)
+                ready[j].record(st.copy_in)
+
+        for j in range(min(2, len(mbs))):
+            pull(j)
+        for j, (o, m) in enumerate(mbs):
+            g0 = start + o
+            cur.wait_event(ready[j])
+            mb = {k: st.stage[j & 1][k][:m] for k in names}
+            if self.direct_out:
+                self._decode(mb["content"], mb["f0"], mb["energy"], mb.get("rand01"), out=st.win["result"][g0:g0 + m])
+                done[j].record(cur)
+            else:
+                if j >= 2:
+                    cur.wait_event(pushed[j - 2])
+                y = st.ybuf[j & 1][:m]
+                self._decode(mb["content"], mb["f0"], mb["energy"], mb.get("rand01"), out=y)
+                done[j].record(cur)
+                with torch.cuda.stream(st.copy_out):
+                    st.copy_out.wait_event(done[j])
+                    st.win["result"][g0:g0 + m].copy_(y, non_blocking=True)
+                    pushed[j].record(st.copy_out)
+            if j + 2 < len(mbs):
+                pull(j + 2)
+        cur.synchronize()
+        st.copy_out.synchronize()
+        dist.barrier(group=self.group)
+        return None
 
     def infer(self, content=None, f0=None, energy=None, rand01=None) -> Optional[torch.Tensor]:
-        rank, _ = _world(self.group)
+        rank, world = _world(self.group)
         fields = None
         if content is not None:
             fields = {"content": content, "f0": f0, "energy": energy}
             if rand01 is not None:
                 fields["rand01"] = rand01
+        if self.transport == "p2p" and world > 1:
+            return self._infer_p2p(fields)
 
         def fn(mb: Fields) -> torch.Tensor:
             return self._decode(mb["content"], mb["f0"], mb["energy"], mb.get("rand01"))

@@ -188,7 +188,11 @@ class Decoder(nn.Module):
 
     # ---- reference API ------------------------------------------------------------------------
     @torch.inference_mode()
-    def infer(self, content, f0, energy, *, rand01: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def infer(self, content, f0, energy, *, rand01: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """`out` (extension): write the waveform [B, L] into this fp32 buffer instead of a fresh tensor.  It may live on
+        a peer GPU that this device can address (a `tinyvc_b200.peer` window): the last kernel then stores straight
+        into the peer's HBM over NVLink, which is how the sharded mode gathers without a copy."""
         content, f0, energy, B, Lf = self._prep(content, f0, energy)
         dev = content.device
         L = _lib.lib()
@@ -197,7 +201,10 @@ class Decoder(nn.Module):
             rand01 = self._rand(rand01, B, Lf, dev)
         elif getattr(self, "_noise_seeded_for", None) != h.value:
             self.seed_noise()            # the draw of decoder.py:78 happens inside the noise kernel
-        out = torch.empty(B, Lf * FRAME, device=dev, dtype=torch.float32)
+        if out is None:
+            out = torch.empty(B, Lf * FRAME, device=dev, dtype=torch.float32)
+        elif not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, Lf * FRAME)):
+            raise RuntimeError(f"Decoder.infer: out must be a contiguous CUDA fp32 tensor of shape {(B, Lf * FRAME)}")
         step = self._batch_chunk(B, Lf)
         with torch.cuda.device(dev):
             for b0 in range(0, B, step):

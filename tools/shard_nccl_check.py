@@ -28,7 +28,8 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     dec = load_synth_weights(Decoder().eval(), seed=7).to(dev)
     B, Lf = int(os.environ.get("CHECK_B", 37)), int(os.environ.get("CHECK_LF", 50))      # ragged: 37 utterances
-    sd = ShardedDecoder(dec, dev, micro_batch=int(os.environ.get("CHECK_MB", 8)))
+    sd = ShardedDecoder(dec, dev, micro_batch=int(os.environ.get("CHECK_MB", 8)), transport=os.environ.get("CHECK_TRANSPORT", "auto"),
+                        direct_out=os.environ.get("CHECK_DIRECT", "1") == "1")
     inp = None
     if rank == 0:
         inp = {k: v.to(dev) for k, v in synth.decoder_inputs(B, Lf, seed=77).items()}
@@ -47,7 +48,7 @@ def main():
         ref = dec.infer(inp["content"], inp["f0"], inp["energy"], rand01=inp["rand01"])
         torch.cuda.synchronize()
         res["local_ms"] = (time.perf_counter() - t0) * 1e3
-        res.update(world=world, utterances=B, frames=Lf, identical=bool(torch.equal(out, ref)),
+        res.update(transport=sd.transport, direct_out=sd.direct_out, world=world, utterances=B, frames=Lf, identical=bool(torch.equal(out, ref)),
                    max_abs_diff=float((out - ref).abs().max()))
         print(json.dumps(res), flush=True)
         assert res["identical"], "sharded result differs from the single-GPU result"

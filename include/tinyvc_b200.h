@@ -36,9 +36,8 @@ const char* tvc_version(void);
 /* Runtime switches.  ("conv_impl","tc"|"fp32"): Decoder.infer on the tcgen05 tensor-core plan (default)
  * or on the exact-fp32 CUDA-core plan.  ("graphs","1"|"0"): tvc_decoder_infer replays a captured CUDA
  * graph when it is called again with the same buffers (default on).  ("fused_up","1"|"0"): the 24-channel
- * Upsample block as one fused kernel (default) or five conv launches.  ("chain","0"|"1"): Downsample 1-4 +
- * Upsample 0-3 as one persistent cooperative launch with in-kernel grid barriers (see DESIGN.md for the measured
- * trade-off).  ("pdl","0"|"1"): programmatic dependent launch (default off).  ("profile","0"|"1").
+ * Upsample block as one fused kernel (default) or five conv launches.  ("pdl","0"|"1"): programmatic dependent
+ * launch (default off).  ("profile","0"|"1").
  * Returns non-zero for unknown keys.                                                                */
 int tvc_set_option(const char* key, const char* value);
 /* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */

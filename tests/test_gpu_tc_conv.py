@@ -35,6 +35,21 @@ def _ref(x, w, b, dil, aux_x, aux_w, aux_b, aux_mode, res, epi_act):
     return y
 
 
+# Padded mode (tc_conv.cuh): the input planes carry `pin` stored replicate rows per utterance side, the plane output
+# `pout`; the probe also checks that the epilogue wrote every replicate row of the output.  (case, (pin, pout))
+PAD_CASES = [
+    ((4, 36, 384, 384, 3, 1, 0, 0, False, 0, 1, 48), (1, 3)),
+    ((4, 36, 384, 384, 3, 3, 384, 2, True, 0, 1, 48), (3, 9)),
+    ((4, 36, 384, 384, 3, 27, 384, 2, True, 0, 0, 48), (27, 0)),
+    ((3, 108, 192, 192, 3, 9, 0, 0, False, 0, 1, 64), (9, 27)),
+    ((5, 2, 384, 384, 3, 27, 384, 2, True, 0, 0, 48), (27, 0)),
+    ((7, 1, 48, 48, 3, 2, 0, 0, False, 0, 1, 48), (2, 4)),
+    ((3, 100, 48, 96, 3, 4, 48, 1, False, 0, 0, 48), (4, 0)),
+    ((2, 432, 96, 96, 3, 9, 0, 0, False, 0, 1, 48), (9, 27)),
+    ((2, 1000, 24, 24, 3, 27, 24, 2, True, 0, 1, 24), (27, 5)),
+    ((9, 33, 17, 24, 3, 1, 0, 0, False, 0, 0, 24), (6, 1)),
+]
+
 CASES = [
     # (B, T, Cin, Cout, K, dil, aux_cin, aux_mode, use_res, epi_act, out_act, NT)
     (2, 300, 24, 24, 3, 1, 0, 0, False, 0, 1, 24),
@@ -50,8 +65,17 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("case,pads", PAD_CASES, ids=[f"p{i}" for i in range(len(PAD_CASES))])
+def test_tc_conv_padded_mode(case, pads):
+    _check(case, pads)
+
+
 @pytest.mark.parametrize("case", CASES, ids=[f"c{i}" for i in range(len(CASES))])
 def test_tc_conv_matches_fp64(case):
+    _check(case)
+
+
+def _check(case, pads=None):
     from tinyvc_b200 import _lib
     B, T, Cin, Cout, K, dil, aux_cin, aux_mode, use_res, epi_act, out_act, NT = case
     g = torch.Generator().manual_seed(hash(case) % (2**31))
@@ -80,8 +104,13 @@ def test_tc_conv_matches_fp64(case):
     awc = aux_w.contiguous() if aux_w is not None else None
     abc = aux_b.contiguous() if aux_b is not None else None
     ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
-    rc = _lib.lib().tvc_tc_conv_probe(ptr(xd), ptr(wc), ptr(bc), B, T, Cin, Cout, K, dil, ptr(auxd), ptr(awc), ptr(abc),
-                                      aux_cin, aux_mode, ptr(resd), epi_act, out_act, NT, ptr(y), ptr(yp), None)
+    if pads:
+        _lib.set_option("probe_pad", f"{pads[0]},{pads[1]}")
+    try:
+        rc = _lib.lib().tvc_tc_conv_probe(ptr(xd), ptr(wc), ptr(bc), B, T, Cin, Cout, K, dil, ptr(auxd), ptr(awc), ptr(abc),
+                                          aux_cin, aux_mode, ptr(resd), epi_act, out_act, NT, ptr(y), ptr(yp), None)
+    finally:
+        _lib.set_option("probe_pad", "0,0")
     _lib.check(rc, "tvc_tc_conv_probe")
     torch.cuda.synchronize()
     got = y.cpu().double()

@@ -27,6 +27,7 @@ void set_error(const char* fmt, ...) {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static bool g_use_graphs = true;
+static int g_probe_pad_in = 0, g_probe_pad_out = 0;     // tvc_set_option("probe_pad", ...): tests only
 bool g_pdl = false;      // programmatic dependent launch between the decoder plan's kernels (measured: no gain while a
                          // tc_conv CTA fills an SM's registers and shared memory, so successors cannot become resident early)
 
@@ -101,15 +102,15 @@ using namespace tvc;
 struct DecoderGraphKey {
     const void *content, *f0, *energy, *rand01, *out, *ws;
     int B, Lf, impl;
+    unsigned opts;                       // plan options (nets_tc.cuh plan_options): they change the launch sequence
     bool operator==(const DecoderGraphKey& o) const {
         return content == o.content && f0 == o.f0 && energy == o.energy && rand01 == o.rand01 && out == o.out &&
-               ws == o.ws && B == o.B && Lf == o.Lf && impl == o.impl;
+               ws == o.ws && B == o.B && Lf == o.Lf && impl == o.impl && opts == o.opts;
     }
 };
 struct DecoderGraph {
     DecoderGraphKey key;
     cudaGraphExec_t exec = nullptr;
-    void* chain_dev = nullptr;       // op tables + grid-barrier counters of the graph's chained launches (ChainSink)
     unsigned long long launches = 0, last_use = 0;
 };
 struct tvc_decoder {
@@ -120,10 +121,8 @@ struct tvc_decoder {
     cudaStream_t cap_stream = nullptr;
     unsigned long long tick = 0;
     ~tvc_decoder() {
-        for (DecoderGraph& g : graphs) {
+        for (DecoderGraph& g : graphs)
             if (g.exec) cudaGraphExecDestroy(g.exec);
-            if (g.chain_dev) cudaFree(g.chain_dev);
-        }
         if (cap_stream) cudaStreamDestroy(cap_stream);
     }
 };
@@ -159,7 +158,14 @@ int tvc_set_option(const char* key, const char* value) {
     if (!strcmp(key, "tc_trace")) return tc_trace_arm(value);          // developer: "k0,k1,..." launch ordinals
     if (!strcmp(key, "tc_trace_dump")) return tc_trace_dump(value);    // developer: write the timeline to a file
     if (!strcmp(key, "fused_up")) { set_fused_up(!strcmp(value, "1")); return 0; }
-    if (!strcmp(key, "chain")) { set_chain(!strcmp(value, "1")); return 0; }
+    if (!strcmp(key, "pad_up_max_t")) { set_pad_max_t(atoi(value), -1); return 0; }
+    if (!strcmp(key, "pad_down_max_t")) { set_pad_max_t(-1, atoi(value)); return 0; }
+    if (!strcmp(key, "probe_pad")) {                                   // tests: tvc_tc_conv_probe in padded mode
+        int a = 0, b = 0;
+        if (sscanf(value, "%d,%d", &a, &b) != 2 || a < 0 || b < 0) return 1;
+        g_probe_pad_in = a; g_probe_pad_out = b;
+        return 0;
+    }
     if (!strcmp(key, "pdl")) {
         g_pdl = !strcmp(value, "1");
         return 0;
@@ -292,7 +298,7 @@ int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, co
     // that set is seen (callers that reuse their buffers -- serving loops, the Python wrapper's cached
     // workspace -- then pay one graph launch instead of ~100 kernel launches per call).
     std::lock_guard<std::mutex> lock(h->mu);
-    const DecoderGraphKey key{content, f0, energy, rand01, out, workspace, B, Lf, impl | (g_pdl ? 256 : 0) | (plan_options() << 9)};
+    const DecoderGraphKey key{content, f0, energy, rand01, out, workspace, B, Lf, impl | (g_pdl ? 256 : 0), plan_options()};
     ++h->tick;
     for (DecoderGraph& g : h->graphs)
         if (g.key == key) {
@@ -311,50 +317,31 @@ int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, co
     }
     if (!h->cap_stream) TVC_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
     const unsigned long long n0 = g_launches.load();
-    DecoderGraph g;
-    ChainSink sink;
-    TVC_CUDA(cudaMalloc(&g.chain_dev, kChainSinkBytes));
-    sink.dev = (unsigned char*)g.chain_dev;
-    sink.cap = kChainSinkBytes;
-    sink.deferred = true;
-    cudaError_t be = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal);
-    if (be != cudaSuccess) {
-        cudaFree(g.chain_dev);
-        TVC_CUDA(be);
-    }
+    TVC_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
     int rc = 0;
     {
         Arena A(workspace, workspace_bytes, false);
-        rc = h->m.infer(A, h->cap_stream, content, f0, energy, rand01, out, B, Lf, impl, &sink);
+        rc = h->m.infer(A, h->cap_stream, content, f0, energy, rand01, out, B, Lf, impl);
     }
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
-    if (rc || ce != cudaSuccess || !graph) {
+    if (rc) {
         if (graph) cudaGraphDestroy(graph);
-        cudaFree(g.chain_dev);
-        if (rc) return rc;
-        TVC_REQUIRE(false, "tvc_decoder_infer: graph capture failed: %s", cudaGetErrorString(ce));
+        return rc;
     }
-    // op tables of the chained launches (and their zeroed barrier counters): uploaded once, outside the graph
-    sink.host.resize(kChainSinkBytes, 0);
-    if (cudaMemcpy(g.chain_dev, sink.host.data(), kChainSinkBytes, cudaMemcpyHostToDevice) != cudaSuccess) {
-        cudaGraphDestroy(graph);
-        cudaFree(g.chain_dev);
-        TVC_REQUIRE(false, "tvc_decoder_infer: chain table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-    }
+    TVC_REQUIRE(ce == cudaSuccess && graph, "tvc_decoder_infer: graph capture failed: %s", cudaGetErrorString(ce));
+    DecoderGraph g;
     g.key = key;
     g.launches = g_launches.load() - n0;
     g.last_use = h->tick;
     const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (ie != cudaSuccess) cudaFree(g.chain_dev);
     TVC_REQUIRE(ie == cudaSuccess, "tvc_decoder_infer: graph instantiation failed: %s", cudaGetErrorString(ie));
     if (h->graphs.size() >= 8) {               // evict the least recently used
         size_t victim = 0;
         for (size_t i = 1; i < h->graphs.size(); ++i)
             if (h->graphs[i].last_use < h->graphs[victim].last_use) victim = i;
         cudaGraphExecDestroy(h->graphs[victim].exec);
-        if (h->graphs[victim].chain_dev) cudaFree(h->graphs[victim].chain_dev);
         h->graphs.erase(h->graphs.begin() + victim);
     }
     h->graphs.push_back(g);
@@ -722,10 +709,59 @@ int tvc_tc_conv_probe(const float* x, const float* w, const float* bias, int B, 
     }
     a.y32 = y_cl; a.y32_cs = o_cs; a.y_hi = y_hi; a.y_lo = y_lo; a.y_cs = o_cs;
     a.epi_act = epi_act; a.out_act = out_act;
-    PROBE_TRY(tc_conv_launch(W, a, s));
+    // tvc_set_option("probe_pad", "Pin,Pout"): run the conv in padded mode (tc_conv.cuh) -- the input planes are re-laid
+    // with Pin stored replicate rows, the plane output is produced with Pout and checked: stripping and re-padding it
+    // must reproduce it bit for bit (i.e. the epilogue wrote every replicate row), then it is stripped for the caller.
+    bf16 *ap_hi = nullptr, *ap_lo = nullptr, *yp_hi = nullptr, *yp_lo = nullptr, *yq = nullptr;
+    const int pin = K == 3 ? g_probe_pad_in : 0, pout = K == 3 ? g_probe_pad_out : 0;
+    auto cleanup2 = [&] { cudaStreamSynchronize(s); cudaFree(ap_hi); cudaFree(ap_lo); cudaFree(yp_hi); cudaFree(yp_lo); cudaFree(yq); };
+    if (pin > 0) {
+        const long long rows_pi = (long long)B * (T + 2 * pin), rows_po = (long long)B * (T + 2 * pout);
+        if (cudaMalloc(&ap_hi, rows_pi * a_cs * 2) != cudaSuccess || cudaMalloc(&ap_lo, rows_pi * a_cs * 2) != cudaSuccess ||
+            cudaMalloc(&yp_hi, rows_po * o_cs * 2) != cudaSuccess || cudaMalloc(&yp_lo, rows_po * o_cs * 2) != cudaSuccess ||
+            cudaMalloc(&yq, rows_po * o_cs * 2) != cudaSuccess) {
+            set_error("probe: cudaMalloc failed");
+            cleanup2(); cleanup();
+            return 1;
+        }
+        cudaMemsetAsync(yp_hi, 0xff, rows_po * o_cs * 2, s);
+        cudaMemsetAsync(yp_lo, 0xff, rows_po * o_cs * 2, s);
+        rc = plane_repad(a_hi, ap_hi, B, T, a_cs, 0, pin, s);
+        if (!rc) rc = plane_repad(a_lo, ap_lo, B, T, a_cs, 0, pin, s);
+        a.a_hi = ap_hi; a.a_lo = ap_lo; a.a_pad = pin;
+        a.y_hi = yp_hi; a.y_lo = yp_lo; a.y_pad = pout;
+        if (!rc) rc = tc_conv_launch(W, a, s);
+        // strip -> y_hi / y_lo (what the caller reads), re-pad -> compare with what the kernel wrote
+        for (int pl = 0; pl < 2 && !rc; ++pl) {
+            bf16* padded = pl ? yp_lo : yp_hi;
+            bf16* plain = pl ? y_lo : y_hi;
+            rc = plane_repad(padded, plain, B, T, o_cs, pout, 0, s);
+            if (!rc) rc = plane_repad(plain, yq, B, T, o_cs, 0, pout, s);
+            if (!rc) {
+                const size_t n = (size_t)rows_po * o_cs;
+                const size_t nc = (size_t)rows_po * (size_t)(align_up(Cout, 8));      // chunks past Cout are never written
+                std::vector<uint16_t> h1(n), h2(n);
+                cudaStreamSynchronize(s);
+                cudaMemcpy(h1.data(), padded, n * 2, cudaMemcpyDeviceToHost);
+                cudaMemcpy(h2.data(), yq, n * 2, cudaMemcpyDeviceToHost);
+                if (memcmp(h1.data(), h2.data(), nc * 2) != 0) {
+                    size_t bad = 0, firstbad = n;
+                    for (size_t i = 0; i < nc; ++i)
+                        if (h1[i] != h2[i]) { if (firstbad == n) firstbad = i; ++bad; }
+                    set_error("probe: padded plane output: %zu elements differ from the replicate-padded reference (first at %zu, plane %d)",
+                              bad, firstbad, pl);
+                    rc = 1;
+                }
+            }
+        }
+        if (rc) { cleanup2(); cleanup(); return rc; }
+    } else {
+        PROBE_TRY(tc_conv_launch(W, a, s));
+    }
     if (y) PROBE_TRY(cl_to_cf(y_cl, y, B, Cout, T, o_cs, s));
     if (y_planes) PROBE_TRY(planes_to_cf(y_hi, y_lo, y_planes, B, Cout, T, o_cs, s));
     PROBE_CUDA(cudaStreamSynchronize(s));
+    cleanup2();
     cleanup();
     return 0;
 #undef PROBE_CUDA

@@ -408,11 +408,11 @@ int DecoderModel::filter_net(Arena& A, cudaStream_t s, const float* content, con
 
 // Decoder.infer (decoder.py:253-257).
 int DecoderModel::infer(Arena& A, cudaStream_t s, const float* content, const float* f0, const float* energy,
-                        const float* rand01, float* out, int B, int Lf, int impl, ChainSink* sink) {
+                        const float* rand01, float* out, int B, int Lf, int impl) {
     if (impl == CONV_IMPL_TC) {
         static const DecoderTC shape_only;   // dry runs (workspace sizing) never touch weights
         TVC_REQUIRE(A.dry || (tc && tc->ready), "decoder: tensor-core plan not initialised");
-        return (A.dry && !tc ? shape_only : *tc).infer(A, s, content, f0, energy, rand01, out, B, Lf, sink);
+        return (A.dry && !tc ? shape_only : *tc).infer(A, s, content, f0, energy, rand01, out, B, Lf);
     }
     const int L = Lf * kFrame;
     const size_t m = A.mark();

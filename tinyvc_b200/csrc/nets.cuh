@@ -70,7 +70,6 @@ struct Arena {
 };
 
 struct DecoderTC;   // nets_tc.cuh: tensor-core execution plan
-struct ChainSink;   // nets_tc.cuh: where chained launches keep their op tables
 
 struct DecoderModel {
     WeightStore store;
@@ -98,7 +97,7 @@ struct DecoderModel {
     int filter_net(Arena& A, cudaStream_t s, const float* content, const float* lf0, const float* src17, float* out,
                    int B, int Lf);
     int infer(Arena& A, cudaStream_t s, const float* content, const float* f0, const float* energy,
-              const float* rand01, float* out, int B, int Lf, int impl, ChainSink* sink = nullptr);   // impl: ConvImpl, chosen by the caller
+              const float* rand01, float* out, int B, int Lf, int impl);   // impl: ConvImpl, chosen by the caller
 };
 
 struct EncoderModel {

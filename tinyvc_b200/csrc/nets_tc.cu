@@ -208,33 +208,12 @@ namespace {
 // tvc_set_option("fused_up", "0"): run the 24-channel Upsample block as five tc_conv launches instead of the fused block
 // kernel (tc_block.cu).  The two are bit-identical (tests/test_gpu_fused_block.py); fused is 263 -> 146 us at config 2.
 bool g_fused_up = true;
-// tvc_set_option("chain", "0"): one launch per conv / resampler for the levels below the full rate.  Default: Downsample 1-4
-// and Upsample 0-3 (16 + 24 ops) run as ONE cooperative persistent launch with grid barriers between the ops
-// (tc_conv.cu tc_chain_kernel); same kernels' arithmetic, so the result is bit-identical.
-bool g_chain = false;
-
-// Hands a finished chain to the device: table into the sink (64-byte aligned), two zeroed counters behind it.
-int flush_chain(TcChain& c, ChainSink& sink, cudaStream_t s, const char* name) {
-    if (!c.n_ops) return 0;
-    const size_t off = (size_t)align_up((int64_t)sink.used, 64), bytes = c.table.size();
-    const size_t sync_off = off + (size_t)align_up((int64_t)bytes, 64);
-    TVC_REQUIRE(sync_off + 64 <= sink.cap, "decoder: chain tables need %zu bytes, %zu reserved", sync_off + 64, sink.cap);
-    sink.used = sync_off + 64;
-    if (sink.deferred) {
-        sink.host.resize(sink.used, 0);                              // counters stay zero in the image
-        memcpy(sink.host.data() + off, c.table.data(), bytes);
-    } else {
-        TVC_CUDA(cudaMemcpyAsync(sink.dev + off, c.table.data(), bytes, cudaMemcpyHostToDevice, s));   // pageable: staged before return
-        TVC_CUDA(cudaMemsetAsync(sink.dev + sync_off, 0, 64, s));
-    }
-    {
-        ProfScope ps(name, s);
-        TVC_TRY(tc_chain_launch(sink.dev + off, c.n_ops, reinterpret_cast<unsigned*>(sink.dev + sync_off), s));
-    }
-    c.table.clear();
-    c.n_ops = 0;
-    return 0;
-}
+// tvc_set_option("pad_max_t", "N"): levels whose utterances have at most N rows keep the replicate padding of their
+// k = 3 convs STORED in the activation planes (tc_conv.cuh, padded mode), so that every operand window is one contiguous
+// tensor copy.  Short utterances (config 2: 36 / 108 / 432 rows at the three lowest rates) otherwise gather their clamped
+// windows row by row with cp.async, tap by tap.  0 = never.  Separate limits for the Downsample blocks (pads 1 / 2 / 4 rows:
+// the row count hardly grows) and the Upsample blocks (pads up to 27 rows: more row tiles re-stream the weights).
+int g_pad_max_t = 0, g_pad_down_max_t = 512;     // same-box A/B (profiles/r02f_pad_ab.log): down 1.010 -> 1.004 ms, up 1.010 -> 1.032 ms
 struct ConvCall {
     TcConvArgs a;
     ConvCall(const Pl& in, int B, int T, int dil = 1) {
@@ -245,37 +224,23 @@ struct ConvCall {
     ConvCall& f32(float* y, int cs) { a.y32 = y; a.y32_cs = cs; return *this; }
     ConvCall& out(const Pl& y, int act) { a.y_hi = y.hi; a.y_lo = y.lo; a.y_cs = y.cs; a.out_act = act; return *this; }
     ConvCall& epi(int act) { a.epi_act = act; return *this; }
+    ConvCall& pad(int in, int out) { a.a_pad = in; a.y_pad = out; return *this; }
 };
 int tc_conv_k(const char* name, const TcConvW& W, const ConvCall& c, cudaStream_t s) {
     ProfScope ps(name, s);
     return tc_conv_launch(W, c.a, s);
 }
 }  // namespace
-#define CONV(name, W, call)                                                  \
-    do {                                                                     \
-        if (A.dry) break;                                                    \
-        if (chaining) TVC_TRY(tc_chain_add_conv(chain, W, (call).a));        \
-        else TVC_TRY(tc_conv_k(name, W, call, s));                           \
-    } while (0)
-#define INTERP(x_, B_, Tin_, Tout_, scale_, C_, y32_, rh_, rl_, ah_, al_)                                           \
-    do {                                                                                                            \
-        if (A.dry) break;                                                                                           \
-        if (chaining) TVC_TRY(tc_chain_add_interp(chain, x_, B_, Tin_, Tout_, scale_, C_, y32_, rh_, rl_, ah_, al_)); \
-        else { ProfScope ps__("interp_cl(", s); TVC_TRY(interp_cl(x_, B_, Tin_, Tout_, scale_, C_, y32_, rh_, rl_, ah_, al_, s)); } \
+#define CONV(name, W, call)                                   \
+    do {                                                      \
+        if (!A.dry) TVC_TRY(tc_conv_k(name, W, call, s));     \
     } while (0)
 
 int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float* f0, const float* energy,
-                     const float* rand01, float* out, int B, int Lf, ChainSink* sink) const {
+                     const float* rand01, float* out, int B, int Lf) const {
     const int L = Lf * kFrame;
     const long long rowsF = (long long)B * Lf, rowsL = (long long)B * L;
     const size_t m0 = A.mark();
-    // chain tables: the caller's sink (captured graph), else a slice of the workspace (always reserved: stable sizing)
-    ChainSink local;
-    local.dev = (unsigned char*)A.bytes(kChainSinkBytes);
-    local.cap = kChainSinkBytes;
-    if (!sink) sink = &local;
-    TcChain chain;
-    bool chaining = false;
 
     // ---- frame-rate inputs -> [SourceNet x (128) | FilterNet x0 (384)], channels-last fp32 [rowsF][512]
     float* e_fr = A.f32(rowsF);
@@ -335,17 +300,20 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         skip32[i + 1] = A.f32(rows * cout);
         skipP[i + 1] = planes(A, rows, cout);
         const size_t m = A.mark();
-        Pl xr = planes(A, rows, cin), xa = planes(A, rows, cin), a = planes(A, rows, cin), c = planes(A, rows, cin);
+        // stored replicate padding for short utterances: each tensor carries the dilation of the conv that reads it
+        const bool pad = tout <= g_pad_down_max_t;
+        const int P1 = pad ? 1 : 0, P2 = pad ? 2 : 0, P4 = pad ? 4 : 0;
+        Pl xr = planes(A, rows, cin), xa = planes(A, (long long)B * (tout + 2 * P1), cin),
+           a = planes(A, (long long)B * (tout + 2 * P2), cin), c = planes(A, (long long)B * (tout + 2 * P4), cin);
         ARENA_OK();
         const float scale = (float)(1.0 / (1.0 / (double)fac));   // F.interpolate(scale_factor=1/f)
-        chaining = g_chain;                                        // Downsample 1-4 and Upsample 0-3: one persistent launch
-        INTERP(skip32[i], B, tin, tout, scale, cin, nullptr, xr.hi, xr.lo, xa.hi, xa.lo);
+        RUN(interp_cl(skip32[i], B, tin, tout, scale, cin, nullptr, xr.hi, xr.lo, xa.hi, xa.lo, s, P1));
         const char* const n1[4] = {"tc_down1_c1(", "tc_down2_c1(", "tc_down3_c1(", "tc_down4_c1("};
         const char* const n2[4] = {"tc_down1_c2(", "tc_down2_c2(", "tc_down3_c2(", "tc_down4_c2("};
         const char* const n3[4] = {"tc_down1_c3(", "tc_down2_c3(", "tc_down3_c3(", "tc_down4_c3("};
-        CONV(n1[i], down[i].c1, ConvCall(xa, B, tout, 1).out(a, TC_ACT_LRELU));
-        CONV(n2[i], down[i].c2, ConvCall(a, B, tout, 2).out(c, TC_ACT_LRELU));
-        CONV(n3[i], down[i].c3, ConvCall(c, B, tout, 4).aux(xr).f32(skip32[i + 1], cout).out(skipP[i + 1], TC_ACT_NONE));
+        CONV(n1[i], down[i].c1, ConvCall(xa, B, tout, 1).pad(P1, P2).out(a, TC_ACT_LRELU));
+        CONV(n2[i], down[i].c2, ConvCall(a, B, tout, 2).pad(P2, P4).out(c, TC_ACT_LRELU));
+        CONV(n3[i], down[i].c3, ConvCall(c, B, tout, 4).pad(P4, 0).aux(xr).f32(skip32[i + 1], cout).out(skipP[i + 1], TC_ACT_NONE));
         A.release(m);
     }
     // ---- FilterNet up path (decoder.py:214-219,230-233)
@@ -362,20 +330,20 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         const size_t m = A.mark();
         float* xi = A.f32(rows * c);
         float* y = A.f32(rows * c);
-        Pl p0 = planes(A, rows, c), p1 = planes(A, rows, c);
+        const bool fused = g_fused_up && c == 24 && tc_up24_block_supported(u.c1, u.c2, u.c3, u.c4, u.c5);
+        // stored replicate padding (see g_pad_max_t): p0 holds c1's input (1 row), later c3's (9); p1 c2's (3), later c4's (27)
+        const bool pad = !fused && tout <= g_pad_max_t;
+        const int Q1 = pad ? 1 : 0, Q3 = pad ? 3 : 0, Q9 = pad ? 9 : 0, Q27 = pad ? 27 : 0;
+        Pl p0 = planes(A, (long long)B * (tout + 2 * Q9), c), p1 = planes(A, (long long)B * (tout + 2 * Q27), c);
         ARENA_OK();
         const float scale = (float)(1.0 / (double)fac);           // F.interpolate(scale_factor=f)
-        if (i == 4 && chaining) {                                   // the full-rate block has its own kernel(s)
-            if (!A.dry) TVC_TRY(flush_chain(chain, *sink, s, "tc_chain_low("));
-            chaining = false;
-        }
-        INTERP(x, B, tin, tout, scale, c, xi, nullptr, nullptr, p0.hi, p0.lo);
+        RUN(interp_cl(x, B, tin, tout, scale, c, xi, nullptr, nullptr, p0.hi, p0.lo, s, Q1));
         const char* const un[5][5] = {{"tc_up0_c1(", "tc_up0_c2(", "tc_up0_c3(", "tc_up0_c4(", "tc_up0_c5("},
                                       {"tc_up1_c1(", "tc_up1_c2(", "tc_up1_c3(", "tc_up1_c4(", "tc_up1_c5("},
                                       {"tc_up2_c1(", "tc_up2_c2(", "tc_up2_c3(", "tc_up2_c4(", "tc_up2_c5("},
                                       {"tc_up3_c1(", "tc_up3_c2(", "tc_up3_c3(", "tc_up3_c4(", "tc_up3_c5("},
                                       {"tc_up4_c1(", "tc_up4_c2(", "tc_up4_c3(", "tc_up4_c4(", "tc_up4_c5("}};
-        if (g_fused_up && c == 24 && tc_up24_block_supported(u.c1, u.c2, u.c3, u.c4, u.c5)) {
+        if (fused) {
             // the whole block in one kernel (tc_block.cu); same arithmetic as the five launches below
             TcUpBlockArgs fa;
             fa.p_hi = p0.hi; fa.p_lo = p0.lo; fa.c_hi = cond.hi; fa.c_lo = cond.lo; fa.xi = xi; fa.xo = xo; fa.xo_cs = cn;
@@ -388,10 +356,10 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
             x = xo; tin = tout;
             continue;
         }
-        CONV(un[i][0], u.c1, ConvCall(p0, B, tout, 1).out(p1, TC_ACT_LRELU));
-        CONV(un[i][1], u.c2, ConvCall(p1, B, tout, 3).aux(cond).res(xi, c).f32(y, c).out(p0, TC_ACT_LRELU));
-        CONV(un[i][2], u.c3, ConvCall(p0, B, tout, 9).out(p1, TC_ACT_LRELU));
-        CONV(un[i][3], u.c4, ConvCall(p1, B, tout, 27).aux(cond).res(y, c).out(p0, TC_ACT_NONE));
+        CONV(un[i][0], u.c1, ConvCall(p0, B, tout, 1).pad(Q1, Q3).out(p1, TC_ACT_LRELU));
+        CONV(un[i][1], u.c2, ConvCall(p1, B, tout, 3).pad(Q3, Q9).aux(cond).res(xi, c).f32(y, c).out(p0, TC_ACT_LRELU));
+        CONV(un[i][2], u.c3, ConvCall(p0, B, tout, 9).pad(Q9, Q27).out(p1, TC_ACT_LRELU));
+        CONV(un[i][3], u.c4, ConvCall(p1, B, tout, 27).pad(Q27, 0).aux(cond).res(y, c).out(p0, TC_ACT_NONE));
         CONV(un[i][4], u.c5, ConvCall(p0, B, tout, 1).f32(xo, cn));
         A.release(m);
         x = xo; tin = tout;
@@ -403,7 +371,10 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
 
 void set_fused_up(bool on) { g_fused_up = on; }
 bool fused_up() { return g_fused_up; }
-void set_chain(bool on) { g_chain = on; }
-unsigned plan_options() { return (g_fused_up ? 1u : 0u) | (g_chain ? 2u : 0u); }
+void set_pad_max_t(int up, int down) {
+    if (up >= 0) g_pad_max_t = up > 2047 ? 2047 : up;
+    if (down >= 0) g_pad_down_max_t = down > 2047 ? 2047 : down;
+}
+unsigned plan_options() { return (g_fused_up ? 1u : 0u) | ((unsigned)g_pad_max_t << 1) | ((unsigned)g_pad_down_max_t << 12); }
 
 }  // namespace tvc

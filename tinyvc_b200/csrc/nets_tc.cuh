@@ -3,20 +3,7 @@
 #include "nets.cuh"
 #include "tc_kernels.cuh"
 
-#include <vector>
-
 namespace tvc {
-
-// Where the op tables of chained launches (tc_conv.cuh TcChain) live on the device.  Eager calls carve the region out of the
-// workspace and upload with cudaMemcpyAsync; a captured graph owns a device buffer instead (`deferred`): the plan only
-// collects the host image and the caller uploads it once, after the capture, so a replay contains no copy at all.
-struct ChainSink {
-    unsigned char* dev = nullptr;
-    size_t cap = 0, used = 0;
-    bool deferred = false;
-    std::vector<unsigned char> host;
-};
-constexpr size_t kChainSinkBytes = 96 * 1024;
 
 struct DecoderTC {
     TcConvW frame_in;             // [content 768 | e_fr | log f0] -> [SourceNet 128 | FilterNet 384]
@@ -36,14 +23,15 @@ struct DecoderTC {
     ~DecoderTC();
     int init(const WeightStore& store);
     // Decoder.infer (decoder.py:253-257) on the tensor-core path.
-    // sink: nullptr = chain tables go into the workspace (eager call); else see ChainSink
     int infer(Arena& A, cudaStream_t s, const float* content, const float* f0, const float* energy, const float* rand01,
-              float* out, int B, int Lf, ChainSink* sink = nullptr) const;
+              float* out, int B, int Lf) const;
 };
 
 void set_fused_up(bool on);          // tvc_set_option("fused_up", "0"|"1"): fused 24-channel Upsample block (default on)
 bool fused_up();
-void set_chain(bool on);             // tvc_set_option("chain", "0"|"1"): low-rate Down / Up blocks as one persistent launch
+// tvc_set_option("pad_up_max_t" | "pad_down_max_t", "N"): Upsample / Downsample blocks of levels whose utterances have
+// <= N rows store the replicate padding of their k = 3 convs (tc_conv.cuh, padded mode); -1 leaves a limit unchanged
+void set_pad_max_t(int up, int down);
 unsigned plan_options();             // bit set of the options that change the launch plan (part of the graph-cache key)
 
 }  // namespace tvc

@@ -51,7 +51,10 @@ struct alignas(64) TcKParams {
     const float *bias, *film_bias, *res;
     float* y32;
     bf16 *y_hi, *y_lo;
-    long long rows;
+    long long rows;                // B * T: rows of the aux input, the residual and the outputs
+    long long rows_a;              // rows of the main input planes (= rows, or B * (T + 2 * a_pad) in padded mode)
+    long long rows_y;              // rows of the plane output (B * (T + 2 * y_pad))
+    int a_pad, y_pad, Tp;          // padded mode: replicate rows stored on either side of every utterance; Tp = T + 2 * a_pad
     long long tile_elems;
     int a_cs, x_cs, res_cs, y32_cs, y_cs;
     int T, dil, taps, nkb, aux_nkb, aux_mode, KB, NT, NTp, Cout;
@@ -60,6 +63,8 @@ struct alignas(64) TcKParams {
     long long row_tiles;
     int n_tiles;
     int halo;                      // 1: one stage holds a (128 + 2*dil)-row window shared by the 3 taps (tiles never straddle utterances)
+                                   // 2: the same over an input whose replicate padding is STORED (a_pad >= dil rows on either side of
+                                   //    every utterance): tiles walk the padded row space, every window is one contiguous tensor copy
     int R;                         // rows per A stage (128, or 128 + 2*dil in halo mode)
     int tiles_per_utt;             // halo mode
     uint32_t a_stage_bytes, b_stage_bytes;
@@ -67,23 +72,6 @@ struct alignas(64) TcKParams {
     int epi_act, out_act;
     int dbg;   // ablation switches for profiling (TVC_TC_DBG): 1 no loads, 2 no MMAs, 4 no epilogue math/stores
     uint2* trace;   // developer timeline (TVC_TC_TRACE): CTA 0 logs {clock, role|event|tile|stage} per pipeline event
-};
-
-// Chain tables (device memory, written by the host before the launch): a conv, or a linear resampler between convs.
-enum { TC_OP_CONV = 0, TC_OP_INTERP = 1 };
-struct TcInterpOp {
-    const float* x;
-    float* y32;
-    bf16 *r_hi, *r_lo, *a_hi, *a_lo;
-    long long rows_in, rows_out, chunks;
-    int Tin, Tout;
-    float scale;
-    int pad_;
-};
-struct alignas(64) TcChainOp {
-    TcKParams conv;
-    TcInterpOp interp;
-    int type;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -116,12 +104,12 @@ struct TileWalk {
     __device__ TileWalk(const TcKParams& p, long long tile) {
         n_tile = (int)(tile / p.row_tiles);
         row_tile = tile - (long long)n_tile * p.row_tiles;
-        bq = p.halo ? (int)(row_tile / p.tiles_per_utt) : 0;
-        tt0 = p.halo ? (int)(row_tile - (long long)bq * p.tiles_per_utt) * kTileM : 0;
+        bq = p.halo == 1 ? (int)(row_tile / p.tiles_per_utt) : 0;
+        tt0 = p.halo == 1 ? (int)(row_tile - (long long)bq * p.tiles_per_utt) * kTileM : 0;
     }
     __device__ void next(const TcKParams& p) {
         if (++row_tile == p.row_tiles) { row_tile = 0; ++n_tile; bq = 0; tt0 = 0; return; }
-        if (p.halo) {
+        if (p.halo == 1) {
             tt0 += kTileM;
             if (tt0 >= p.T) { tt0 = 0; ++bq; }
         }
@@ -151,77 +139,20 @@ struct Tracer {
 //   warps 13-16  producers: TMA tensor copies (interior windows, 1x1 / aux stages) or per-thread cp.async gathers (edge
 //                windows, flat k = 3 stages) into the smem ring; a producer never waits for its loads
 // ---------------------------------------------------------------------------------------------
-// ---- chain mode: several convs (and the resamplers between them) in ONE persistent launch ------------------------
-// A chain kernel walks a table of ops; every CTA finishes its tiles of op k, then all CTAs meet at a grid barrier
-// (one global counter; release: stores + fence + red.add, acquire: spin on ld.acquire) before anyone reads op k's output.
-// The first weight stages of op k + 1 are requested BEFORE the barrier wait (weights depend on nobody), so the DRAM
-// round trip of a cold weight image hides behind the slowest CTA of op k.
-struct ChainSync {
-    unsigned* counter;      // arrivals so far (monotonic inside one launch; reset by the last CTA to leave)
-    unsigned target;        // arrivals that must have happened before this op may read its inputs (0: nothing to wait for)
-};
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
-// Every thread of the CTA calls this exactly once per op (named barrier 1); thread 0 does the waiting.
-__device__ __forceinline__ void chain_wait(const ChainSync& cs) {
-    if (threadIdx.x == 0 && cs.target) {
-        const long long t0 = clock64();
-        while (ld_acquire_gpu(cs.counter) < cs.target) {
-            if (clock64() - t0 > 4000000000LL) __trap();      // a protocol error fails the launch instead of hanging the GPU
-        }
-        __threadfence();
-    }
-    __syncwarp();
-    asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
-    fence_proxy_async_global();      // the tensor copies that follow read what other SMs wrote with ordinary stores
-}
-template <bool CHAIN>
-__device__ __forceinline__ void dep_wait(const ChainSync& cs) {
-    if constexpr (CHAIN) chain_wait(cs);
-    else pdl_wait();
-}
-// activations another CTA of the same launch may have written: never through the non-coherent path in chain mode
-template <bool CHAIN>
-__device__ __forceinline__ float4 ld_act4(const float4* p) {
-    if constexpr (CHAIN) return *p;
-    else return __ldg(p);
-}
-
-// barriers of one conv op: full[ring], empty[ring], acc_full[2], acc_empty[2], wfull (see the offsets in tc_conv_body)
-__device__ __forceinline__ void mbar_inval(uint32_t bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void tc_init_barriers(const TcKParams& p, uint32_t bar_base, int prev_ring) {
-    const uint32_t acc_full = bar_base + 16u * (uint32_t)p.ring, acc_empty = acc_full + 16u, wfull = acc_full + 40u;
-    if (prev_ring > 0) {                                           // chain mode: the previous conv's barriers live here
-        const uint32_t pa = bar_base + 16u * (uint32_t)prev_ring;
-        for (int s = 0; s < 2 * prev_ring; ++s) mbar_inval(bar_base + 8u * s);
-        mbar_inval(pa); mbar_inval(pa + 8); mbar_inval(pa + 16); mbar_inval(pa + 24); mbar_inval(pa + 40);
-    }
-    for (int s = 0; s < p.ring; ++s) {
-        mbar_init(bar_base + 8u * s, kTileM + 1);              // full: 128 gather arrivals + 1 expect_tx
-        mbar_init(bar_base + 8u * (p.ring + s), 1);            // empty: one tcgen05.commit
-    }
-    mbar_init(wfull, 1);
-    mbar_init(acc_full, 1); mbar_init(acc_full + 8, 1);
-    mbar_init(acc_empty, kEpiWarps); mbar_init(acc_empty + 8, kEpiWarps);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
-// One conv op, all roles.  `p`: the op's parameters (kernel parameter space, or shared memory in chain mode); `pm`: the same
-// parameters where the TMA unit can read the tensor maps (parameter or global space); `smem`: ring base; barriers at `bar_base`.
-template <int SPEC, bool CHAIN>
-__device__ __forceinline__ void tc_conv_body(const TcKParams& p, const TcKParams* pm, uint8_t* smem, const uint32_t bar_base,
-                                             const uint32_t tmem, const ChainSync cs) {
+template <int SPEC>
+__global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcKParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    pdl_launch_dependents();      // the next kernel of the plan may start its prologue as soon as SM resources free up
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
     const uint32_t smem_base = smem_u32(smem);
+    // barriers: full[ring], empty[ring], acc_full[2], acc_empty[2]
     const uint32_t wreg = smem_base + (uint32_t)p.ring_alloc * stage_bytes;       // resident weight image (w_bytes, may be 0)
+    const uint32_t bar_base = wreg + p.w_bytes;
     const uint32_t acc_full = bar_base + 16u * (uint32_t)p.ring;
     const uint32_t acc_empty = acc_full + 16u;
     const uint32_t wfull = acc_full + 40u;                                        // weights-resident: image has landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)p.ring_alloc * stage_bytes + p.w_bytes + 16 * p.ring + 32);
 
     constexpr bool kGeneric = SPEC < 0;
     constexpr EpiSpec kS = epi_spec(SPEC < 0 ? 0 : SPEC);
@@ -236,13 +167,30 @@ __device__ __forceinline__ void tc_conv_body(const TcKParams& p, const TcKParams
     const long long tile_beg = (long long)blockIdx.x * per_cta;
     const long long tile_end = tile_beg + per_cta < n_tiles_total ? tile_beg + per_cta : n_tiles_total;
 
+    if (tid == 0) {
+        for (int s = 0; s < p.ring; ++s) {
+            mbar_init(bar_base + 8u * s, kTileM + 1);              // full: 128 gather arrivals + 1 expect_tx
+            mbar_init(bar_base + 8u * (p.ring + s), 1);            // empty: one tcgen05.commit
+        }
+        mbar_init(wfull, 1);
+        mbar_init(acc_full, 1); mbar_init(acc_full + 8, 1);
+        mbar_init(acc_empty, kEpiWarps); mbar_init(acc_empty + 8, kEpiWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
     if (warp >= kProdWarp0 && warp < kMmaWarp2) {
         // ================= producers =================
         // Lane mapping: producer thread j serves tile row j (and window row j + 128 in halo mode) and walks the
         // stage's 8-channel chunks.  With chunk-major operands a warp-level cp.async moves 32 consecutive rows of
         // one chunk: 512 contiguous bytes in global memory and in shared memory (no bank conflicts).
         const int j = tid - kProdWarp0 * 32;
-        const long long chunk_bytes = p.rows * 16;     // bytes between consecutive 8-channel chunk arrays of a plane
+        // bytes between consecutive 8-channel chunk arrays of a plane (gathers; the padded main input never gathers)
+        const long long chunk_bytes = p.rows * 16;
         // Ring state per issuing warp: with two MMA warps the ring is split in two halves (tile parity picks the half), so
         // that every thread meets the phases of the barriers it waits on strictly in order (a parity wait cannot tell
         // phase u from phase u - 2).  rs = slot inside the half, rp = parity of the slot's previous use.
@@ -275,7 +223,7 @@ __device__ __forceinline__ void tc_conv_body(const TcKParams& p, const TcKParams
                 }
             }
         }
-        dep_wait<CHAIN>(cs);
+        pdl_wait();
         Tracer tr(j == 0 ? p.trace : nullptr, 0);
         for (long long tile = tile_beg; tile < tile_end; ++tile, tw.next(p)) {
             const long long row_tile = tw.row_tile;
@@ -290,6 +238,15 @@ __device__ __forceinline__ void tc_conv_body(const TcKParams& p, const TcKParams
                     const unsigned bq = g / (unsigned)p.T;
                     bT = (int)(bq * (unsigned)p.T);
                     tq = (int)g - bT;
+                }
+            } else if (p.halo == 2) {
+                // padded mode: tile row j is padded row g of the main input; the aux operand (not padded) is gathered from
+                // the row of the same (utterance, time); pad rows produce nothing and get zeros
+                const unsigned g = (unsigned)(row_tile * kTileM) + (unsigned)j;
+                if ((long long)g < p.rows_a) {
+                    const unsigned bq = g / (unsigned)p.Tp;
+                    const int t = (int)(g - bq * (unsigned)p.Tp) - p.a_pad;
+                    if (t >= 0 && t < p.T) { bT = (int)(bq * (unsigned)p.T); tq = t; }
                 }
             } else {
                 tt0 = tw.tt0;
@@ -317,11 +274,13 @@ __device__ __forceinline__ void tc_conv_body(const TcKParams& p, const TcKParams
                 int win = kTileM, org = 0;
                 long long start;
                 bool edge = false;
-                if (p.halo) {
+                if (p.halo == 1) {
                     win = is_aux ? kTileM : p.R;
                     org = tt0 - (is_aux ? 0 : p.dil);
                     start = (long long)baseT + org;
                     edge = org < 0 || org + win > p.T;
+                } else if (p.halo == 2) {
+                    start = row_tile * kTileM - (is_aux ? 0 : p.dil);      // padded rows: the window never leaves its utterance's pads
                 } else {
                     start = row_tile * kTileM;
                 }
@@ -339,9 +298,9 @@ __device__ __forceinline__ void tc_conv_body(const TcKParams& p, const TcKParams
                         bulk_g2s(a_dst + p.a_stage_bytes, wt, b_bytes, full);
                     }
                 } else if (tma && j == 32) {
-                    tma_load_3d(a_dst, is_aux ? &pm->tm_x_hi : &pm->tm_a_hi, 0, (int)((start - off) >> 3), kb * chunks, full);
+                    tma_load_3d(a_dst, is_aux ? &p.tm_x_hi : &p.tm_a_hi, 0, (int)((start - off) >> 3), kb * chunks, full);
                 } else if (tma && j == 64) {
-                    tma_load_3d(a_dst + plane, is_aux ? &pm->tm_x_lo : &pm->tm_a_lo, 0, (int)((start - off) >> 3), kb * chunks, full);
+                    tma_load_3d(a_dst + plane, is_aux ? &p.tm_x_lo : &p.tm_a_lo, 0, (int)((start - off) >> 3), kb * chunks, full);
                 }
                 wt += b_bytes >> 1;
                 int n_ok = (cs >> 3) - kb * chunks;            // chunks of this stage that exist in the tensor; the rest are zero-filled
@@ -350,7 +309,7 @@ __device__ __forceinline__ void tc_conv_body(const TcKParams& p, const TcKParams
                 const char* g_hi = reinterpret_cast<const char*>(src_hi) + (long long)kb * chunks * chunk_bytes;
                 const char* g_lo = reinterpret_cast<const char*>(src_lo) + (long long)kb * chunks * chunk_bytes;
                 if ((p.dbg & 1) || tma) {
-                } else if (!p.halo) {
+                } else if (p.halo != 1) {
                     const int shift = is_aux ? 0 : (tap - half) * p.dil;
                     int tt = tq + shift;
                     tt = tt < 0 ? 0 : (tt > p.T - 1 ? p.T - 1 : tt);                    // replicate padding
@@ -410,7 +369,6 @@ __device__ __forceinline__ void tc_conv_body(const TcKParams& p, const TcKParams
         // walk is a few adds, main and aux stages have their own loops with pre-built descriptor words, and a stage's
         // TAPS x KS x 3 MMAs are straight-line code.
         {
-            if constexpr (CHAIN) chain_wait(cs);                 // every thread of the CTA takes part in the op's barrier
             const bool leader = elect_one() != 0;
             const bool issue = leader && !(p.dbg & 2);
             const uint32_t desc_hi = (128u >> 4) | (1u << 14);      // SBO = 128 bytes, descriptor version 1
@@ -437,6 +395,7 @@ __device__ __forceinline__ void tc_conv_body(const TcKParams& p, const TcKParams
             }
             uint32_t idesc_m = umma_idesc(kTileM, NTp), idesc_x = film ? umma_idesc(kTileM, 2u * NTp) : idesc_m;
             const bool halo_main = p.halo != 0;
+            const bool utt_walk = p.halo == 1;       // padded mode: tiles start on multiples of 128 padded rows (row0 stays 0 mod 8)
             int n_aux = p.aux_nkb;
             // tile walk state (halo mode: operand row of the tile's first output row; only its low 3 bits matter)
             uint32_t T = (uint32_t)p.T, tt0 = 0, row0 = 0;
@@ -543,7 +502,7 @@ __device__ __forceinline__ void tc_conv_body(const TcKParams& p, const TcKParams
               }
                 // next tile of the walk (row tiles first, then the next channel tile starts again at row 0)
                 if (--rt_left == 0) { rt_left = p.row_tiles; tt0 = 0; row0 = 0; }
-                else if (halo_main) {
+                else if (utt_walk) {
                     tt0 += kTileM; row0 += kTileM;
                     if (tt0 >= T) { row0 += T - tt0; tt0 = 0; }        // first row of the next utterance
                 }
@@ -559,7 +518,7 @@ __device__ __forceinline__ void tc_conv_body(const TcKParams& p, const TcKParams
         const int out_act = kGeneric ? p.out_act : kS.out_act;
         const int quarter = warp & 3, slot = warp >> 2;
         const int rloc = quarter * 32 + lane;
-        dep_wait<CHAIN>(cs);      // residual reads and output writes must follow the previous grid / op
+        pdl_wait();               // residual reads and output writes must follow the previous grid
         const int n_groups = p.NT >> 3;
         uint32_t tcount = 0;
         TileWalk tw(p, tile_beg);
@@ -569,15 +528,35 @@ __device__ __forceinline__ void tc_conv_body(const TcKParams& p, const TcKParams
             const uint32_t buf = tcount & 1u, buse = tcount >> 1;
             const int n_tile = tw.n_tile;
             tr.log(trole, 0, (int)tcount, 0);
-            long long row;
-            bool valid;
+            long long row, rowp;                 // output row (residual, fp32 output) and row of the plane output
+            bool valid, first = false, last = false;
             if (!p.halo) {
                 row = tw.row_tile * kTileM + rloc;
                 valid = row < p.rows;
+                rowp = row;
+            } else if (p.halo == 2) {
+                // padded mode: tile rows are padded input rows; pad rows produce nothing.  The plane output may carry its own
+                // padding (y_pad rows on either side of every utterance): the threads that own t = 0 and t = T - 1 also store
+                // the replicate rows, so the next conv's windows never leave the tensor (replicate padding, decoder.py:144-146).
+                const unsigned g = (unsigned)(tw.row_tile * kTileM) + (unsigned)rloc;
+                valid = false;
+                row = 0; rowp = 0;
+                if ((long long)g < p.rows_a) {
+                    const unsigned bq = g / (unsigned)p.Tp;
+                    const int t = (int)(g - bq * (unsigned)p.Tp) - p.a_pad;
+                    if (t >= 0 && t < p.T) {
+                        valid = true;
+                        row = (long long)bq * p.T + t;
+                        rowp = (long long)bq * (p.T + 2 * p.y_pad) + p.y_pad + t;
+                        first = t == 0;
+                        last = t == p.T - 1;
+                    }
+                }
             } else {
                 const int t = tw.tt0 + rloc;
                 row = (long long)tw.bq * p.T + t;
                 valid = t < p.T;
+                rowp = row;
             }
             const uint32_t lane_addr = tmem + buf * acc_cols + ((uint32_t)(quarter * 32) << 16);
             const float* bias = p.bias + n_tile * p.NTp;               // padded channel space
@@ -590,8 +569,8 @@ __device__ __forceinline__ void tc_conv_body(const TcKParams& p, const TcKParams
                 float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
                 if (has_res && live) {                                 // issued before the accumulator wait
                     const float4* rp = reinterpret_cast<const float4*>(p.res + ((long long)(ch >> 3) * p.rows + row) * 8);
-                    r0 = ld_act4<CHAIN>(rp);
-                    r1 = ld_act4<CHAIN>(rp + 1);
+                    r0 = __ldg(rp);
+                    r1 = __ldg(rp + 1);
                 }
                 // per-channel constants: requested before the accumulator wait so their latency hides behind it
                 const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cg * 8));
@@ -646,8 +625,22 @@ __device__ __forceinline__ void tc_conv_body(const TcKParams& p, const TcKParams
                     uint32_t h[4], l[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) split2(apply_act(v[2 * i], out_act), apply_act(v[2 * i + 1], out_act), h[i], l[i]);
-                    *reinterpret_cast<uint4*>(p.y_hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<uint4*>(p.y_lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+                    const uint4 hv = make_uint4(h[0], h[1], h[2], h[3]), lv = make_uint4(l[0], l[1], l[2], l[3]);
+                    const long long op = ((long long)(ch >> 3) * p.rows_y + rowp) * 8;
+                    *reinterpret_cast<uint4*>(p.y_hi + op) = hv;
+                    *reinterpret_cast<uint4*>(p.y_lo + op) = lv;
+                    if (first) {
+                        for (int q = 1; q <= p.y_pad; ++q) {
+                            *reinterpret_cast<uint4*>(p.y_hi + op - 8 * q) = hv;
+                            *reinterpret_cast<uint4*>(p.y_lo + op - 8 * q) = lv;
+                        }
+                    }
+                    if (last) {
+                        for (int q = 1; q <= p.y_pad; ++q) {
+                            *reinterpret_cast<uint4*>(p.y_hi + op + 8 * q) = hv;
+                            *reinterpret_cast<uint4*>(p.y_lo + op + 8 * q) = lv;
+                        }
+                    }
                 }
             }
             if (!waited) {                                             // a slot without column groups still takes part
@@ -659,134 +652,9 @@ __device__ __forceinline__ void tc_conv_body(const TcKParams& p, const TcKParams
             tr.log(trole, 3, (int)tcount, 0);
         }
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Persistent, warp-specialised: each CTA walks tiles (row tile, channel tile) round-robin.
-//   warps 0-11   epilogue: TMEM lane quarter = warp & 3, column slot = warp >> 2 (8-channel groups
-//                slot, slot+3, ...); accumulators are double-buffered in TMEM
-//   warp  12     TMEM allocation + single-thread tcgen05.mma issue
-//   warps 13-16  producers: TMA tensor copies (interior windows, 1x1 / aux stages) or per-thread cp.async gathers (edge
-//                windows, flat k = 3 stages) into the smem ring; a producer never waits for its loads
-// ---------------------------------------------------------------------------------------------
-template <int SPEC>
-__global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcKParams p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    pdl_launch_dependents();      // the next kernel of the plan may start its prologue as soon as SM resources free up
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
-    const uint32_t bar_base = smem_u32(smem) + (uint32_t)p.ring_alloc * stage_bytes + p.w_bytes;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)p.ring_alloc * stage_bytes + p.w_bytes + 16 * p.ring + 32);
-    if (tid == 0) tc_init_barriers(p, bar_base, 0);
-    if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    tc_conv_body<SPEC, false>(p, &p, smem, bar_base, tmem, ChainSync{nullptr, 0u});
     tc_fence_before();
     __syncthreads();
     if (warp == kMmaWarp) tmem_dealloc(tmem, p.tmem_cols);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Chain kernel: a table of ops (convs with the runtime-flag epilogue, linear resamplers) in one cooperative launch.
-// Shared memory: [0, 256) mbarriers | [256, 260) TMEM slot | [512, 512 + sizeof(TcChainOp)) the current op | [2048, ...) ring.
-// ---------------------------------------------------------------------------------------------
-constexpr uint32_t kChainOpOff = 512, kChainRingOff = 2048;
-static_assert(sizeof(TcChainOp) <= kChainRingOff - kChainOpOff && sizeof(TcChainOp) % 16 == 0, "chain op does not fit its slot");
-
-__device__ __forceinline__ void chain_interp(const TcInterpOp& ip, const ChainSync& cs) {
-    chain_wait(cs);
-    // one thread per (8-channel chunk, output row), as interp_cl_kernel (tc_frame.cu); inputs by ordinary loads
-    const long long total = ip.rows_out * ip.chunks;
-    for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (long long)gridDim.x * kThreads) {
-        const long long q = idx / ip.rows_out, row = idx - q * ip.rows_out;
-        const unsigned bu = (unsigned)row / (unsigned)ip.Tout;
-        const long long b = bu;
-        const int t = (int)((unsigned)row - bu * (unsigned)ip.Tout);
-        const LinCoord c = lin_coord(t, ip.scale, ip.Tin);
-        const float4* p0 = reinterpret_cast<const float4*>(ip.x + (q * ip.rows_in + b * ip.Tin + c.i0) * 8);
-        const float4* p1 = reinterpret_cast<const float4*>(ip.x + (q * ip.rows_in + b * ip.Tin + c.i1) * 8);
-        const float4 x0 = p0[0], x1 = p0[1], z0 = p1[0], z1 = p1[1];
-        float v[8] = {lin_blend(x0.x, z0.x, c), lin_blend(x0.y, z0.y, c), lin_blend(x0.z, z0.z, c), lin_blend(x0.w, z0.w, c),
-                      lin_blend(x1.x, z1.x, c), lin_blend(x1.y, z1.y, c), lin_blend(x1.z, z1.z, c), lin_blend(x1.w, z1.w, c)};
-        const long long o = (q * ip.rows_out + row) * 8;
-        if (ip.y32) {
-            reinterpret_cast<float4*>(ip.y32 + o)[0] = make_float4(v[0], v[1], v[2], v[3]);
-            reinterpret_cast<float4*>(ip.y32 + o)[1] = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        if (ip.r_hi) {
-            uint32_t h[4], l[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
-            *reinterpret_cast<uint4*>(ip.r_hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<uint4*>(ip.r_lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
-        }
-        if (ip.a_hi) {
-            uint32_t h[4], l[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) split2(leaky01(v[2 * i]), leaky01(v[2 * i + 1]), h[i], l[i]);
-            *reinterpret_cast<uint4*>(ip.a_hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<uint4*>(ip.a_lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const TcChainOp* __restrict__ ops, int n_ops, unsigned* sync) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t bar_base = smem_u32(smem);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
-    TcChainOp* cur = reinterpret_cast<TcChainOp*>(smem + kChainOpOff);
-    if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    // the table is cold (the host wrote it once): pull it into L2 now, so that staging op k later is an L2 hit
-    for (int i = tid; i < n_ops * (int)(sizeof(TcChainOp) / 128); i += kThreads)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(ops) + (size_t)i * 128));
-    int prev_ring = 0;                        // ring depth of the previous conv op (its barriers are invalidated before re-use)
-    for (int k = 0; k < n_ops; ++k) {
-        // stage the op's parameters in shared memory (the table is host-written before the launch: read-only here)
-        for (int i = tid; i < (int)(sizeof(TcChainOp) / 16); i += kThreads)
-            reinterpret_cast<uint4*>(cur)[i] = __ldg(reinterpret_cast<const uint4*>(ops + k) + i);
-        __syncthreads();
-        const ChainSync cs{sync, k ? (unsigned)k * gridDim.x : 0u};
-        if (tid >= 32 && tid < 36) {           // tensor maps of this op (first iteration) and the next one -> descriptor cache
-            const int m = tid - 32;
-            for (int kk = k ? k + 1 : 0; kk <= k + 1 && kk < n_ops; ++kk) {
-                const TcChainOp* o = ops + kk;
-                if (o->type == TC_OP_CONV && (m < 2 ? o->conv.tma_main : o->conv.tma_aux))
-                    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<const char*>(&o->conv.tm_a_hi) + (size_t)m * 128) : "memory");
-            }
-        }
-        if (cur->type == TC_OP_CONV) {
-            if (tid == 0) tc_init_barriers(cur->conv, bar_base, prev_ring);
-            prev_ring = cur->conv.ring;
-            __syncthreads();
-            tc_conv_body<-1, true>(cur->conv, &ops[k].conv, smem + kChainRingOff, bar_base, tmem, cs);
-        } else {
-            chain_interp(cur->interp, cs);
-        }
-        // release: this CTA's stores of op k (generic proxy) become visible to every SM, tensor copies included
-        fence_proxy_async_global();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (tid == 0 && k + 1 < n_ops) {
-            __threadfence();
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(sync) : "memory");
-        }
-    }
-    // the last CTA to leave resets the counters, so a replayed launch (CUDA graph) starts from zero again
-    if (tid == 0) {
-        const unsigned left = atomicAdd(sync + 1, 1u);
-        if (left == gridDim.x - 1) { sync[0] = 0u; sync[1] = 0u; __threadfence(); }
-    }
-    __syncthreads();
-    if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
 
 // ---- host side --------------------------------------------------------------------------------
@@ -915,7 +783,6 @@ int tc_conv_init() {
     TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
     TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
     TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
-    TVC_CUDA(cudaFuncSetAttribute(tc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem + (int)kChainRingOff));
     return 0;
 }
 
@@ -993,8 +860,7 @@ int tc_make_plane_map(CUtensorMap* m, const bf16* base, long long rows, int nch,
     return 0;
 }
 
-// Fills the kernel parameters of one conv.  chain: the op runs inside tc_chain_kernel (grid = all SMs, no timeline slot).
-static int tc_conv_params(const TcConvW& W, const TcConvArgs& a, bool chain, TcKParams& p, int& spec, size_t& smem, unsigned& grid) {
+int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     TVC_REQUIRE(W.w && a.a_hi && a.a_lo, "tc_conv: missing weights or input");
     TVC_REQUIRE(a.B > 0 && a.T > 0, "tc_conv: empty problem B=%d T=%d", a.B, a.T);
     TVC_REQUIRE(a.a_cs % 8 == 0 && a.a_cs >= W.Cin, "tc_conv: input channel stride %d (need multiple of 8 >= %d)", a.a_cs, W.Cin);
@@ -1002,26 +868,35 @@ static int tc_conv_params(const TcConvW& W, const TcConvArgs& a, bool chain, TcK
     TVC_REQUIRE(!a.y_hi || (a.y_lo && a.y_cs % 8 == 0), "tc_conv: plane output needs both planes and a stride multiple of 8");
     TVC_REQUIRE(!a.y32 || a.y32_cs % 8 == 0, "tc_conv: fp32 output capacity must be a multiple of 8 channels");
     TVC_REQUIRE(!a.res || (a.res_cs % 8 == 0 && a.res_cs >= (int)align_up(W.Cout, 8)), "tc_conv: residual capacity must be a multiple of 8 covering Cout rounded up to 8");
+    TcKParams p;
     p.a_hi = a.a_hi; p.a_lo = a.a_lo; p.x_hi = a.x_hi; p.x_lo = a.x_lo; p.w = W.w;
     p.bias = W.bias; p.film_bias = W.film_bias; p.res = a.res; p.y32 = a.y32; p.y_hi = a.y_hi; p.y_lo = a.y_lo;
     p.rows = (long long)a.B * a.T; p.tile_elems = (long long)W.tile_elems;
+    TVC_REQUIRE(a.a_pad >= 0 && a.y_pad >= 0 && (a.a_pad == 0 || (W.taps == 3 && a.a_pad >= a.dil)),
+                "tc_conv: input padding %d must cover the dilation %d of a k = 3 conv", a.a_pad, a.dil);
+    TVC_REQUIRE(a.y_pad == 0 || (a.a_pad > 0 && a.y_hi), "tc_conv: a padded plane output needs the padded mode (a_pad > 0)");
+    p.a_pad = a.a_pad; p.y_pad = a.y_pad; p.Tp = a.T + 2 * a.a_pad;
+    p.rows_a = (long long)a.B * p.Tp;
+    p.rows_y = (long long)a.B * (a.T + 2 * a.y_pad);
+    TVC_REQUIRE(p.rows_a < (1LL << 31) && p.rows_y < (1LL << 31), "tc_conv: too many rows");
     p.a_cs = a.a_cs; p.x_cs = a.x_cs; p.res_cs = a.res_cs; p.y32_cs = a.y32_cs; p.y_cs = a.y_cs;
     p.T = a.T; p.dil = a.dil; p.taps = W.taps; p.nkb = W.nkb; p.aux_nkb = W.aux_nkb; p.aux_mode = W.aux_mode;
     p.KB = W.KB; p.NT = W.NT; p.NTp = W.NTp; p.Cout = W.Cout;
     p.epi_act = a.epi_act; p.out_act = a.out_act;
     static const int dbg = getenv("TVC_TC_DBG") ? atoi(getenv("TVC_TC_DBG")) : 0;
     p.dbg = dbg;
-    p.trace = chain ? nullptr : tc_trace_slot();
+    p.trace = tc_trace_slot();
     // halo mode: k=3 convs whose utterances fill their 128-row tiles well share one row window across the taps
     const int tpu = cdiv(a.T, kTileM);
     p.halo = (W.taps == 3 && (double)a.T / ((double)tpu * kTileM) >= 0.75 && !g_force_flat) ? 1 : 0;
+    if (a.a_pad > 0) p.halo = 2;         // stored replicate padding: every window is a contiguous tensor copy
     p.tiles_per_utt = tpu;
     p.R = p.halo ? kTileM + 2 * a.dil : kTileM;
     TVC_REQUIRE(a.dil >= 1 && a.dil <= 64, "tc_conv: dilation %d out of range", a.dil);
     // Stage geometry: a main / aux stage holds G row groups of 8 rows per chunk column: the window (R or 128 rows) plus
     // up to 7 leading rows, because a TMA box starts on a multiple of 8 operand rows.
     const int g_main = p.halo ? (p.R + 7 + 7) / 8 : kTileM / 8;
-    const int g_aux = p.halo ? (kTileM + 7 + 7) / 8 : kTileM / 8;
+    const int g_aux = p.halo == 1 ? (kTileM + 7 + 7) / 8 : kTileM / 8;      // padded mode gathers the aux rows (no offset)
     p.lbo_main = (uint32_t)g_main * 128u;
     p.lbo_aux = (uint32_t)g_aux * 128u;
     const int n_rows_max = W.aux_mode == TC_AUX_FILM ? 2 * W.NTp : W.NTp;
@@ -1030,10 +905,11 @@ static int tc_conv_params(const TcConvW& W, const TcConvArgs& a, bool chain, TcK
     static const int tma_env = getenv("TVC_TC_TMA") ? atoi(getenv("TVC_TC_TMA")) : 1;
     memset(&p.tm_a_hi, 0, 4 * sizeof(CUtensorMap));
     p.tma_main = (tma_env && (p.halo || W.taps == 1)) ? 1 : 0;
-    p.tma_aux = (tma_env && W.aux_mode != TC_AUX_NONE) ? 1 : 0;
+    p.tma_aux = (tma_env && W.aux_mode != TC_AUX_NONE && p.halo != 2) ? 1 : 0;
+    TVC_REQUIRE(p.halo != 2 || p.tma_main, "tc_conv: the padded mode needs tensor copies (TVC_TC_TMA=0 is set)");
     if (p.tma_main) {
-        TVC_TRY(tc_make_plane_map(&p.tm_a_hi, a.a_hi, p.rows, a.a_cs / 8, W.KB / 8, g_main));
-        TVC_TRY(tc_make_plane_map(&p.tm_a_lo, a.a_lo, p.rows, a.a_cs / 8, W.KB / 8, g_main));
+        TVC_TRY(tc_make_plane_map(&p.tm_a_hi, a.a_hi, p.rows_a, a.a_cs / 8, W.KB / 8, g_main));
+        TVC_TRY(tc_make_plane_map(&p.tm_a_lo, a.a_lo, p.rows_a, a.a_cs / 8, W.KB / 8, g_main));
     }
     if (p.tma_aux) {
         TVC_TRY(tc_make_plane_map(&p.tm_x_hi, a.x_hi, p.rows, a.x_cs / 8, W.KB / 8, g_aux));
@@ -1060,11 +936,11 @@ static int tc_conv_params(const TcConvW& W, const TcConvArgs& a, bool chain, TcK
     while (tc < cols) tc <<= 1;
     TVC_REQUIRE(tc <= 512, "tc_conv: %u TMEM columns needed (> 512)", cols);
     p.tmem_cols = tc;
-    p.row_tiles = p.halo ? (long long)a.B * tpu : (p.rows + kTileM - 1) / kTileM;
+    p.row_tiles = p.halo == 1 ? (long long)a.B * tpu : (p.rows_a + kTileM - 1) / kTileM;
     p.n_tiles = W.n_tiles;
-    smem = (size_t)ring * stage + p.w_bytes + 16 * ring + 64;
+    const size_t smem = (size_t)ring * stage + p.w_bytes + 16 * ring + 64;
     const long long tiles = p.row_tiles * p.n_tiles;
-    grid = (unsigned)((tiles < g_num_sms && !chain) ? tiles : g_num_sms);
+    const unsigned grid = (unsigned)(tiles < g_num_sms ? tiles : g_num_sms);
     // Two MMA-issuing warps (each with its own half of the ring) when a CTA has several tiles to alternate and the ring
     // is deep enough that half of it still prefetches ahead.
     // Same-box A/B (profiles/r01z_ab_issuer_modes.log): tiles of one K-stage gain 3-6 % from the second issuer, FiLM / deep-K
@@ -1073,7 +949,7 @@ static int tc_conv_params(const TcConvW& W, const TcConvArgs& a, bool chain, TcK
     const int stages_per_tile = (p.halo ? W.nkb : W.taps * W.nkb) + (W.aux_mode ? W.aux_nkb : 0);
     p.mma2 = (mma2_env && ring >= 4 && tiles >= 2LL * grid && (mma2_env != 2 || stages_per_tile == 1)) ? 1 : 0;   // 2: single-stage tiles only
     if (p.mma2 && (ring & 1)) p.ring = ring - 1;                   // equal halves (the smem layout keeps the full ring)
-    spec = -1;
+    int spec = -1;
     for (int i = 0; i < kNumSpecs; ++i) {
         const EpiSpec e = epi_spec(i);
         if ((e.film != 0) == (W.aux_mode == TC_AUX_FILM) && (e.res != 0) == (a.res != nullptr) && (e.y32 != 0) == (a.y32 != nullptr) &&
@@ -1083,15 +959,6 @@ static int tc_conv_params(const TcConvW& W, const TcConvArgs& a, bool chain, TcK
         }
     }
     if (g_force_generic) spec = -1;
-    return 0;
-}
-
-int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
-    TcKParams p;
-    int spec = -1;
-    size_t smem = 0;
-    unsigned grid = 0;
-    TVC_TRY(tc_conv_params(W, a, false, p, spec, smem, grid));
     switch (spec) {
         case 0: TVC_LAUNCH_PDL(tc_conv_kernel<0>, grid, kThreads, smem, s, p); break;
         case 1: TVC_LAUNCH_PDL(tc_conv_kernel<1>, grid, kThreads, smem, s, p); break;
@@ -1103,58 +970,6 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
         case 7: TVC_LAUNCH_PDL(tc_conv_kernel<7>, grid, kThreads, smem, s, p); break;
         default: TVC_LAUNCH_PDL(tc_conv_kernel<-1>, grid, kThreads, smem, s, p); break;
     }
-    TVC_LAUNCH_CHECK();
-    return 0;
-}
-
-// ---- chains ----------------------------------------------------------------------------------------
-size_t tc_chain_op_bytes() { return sizeof(TcChainOp); }
-
-int tc_chain_add_conv(TcChain& c, const TcConvW& W, const TcConvArgs& a) {
-    TcChainOp op;
-    memset(&op, 0, sizeof(op));
-    op.type = TC_OP_CONV;
-    int spec = -1;
-    size_t smem = 0;
-    unsigned grid = 0;
-    TVC_TRY(tc_conv_params(W, a, true, op.conv, spec, smem, grid));
-    TVC_REQUIRE(smem <= (size_t)kTcMaxSmem, "tc_chain: op needs %zu bytes of shared memory", smem);
-    const unsigned char* b = reinterpret_cast<const unsigned char*>(&op);
-    c.table.insert(c.table.end(), b, b + sizeof(op));
-    ++c.n_ops;
-    return 0;
-}
-
-int tc_chain_add_interp(TcChain& c, const float* x, int B, int Tin, int Tout, float scale, int C, float* y32, bf16* r_hi,
-                        bf16* r_lo, bf16* a_hi, bf16* a_lo) {
-    TVC_REQUIRE(x && C % 8 == 0 && B > 0 && Tin > 0 && Tout > 0, "tc_chain: bad resampler op");
-    TcChainOp op;
-    memset(&op, 0, sizeof(op));
-    op.type = TC_OP_INTERP;
-    op.interp.x = x; op.interp.y32 = y32; op.interp.r_hi = r_hi; op.interp.r_lo = r_lo; op.interp.a_hi = a_hi; op.interp.a_lo = a_lo;
-    op.interp.rows_in = (long long)B * Tin; op.interp.rows_out = (long long)B * Tout; op.interp.chunks = C / 8;
-    op.interp.Tin = Tin; op.interp.Tout = Tout; op.interp.scale = scale;
-    const unsigned char* b = reinterpret_cast<const unsigned char*>(&op);
-    c.table.insert(c.table.end(), b, b + sizeof(op));
-    ++c.n_ops;
-    return 0;
-}
-
-int tc_chain_launch(const void* dev_table, int n_ops, unsigned* dev_sync, cudaStream_t s) {
-    TVC_REQUIRE(dev_table && dev_sync && n_ops > 0, "tc_chain: nothing to launch");
-    TVC_REQUIRE(((uintptr_t)dev_table & 63) == 0, "tc_chain: the op table must be 64-byte aligned (tensor maps)");
-    // cooperative: all CTAs must be resident at once (they meet at grid barriers); one CTA per SM by shared-memory size
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)g_num_sms);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = kTcMaxSmem + kChainRingOff;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeCooperative;
-    at[0].val.cooperative = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    TVC_CUDA(cudaLaunchKernelEx(&cfg, tc_chain_kernel, (const TcChainOp*)dev_table, n_ops, dev_sync));
     TVC_LAUNCH_CHECK();
     return 0;
 }

@@ -17,7 +17,6 @@
 // 2^-11 for one TF32 product, which SURVEY.md section 0 shows is not enough for RMSE < 1e-4).
 #pragma once
 #include <cuda_bf16.h>
-#include <vector>
 
 #include "tvc_common.cuh"
 
@@ -60,6 +59,12 @@ struct TcConvArgs {
     int x_cs = 0;
     int dil = 1;
     int B = 0, T = 0;                  // taps are clamped inside each utterance of T rows (replicate padding)
+    // Stored replicate padding ("padded mode", k = 3 convs): the main input planes hold a_pad >= dil extra rows on either
+    // side of every utterance (rows b * (T + 2 * a_pad) + [0, a_pad) repeat t = 0, the last a_pad repeat t = T - 1), so a
+    // tap is a shifted view and every operand window is one contiguous tensor copy, whatever T is (short utterances
+    // otherwise gather their clamped windows row by row).  y_pad: the plane output is written in the same form for
+    // the next k = 3 conv (its replicate rows included).  The aux input, the residual and y32 are never padded.
+    int a_pad = 0, y_pad = 0;
     const float* res = nullptr;        // fp32 residual (chunk-major, same rows), added after bias / FiLM
     int res_cs = 0;
     float* y32 = nullptr;              // fp32 output (chunk-major, nullable)
@@ -72,19 +77,6 @@ struct TcConvArgs {
 int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s);
 int tc_conv_init();
 
-// Chains: several convs (and the linear resamplers between them) as ONE persistent cooperative launch; the ops run in
-// order, separated by grid barriers inside the kernel (tc_conv.cu).  The host builds the table, copies it to device memory
-// (64-byte aligned, tc_chain_op_bytes() per op) and passes it with two zero-initialised counters (`dev_sync`).
-struct TcChain {
-    std::vector<unsigned char> table;
-    int n_ops = 0;
-};
-size_t tc_chain_op_bytes();
-int tc_chain_add_conv(TcChain& c, const TcConvW& W, const TcConvArgs& a);
-// F.interpolate(mode='linear') of chunk-major fp32 rows (tc_kernels.cuh interp_cl: same outputs, same arithmetic)
-int tc_chain_add_interp(TcChain& c, const float* x, int B, int Tin, int Tout, float scale, int C, float* y32, bf16* r_hi,
-                        bf16* r_lo, bf16* a_hi, bf16* a_lo);
-int tc_chain_launch(const void* dev_table, int n_ops, unsigned* dev_sync, cudaStream_t s);
 // developer timeline of selected tc_conv launches (ordinals counted from arming); see tc_conv.cu Tracer
 int tc_trace_arm(const char* ordinals);
 int tc_trace_dump(const char* path);
@@ -98,5 +90,8 @@ int cf_to_planes(const float* x, bf16* hi, bf16* lo, int B, int C, int T, int cs
 int cf_to_cl(const float* x, float* y, int B, int C, int T, int cs, cudaStream_t s);
 int cl_to_cf(const float* x, float* y, int B, int C, int T, int cs, cudaStream_t s);
 int planes_to_cf(const bf16* hi, const bf16* lo, float* y, int B, int C, int T, int cs, cudaStream_t s);
+// re-pads one plane: out row (b, tp) of a tensor with pad_out replicate rows per side <- in row (b, clamp(tp - pad_out, 0, T - 1))
+// of a tensor with pad_in (parity probes: builds padded inputs, strips padded outputs)
+int plane_repad(const bf16* in, bf16* out, int B, int T, int cs, int pad_in, int pad_out, cudaStream_t s);
 
 }  // namespace tvc

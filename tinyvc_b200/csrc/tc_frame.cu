@@ -48,7 +48,7 @@ __device__ __forceinline__ void store_planes8(bf16* hi, bf16* lo, long long off,
 __global__ void __launch_bounds__(256) interp_cl_kernel(const float* __restrict__ x, int Tin, int Tout, float scale,
                                                         long long rows_in, long long rows_out, float* __restrict__ y32,
                                                         bf16* __restrict__ r_hi, bf16* __restrict__ r_lo,
-                                                        bf16* __restrict__ a_hi, bf16* __restrict__ a_lo) {
+                                                        bf16* __restrict__ a_hi, bf16* __restrict__ a_lo, int a_pad) {
     TVC_PDL_PROLOGUE();
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows_out) return;
@@ -71,7 +71,18 @@ __global__ void __launch_bounds__(256) interp_cl_kernel(const float* __restrict_
     if (a_hi) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = leaky01(v[k]);
-        store_planes8(a_hi, a_lo, o, v);
+        if (a_pad == 0) {
+            store_planes8(a_hi, a_lo, o, v);
+        } else {
+            // stored replicate padding (tc_conv.cuh, padded mode): a_pad extra rows on either side of every utterance
+            const long long Tp = Tout + 2 * a_pad, rows_p = (rows_out / Tout) * Tp;
+            const long long op = (q * rows_p + b * Tp + a_pad + t) * 8;
+            store_planes8(a_hi, a_lo, op, v);
+            if (t == 0)
+                for (int k = 1; k <= a_pad; ++k) store_planes8(a_hi, a_lo, op - 8 * k, v);
+            if (t == Tout - 1)
+                for (int k = 1; k <= a_pad; ++k) store_planes8(a_hi, a_lo, op + 8 * k, v);
+        }
     }
 }
 
@@ -198,11 +209,11 @@ __global__ void __launch_bounds__(256) out_conv_k7_cl_kernel(const float* __rest
 }  // namespace
 
 int interp_cl(const float* x, int B, int Tin, int Tout, float scale, int C, float* y32, bf16* r_hi, bf16* r_lo, bf16* a_hi,
-              bf16* a_lo, cudaStream_t s) {
+              bf16* a_lo, cudaStream_t s, int a_pad) {
     TVC_REQUIRE(C % 8 == 0, "interp_cl: channel count %d must be a multiple of 8", C);
     const long long rows_in = (long long)B * Tin, rows_out = (long long)B * Tout;
     TVC_REQUIRE(rows_out < (1LL << 31) && rows_in < (1LL << 31), "interp_cl: too many rows");
-    TVC_LAUNCH_PDL(interp_cl_kernel, dim3(cdiv(rows_out, 256), C / 8), 256, 0, s, x, Tin, Tout, scale, rows_in, rows_out, y32, r_hi, r_lo, a_hi, a_lo);
+    TVC_LAUNCH_PDL(interp_cl_kernel, dim3(cdiv(rows_out, 256), C / 8), 256, 0, s, x, Tin, Tout, scale, rows_in, rows_out, y32, r_hi, r_lo, a_hi, a_lo, a_pad);
     TVC_LAUNCH_CHECK();
     return 0;
 }

@@ -6,8 +6,9 @@ namespace tvc {
 
 // tc_frame.cu
 // all channels-last tensors are chunk-major (tc_conv.cuh); row counts follow from B and T
+// a_pad > 0: the activation planes (a_hi / a_lo) are written with stored replicate padding (tc_conv.cuh, padded mode)
 int interp_cl(const float* x, int B, int Tin, int Tout, float scale, int C, float* y32, bf16* r_hi, bf16* r_lo, bf16* a_hi,
-              bf16* a_lo, cudaStream_t s);
+              bf16* a_lo, cudaStream_t s, int a_pad = 0);
 int dwconv_ln_cl(const float* x, const float* w7, const float* wb, const float* gamma, const float* beta,
                  bf16* hi, bf16* lo, int B, int T, cudaStream_t s);
 int grn_apply_cl(const float* y, const float* gamma, const float* beta, bf16* hi, bf16* lo, int B, int C, int T,

@@ -111,7 +111,26 @@ __global__ void __launch_bounds__(256) cl_to_cf_kernel(const float* __restrict__
     }
 }
 
+__global__ void __launch_bounds__(256) plane_repad_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int T, int pad_in,
+                                                         int pad_out, long long rows_in, long long rows_out) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows_out) return;
+    const long long q = blockIdx.y, Tpo = T + 2 * pad_out, Tpi = T + 2 * pad_in;
+    const long long b = row / Tpo;
+    int t = (int)(row - b * Tpo) - pad_out;
+    t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
+    out[q * rows_out + row] = in[q * rows_in + b * Tpi + pad_in + t];
+}
+
 }  // namespace
+
+int plane_repad(const bf16* in, bf16* out, int B, int T, int cs, int pad_in, int pad_out, cudaStream_t s) {
+    const long long rows_in = (long long)B * (T + 2 * pad_in), rows_out = (long long)B * (T + 2 * pad_out);
+    plane_repad_kernel<<<dim3(cdiv(rows_out, 256), cs / 8), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out),
+                                                                         T, pad_in, pad_out, rows_in, rows_out);
+    TVC_LAUNCH_CHECK();
+    return 0;
+}
 
 int cf_to_planes(const float* x, bf16* hi, bf16* lo, int B, int C, int T, int cs, int act, cudaStream_t s,
                  const float* extra0, const float* extra1) {

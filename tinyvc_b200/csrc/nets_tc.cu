@@ -326,11 +326,23 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         const long long rows = (long long)B * tout;
         const Pl& cond = skipP[4 - i];
         TVC_REQUIRE(skipT[4 - i] == tout && cond.cs == c, "filter_net: skip %d shape mismatch", 4 - i);
+        const bool fused = g_fused_up && i == 4 && fac == 5 && c == 24 && tc_up24_block_supported(u.c1, u.c2, u.c3, u.c4, u.c5);
+        if (fused) {
+            // resampler, the five convs and the output layer in one kernel (tc_block.cu); same arithmetic as the launches below
+            TcUpBlockArgs fa;
+            fa.x4 = x; fa.c_hi = cond.hi; fa.c_lo = cond.lo; fa.out_w = out_w; fa.out_b = out_b; fa.out = out;
+            fa.B = B; fa.T = tout; fa.T4 = tin; fa.scale = (float)(1.0 / (double)fac);
+            if (!A.dry) {
+                ProfScope ps("tc_up4_fused(", s);
+                TVC_TRY(tc_up24_block_launch(u.c1, u.c2, u.c3, u.c4, u.c5, fa, s));
+            }
+            A.release(m0);
+            return 0;
+        }
         float* xo = A.f32(rows * cn);
         const size_t m = A.mark();
         float* xi = A.f32(rows * c);
         float* y = A.f32(rows * c);
-        const bool fused = g_fused_up && c == 24 && tc_up24_block_supported(u.c1, u.c2, u.c3, u.c4, u.c5);
         // stored replicate padding (see g_pad_max_t): p0 holds c1's input (1 row), later c3's (9); p1 c2's (3), later c4's (27)
         const bool pad = !fused && tout <= g_pad_max_t;
         const int Q1 = pad ? 1 : 0, Q3 = pad ? 3 : 0, Q9 = pad ? 9 : 0, Q27 = pad ? 27 : 0;
@@ -343,19 +355,6 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
                                       {"tc_up2_c1(", "tc_up2_c2(", "tc_up2_c3(", "tc_up2_c4(", "tc_up2_c5("},
                                       {"tc_up3_c1(", "tc_up3_c2(", "tc_up3_c3(", "tc_up3_c4(", "tc_up3_c5("},
                                       {"tc_up4_c1(", "tc_up4_c2(", "tc_up4_c3(", "tc_up4_c4(", "tc_up4_c5("}};
-        if (fused) {
-            // the whole block in one kernel (tc_block.cu); same arithmetic as the five launches below
-            TcUpBlockArgs fa;
-            fa.p_hi = p0.hi; fa.p_lo = p0.lo; fa.c_hi = cond.hi; fa.c_lo = cond.lo; fa.xi = xi; fa.xo = xo; fa.xo_cs = cn;
-            fa.B = B; fa.T = tout;
-            if (!A.dry) {
-                ProfScope ps("tc_up4_fused(", s);
-                TVC_TRY(tc_up24_block_launch(u.c1, u.c2, u.c3, u.c4, u.c5, fa, s));
-            }
-            A.release(m);
-            x = xo; tin = tout;
-            continue;
-        }
         CONV(un[i][0], u.c1, ConvCall(p0, B, tout, 1).pad(Q1, Q3).out(p1, TC_ACT_LRELU));
         CONV(un[i][1], u.c2, ConvCall(p1, B, tout, 3).pad(Q3, Q9).aux(cond).res(xi, c).f32(y, c).out(p0, TC_ACT_LRELU));
         CONV(un[i][2], u.c3, ConvCall(p0, B, tout, 9).pad(Q9, Q27).out(p1, TC_ACT_LRELU));

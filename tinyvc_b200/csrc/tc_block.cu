@@ -1,33 +1,38 @@
-// Fused Upsample block at the FilterNet's highest rate (24 channels), sm_100a.  EXPERIMENTAL (default off).
+// Fused Upsample block at the FilterNet's highest rate (24 channels) + the output layer, sm_100a.
 //
-//   p  = lrelu(x)                       (input planes, produced by the resampler)
+//   x  = interp(x4, x5)                 F.interpolate(scale_factor=5, mode='linear')   (module/tinyvc/decoder.py:174)
+//   p  = lrelu(x)
 //   h1 = lrelu(c1(p))                   k = 3, dil 1
-//   y  = FiLM1(c2(h1); cond) + x        k = 3, dil 3          (module/tinyvc/decoder.py:165-171, FiLM :88-97)
+//   y  = FiLM1(c2(h1); cond) + x        k = 3, dil 3          (decoder.py:165-171, FiLM :88-97)
 //   h3 = lrelu(c3(lrelu(y)))            k = 3, dil 9
 //   z  = FiLM2(c4(h3); cond) + y        k = 3, dil 27
 //   xo = c5(z)                          1 x 1
+//   out = output_layer(xo)              k = 7, replicate pad 3, 24 -> 1                (decoder.py:220,233)
 //
-// Unfused, the five convs move ~1.5 KB per time row through L2 / HBM (every 24-channel intermediate is written as
-// split planes and read back, the fp32 residual too) and are bandwidth-bound.  Here a CTA owns a WINDOW of 512 rows of
-// one utterance (4 MMA tiles of 128 rows), keeps every intermediate in shared memory as ready-made UMMA operands
-// (chunk-major split planes are exactly the K-major smem order) and the fp32 residual `y` in TMEM, and produces the
-// 432 rows in the middle of the window: the 40 rows on either side (1 + 3 + 9 + 27) are recomputed by the
-// neighbouring windows.  Per row it reads p, x and cond (cond twice, the second time from L2) and writes xo.
+// Unfused, this chain moves ~1.9 KB per time row through L2 / HBM (the x5 resampler writes the fp32 residual and the
+// activation planes, every 24-channel intermediate is written as split planes and read back, the output conv re-reads xo)
+// and is bandwidth-bound.  Here a CTA owns a WINDOW of 512 rows of one utterance (4 MMA tiles of 128 rows), builds the
+// resampled input in shared memory from the low-rate tensor (19 B per row instead of 192), keeps every intermediate in
+// shared memory as ready-made UMMA operands (chunk-major split planes are exactly the K-major smem order), the fp32
+// residual `y` in TMEM and xo in shared memory, and produces the 426 waveform samples in the middle of the window: the
+// 43 rows on either side (1 + 3 + 9 + 27 for the convs, 3 for the output layer) are recomputed by the neighbouring
+// windows.  Per row it reads x4 (1/5 row), cond (twice, the second time from L2) and writes 4 bytes.
 //
-// The arithmetic (MMA order per tile, epilogue operations) is that of tc_conv.cu, so the result is expected to be
-// bit-identical to the five separate launches; tools/fused_block_check.py compares the two.
+// The arithmetic (resampler formula, MMA order per tile, epilogue operations, the output conv's summation order) is that
+// of interp_cl / tc_conv.cu / out_conv_k7_cl, so the result is bit-identical to the separate launches
+// (tests/test_gpu_fused_block.py compares the two).
 //
-// Shared memory (bytes):   [buffer A: hi|lo planes, 3 chunks x 584 slots x 16 B][buffer B: same][cond ring: 2 x (hi|lo, 3 chunks
-//   x 136 slots)][weight images of c1..c5, resident][mbarriers].  Slot s of a buffer holds operand row R0 + s (R0 a
-//   multiple of 8 so that one TMA box per plane lands the input in place); window row 0 sits at slot sh in [32, 40).
+// Shared memory (bytes):   [buffer A: hi|lo planes, 3 chunks x 584 slots x 16 B][cond ring: 2 x (hi|lo, 3 chunks x 136 slots)]
+//   [buffer B][weight images of c1..c5, resident][output-layer weights][mbarriers].  Window row r lives in slot 32 + r.
 //   Activations have 24 channels but a K-step is 16: the second K-step's upper chunk aliases the first chunk of
-//   whatever follows (lo plane, next buffer, cond ring, weights -- all finite bf16, all zero-initialised) and meets
-//   zero weights.
-// Warp roles (448 threads): warps 0-11 epilogue (4 TMEM lane quarters x 3 column groups), warp 12 MMA issue,
-//   warp 13 TMA producer (weights once, one window of p per segment, a cond tile per FiLM tile).
+//   whatever follows (lo plane, cond ring, weights -- all finite bf16, zero-initialised) and meets zero weights.
+// Warp roles (576 threads): warps 0-11 epilogue (4 TMEM lane quarters x 3 column groups) and the output conv, warp 12 MMA
+//   issue, warp 13 TMA producer (weights once, a cond tile per FiLM tile), warps 14-17 build the next window's input
+//   (resample, leaky-ReLU, split) in the idle buffer as soon as c4's MMAs have retired (in_free), i.e. behind c5, its
+//   epilogues and the output conv.
 // Layer l + 1 of tile j starts once the epilogues of layer l for tiles j - 1, j, j + 1 have published their rows
-// (act_ready[j] mbarriers); buffers ping-pong (L1: in -> other, L2: other -> in, ...); the next segment's input is
-// fetched into `other` as soon as c4's MMAs have retired (in_free), so it lands behind c5 and the epilogues.
+// (act_ready[j] mbarriers); buffers ping-pong (L1: in -> other, L2: other -> in, ...).  c5's epilogue stores xo (fp32) over
+// the rows of `in` its own MMA has finished reading; the output conv runs between two named barriers of the epilogue warps.
 #include <cuda.h>
 #include <cstdlib>
 #include <cstring>
@@ -42,8 +47,9 @@ namespace {
 constexpr int kBM = 128;                      // rows per MMA tile
 constexpr int kBT = 4;                        // MMA tiles per window
 constexpr int kBW = kBM * kBT;                // window rows
-constexpr int kBHalo = 40;                    // 1 + 3 + 9 + 27: rows a window cannot produce on either side
-constexpr int kBS = kBW - 2 * kBHalo;         // rows a window produces (432)
+constexpr int kBConvHalo = 40;                // 1 + 3 + 9 + 27: rows at either end of a window where c1..c4 lack their taps
+constexpr int kBHalo = kBConvHalo + 3;        // + the output layer's 3: rows a window cannot produce on either side
+constexpr int kBS = kBW - 2 * kBHalo;         // samples a window produces (426)
 constexpr int kBPad = 32;                     // slots in front of window row 0 (>= the largest dilation, multiple of 8)
 constexpr int kBSlots = kBW + 72;             // pad + alignment slack (< 8) + window + 27, rounded up to a multiple of 8
 constexpr int kBMaxDil = 27;
@@ -55,47 +61,69 @@ constexpr uint32_t kCondLbo = kCondG * 128;
 constexpr uint32_t kCondPlane = 3 * kCondLbo;
 constexpr uint32_t kCondStage = 2 * kCondPlane;
 constexpr uint32_t kCondRing = 2;
-constexpr uint32_t kOffA = 0, kOffB = kActBuf, kOffCond = 2 * kActBuf, kOffW = kOffCond + kCondRing * kCondStage;
+// Order matters: the K-step that covers channels 16-31 reads a fourth chunk that does not exist (24 channels), i.e. the
+// first chunk of whatever follows the plane at the same row slots -- for a hi plane its own lo plane, for buffer A's lo plane
+// the cond ring, for buffer B's lo plane the weight images: always finite bf16 (it meets zero weights, but 0 x NaN = NaN).
+// The same holds for a cond stage (its lo plane is followed by the next stage, the last one by kCondTail zeros).
+// Neither a buffer nor the cond ring may be followed directly by a buffer: at the end of a segment a buffer holds fp32 xo.
+constexpr uint32_t kCondTail = 18 * 128;      // >= kCondLbo, zero for the life of the kernel
+constexpr uint32_t kOffA = 0, kOffCond = kActBuf, kOffB = kOffCond + kCondRing * kCondStage + kCondTail, kOffW = kOffB + kActBuf;
+static_assert(kCondTail >= kCondLbo, "the alias of the last cond stage's fourth chunk must stay inside the zero tail");
 constexpr uint32_t kWMain = 3 * 4096, kWAux = 8192, kW5 = 4096;           // image bytes: 3 taps x (KB 32 x NTp 32 x hi|lo), FiLM 1x1, c5
 constexpr uint32_t kWBytes = 4 * kWMain + 2 * kWAux + kW5;
-constexpr uint32_t kOffBar = kOffW + kWBytes;
+constexpr uint32_t kOffOutW = kOffW + kWBytes;                            // output layer: [7 taps][24 channels] fp32, then the bias
+constexpr uint32_t kOffBar = kOffOutW + 1024;
 constexpr uint32_t kBlockSmem = kOffBar + 256;
 constexpr uint32_t kAccCols = 96;             // conv | FiLM scale | FiLM shift, 32 columns each
 constexpr uint32_t kYCol0 = 2 * kAccCols;     // TMEM columns of the fp32 residual y: 32 per tile
-constexpr int kBEpiWarps = 12, kBMmaWarp = 12, kBProdWarp = 13, kBThreads = 448;
+constexpr int kBEpiWarps = 12, kBMmaWarp = 12, kBProdWarp = 13, kBLoadWarp0 = 14, kBLoadWarps = 4, kBThreads = 576;
+constexpr int kBEpiThreads = kBEpiWarps * 32;
+constexpr int kBInRows = kBW + 2;             // rows -1 .. 512 of the window: what c1 (dil 1) reads
 static_assert(kBPad >= kBMaxDil && kBPad % 8 == 0 && kBSlots % 8 == 0, "slot geometry");
 static_assert(kBPad + 7 + kBW + kBMaxDil <= kBSlots, "buffer too short");
 static_assert(kOffB % 128 == 0 && kOffCond % 128 == 0 && kCondStage % 128 == 0 && kCondPlane % 128 == 0 && kActPlane % 128 == 0, "TMA alignment");
 static_assert(kBlockSmem <= 227 * 1024, "shared memory");
 
 struct alignas(64) UpBlockParams {
-    CUtensorMap tm_p_hi, tm_p_lo, tm_c_hi, tm_c_lo;   // [3 chunks][row / 8][128 B] views; boxes of 73 / 17 row groups
+    CUtensorMap tm_c_hi, tm_c_lo;                     // [3 chunks][row / 8][128 B] views of the cond planes; boxes of 17 row groups
     const bf16* w[5];
     uint32_t w_bytes[5], w_off16[5];                  // image sizes and their offsets (16-byte units) in the resident region
     const float* bias[5];
     const float* film_bias[2];
-    const float* xi;
-    float* xo;
-    long long rows, n_seg;
-    int T, segs_per_utt, xo_cs;
+    const float* x4;                                  // block input before resampling: fp32 chunk-major, B * T4 rows x 24 channels
+    const float *out_w, *out_b;                       // output_layer.weight [1][24][7], .bias [1]
+    float* out;                                       // waveform [B][T]
+    long long rows, rows4, n_seg;
+    int T, T4, segs_per_utt;
+    float scale;                                      // resampler scale (float)(1 / 5)
     int dil[4];
 };
 
 // Geometry of one segment (window) of the walk: seg = utterance * segs_per_utt + k.
 struct SegGeo {
-    long long baseT;   // operand row of the utterance's first time step
-    long long R0;      // operand row held by buffer slot 0 (multiple of 8; negative / past the end reads as zeros)
-    int w0;            // time step of window row 0 (k * 432 - 40; negative for the first window)
-    int sh;            // buffer slot of window row 0
+    long long baseT;   // output row of the utterance's first time step
+    long long base4;   // row of its first time step in the low-rate input
+    int w0;            // time step of window row 0 (k * 426 - 43; negative for the first window)
+    static constexpr int sh = kBPad;   // buffer slot of window row 0
     __device__ SegGeo(const UpBlockParams& p, long long seg) {
         const long long bq = seg / p.segs_per_utt;
         const int k = (int)(seg - bq * p.segs_per_utt);
         baseT = bq * p.T;
+        base4 = bq * p.T4;
         w0 = k * kBS - kBHalo;
-        R0 = (baseT + w0 - kBPad) & ~7LL;
-        sh = (int)(baseT + w0 - R0);
     }
 };
+
+// 8 channels (chunk q) of the resampled block input at time t of the utterance whose low-rate rows start at base4:
+// interp_cl's arithmetic (tc_frame.cu), so the values are the ones the separate resampler launch produces.
+__device__ __forceinline__ void resample8(const UpBlockParams& p, long long base4, int q, int t, float v[8]) {
+    const LinCoord c = lin_coord(t, p.scale, p.T4);
+    const float4* p0 = reinterpret_cast<const float4*>(p.x4 + ((long long)q * p.rows4 + base4 + c.i0) * 8);
+    const float4* p1 = reinterpret_cast<const float4*>(p.x4 + ((long long)q * p.rows4 + base4 + c.i1) * 8);
+    const float4 x0 = __ldg(p0), x1 = __ldg(p0 + 1), z0 = __ldg(p1), z1 = __ldg(p1 + 1);
+    v[0] = lin_blend(x0.x, z0.x, c); v[1] = lin_blend(x0.y, z0.y, c); v[2] = lin_blend(x0.z, z0.z, c); v[3] = lin_blend(x0.w, z0.w, c);
+    v[4] = lin_blend(x1.x, z1.x, c); v[5] = lin_blend(x1.y, z1.y, c); v[6] = lin_blend(x1.z, z1.z, c); v[7] = lin_blend(x1.w, z1.w, c);
+}
 
 __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __grid_constant__ UpBlockParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -107,7 +135,7 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 128);
 
     if (tid == 0) {
-        mbar_init(wfull, 1); mbar_init(in_full, 1); mbar_init(in_free, 1);
+        mbar_init(wfull, 1); mbar_init(in_full, kBLoadWarps); mbar_init(in_free, 1);
         for (uint32_t s = 0; s < kCondRing; ++s) { mbar_init(cond_full + 8 * s, 1); mbar_init(cond_empty + 8 * s, 1); }
         for (uint32_t b = 0; b < 2; ++b) { mbar_init(acc_full + 8 * b, 1); mbar_init(acc_empty + 8 * b, kBEpiWarps); }
         for (uint32_t j = 0; j < kBT; ++j) mbar_init(act_ready + 8 * j, kBEpiWarps);
@@ -115,6 +143,12 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
     }
     // activation buffers and cond ring start as zeros: rows nobody writes and the aliased "fourth chunk" must be finite
     for (uint32_t i = tid; i < kOffW / 16; i += kBThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // output layer weights, re-laid [tap][channel] (torch keeps [channel][tap]), bias behind them
+    for (int e = tid; e < 24 * 7 + 1; e += kBThreads) {
+        float* ws = reinterpret_cast<float*>(smem + kOffOutW);
+        if (e < 24 * 7) ws[(e % 7) * 24 + e / 7] = __ldg(p.out_w + e);
+        else ws[e] = __ldg(p.out_b);
+    }
     fence_proxy_async();
     if (warp == kBMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
@@ -132,11 +166,6 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
             long long it = 0;
             for (long long seg = blockIdx.x; seg < p.n_seg; seg += gridDim.x, ++it) {
                 const SegGeo g(p, seg);
-                const uint32_t dst = sb + ((it & 1) ? kOffB : kOffA);
-                if (it > 0) mbar_wait(in_free, (uint32_t)(it - 1) & 1u);       // c4 of the previous segment has read this buffer
-                mbar_arrive_expect_tx(in_full, kActBuf);
-                tma_load_3d(dst, &p.tm_p_hi, 0, (int)(g.R0 >> 3), 0, in_full);
-                tma_load_3d(dst + kActPlane, &p.tm_p_lo, 0, (int)(g.R0 >> 3), 0, in_full);
                 for (int pass = 0; pass < 2; ++pass) {                          // FiLM1 (c2), FiLM2 (c4)
                     for (int j = 0; j < kBT; ++j) {
                         const long long row0 = g.baseT + g.w0 + (long long)j * kBM;
@@ -169,24 +198,8 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
         long long it = 0;
         for (long long seg = blockIdx.x; seg < p.n_seg; seg += gridDim.x, ++it) {
             const SegGeo g(p, seg);
-            const uint32_t in_off = (it & 1) ? kOffB : kOffA;
             const uint32_t in16 = (it & 1) ? b16 : a16, ot16 = (it & 1) ? a16 : b16;
-            mbar_wait(in_full, (uint32_t)it & 1u);
-            // replicate padding of the input for c1 (dil 1): t = -1 <- t = 0 and t = T <- t = T - 1, where the window has them
-            if (lane < 12) {
-                const int which = lane / 6, e = lane % 6;
-                uint8_t* col = smem + in_off + (e / 3) * kActPlane + (e % 3) * kActLbo;
-                if (which == 0 && g.w0 <= 0) {
-                    const int s0 = g.sh - g.w0;
-                    *reinterpret_cast<uint4*>(col + (s0 - 1) * 16) = *reinterpret_cast<const uint4*>(col + s0 * 16);
-                }
-                if (which == 1 && p.T - 1 < g.w0 + kBW) {
-                    const int sT = g.sh + (p.T - 1 - g.w0);
-                    *reinterpret_cast<uint4*>(col + (sT + 1) * 16) = *reinterpret_cast<const uint4*>(col + sT * 16);
-                }
-            }
-            fence_proxy_async();
-            __syncwarp();
+            mbar_wait(in_full, (uint32_t)it & 1u);             // the loader warps have built this window's input (replicate rows included)
             tc_fence_after();
 #pragma unroll 1
             for (int l = 0; l < 5; ++l) {
@@ -235,6 +248,36 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
             }
         }
         __syncwarp();
+    } else if (warp >= kBLoadWarp0) {
+        // ================= input builders: p = lrelu(interp(x4)) as split planes, window rows -1 .. 512 =================
+        // One (row, chunk) item = 8 channels: two low-rate rows in (L1 / L2 hits: 5 neighbours share them), 32 B of planes
+        // out; consecutive lanes take consecutive rows (conflict-free 16-byte shared stores).  Time steps are clamped to the
+        // utterance, which is c1's replicate padding.
+        const int lt = tid - kBLoadWarp0 * 32;
+        constexpr int kItems = 3 * kBInRows, kLT = kBLoadWarps * 32;
+        long long it = 0;
+        for (long long seg = blockIdx.x; seg < p.n_seg; seg += gridDim.x, ++it) {
+            const SegGeo g(p, seg);
+            uint8_t* dst = smem + ((it & 1) ? kOffB : kOffA);
+            if (it > 0) mbar_wait(in_free, (uint32_t)(it - 1) & 1u);           // c4 of the previous segment has read this buffer
+#pragma unroll 4
+            for (int idx = lt; idx < kItems; idx += kLT) {
+                const int q = idx / kBInRows, r = idx - q * kBInRows - 1;
+                int t = g.w0 + r;
+                t = t < 0 ? 0 : (t > p.T - 1 ? p.T - 1 : t);
+                float v[8];
+                resample8(p, g.base4, q, t, v);
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split2(leaky01(v[2 * i]), leaky01(v[2 * i + 1]), h[i], l[i]);
+                uint8_t* o = dst + q * kActLbo + (SegGeo::sh + r) * 16;
+                *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(o + kActPlane) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+            fence_proxy_async();                                               // c1's MMAs read these rows
+            __syncwarp();
+            if (lane == 0) mbar_arrive(in_full);
+        }
     } else {
         // ================= epilogue: warp = (lane quarter, 8-channel group) =================
         const int quarter = warp & 3, cg = warp >> 2;
@@ -264,12 +307,8 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
                     const int r = j * kBM + rloc, t = g.w0 + r;
                     const bool inside = t >= 0 && t < p.T;
                     const long long row = g.baseT + t;
-                    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-                    if (l == 1 && inside) {                                          // residual x, requested before the wait
-                        const float4* rp = reinterpret_cast<const float4*>(p.xi + ((long long)cg * p.rows + row) * 8);
-                        r0 = __ldg(rp);
-                        r1 = __ldg(rp + 1);
-                    }
+                    float xr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (l == 1 && inside) resample8(p, g.base4, cg, t, xr);          // residual x = interp(x4), loads issued before the wait
                     mbar_wait(acc_full + 8u * buf, buse & 1u);
                     tc_fence_after();
                     const uint32_t ta = tmem + buf * kAccCols + lane_sel + (uint32_t)(cg * 8);
@@ -289,8 +328,8 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
                             v[i] = __fadd_rn(__fmul_rn(v[i], __fadd_rn(sc[i], sbv[i])), __fadd_rn(sf[i], hbv[i]));
                     }
                     if (l == 1) {
-                        v[0] = __fadd_rn(v[0], r0.x); v[1] = __fadd_rn(v[1], r0.y); v[2] = __fadd_rn(v[2], r0.z); v[3] = __fadd_rn(v[3], r0.w);
-                        v[4] = __fadd_rn(v[4], r1.x); v[5] = __fadd_rn(v[5], r1.y); v[6] = __fadd_rn(v[6], r1.z); v[7] = __fadd_rn(v[7], r1.w);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = __fadd_rn(v[i], xr[i]);
                         tmem_st8(ya, v);                                              // y stays in TMEM until c4's epilogue
                         tmem_st_wait();
                     }
@@ -304,7 +343,7 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
 #pragma unroll
                             for (int i = 0; i < 4; ++i) split2(apply_act(v[2 * i], act), apply_act(v[2 * i + 1], act), h[i], lw[i]);
                             const uint4 hv = make_uint4(h[0], h[1], h[2], h[3]), lv = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-                            const int sl = g.sh + r;
+                            const int sl = SegGeo::sh + r;
                             *reinterpret_cast<uint4*>(out + sl * 16) = hv;
                             *reinterpret_cast<uint4*>(out + kActPlane + sl * 16) = lv;
                             if (t == 0) {                                            // replicate padding for the next conv's taps
@@ -321,10 +360,12 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
                             }
                         }
                         fence_proxy_async();                                         // the next layer's MMAs read these rows
-                    } else if (inside && r >= kBHalo && r < kBHalo + kBS && cg * 8 + 8 <= p.xo_cs) {
-                        float4* o = reinterpret_cast<float4*>(p.xo + ((long long)cg * p.rows + row) * 8);
-                        o[0] = make_float4(v[0], v[1], v[2], v[3]);
-                        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    } else if (inside) {
+                        // xo (fp32) over the rows of `in` that this tile's own MMA has finished reading (c5 is 1 x 1): channels
+                        // 0-3 of the chunk where the hi plane's row was, 4-7 where the lo plane's was
+                        uint8_t* o = smem + in_off + cg * kActLbo + (SegGeo::sh + r) * 16;
+                        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<float4*>(o + kActPlane) = make_float4(v[4], v[5], v[6], v[7]);
                     }
                     tc_fence_before();
                     __syncwarp();
@@ -334,6 +375,35 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
                     }
                 }
             }
+            // ---- output layer (decoder.py:220,233): k = 7, replicate pad 3, 24 -> 1, out_conv_k7_cl's summation order.
+            //      xo of all four tiles must be in place; the next segment's first epilogue overwrites this buffer.
+            asm volatile("bar.sync 1, %0;" ::"n"(kBEpiThreads) : "memory");
+            {
+                const float* ws = reinterpret_cast<const float*>(smem + kOffOutW);
+                const uint8_t* xs = smem + in_off;
+                for (int r = kBHalo + tid; r < kBHalo + kBS; r += kBEpiThreads) {
+                    const int t = g.w0 + r;
+                    if (t < 0 || t >= p.T) continue;
+                    float acc = ws[24 * 7];
+#pragma unroll
+                    for (int jt = 0; jt < 7; ++jt) {
+                        int tt = t + jt - 3;
+                        tt = tt < 0 ? 0 : (tt > p.T - 1 ? p.T - 1 : tt);
+                        const uint8_t* row = xs + (SegGeo::sh + (tt - g.w0)) * 16;
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) {
+                            const float4 xv = *reinterpret_cast<const float4*>(row + (q >> 1) * kActLbo + (q & 1) * kActPlane);
+                            const float4 wv = *reinterpret_cast<const float4*>(ws + jt * 24 + q * 4);
+                            acc = fmaf(wv.x, xv.x, acc);
+                            acc = fmaf(wv.y, xv.y, acc);
+                            acc = fmaf(wv.z, xv.z, acc);
+                            acc = fmaf(wv.w, xv.w, acc);
+                        }
+                    }
+                    p.out[g.baseT + t] = acc;
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kBEpiThreads) : "memory");
         }
     }
     tc_fence_before();
@@ -358,18 +428,17 @@ bool tc_up24_block_supported(const TcConvW& c1, const TcConvW& c2, const TcConvW
 int tc_up24_block_launch(const TcConvW& c1, const TcConvW& c2, const TcConvW& c3, const TcConvW& c4, const TcConvW& c5,
                          const TcUpBlockArgs& a, cudaStream_t s) {
     TVC_REQUIRE(tc_up24_block_supported(c1, c2, c3, c4, c5), "tc_up24_block: conv shapes are not the 24-channel Upsample block");
-    TVC_REQUIRE(a.p_hi && a.p_lo && a.c_hi && a.c_lo && a.xi && a.xo && a.B > 0 && a.T > 0, "tc_up24_block: missing argument");
-    TVC_REQUIRE(a.xo_cs % 8 == 0 && a.xo_cs >= 8, "tc_up24_block: output capacity %d", a.xo_cs);
+    TVC_REQUIRE(a.x4 && a.c_hi && a.c_lo && a.out_w && a.out_b && a.out && a.B > 0 && a.T > 0, "tc_up24_block: missing argument");
+    TVC_REQUIRE(a.T4 > 0 && a.T == 5 * a.T4, "tc_up24_block: the block resamples x5 (T = %d, T4 = %d)", a.T, a.T4);
     for (int i = 0; i < 4; ++i)
         TVC_REQUIRE(a.dil[i] >= 1 && a.dil[i] <= kBMaxDil, "tc_up24_block: dilation %d out of range", a.dil[i]);
-    TVC_REQUIRE(a.dil[0] == 1 && a.dil[0] + a.dil[1] + a.dil[2] + a.dil[3] <= kBHalo, "tc_up24_block: dilations exceed the window halo");
+    TVC_REQUIRE(a.dil[0] == 1 && a.dil[0] + a.dil[1] + a.dil[2] + a.dil[3] <= kBConvHalo, "tc_up24_block: dilations exceed the window halo");
     static PerDeviceOnce attr;
     TVC_TRY(attr.run([] { TVC_CUDA(cudaFuncSetAttribute(tc_up24_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlockSmem)); return 0; }));
     UpBlockParams p;
     memset(&p, 0, sizeof(p));
     p.rows = (long long)a.B * a.T;
-    TVC_TRY(tc_make_plane_map(&p.tm_p_hi, a.p_hi, p.rows, 3, 3, kBSlots / 8));
-    TVC_TRY(tc_make_plane_map(&p.tm_p_lo, a.p_lo, p.rows, 3, 3, kBSlots / 8));
+    p.rows4 = (long long)a.B * a.T4;
     TVC_TRY(tc_make_plane_map(&p.tm_c_hi, a.c_hi, p.rows, 3, 3, kCondG));
     TVC_TRY(tc_make_plane_map(&p.tm_c_lo, a.c_lo, p.rows, 3, 3, kCondG));
     const TcConvW* cw[5] = {&c1, &c2, &c3, &c4, &c5};
@@ -384,8 +453,8 @@ int tc_up24_block_launch(const TcConvW& c1, const TcConvW& c2, const TcConvW& c3
     TVC_REQUIRE(off == kWBytes, "tc_up24_block: weight images total %u bytes, expected %u", off, kWBytes);
     p.film_bias[0] = c2.film_bias;
     p.film_bias[1] = c4.film_bias;
-    p.xi = a.xi; p.xo = a.xo; p.xo_cs = a.xo_cs;
-    p.T = a.T;
+    p.x4 = a.x4; p.out_w = a.out_w; p.out_b = a.out_b; p.out = a.out;
+    p.T = a.T; p.T4 = a.T4; p.scale = a.scale;
     p.segs_per_utt = cdiv(a.T, kBS);
     p.n_seg = (long long)a.B * p.segs_per_utt;
     for (int i = 0; i < 4; ++i) p.dil[i] = a.dil[i];

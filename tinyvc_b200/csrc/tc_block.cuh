@@ -1,18 +1,18 @@
-// Fused Upsample block of the FilterNet's highest rate (24 channels): c1 -> c2+FiLM1+residual -> c3 -> c4+FiLM2+residual
-// -> c5 in ONE kernel, intermediates in shared memory / TMEM (module/tinyvc/decoder.py:165-171).  EXPERIMENTAL: off
-// unless tvc_set_option("fused_up", "1"); see tc_block.cu for its state.
+// Fused Upsample block of the FilterNet's highest rate (24 channels) + output layer: x5 resampler -> c1 -> c2+FiLM1+residual
+// -> c3 -> c4+FiLM2+residual -> c5 -> output_layer (k = 7) in ONE kernel, intermediates in shared memory / TMEM
+// (module/tinyvc/decoder.py:165-190,220,233).  tvc_set_option("fused_up", "0") runs the separate launches instead.
 #pragma once
 #include "tc_conv.cuh"
 
 namespace tvc {
 
 struct TcUpBlockArgs {
-    const bf16 *p_hi = nullptr, *p_lo = nullptr;       // lrelu(x) planes of the up-sampled input, 24 channels of capacity
-    const bf16 *c_hi = nullptr, *c_lo = nullptr;       // skip tensor (FiLM condition) planes, 24 channels of capacity
-    const float* xi = nullptr;                         // up-sampled input, fp32 chunk-major (residual of c2), 24 channels
-    float* xo = nullptr;                               // c5 output, fp32 chunk-major, xo_cs channels of capacity
-    int xo_cs = 0;
-    int B = 0, T = 0;
+    const float* x4 = nullptr;                         // block input BEFORE the x5 resampler: fp32 chunk-major, B * T4 rows, 24 channels
+    const bf16 *c_hi = nullptr, *c_lo = nullptr;       // skip tensor (FiLM condition) planes, B * T rows, 24 channels of capacity
+    const float *out_w = nullptr, *out_b = nullptr;    // output_layer.weight [1][24][7] / .bias [1] (torch layout)
+    float* out = nullptr;                              // waveform [B][T]
+    int B = 0, T = 0, T4 = 0;                          // T = 5 * T4
+    float scale = 0.2f;                                // F.interpolate's source-index scale, (float)(1 / 5)
     int dil[4] = {1, 3, 9, 27};                        // dilations of c1..c4 (c5 is 1x1)
 };
 

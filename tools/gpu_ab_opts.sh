@@ -7,7 +7,7 @@ for opts in "$@"; do
 import json, sys
 try:
     d = json.load(open("gpurun_out/bench_ab_tmp.json")); k = d["roofline"]["breakdown"]["per_kernel_ms_per_step"]
-    top = [(n, v) for n, v in sorted(k.items()) if n.startswith("tc_down") and n != "tc_down0"]
+    top = sorted(k.items(), key=lambda kv: -kv[1])[:8]
     print(f"opts={sys.argv[1]!r} ms_per_step={d['ms_per_step']:.4f} value={d['value']/1e6:.1f}M e2e={d['e2e']['value']/1e6:.1f}M launches/step={d['gpu_launches']/d['steps']:.0f}", {n: round(v, 4) for n, v in top})
 except Exception as e:
     print(f"opts={sys.argv[1]!r} FAILED {e}"); print(open("gpurun_out/bench_ab_tmp.err").read()[-2000:])

@@ -28,8 +28,9 @@ static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static bool g_use_graphs = true;
 static int g_probe_pad_in = 0, g_probe_pad_out = 0;     // tvc_set_option("probe_pad", ...): tests only
-bool g_pdl = false;      // programmatic dependent launch between the decoder plan's kernels (measured: no gain while a
-                         // tc_conv CTA fills an SM's registers and shared memory, so successors cannot become resident early)
+bool g_pdl = true;       // programmatic dependent launch between the decoder plan's kernels: the next kernel's CTAs start their
+                         // set-up (mbarriers, TMEM, weight prefetch) on SMs the current one leaves idle (most layers of the
+                         // low rates have fewer tiles than SMs); same-box A/B 0.986 -> 0.955 ms (profiles/r02h_pdl_ab.log)
 
 // ---- event profiler ----------------------------------------------------------------------------
 struct ProfEntry { std::string name; cudaEvent_t a, b; };

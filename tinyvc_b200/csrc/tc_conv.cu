@@ -129,6 +129,10 @@ struct Tracer {
             base[n++] = make_uint2((uint32_t)clock64(), ((uint32_t)role << 28) | ((uint32_t)ev << 24) | (((uint32_t)tile & 0xffffu) << 8) | ((uint32_t)stage & 0xffu));
         }
     }
+    // an event with a time stamp taken earlier (kernel entry), or a value of another clock (globaltimer, ns)
+    __device__ __forceinline__ void log_at(int role, int ev, uint32_t stamp) {
+        if (base && n < kTraceRegion) base[n++] = make_uint2(stamp, ((uint32_t)role << 28) | ((uint32_t)ev << 24));
+    }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -144,6 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     extern __shared__ __align__(1024) uint8_t smem[];
     pdl_launch_dependents();      // the next kernel of the plan may start its prologue as soon as SM resources free up
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t t_entry = (uint32_t)clock64();                  // developer timeline only
     const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
     const uint32_t smem_base = smem_u32(smem);
     // barriers: full[ring], empty[ring], acc_full[2], acc_empty[2]
@@ -167,21 +172,34 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     const long long tile_beg = (long long)blockIdx.x * per_cta;
     const long long tile_end = tile_beg + per_cta < n_tiles_total ? tile_beg + per_cta : n_tiles_total;
 
-    if (tid == 0) {
-        for (int s = 0; s < p.ring; ++s) {
-            mbar_init(bar_base + 8u * s, kTileM + 1);              // full: 128 gather arrivals + 1 expect_tx
-            mbar_init(bar_base + 8u * (p.ring + s), 1);            // empty: one tcgen05.commit
+    // Set-up is split so that the first loads are in flight ~1 us earlier (profiles/r02h_tc_trace_view.txt: barrier
+    // initialisation + TMEM allocation + a CTA-wide barrier took ~2 000 cycles before any producer moved): the lead producer
+    // thread initialises the mbarriers, the four producer warps meet on named barrier 2 and start fetching; everybody else
+    // (epilogue and MMA warps) additionally waits for the TMEM allocation on named barrier 1, which the first producer warp
+    // only signals.
+    constexpr int kSetupThreads = kThreads - 4 * 32 + 32;          // non-producers + the signalling producer warp
+    uint32_t tmem = 0;
+    if (warp >= kProdWarp0 && warp < kMmaWarp2) {
+        if (tid == kProdWarp0 * 32) {
+            for (int s = 0; s < p.ring; ++s) {
+                mbar_init(bar_base + 8u * s, kTileM + 1);          // full: 128 gather arrivals + 1 expect_tx
+                mbar_init(bar_base + 8u * (p.ring + s), 1);        // empty: one tcgen05.commit
+            }
+            mbar_init(wfull, 1);
+            mbar_init(acc_full, 1); mbar_init(acc_full + 8, 1);
+            mbar_init(acc_empty, kEpiWarps); mbar_init(acc_empty + 8, kEpiWarps);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        mbar_init(wfull, 1);
-        mbar_init(acc_full, 1); mbar_init(acc_full + 8, 1);
-        mbar_init(acc_empty, kEpiWarps); mbar_init(acc_empty + 8, kEpiWarps);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (warp == kProdWarp0) asm volatile("bar.arrive 1, %0;" ::"n"(kSetupThreads) : "memory");
+    } else {
+        if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+        tc_fence_before();
+        asm volatile("bar.sync 1, %0;" ::"n"(kSetupThreads) : "memory");
+        tc_fence_after();
+        tmem = *tmem_slot;
     }
-    if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
 
     if (warp >= kProdWarp0 && warp < kMmaWarp2) {
         // ================= producers =================
@@ -420,6 +438,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
             const uint32_t sbase = mine * rhalf;                          // first slot of this warp's half (single issuer: 0)
             ring = rhalf;                                                  // wrap point of this warp's slot counter
             Tracer tr((leader && mine == 0) ? p.trace : nullptr, 1);
+            if (p.trace) {                                                 // ev 6: kernel entry, ev 8: globaltimer (ns) now
+                unsigned long long gt;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+                tr.log_at(1, 6, t_entry);
+                tr.log_at(1, 8, (uint32_t)gt);
+                tr.log(1, 7, 0, 0);                                        // ev 7: the MMA warp is ready to issue
+            }
             const long long n_my = tile_end - tile_beg;
             if (wres && n_my > 0) { mbar_wait(wfull, 0u); tc_fence_after(); }
             for (long long it = 0; it < n_my; ++it, ++tcount) {
@@ -654,6 +679,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (p.trace && blockIdx.x == 0 && tid == 0) {                  // developer timeline: all roles of CTA 0 are done (ev 9, ev 10 = ns)
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        p.trace[4 * kTraceRegion - 2] = make_uint2((uint32_t)clock64(), (3u << 28) | (9u << 24));
+        p.trace[4 * kTraceRegion - 1] = make_uint2((uint32_t)gt, (3u << 28) | (10u << 24));
+    }
     if (warp == kMmaWarp) tmem_dealloc(tmem, p.tmem_cols);
 }
 
@@ -822,7 +853,10 @@ int tc_trace_dump(const char* path) {
         for (int r = 0; r < 4; ++r)
             for (int e = 0; e < kTraceRegion; ++e) {
                 const uint2 v = h[((size_t)i * 4 + r) * kTraceRegion + e];
-                if (!v.y && !v.x) break;
+                if (!v.y && !v.x) {
+                    if (e < kTraceRegion - 2) e = kTraceRegion - 3;      // the kernel-exit stamps sit in the last two slots
+                    continue;
+                }
                 fprintf(f, "%d %u %u %u %u %u\n", g_trace_want[i], v.y >> 28, (v.y >> 24) & 15u, (v.y >> 8) & 0xffffu, v.y & 0xffu, v.x);
             }
     fclose(f);

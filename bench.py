@@ -326,6 +326,8 @@ def scatter_gather(dec, dev, rank: int, world: int, steps: int, barrier) -> dict
         want = dec.infer(small["content"], small["f0"], small["energy"], rand01=small["rand01"])
         res["bit_identical_to_one_gpu"] = bool(torch.equal(got, want))
     barrier()
+    sdp.close()
+    sd.close()
     del full
     torch.cuda.empty_cache()
     return res
@@ -513,6 +515,8 @@ def run_ours(args) -> None:
 
 
 def main() -> None:
+    import faulthandler
+    faulthandler.enable()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -48,10 +48,17 @@ int tvc_profile_report(char* buf, size_t n);
 /* Measurement aid (bench.py's `fp32_flop_fraction` denominator): sustained CUDA-core FP32 FMA rate of the current
  * device in TFLOP/s, from a register-resident FMA micro-benchmark timed with CUDA events.            */
 int tvc_measure_fp32_peak(double* tflops, void* stream);
-/* Multi-GPU (tinyvc_b200/shard.py, one process per GPU): lets kernels of the CURRENT device load / store memory of
- * `peer_device` (cudaDeviceEnablePeerAccess), which is what allows tvc_decoder_infer's last kernel to store its
- * waveform straight into a result buffer that lives on another GPU of the box (NVLink / NVSwitch).  Idempotent.  */
-int tvc_enable_peer_access(int peer_device);
+/* Multi-GPU (tinyvc_b200/shard.py, one process per GPU, one box): a result buffer on the owner's GPU that the kernels of
+ * every other rank's GPU store into directly over NVLink / NVSwitch (tvc_decoder_infer's last kernel writes its waveform
+ * block into it, so the sharded mode has no gather step).
+ *   tvc_peer_alloc : owner.  cudaMalloc on the current device + its CUDA IPC handle (64 bytes, to be sent to the peers).
+ *   tvc_peer_open  : peer.   Maps the owner's buffer into the CURRENT device's address space (cudaIpcOpenMemHandle with lazy
+ *                    peer access), which is what makes it addressable by this device's kernels.
+ *   tvc_peer_close / tvc_peer_free : undo the two.                                                                     */
+int tvc_peer_alloc(size_t bytes, void** ptr, unsigned char handle[64]);
+int tvc_peer_open(const unsigned char handle[64], void** ptr);
+int tvc_peer_close(void* ptr);
+int tvc_peer_free(void* ptr);
 
 /* ---- parameter contract: flat fp32 buffers in torch state_dict() order ------------------- */
 /* kind: 0 = Decoder (module/tinyvc/decoder.py:236-251), 1 = Encoder (encoder.py:100-106).     */

@@ -32,7 +32,10 @@ _SIGNATURES = {
     "tvc_launch_count": (ctypes.c_ulonglong, []),
     "tvc_measure_fp32_peak": (c_int, [ctypes.POINTER(ctypes.c_double), c_void_p]),
     "tvc_profile_report": (c_int, [c_char_p, c_size_t]),
-    "tvc_enable_peer_access": (c_int, [c_int]),
+    "tvc_peer_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_ubyte)]),
+    "tvc_peer_open": (c_int, [ctypes.POINTER(ctypes.c_ubyte), ctypes.POINTER(c_void_p)]),
+    "tvc_peer_close": (c_int, [c_void_p]),
+    "tvc_peer_free": (c_int, [c_void_p]),
     "tvc_param_count": (c_int, [c_int]),
     "tvc_param_name": (c_char_p, [c_int, c_int]),
     "tvc_param_numel": (c_int64, [c_int, c_int]),

@@ -223,16 +223,43 @@ int tvc_measure_fp32_peak(double* tflops, void* stream) {
     API_END
 }
 
-int tvc_enable_peer_access(int peer_device) {
+int tvc_peer_alloc(size_t bytes, void** ptr, unsigned char handle[64]) {
     API_BEGIN
-    int dev = 0, can = 0;
-    TVC_CUDA(cudaGetDevice(&dev));
-    if (dev == peer_device) return 0;
-    TVC_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
-    TVC_REQUIRE(can, "tvc_enable_peer_access: device %d cannot address device %d", dev, peer_device);
-    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
-    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
-    TVC_CUDA(e);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    TVC_REQUIRE(ptr && handle && bytes > 0, "tvc_peer_alloc: bad arguments");
+    void* p = nullptr;
+    TVC_CUDA(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        TVC_CUDA(e);
+    }
+    memcpy(handle, &h, sizeof(h));
+    *ptr = p;
+    return 0;
+    API_END
+}
+int tvc_peer_open(const unsigned char handle[64], void** ptr) {
+    API_BEGIN
+    TVC_REQUIRE(ptr && handle, "tvc_peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    TVC_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr = p;
+    return 0;
+    API_END
+}
+int tvc_peer_close(void* ptr) {
+    API_BEGIN
+    if (ptr) TVC_CUDA(cudaIpcCloseMemHandle(ptr));
+    return 0;
+    API_END
+}
+int tvc_peer_free(void* ptr) {
+    API_BEGIN
+    if (ptr) TVC_CUDA(cudaFree(ptr));
     return 0;
     API_END
 }

@@ -49,6 +49,57 @@ def share_from(owner: int, tensors: Optional[Dict[str, torch.Tensor]], group=Non
     return open_handles(box[0])
 
 
+class _RawCuda:
+    """Minimal `__cuda_array_interface__` carrier: lets torch alias device memory it did not allocate."""
+
+    def __init__(self, ptr: int, shape, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class ResultWindow:
+    """A [n, L] fp32 result buffer on the owner's GPU that every rank's KERNELS can store into.
+
+    torch's IPC tensors are opened in a context of the owner's device, which is enough for copy engines but not for
+    stores issued by another GPU's kernels; the library therefore allocates the buffer itself (`tvc_peer_alloc`) and
+    every other rank maps it into ITS OWN device's address space (`tvc_peer_open`: `cudaIpcOpenMemHandle` with lazy peer
+    access under the rank's device).  `tensor` aliases the memory as a torch tensor on this rank's device.
+    Collective: construct on every rank of the group in the same order."""
+
+    def __init__(self, owner: int, shape, device: torch.device, group=None):
+        import ctypes
+
+        from . import _lib
+        self.device = torch.device(device)
+        self.owner = dist.get_rank(group) == owner
+        self._ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        n = 1
+        for d in shape:
+            n *= int(d)
+        with torch.cuda.device(self.device):
+            if self.owner:
+                _lib.check(_lib.lib().tvc_peer_alloc(max(n, 1) * 4, ctypes.byref(self._ptr), handle), "tvc_peer_alloc")
+            box = [bytes(handle) if self.owner else None]
+            src = dist.get_global_rank(group, owner) if group is not None else owner
+            dist.broadcast_object_list(box, src=src, group=group)
+            if not self.owner:
+                h = (ctypes.c_ubyte * 64).from_buffer_copy(box[0])
+                _lib.check(_lib.lib().tvc_peer_open(h, ctypes.byref(self._ptr)), "tvc_peer_open")
+            # torch labels the alias with the device it finds the memory on (the owner's ordinal); that label is only used
+            # for slicing and copies -- kernels receive the raw address, which is valid under this rank's device
+            self.tensor = torch.as_tensor(_RawCuda(self._ptr.value, shape))
+
+    def close(self) -> None:
+        from . import _lib
+        if self._ptr:
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize(self.device)
+                fn = _lib.lib().tvc_peer_free if self.owner else _lib.lib().tvc_peer_close
+                fn(self._ptr)
+            self._ptr = None
+            self.tensor = None
+
+
 def p2p_available(device: torch.device, owner_device: int) -> bool:
     """Whether kernels / copy engines of `device` can address the owner's GPU directly."""
     if device.type != "cuda":

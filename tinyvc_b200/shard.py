@@ -176,7 +176,8 @@ class _P2PState:
         self.win: Dict[str, torch.Tensor] = {}
         self.n = 0
         self.names: Tuple[str, ...] = ()
-        self.result: Optional[torch.Tensor] = None      # owner only
+        self.result: Optional[torch.Tensor] = None      # the gathered waveforms: owner's buffer, mapped on every rank
+        self.window = None                              # peer.ResultWindow behind `result`
         self.stage: List[Fields] = []                   # two input staging sets (non-owners)
         self.ybuf: List[torch.Tensor] = []              # two output staging buffers (non-owners, copy-out mode)
         self.copy_in: Optional[torch.cuda.Stream] = None
@@ -252,30 +253,56 @@ class ShardedDecoder:
             for k in names:
                 if not fields[k].is_contiguous():
                     raise RuntimeError(f"ShardedDecoder: {k} must be contiguous on rank 0 (it is published as a peer window)")
-            L = fields["energy"].shape[-1]
-            st.result = torch.empty((n, L), device=self.device, dtype=torch.float32)
             st.key, st.names, st.n = key, names, n
-            st.win = peer.share_from(0, {**{k: fields[k] for k in names}, "result": st.result}, self.group)
+            st.win = peer.share_from(0, {k: fields[k] for k in names}, self.group)
+            L = int(fields["energy"].shape[-1])
+            hdr2 = torch.tensor([L], dtype=torch.int64, device=self.device)
         else:
             st.win = peer.share_from(0, None, self.group)
-            st.names = tuple(sorted(k for k in st.win if k != "result"))
+            st.names = tuple(sorted(st.win))
             st.n = int(hdr[1])
             st.key = ("remote", st.n)
             st.stage, st.ybuf = [], []
-            # first touch of the owner's GPU from this process.  Copy engines need nothing, but the conversion's last
-            # kernel STORES into the owner's result tensor (direct_out): kernels of this device may only address the
-            # owner's memory once peer access is enabled in THIS direction (torch's peer copies enable the other one).
-            owner_dev = st.win["result"].device.index
-            if self.direct_out and owner_dev != self.device.index:
-                from . import _lib
-                with torch.cuda.device(self.device):
-                    _lib.check(_lib.lib().tvc_enable_peer_access(owner_dev), "tvc_enable_peer_access")
+            hdr2 = torch.zeros(1, dtype=torch.int64, device=self.device)
+            # first touch of the owner's GPU from this process: a tiny peer copy makes torch set the copy path up
             probe = torch.empty(1, device=self.device)
-            probe.copy_(st.win["result"].view(-1)[:1])
+            probe.copy_(st.win[st.names[0]].view(-1)[:1])
             torch.cuda.synchronize(self.device)
+        dist.broadcast(hdr2, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        # the result lives in a buffer the library allocated on rank 0 and every rank mapped under its own device, so that
+        # the conversion's last kernel can store into it from any GPU (peer.ResultWindow)
+        if st.window is not None:
+            st.window.close()
+        st.window = peer.ResultWindow(0, (st.n, int(hdr2[0])), self.device, self.group)
+        st.result = st.window.tensor
         if st.copy_in is None:
             st.copy_in = torch.cuda.Stream(self.device)
             st.copy_out = torch.cuda.Stream(self.device)
+
+    def close(self) -> None:
+        """Collective.  Releases the peer windows: the other ranks drop their mappings of rank 0's tensors first, then rank 0
+        frees the result buffer.  (The tensor `infer` returned on rank 0 aliases that buffer: clone it to keep it.)"""
+        rank, world = _world(self.group)
+        st = self._p2p
+        if world > 1 and self.transport == "p2p" and st.key is not None:
+            torch.cuda.synchronize(self.device)
+            if rank != 0:
+                st.win, st.stage, st.ybuf = {}, [], []
+                if st.window is not None:
+                    st.window.close()
+                    st.window = None
+                import gc
+                gc.collect()
+                torch.cuda.ipc_collect()               # torch releases its IPC references lazily
+            dist.barrier(group=self.group)
+            if rank == 0:
+                st.win = {}
+                if st.window is not None:
+                    st.window.close()
+                    st.window = None
+            st.result = None
+            st.key = None
+            dist.barrier(group=self.group)
 
     def _infer_p2p(self, fields: Optional[Fields]) -> Optional[torch.Tensor]:
         rank, world = _world(self.group)
@@ -301,7 +328,7 @@ class ShardedDecoder:
             st.stage = [{k: torch.empty((mmax, *st.win[k].shape[1:]), device=self.device, dtype=torch.float32) for k in names}
                         for _ in range(2)]
             if not self.direct_out:
-                st.ybuf = [torch.empty((mmax, st.win["result"].shape[1]), device=self.device, dtype=torch.float32) for _ in range(2)]
+                st.ybuf = [torch.empty((mmax, st.result.shape[1]), device=self.device, dtype=torch.float32) for _ in range(2)]
         ready = [torch.cuda.Event() for _ in mbs]
         done = [torch.cuda.Event() for _ in mbs]
         pushed = [torch.cuda.Event() for _ in mbs]
@@ -323,7 +350,7 @@ class ShardedDecoder:
             cur.wait_event(ready[j])
             mb = {k: st.stage[j & 1][k][:m] for k in names}
             if self.direct_out:
-                self._decode(mb["content"], mb["f0"], mb["energy"], mb.get("rand01"), out=st.win["result"][g0:g0 + m])
+                self._decode(mb["content"], mb["f0"], mb["energy"], mb.get("rand01"), out=st.result[g0:g0 + m])
                 done[j].record(cur)
             else:
                 if j >= 2:
@@ -333,7 +360,7 @@ class ShardedDecoder:
                 done[j].record(cur)
                 with torch.cuda.stream(st.copy_out):
                     st.copy_out.wait_event(done[j])
-                    st.win["result"][g0:g0 + m].copy_(y, non_blocking=True)
+                    st.result[g0:g0 + m].copy_(y, non_blocking=True)
                     pushed[j].record(st.copy_out)
             if j + 2 < len(mbs):
                 pull(j + 2)

@@ -27,6 +27,7 @@ void set_error(const char* fmt, ...) {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static bool g_use_graphs = true;
+static bool g_encoder_tc = true;     // tvc_set_option("encoder_impl", "tc"|"fp32"): Encoder on tcgen05 (default) or exact-fp32 CUDA cores
 static int g_probe_pad_in = 0, g_probe_pad_out = 0;     // tvc_set_option("probe_pad", ...): tests only
 bool g_pdl = true;       // programmatic dependent launch between the decoder plan's kernels: the next kernel's CTAs start their
                          // set-up (mbarriers, TMEM, weight prefetch) on SMs the current one leaves idle (most layers of the
@@ -154,6 +155,12 @@ int tvc_set_option(const char* key, const char* value) {
         if (!strcmp(value, "fp32")) { g_conv_impl = CONV_IMPL_FP32; return 0; }
         if (!strcmp(value, "tc")) { g_conv_impl = CONV_IMPL_TC; return 0; }
         set_error("conv_impl: unknown value '%s'", value);
+        return 2;
+    }
+    if (!strcmp(key, "encoder_impl")) {
+        if (!strcmp(value, "fp32")) { g_encoder_tc = false; return 0; }
+        if (!strcmp(value, "tc")) { g_encoder_tc = true; return 0; }
+        set_error("encoder_impl: unknown value '%s'", value);
         return 2;
     }
     if (!strcmp(key, "tc_trace")) return tc_trace_arm(value);          // developer: "k0,k1,..." launch ordinals
@@ -456,9 +463,21 @@ int tvc_encoder_destroy(tvc_encoder_t h) { delete h; return 0; }
 
 size_t tvc_encoder_workspace_bytes(int B, int Lf) {
     if (B <= 0 || Lf <= 0) return 0;
-    // x, t1 [B,384,Lf]; t2 [B,768,Lf]; sc [B,768]; logits [B,512,Lf]  (+ alignment slack)
     const size_t f = sizeof(float);
-    return (size_t)B * Lf * f * (384 + 384 + 768 + 512) + (size_t)B * 768 * f + 16 * 256;
+    // exact-fp32 plan: x, t1 [B,384,Lf]; t2 [B,768,Lf]; sc [B,768]; logits [B,512,Lf]  (+ alignment slack)
+    const size_t fp32_plan = (size_t)B * Lf * f * (384 + 384 + 768 + 512) + (size_t)B * 768 * f + 16 * 256;
+    // tensor-core plan: dry run of the same launch sequence
+    static const EncoderTC shape_only = [] {
+        EncoderTC e;
+        e.ssl.C = 384; e.ssl.c0 = 0; e.ssl.mid.resize(6); e.ssl.out.Cout = 768;
+        e.pitch.C = 128; e.pitch.c0 = 384; e.pitch.mid.resize(4); e.pitch.out.Cout = 512;
+        return e;
+    }();
+    Arena A(nullptr, 0, true);
+    float dummy = 0.f;
+    (void)shape_only.forward(A, nullptr, &dummy, &dummy, &dummy, B, Lf);
+    const size_t tc_plan = A.peak + (size_t)B * 512 * Lf * f + 16 * 256;
+    return tc_plan > fp32_plan ? tc_plan : fp32_plan;
 }
 
 int tvc_encoder_forward(tvc_encoder_t h, const float* spec, float* z, float* logits, float* f0, int B, int Lf,
@@ -468,6 +487,15 @@ int tvc_encoder_forward(tvc_encoder_t h, const float* spec, float* z, float* log
     CHECK_SHAPES();
     Arena A(workspace, workspace_bytes, false);
     cudaStream_t s = (cudaStream_t)stream;
+    if (g_encoder_tc) {
+        TVC_REQUIRE(h->m.tc && h->m.tc->ready, "tvc_encoder_forward: tensor-core plan not initialised");
+        float* lg = logits;
+        if (!lg && f0) lg = A.f32((int64_t)B * 512 * Lf);
+        TVC_REQUIRE(!A.overflow, "workspace too small");
+        if (z || lg) TVC_TRY(h->m.tc->forward(A, s, spec, z, lg, B, Lf));
+        if (f0) TVC_TRY(pitch_decode(lg, f0, B, 512, Lf, s));
+        return 0;
+    }
     if (z) TVC_TRY(h->m.run_stack(A, s, h->m.ssl, spec, z, B, Lf));
     if (logits || f0) {
         float* lg = logits ? logits : A.f32((int64_t)B * 512 * Lf);

@@ -436,6 +436,8 @@ int DecoderModel::infer(Arena& A, cudaStream_t s, const float* content, const fl
 // =============================================================================================
 // encoder
 // =============================================================================================
+EncoderModel::~EncoderModel() { delete tc; }
+
 int EncoderModel::init(const float* params, int64_t numel) {
     build_encoder_table(store.table);
     TVC_TRY(store.load(params, numel));
@@ -457,6 +459,8 @@ int EncoderModel::init(const float* params, int64_t numel) {
         TVC_TRY(store.make_conv(p + ".output_layer", d.st->out, s));
     }
     TVC_CUDA(cudaStreamSynchronize(s));
+    tc = new EncoderTC();
+    TVC_TRY(tc->init(store));
     return 0;
 }
 

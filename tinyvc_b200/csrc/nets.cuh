@@ -100,8 +100,12 @@ struct DecoderModel {
               const float* rand01, float* out, int B, int Lf, int impl);   // impl: ConvImpl, chosen by the caller
 };
 
+struct EncoderTC;   // nets_tc.cuh: tensor-core execution plan
+
 struct EncoderModel {
     WeightStore store;
+    EncoderTC* tc = nullptr;
+    ~EncoderModel();
     struct Stack {
         ConvW in, out;
         const float *ln_g = nullptr, *ln_b = nullptr;

@@ -368,6 +368,115 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
     return 0;
 }
 
+// =============================================================================================
+// Encoder on the tensor-core path
+// =============================================================================================
+EncoderTC::~EncoderTC() {
+    in.free_all();
+    for (Stack* st : {&ssl, &pitch}) {
+        st->out.free_all();
+        for (auto& b : st->mid) { b.c2.free_all(); b.c3.free_all(); }
+    }
+    if (w7_buf) cudaFree(w7_buf);
+}
+
+int EncoderTC::init(const WeightStore& store) {
+    HostW H;
+    H.table = &store.table;
+    H.flat.resize((size_t)store.table.total);
+    TVC_CUDA(cudaMemcpy(H.flat.data(), store.flat, sizeof(float) * H.flat.size(), cudaMemcpyDeviceToHost));
+    const int kSslDilTc[6] = {1, 3, 9, 1, 1, 1};               // encoder.py:80
+    struct Def { Stack* st; const char* name; int C, layers, c0; };
+    const Def defs[2] = {{&ssl, "ssl_feature_estimator", 384, 6, 0}, {&pitch, "pitch_estimator", 128, 4, 384}};
+    // ---- merged input layers: rows [0, 384) ssl.input_layer, [384, 512) pitch.input_layer  (encoder.py:27,84)
+    {
+        std::vector<float> w((size_t)512 * kBins), b(512);
+        for (const Def& d : defs) {
+            const std::string p = d.name;
+            const float *iw = H.get(p + ".input_layer.weight"), *ib = H.get(p + ".input_layer.bias");
+            TVC_REQUIRE(iw && ib, "tc encoder weights: missing %s.input_layer", d.name);
+            memcpy(&w[(size_t)d.c0 * kBins], iw, sizeof(float) * (size_t)d.C * kBins);
+            memcpy(&b[d.c0], ib, sizeof(float) * d.C);
+        }
+        TVC_TRY(tc_pack_conv(w.data(), b.data(), 512, kBins, 1, nullptr, nullptr, 0, 0, 128, in));
+    }
+    // ---- depth-wise weights of all blocks, repacked [7][C]
+    size_t w7_total = 0;
+    for (const Def& d : defs) w7_total += (size_t)d.layers * 7 * d.C;
+    std::vector<float> w7(w7_total);
+    TVC_CUDA(cudaMalloc(&w7_buf, sizeof(float) * w7_total));
+    size_t w7_off = 0;
+    for (const Def& d : defs) {
+        Stack& st = *d.st;
+        const std::string p = d.name;
+        st.C = d.C; st.c0 = d.c0;
+        st.ln_g = store.raw(p + ".norm.gamma"); st.ln_b = store.raw(p + ".norm.beta");
+        TVC_REQUIRE(st.ln_g && st.ln_b, "tc encoder weights: missing %s.norm", d.name);
+        st.mid.resize(d.layers);
+        for (int i = 0; i < d.layers; ++i) {
+            const std::string q = p + ".mid_layers." + std::to_string(i);
+            Blk& k = st.mid[i];
+            k.dil = d.st == &ssl ? kSslDilTc[i] : 1;
+            const float* dw = H.get(q + ".c1.weight");         // [C][1][7]
+            TVC_REQUIRE(dw, "tc encoder weights: missing %s.c1", q.c_str());
+            for (int c = 0; c < d.C; ++c)
+                for (int j = 0; j < 7; ++j) w7[w7_off + (size_t)j * d.C + c] = dw[c * 7 + j];
+            k.w7 = w7_buf + w7_off;
+            w7_off += (size_t)7 * d.C;
+            k.wb = store.raw(q + ".c1.bias");
+            k.ln_g = store.raw(q + ".norm.gamma"); k.ln_b = store.raw(q + ".norm.beta");
+            k.grn_g = store.raw(q + ".grn.gamma"); k.grn_b = store.raw(q + ".grn.beta");
+            TVC_REQUIRE(k.wb && k.ln_g && k.ln_b && k.grn_g && k.grn_b, "tc encoder weights: incomplete %s", q.c_str());
+            TVC_TRY(pack_named(H, q + ".c2", 128, k.c2));
+            TVC_TRY(pack_named(H, q + ".c3", d.C == 384 ? 96 : 64, k.c3));
+        }
+        TVC_TRY(pack_named(H, p + ".output_layer", 128, st.out));
+    }
+    TVC_CUDA(cudaMemcpy(w7_buf, w7.data(), sizeof(float) * w7_total, cudaMemcpyHostToDevice));
+    ready = true;
+    return 0;
+}
+
+int EncoderTC::forward(Arena& A, cudaStream_t s, const float* spec, float* z, float* logits, int B, int Lf) const {
+    const long long rows = (long long)B * Lf;
+    const size_t m0 = A.mark();
+    constexpr int kSpecCs = 968;
+    float* fx = A.f32(rows * 512);                 // [ssl x (384) | pitch x (128)], fp32 chunk-major
+    {
+        const size_t m = A.mark();
+        Pl sp = planes(A, rows, kSpecCs);
+        ARENA_OK();
+        RUN(cf_to_planes(spec, sp.hi, sp.lo, B, kBins, Lf, kSpecCs, TC_ACT_NONE, s));
+        CONV("tc_enc_in(", in, ConvCall(sp, B, Lf).f32(fx, 512));
+        A.release(m);
+    }
+    const Stack* stacks[2] = {&ssl, &pitch};
+    float* outs[2] = {z, logits};
+    for (int k = 0; k < 2; ++k) {
+        if (!outs[k]) continue;
+        const Stack& st = *stacks[k];
+        const int C = st.C, Cout = st.out.Cout;
+        const size_t m = A.mark();
+        float* x = fx + cm(0, st.c0, rows);        // this stack's channels of the merged product (a chunk-major view)
+        Pl t1 = planes(A, rows, C), xp = planes(A, rows, C), t2p = planes(A, rows, 2 * C);
+        float* t2 = A.f32(rows * 2 * C);
+        float* y = A.f32(rows * Cout);
+        ARENA_OK();
+        RUN(cnxt_ln_cl(x, nullptr, nullptr, st.ln_g, st.ln_b, xp.hi, xp.lo, x, B, C, Lf, 1, s));       // encoder.py:29,86
+        for (const Blk& b : st.mid) {              // convnext.py:49-58
+            RUN(cnxt_ln_cl(x, b.w7, b.wb, b.ln_g, b.ln_b, t1.hi, t1.lo, nullptr, B, C, Lf, b.dil, s));
+            CONV("tc_enc_c2(", b.c2, ConvCall(t1, B, Lf).f32(t2, 2 * C).epi(TC_ACT_GELU));
+            RUN(grn_apply_cl(t2, b.grn_g, b.grn_b, t2p.hi, t2p.lo, B, 2 * C, Lf, s));
+            CONV("tc_enc_c3(", b.c3, ConvCall(t2p, B, Lf).res(x, C).f32(x, C).out(xp, TC_ACT_NONE));
+        }
+        CONV("tc_enc_out(", st.out, ConvCall(xp, B, Lf).f32(y, Cout));
+        RUN(cl_to_cf(y, outs[k], B, Cout, Lf, Cout, s));
+        A.release(m);
+    }
+    A.release(m0);
+    return 0;
+}
+
 void set_fused_up(bool on) { g_fused_up = on; }
 bool fused_up() { return g_fused_up; }
 void set_pad_max_t(int up, int down) {

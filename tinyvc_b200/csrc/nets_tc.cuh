@@ -27,6 +27,29 @@ struct DecoderTC {
               float* out, int B, int Lf) const;
 };
 
+// Tensor-core execution plan of the Encoder (module/tinyvc/encoder.py:11-116): both ConvNeXt stacks with every dense 1x1
+// conv on tc_conv_kernel (split bf16 x3, fp32 TMEM accumulation), activations channels-last chunk-major.
+struct EncoderTC {
+    struct Blk {
+        const float *w7 = nullptr, *wb = nullptr, *ln_g = nullptr, *ln_b = nullptr, *grn_g = nullptr, *grn_b = nullptr;
+        TcConvW c2, c3;
+        int dil = 1;
+    };
+    struct Stack {
+        int C = 0, c0 = 0;            // width, first channel inside the merged input product
+        const float *ln_g = nullptr, *ln_b = nullptr;
+        std::vector<Blk> mid;
+        TcConvW out;
+    } ssl, pitch;
+    TcConvW in;                   // both input layers as one product over the spectrogram: 961 -> [ssl 384 | pitch 128]
+    float* w7_buf = nullptr;      // depth-wise weights repacked [7][C] per block
+    bool ready = false;
+    ~EncoderTC();
+    int init(const WeightStore& store);
+    // z [B,768,Lf] and / or logits [B,512,Lf] (channels-first fp32, nullable) from spec [B,961,Lf]
+    int forward(Arena& A, cudaStream_t s, const float* spec, float* z, float* logits, int B, int Lf) const;
+};
+
 void set_fused_up(bool on);          // tvc_set_option("fused_up", "0"|"1"): fused 24-channel Upsample block (default on)
 bool fused_up();
 // tvc_set_option("pad_up_max_t" | "pad_down_max_t", "N"): Upsample / Downsample blocks of levels whose utterances have

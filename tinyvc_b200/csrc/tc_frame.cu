@@ -134,6 +134,134 @@ __global__ void __launch_bounds__(256) dwconv_ln_cl_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
+// cnxt_ln_cl<C>: the general form for the Encoder's stacks (encoder.py:27-31,84-88; convnext.py:42-43,52-53):
+// C = 128 or 384 channels, depth-wise k = 7 conv with dilation `dil` (replicate padding = clamped time index) followed by
+// LayerNorm over channels, or LayerNorm alone (w7 == nullptr: the stacks' input norm).  One warp per row; lane l owns the
+// float4 groups l, l + 32, ... of the row (4 channels each).  Outputs: split planes (the next conv's operand) and / or fp32.
+// ---------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) cnxt_ln_cl_kernel(const float* __restrict__ x, const float* __restrict__ w7,   // [7][C] repacked
+                                                         const float* __restrict__ wb, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, bf16* __restrict__ hi, bf16* __restrict__ lo,
+                                                         float* __restrict__ y32, int T, int dil, long long rows) {
+    TVC_PDL_PROLOGUE();
+    constexpr int G = C / 128;                    // float4 groups per lane
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const long long b = row / T;
+    const int t = (int)(row - b * T);
+    float v[G][4];
+    if (w7) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(wb) + lane + 32 * g);
+            v[g][0] = bv.x; v[g][1] = bv.y; v[g][2] = bv.z; v[g][3] = bv.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            int tt = t + (j - 3) * dil;
+            tt = tt < 0 ? 0 : (tt > T - 1 ? T - 1 : tt);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int c4 = lane + 32 * g;
+                const float4 xv = __ldg(reinterpret_cast<const float4*>(x + cm(b * T + tt, c4 * 4, rows)));
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(w7 + j * C) + c4);
+                v[g][0] = fmaf(wv.x, xv.x, v[g][0]); v[g][1] = fmaf(wv.y, xv.y, v[g][1]);
+                v[g][2] = fmaf(wv.z, xv.z, v[g][2]); v[g][3] = fmaf(wv.w, xv.w, v[g][3]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(x + cm(row, (lane + 32 * g) * 4, rows)));
+            v[g][0] = xv.x; v[g][1] = xv.y; v[g][2] = xv.z; v[g][3] = xv.w;
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < G; ++g) s += (v[g][0] + v[g][1]) + (v[g][2] + v[g][3]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / (float)C);
+    float q = 0.f;
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float d = v[g][k] - mean;
+            q = fmaf(d, d, q);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = 1.0f / sqrtf(q * (1.0f / (float)C) + 1e-5f);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const int c4 = lane + 32 * g;
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+        const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+        float o4[4] = {fmaf((v[g][0] - mean) * rstd, ga.x, be.x), fmaf((v[g][1] - mean) * rstd, ga.y, be.y),
+                       fmaf((v[g][2] - mean) * rstd, ga.z, be.z), fmaf((v[g][3] - mean) * rstd, ga.w, be.w)};
+        const long long o = cm(row, c4 * 4, rows);
+        if (hi) store_planes4(hi, lo, o, o4);
+        if (y32) *reinterpret_cast<float4*>(y32 + o) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// grn_apply_wide_cl: GRN (convnext.py:23-34) for any channel count (the Encoder's 768 / 256): one block per utterance,
+// a thread owns channels tid, tid + 256, ...; fixed summation order (deterministic).
+// ---------------------------------------------------------------------------------------------
+template <int PER>
+__global__ void __launch_bounds__(256) grn_apply_wide_cl_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, bf16* __restrict__ hi,
+                                                                bf16* __restrict__ lo, int C, int T) {
+    TVC_PDL_PROLOGUE();
+    __shared__ float part[8];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long R = (long long)gridDim.x * T;
+    float g[PER];
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = threadIdx.x + 256 * i;
+        g[i] = 0.f;
+        if (c < C) {
+            const long long base = cm((long long)b * T, c, R);
+            float s = 0.f;
+            for (int t = 0; t < T; ++t) {
+                const float v = __ldg(y + base + (long long)t * 8);
+                s = fmaf(v, v, s);
+            }
+            g[i] = sqrtf(s);
+            tot += g[i];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0) part[warp] = tot;
+    __syncthreads();
+    float all = 0.f;
+    for (int i = 0; i < 8; ++i) all += part[i];
+    const float denom = all / (float)C + 1e-6f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = threadIdx.x + 256 * i;
+        if (c >= C) continue;
+        const long long base = cm((long long)b * T, c, R);
+        const float scale = fmaf(__ldg(gamma + c), g[i] / denom, 1.0f);
+        const float bt = __ldg(beta + c);
+        for (int t = 0; t < T; ++t) {
+            const long long o = base + (long long)t * 8;
+            bf16 h, l;
+            split_bf16(fmaf(__ldg(y + o), scale, bt), h, l);
+            hi[o] = h;
+            lo[o] = l;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // grn_apply_cl: GRN (convnext.py:23-34) on chunk-major channels-last fp32 (B*T rows, C channels) -> split planes:
 //   g[c] = sqrt(sum_t y^2),  n = g / (mean_c g + 1e-6),  out = y * (gamma*n + 1) + beta
 // One block per utterance, thread = channel (coalesced over channels), fixed summation order.
@@ -226,9 +354,24 @@ int dwconv_ln_cl(const float* x, const float* w7, const float* wb, const float* 
     return 0;
 }
 
+int cnxt_ln_cl(const float* x, const float* w7, const float* wb, const float* gamma, const float* beta, bf16* hi, bf16* lo,
+               float* y32, int B, int C, int T, int dil, cudaStream_t s) {
+    const long long rows = (long long)B * T;
+    TVC_REQUIRE(C == 128 || C == 384, "cnxt_ln_cl: C=%d (128 or 384)", C);
+    if (C == 128) TVC_LAUNCH_PDL(cnxt_ln_cl_kernel<128>, cdiv(rows * 32, 256), 256, 0, s, x, w7, wb, gamma, beta, hi, lo, y32, T, dil, rows);
+    else TVC_LAUNCH_PDL(cnxt_ln_cl_kernel<384>, cdiv(rows * 32, 256), 256, 0, s, x, w7, wb, gamma, beta, hi, lo, y32, T, dil, rows);
+    TVC_LAUNCH_CHECK();
+    return 0;
+}
+
 int grn_apply_cl(const float* y, const float* gamma, const float* beta, bf16* hi, bf16* lo, int B, int C, int T,
                  cudaStream_t s) {
-    TVC_REQUIRE(C <= 256, "grn_apply_cl: C=%d > 256", C);
+    if (C > 256) {
+        TVC_REQUIRE(C <= 768, "grn_apply_cl: C=%d > 768", C);
+        TVC_LAUNCH_PDL(grn_apply_wide_cl_kernel<3>, B, 256, 0, s, y, gamma, beta, hi, lo, C, T);
+        TVC_LAUNCH_CHECK();
+        return 0;
+    }
     TVC_LAUNCH_PDL(grn_apply_cl_kernel, B, 256, 0, s, y, gamma, beta, hi, lo, C, T);
     TVC_LAUNCH_CHECK();
     return 0;

@@ -11,6 +11,10 @@ int interp_cl(const float* x, int B, int Tin, int Tout, float scale, int C, floa
               bf16* a_lo, cudaStream_t s, int a_pad = 0);
 int dwconv_ln_cl(const float* x, const float* w7, const float* wb, const float* gamma, const float* beta,
                  bf16* hi, bf16* lo, int B, int T, cudaStream_t s);
+// general ConvNeXt front half: depth-wise k = 7 (dilation `dil`; w7 [7][C] repacked, nullptr = none) + LayerNorm over C
+// (128 or 384) channels -> split planes and / or fp32, chunk-major
+int cnxt_ln_cl(const float* x, const float* w7, const float* wb, const float* gamma, const float* beta, bf16* hi, bf16* lo,
+               float* y32, int B, int C, int T, int dil, cudaStream_t s);
 int grn_apply_cl(const float* y, const float* gamma, const float* beta, bf16* hi, bf16* lo, int B, int C, int T,
                  cudaStream_t s);
 int out_conv_k7_cl(const float* x, const float* w, const float* bias, float* y, int B, int T, cudaStream_t s);

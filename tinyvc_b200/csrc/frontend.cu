@@ -47,35 +47,15 @@ int energy_estimate(const float* wf, float* energy, float* pooled, int B, int L,
 // ---------------------------------------------------------------------------------------------
 // spectrogram (utils/spectrogram.py:8-15): torch.stft(n_fft=1920, hop=480, hann, center=True,
 // pad_mode='reflect').abs()[:, :, 1:].  Frame t = 1..Lf covers samples 480t-960+k, k<1920, of
-// the reflect-padded signal.  The windowed frames are written k-major ([B][1920][Lf]) so the DFT
-// is a 1x1 "conv" with the [1922 x 1920] real basis (rows: 961 cos, 961 -sin) on the dense-conv
-// kernel; a final pass takes hypot(re, im).
+// the reflect-padded signal.  One kernel: windowing, a 1920-point shared-memory FFT (two real frames per complex
+// transform) and the magnitudes, written channels-first (stft_fft.cu).
 // ---------------------------------------------------------------------------------------------
-__global__ void stft_frames_kernel(const float* __restrict__ wf, const float* __restrict__ window,
-                                   float* __restrict__ frames, int L, int Lf, long long total) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int t = (int)(i % Lf);
-    const long long r = i / Lf;
-    const int k = (int)(r % kNfft);
-    const long long b = r / kNfft;
-    int j = kFrame * (t + 1) - kNfft / 2 + k;
-    j = j < 0 ? -j : (j >= L ? 2 * (L - 1) - j : j);
-    frames[i] = __fmul_rn(__ldg(wf + b * L + j), __ldg(window + k));
-}
-
-__global__ void stft_mag_kernel(const float* __restrict__ ri, float* __restrict__ spec, long long per_b /*961*Lf*/,
-                                long long total) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const long long b = i / per_b, r = i - b * per_b;
-    const float* p = ri + b * 2 * per_b;
-    spec[i] = hypotf(__ldg(p + r), __ldg(p + per_b + r));
-}
+int stft_fft_init(float2** tw_out);
+int stft_fft_launch(const float* wf, const float* window, const float2* tw, float* spec, int B, int L, int Lf, cudaStream_t s);
 
 struct StftBasis {
-    float* window = nullptr;   // [1920]
-    ConvW dft;                 // Cin 1920 -> Cout 1922
+    float* window = nullptr;   // [1920] periodic Hann
+    float2* tw = nullptr;      // [1920] e^(-2 pi i m / 1920)
 };
 static std::mutex g_stft_mu;
 static StftBasis g_stft[64];
@@ -87,29 +67,13 @@ static int stft_basis(const StftBasis** out) {
     TVC_REQUIRE(dev >= 0 && dev < 64, "spectrogram: unsupported device ordinal %d", dev);
     std::lock_guard<std::mutex> lock(g_stft_mu);
     if (!g_stft_ready[dev]) {
-        const int CO = 2 * kBins, COP = (int)align_up(CO, 4);
-        std::vector<float> w((size_t)kNfft * COP, 0.f), win(kNfft);
-        for (int k = 0; k < kNfft; ++k) {
-            win[k] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)k / (double)kNfft));   // periodic Hann
-            for (int f = 0; f < kBins; ++f) {
-                const int r = (int)(((long long)f * k) % kNfft);
-                const double ang = 2.0 * M_PI * (double)r / (double)kNfft;
-                w[(size_t)k * COP + f] = (float)std::cos(ang);
-                w[(size_t)k * COP + kBins + f] = (float)(-std::sin(ang));
-            }
-        }
-        float *dw = nullptr, *dwin = nullptr;
-        TVC_CUDA(cudaMalloc(&dw, sizeof(float) * w.size()));
+        std::vector<float> win(kNfft);
+        for (int k = 0; k < kNfft; ++k) win[k] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)k / (double)kNfft));   // periodic Hann
+        float* dwin = nullptr;
         TVC_CUDA(cudaMalloc(&dwin, sizeof(float) * win.size()));
-        TVC_CUDA(cudaMemcpy(dw, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
         TVC_CUDA(cudaMemcpy(dwin, win.data(), sizeof(float) * win.size(), cudaMemcpyHostToDevice));
         g_stft[dev].window = dwin;
-        g_stft[dev].dft.w = dw;
-        g_stft[dev].dft.b = nullptr;
-        g_stft[dev].dft.Cin = kNfft;
-        g_stft[dev].dft.Cout = CO;
-        g_stft[dev].dft.CoutP = COP;
-        g_stft[dev].dft.K = 1;
+        TVC_TRY(stft_fft_init(&g_stft[dev].tw));
         g_stft_ready[dev] = true;
     }
     *out = &g_stft[dev];
@@ -119,24 +83,11 @@ static int stft_basis(const StftBasis** out) {
 int spectrogram_run(Arena& A, cudaStream_t s, const float* wf, float* spec, int B, int L) {
     TVC_REQUIRE(L % kFrame == 0, "spectrogram: L=%d is not a multiple of %d (autopad first)", L, kFrame);
     TVC_REQUIRE(L > kNfft / 2, "spectrogram: reflect padding needs more than %d samples, got %d", kNfft / 2, L);
-    const int Lf = L / kFrame;
-    const size_t m = A.mark();
-    float* frames = A.f32((int64_t)B * kNfft * Lf);
-    float* ri = A.f32((int64_t)B * 2 * kBins * Lf);
-    TVC_REQUIRE(!A.overflow, "workspace too small: need at least %zu bytes, got %zu", A.peak, A.cap);
-    if (!A.dry) {
-        const StftBasis* sb = nullptr;
-        TVC_TRY(stft_basis(&sb));
-        const long long tot = (long long)B * kNfft * Lf;
-        stft_frames_kernel<<<cdiv(tot, 256), 256, 0, s>>>(wf, sb->window, frames, L, Lf, tot);
-        TVC_LAUNCH_CHECK();
-        TVC_TRY(conv_run(A, s, sb->dft, frames, (long long)kNfft * Lf, ri, 2LL * kBins * Lf, B, Lf, 1, PRE_NONE, EPI_NONE));
-        const long long per_b = (long long)kBins * Lf, total = per_b * B;
-        stft_mag_kernel<<<cdiv(total, 256), 256, 0, s>>>(ri, spec, per_b, total);
-        TVC_LAUNCH_CHECK();
-    }
-    A.release(m);
-    return 0;
+    if (A.dry) return 0;
+    const StftBasis* sb = nullptr;
+    TVC_TRY(stft_basis(&sb));
+    ProfScope ps("stft_fft(", s);
+    return stft_fft_launch(wf, sb->window, sb->tw, spec, B, L, L / kFrame, s);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -576,17 +576,18 @@ static int match_chunk_utts(int N, int Lf) {
 size_t tvc_match_workspace_bytes(tvc_index_t h, int B, int Lf) {
     if (!h || B <= 0 || Lf <= 0) return 0;
     const int N = h->m.N;
-    const int bc = std::min(B, match_chunk_utts(N, Lf));
     const size_t f = sizeof(float);
+    const size_t rows = (size_t)B * Lf;
     size_t tot = 0;
-    tot += align_up((size_t)B * kContent * Lf * f, 256);                    // normalised queries
-    tot += align_up((size_t)bc * (h->m.screened ? (size_t)align_up(N, 8) : (size_t)N) * Lf * f, 256);   // sims chunk
-    tot += 2 * align_up((size_t)16 * bc * Lf * 8 * f, 256);                 // partial top-k (values, indices)
-    tot += align_up((size_t)B * Lf * 8 * sizeof(int), 256);                 // indices
-    if (h->m.screened) {
-        tot += 2 * align_up((size_t)bc * Lf * kContent * sizeof(bf16), 256);     // query planes
-        tot += align_up((size_t)bc * Lf * 8 * sizeof(int), 256) + align_up((size_t)bc * Lf * sizeof(int), 256);   // candidates, flags
-    }
+    tot += align_up(rows * kContent * f, 256);                               // normalised queries
+    tot += align_up(rows * 8 * sizeof(int), 256);                            // indices
+    // exact path (IP / L2 / k > 4 / small N): similarity chunk + partial top-k lists
+    const int bc = std::min(B, match_chunk_utts(N, Lf));
+    size_t exact = align_up((size_t)bc * N * Lf * f, 256) + 2 * align_up((size_t)16 * bc * Lf * 8 * f, 256);
+    // screened path: query planes, candidates, flags (the similarity matrix stays on chip)
+    size_t screened = 2 * align_up(rows * kContent * sizeof(bf16), 256) + align_up(rows * 8 * sizeof(int), 256) +
+                      align_up(rows * sizeof(int), 256);
+    tot += h->m.screened ? std::max(exact, screened) : exact;
     return tot + 1024;
 }
 
@@ -600,34 +601,36 @@ int tvc_match_features(tvc_index_t h, const float* source, float* out, int32_t* 
     TVC_REQUIRE(k <= m.N, "match_features: k=%d exceeds the index size %d", k, m.N);
     cudaStream_t s = (cudaStream_t)stream;
     Arena A(workspace, workspace_bytes, false);
-    const int bc = std::min(B, match_chunk_utts(m.N, Lf));
-    float* qn = A.f32((int64_t)B * kContent * Lf);
-    float* sims = A.f32((int64_t)bc * (m.screened ? (int64_t)align_up(m.N, 8) : (int64_t)m.N) * Lf);   // chunk-major needs N rounded up to 8
-    float* pv = A.f32((int64_t)16 * bc * Lf * 8);
-    int* pi = A.i32((int64_t)16 * bc * Lf * 8);
-    int* idx = idx_out ? idx_out : A.i32((int64_t)B * Lf * k);
+    const long long rows = (long long)B * Lf;
+    float* qn = A.f32(rows * kContent);
+    int* idx = idx_out ? idx_out : A.i32(rows * k);
     TVC_REQUIRE(!A.overflow, "workspace too small: need at least %zu bytes, got %zu", A.peak, A.cap);
     TVC_TRY(knn_normalize_queries(source, qn, B, kContent, Lf, m.metric, s));
     if (m.screened && k <= 4) {
-        // similarity product on the tensor cores, exact re-scoring of the nominated candidates (knn.cu)
-        const int N8 = (int)align_up(m.N, 8);
-        bf16* q_hi = (bf16*)A.bytes((size_t)bc * Lf * kContent * sizeof(bf16));
-        bf16* q_lo = (bf16*)A.bytes((size_t)bc * Lf * kContent * sizeof(bf16));
-        int* cand = A.i32((int64_t)bc * Lf * 8);
-        int* flag = A.i32((int64_t)bc * Lf);
+        // Similarity product on the tensor cores with the top candidates selected in its epilogue (the CTA that owns 128
+        // queries sweeps the whole index and keeps 8 candidates per query in registers), then exact fp32 re-scoring of
+        // the nominated candidates (knn.cu).  Nothing of size queries x N is ever written.
+        bf16* q_hi = (bf16*)A.bytes((size_t)rows * kContent * sizeof(bf16));
+        bf16* q_lo = (bf16*)A.bytes((size_t)rows * kContent * sizeof(bf16));
+        int* cand = A.i32(rows * 8);
+        int* flag = A.i32(rows);
         TVC_REQUIRE(!A.overflow, "workspace too small: need at least %zu bytes, got %zu", A.peak, A.cap);
-        for (int b0 = 0; b0 < B; b0 += bc) {
-            const int nb = std::min(bc, B - b0);
-            const float* qc = qn + (long long)b0 * kContent * Lf;
-            TVC_TRY(cf_to_planes(qc, q_hi, q_lo, nb, kContent, Lf, kContent, TC_ACT_NONE, s));
-            TcConvArgs a;
-            a.a_hi = q_hi; a.a_lo = q_lo; a.a_cs = kContent; a.B = nb; a.T = Lf;
-            a.y32 = sims; a.y32_cs = N8;
+        TVC_TRY(cf_to_planes(qn, q_hi, q_lo, B, kContent, Lf, kContent, TC_ACT_NONE, s));
+        TcConvArgs a;
+        a.a_hi = q_hi; a.a_lo = q_lo; a.a_cs = kContent; a.B = B; a.T = Lf;
+        a.topk_cand = cand; a.topk_flag = flag; a.topk_k = k; a.topk_n = m.N; a.topk_eps = kKnnScreenEps;
+        {
+            ProfScope ps("tc_knn_screen(", s);
             TVC_TRY(tc_conv_launch(m.tc, a, s));
-            TVC_TRY(knn_screened_topk(sims, qc, m.index_wn, pv, pi, cand, flag, idx + (long long)b0 * Lf * k, nb, Lf, m.N, k, s));
         }
+        TVC_TRY(knn_rescore_candidates(qn, m.index_wn, cand, flag, idx, B, Lf, m.N, k, s));
         return knn_gather_mean(source, m.index_nc, idx, out, B, kContent, Lf, k, alpha, s);
     }
+    const int bc = std::min(B, match_chunk_utts(m.N, Lf));
+    float* sims = A.f32((int64_t)bc * (int64_t)m.N * Lf);
+    float* pv = A.f32((int64_t)16 * bc * Lf * 8);
+    int* pi = A.i32((int64_t)16 * bc * Lf * 8);
+    TVC_REQUIRE(!A.overflow, "workspace too small: need at least %zu bytes, got %zu", A.peak, A.cap);
     for (int b0 = 0; b0 < B; b0 += bc) {
         const int nb = std::min(bc, B - b0);
         TVC_TRY(conv_run(A, s, m.as_conv, qn + (long long)b0 * kContent * Lf, (long long)kContent * Lf, sims,

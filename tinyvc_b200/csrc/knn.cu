@@ -151,70 +151,19 @@ int knn_topk(const float* sims, float* pv, int* pi, int* idx_out, int B, int T, 
 // =============================================================================================
 // Tensor-core screening (cos metric, k <= 4).  The similarity product runs on tcgen05 with split-bf16 operands
 // (tc_conv.cu; |error| <~ 1e-6 for unit vectors, worst case 3e-5), which is only trusted to nominate candidates:
-//   1. approximate sims (chunk-major fp32 [N/8][R][8]) -> per query the kKnnCand best candidates (ties: lower index)
+//   1. approximate sims -> per query the kKnnCand best candidates (ties: lower index), kept in registers by the
+//      similarity kernel's epilogue while its CTA sweeps the index (tc_conv.cu, fused top-k): the similarity matrix
+//      is never written
 //   2. the candidates are re-scored in exact fp32 with the SAME operation order as the CUDA-core path above
 //      (acc = fma(w[ci], x[ci], acc), ci ascending), and the top-k of those exact scores is the answer
-//   3. if the k-th and the kKnnCand-th approximate scores are closer than kKnnEps (>= 2 x the worst-case
+//   3. if the k-th and the kKnnCand-th approximate scores are closer than kKnnScreenEps (>= 2 x the worst-case
 //      screening error) a true top-k member could have been missed; such queries are re-done by an exact full scan.
 // With |approx - exact| <= delta and a_(k) - a_(kKnnCand) > 2 delta every exact top-k member is among the
 // candidates, so the result is identical to the exact path's.
 // =============================================================================================
 constexpr int kKnnCand = 8;
-constexpr float kKnnEps = 1e-4f;
 
 __device__ __forceinline__ bool knn_better(float x, int n, float y, int m) { return x > y || (x == y && n < m); }
-
-// pass 1: thread = query row, blockIdx.y = segment of 8-reference chunks; coalesced 32-byte reads per chunk
-__global__ void knn_cand_scan_kernel(const float* __restrict__ sims, float* __restrict__ pv, int* __restrict__ pi, int N,
-                                     long long R) {
-    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= R) return;
-    const int nch = (N + 7) >> 3;
-    const int per = (nch + kKnnSeg - 1) / kKnnSeg;
-    const int c0 = blockIdx.y * per, c1 = min(nch, c0 + per);
-    float v[kKnnMaxK];
-    int id[kKnnMaxK];
-#pragma unroll
-    for (int i = 0; i < kKnnMaxK; ++i) {
-        v[i] = -INFINITY;
-        id[i] = -1;
-    }
-    for (int c = c0; c < c1; ++c) {
-        const float4* sp = reinterpret_cast<const float4*>(sims + ((long long)c * R + row) * 8);
-        const float4 a = __ldg(sp), b = __ldg(sp + 1);
-        const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-            if (c * 8 + e < N) topk_insert(v, id, kKnnCand, x[e], c * 8 + e);     // increasing n: '>' keeps the lower index
-    }
-    for (int i = 0; i < kKnnCand; ++i) {
-        pv[((long long)blockIdx.y * R + row) * kKnnMaxK + i] = v[i];
-        pi[((long long)blockIdx.y * R + row) * kKnnMaxK + i] = id[i];
-    }
-}
-
-// pass 2: merge the segments' lists -> candidates [R][kKnnCand]; flag[row] = 1 when the screening margin is too thin
-__global__ void knn_cand_merge_kernel(const float* __restrict__ pv, const int* __restrict__ pi, int* __restrict__ cand,
-                                      int* __restrict__ flag, long long R, int k, int N) {
-    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= R) return;
-    float v[kKnnMaxK];
-    int id[kKnnMaxK];
-#pragma unroll
-    for (int i = 0; i < kKnnMaxK; ++i) {
-        v[i] = -INFINITY;
-        id[i] = -1;
-    }
-    for (int seg = 0; seg < kKnnSeg; ++seg)
-        for (int i = 0; i < kKnnCand; ++i) {
-            const int n = pi[((long long)seg * R + row) * kKnnMaxK + i];
-            if (n >= 0) topk_insert(v, id, kKnnCand, pv[((long long)seg * R + row) * kKnnMaxK + i], n);
-        }
-    for (int i = 0; i < kKnnCand; ++i) cand[row * kKnnCand + i] = id[i];
-    // fewer references than candidates: every reference is a candidate, nothing can be missed
-    const bool thin = N > kKnnCand && !(v[k - 1] - v[kKnnCand - 1] > kKnnEps);      // also true for NaN scores
-    flag[row] = thin ? 1 : 0;
-}
 
 // exact fp32 score of reference n for query (b, t): the CUDA-core path's operation order (conv1d.cu FMA loop)
 __device__ __forceinline__ float knn_exact_score(const float* __restrict__ wrow, const float* __restrict__ q, int T) {
@@ -309,14 +258,10 @@ __global__ void __launch_bounds__(256) knn_exact_fallback_kernel(const float* __
     }
 }
 
-int knn_screened_topk(const float* sims_cm, const float* qn, const float* index_wn, float* pv, int* pi, int* cand, int* flag,
-                      int* idx_out, int B, int T, int N, int k, cudaStream_t s) {
-    TVC_REQUIRE(k >= 1 && k <= 4 && k < kKnnCand, "knn_screened_topk: k=%d unsupported", k);
+int knn_rescore_candidates(const float* qn, const float* index_wn, const int* cand, const int* flag, int* idx_out, int B, int T,
+                           int N, int k, cudaStream_t s) {
+    TVC_REQUIRE(k >= 1 && k <= 4 && k < kKnnCand, "knn_rescore_candidates: k=%d unsupported", k);
     const long long R = (long long)B * T;
-    knn_cand_scan_kernel<<<dim3(cdiv(R, 128), kKnnSeg), 128, 0, s>>>(sims_cm, pv, pi, N, R);
-    TVC_LAUNCH_CHECK();
-    knn_cand_merge_kernel<<<cdiv(R, 128), 128, 0, s>>>(pv, pi, cand, flag, R, k, N);
-    TVC_LAUNCH_CHECK();
     knn_rescore_kernel<<<cdiv(R, 32), 32 * kKnnCand, 0, s>>>(qn, index_wn, cand, idx_out, T, R, k);
     TVC_LAUNCH_CHECK();
     knn_exact_fallback_kernel<<<(unsigned)R, 256, 0, s>>>(qn, index_wn, flag, idx_out, T, N, k);

@@ -70,6 +70,14 @@ struct alignas(64) TcKParams {
     uint32_t a_stage_bytes, b_stage_bytes;
     uint32_t tmem_cols;
     int epi_act, out_act;
+    // fused top-k (kNN screening, SPEC 8): no output tensor; every row keeps its topk_c best columns while its CTA sweeps the
+    // channel tiles (tile order is row-tile major), then writes their indices and a "margin too thin" flag
+    int* topk_cand;                // [rows][kTopkC] column indices, best first (-1: fewer than kTopkC valid columns)
+    int* topk_flag;                // [rows] 1 when score[k-1] - score[kTopkC-1] <= topk_eps (a true member may have been missed)
+    int topk_k, topk_n;            // k of the final selection; number of real columns (channels >= topk_n are padding)
+    float topk_eps;
+    uint32_t topk_smem;            // byte offset of the merge scratch inside dynamic shared memory
+    int row_major;                 // 1: tile id = row_tile * n_tiles + n_tile, whole row tiles per CTA
     int dbg;   // ablation switches for profiling (TVC_TC_DBG): 1 no loads, 2 no MMAs, 4 no epilogue math/stores
     uint2* trace;   // developer timeline (TVC_TC_TRACE): CTA 0 logs {clock, role|event|tile|stage} per pipeline event
 };
@@ -79,10 +87,12 @@ struct alignas(64) TcKParams {
 // convs, so the combinations the decoder uses are compiled with their flags as constants; the generic
 // instantiation (flags read from the parameters) serves everything else (parity probes).
 // ---------------------------------------------------------------------------------------------
-struct EpiSpec { int film, res, y32, planes, epi_act, out_act; };
-constexpr int kNumSpecs = 8;
+struct EpiSpec { int film, res, y32, planes, epi_act, out_act, topk; };
+constexpr int kNumSpecs = 9;
+constexpr int kTopkC = 8;          // candidates kept per row by the fused top-k epilogue
 __host__ __device__ constexpr EpiSpec epi_spec(int i) {
-    return i == 0 ? EpiSpec{0, 0, 1, 0, TC_ACT_NONE, TC_ACT_NONE}      // plain fp32 output
+    return i == 8 ? EpiSpec{0, 0, 0, 0, TC_ACT_NONE, TC_ACT_NONE, 1}   // kNN screening: per-row top candidates, no output tensor
+         : i == 0 ? EpiSpec{0, 0, 1, 0, TC_ACT_NONE, TC_ACT_NONE}      // plain fp32 output
          : i == 1 ? EpiSpec{0, 0, 1, 0, TC_ACT_GELU, TC_ACT_NONE}      // ConvNeXt c2
          : i == 2 ? EpiSpec{0, 1, 1, 1, TC_ACT_NONE, TC_ACT_NONE}      // ConvNeXt c3 (+residual)
          : i == 3 ? EpiSpec{0, 0, 1, 0, TC_ACT_ELU1, TC_ACT_NONE}      // SourceNet heads
@@ -102,12 +112,22 @@ struct TileWalk {
     long long row_tile;
     int n_tile, bq, tt0;     // halo mode: utterance index and first time step of the tile
     __device__ TileWalk(const TcKParams& p, long long tile) {
+        if (p.row_major) {
+            row_tile = tile / p.n_tiles;
+            n_tile = (int)(tile - row_tile * p.n_tiles);
+            bq = 0; tt0 = 0;
+            return;
+        }
         n_tile = (int)(tile / p.row_tiles);
         row_tile = tile - (long long)n_tile * p.row_tiles;
         bq = p.halo == 1 ? (int)(row_tile / p.tiles_per_utt) : 0;
         tt0 = p.halo == 1 ? (int)(row_tile - (long long)bq * p.tiles_per_utt) * kTileM : 0;
     }
     __device__ void next(const TcKParams& p) {
+        if (p.row_major) {
+            if (++n_tile == p.n_tiles) { n_tile = 0; ++row_tile; }
+            return;
+        }
         if (++row_tile == p.row_tiles) { row_tile = 0; ++n_tile; bq = 0; tt0 = 0; return; }
         if (p.halo == 1) {
             tt0 += kTileM;
@@ -168,7 +188,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     const uint32_t acc_cols = (uint32_t)(film ? 3 * p.NTp : p.NTp);
     const long long n_tiles_total = p.row_tiles * p.n_tiles;
     // contiguous tile range of this CTA; tile id = n_tile * row_tiles + row_tile
-    const long long per_cta = (n_tiles_total + gridDim.x - 1) / gridDim.x;
+    const long long per_cta = p.row_major ? ((p.row_tiles + gridDim.x - 1) / gridDim.x) * p.n_tiles
+                                          : (n_tiles_total + gridDim.x - 1) / gridDim.x;
     const long long tile_beg = (long long)blockIdx.x * per_cta;
     const long long tile_end = tile_beg + per_cta < n_tiles_total ? tile_beg + per_cta : n_tiles_total;
 
@@ -547,6 +568,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         const int n_groups = p.NT >> 3;
         uint32_t tcount = 0;
         TileWalk tw(p, tile_beg);
+        // fused top-k state (SPEC 8): this thread's best columns of its row so far, best first
+        [[maybe_unused]] float tkv[kTopkC];
+        [[maybe_unused]] int tki[kTopkC];
         const int trole = warp == 0 ? 2 : 3;
         Tracer tr((lane == 0 && (warp == 0 || warp == kEpiWarps - 1)) ? p.trace : nullptr, trole);
         for (long long tile = tile_beg; tile < tile_end; ++tile, ++tcount, tw.next(p)) {
@@ -587,6 +611,76 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
             const float* bias = p.bias + n_tile * p.NTp;               // padded channel space
             const float* fbias = film ? p.film_bias + 2 * n_tile * p.NTp : nullptr;
             const int ch0 = n_tile * p.NT;                             // first real output channel of this tile
+            if constexpr (!kGeneric && kS.topk != 0) {
+                // ---- kNN screening (feature_retrieval.py:27-28): the similarity tile never leaves the SM.  A thread sees the
+                //      columns of its row in increasing order (its column groups inside a tile, the tiles of the sweep), so a
+                //      strict '>' keeps the lower index on ties, like torch.topk on the CPU.
+                if (n_tile == 0) {
+#pragma unroll
+                    for (int i = 0; i < kTopkC; ++i) { tkv[i] = -INFINITY; tki[i] = -1; }
+                }
+                mbar_wait(acc_full + 8u * buf, buse & 1u);
+                tc_fence_after();
+                for (int cg = slot; cg < n_groups; cg += 3) {
+                    float v[8];
+                    tmem_ld8(lane_addr + (uint32_t)(cg * 8), v);
+                    tmem_ld_wait();
+                    const int n0 = ch0 + cg * 8;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        if (v[e] > tkv[kTopkC - 1] && n0 + e < p.topk_n) {
+                            tkv[kTopkC - 1] = v[e];                  // replace the worst, then bubble up (static indices only:
+                            tki[kTopkC - 1] = n0 + e;                // the lists must stay in registers)
+#pragma unroll
+                            for (int q = kTopkC - 1; q > 0; --q)
+                                if (tkv[q] > tkv[q - 1]) {
+                                    const float tv = tkv[q]; tkv[q] = tkv[q - 1]; tkv[q - 1] = tv;
+                                    const int ti = tki[q]; tki[q] = tki[q - 1]; tki[q - 1] = ti;
+                                }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + 8u * buf);
+                if (n_tile == p.n_tiles - 1) {
+                    // end of the row tile's sweep: the three column slots of a lane quarter merge their lists through shared memory
+                    float* mv = reinterpret_cast<float*>(smem + p.topk_smem);            // [3 slots][128 rows][kTopkC]
+                    int* mi = reinterpret_cast<int*>(mv + 3 * kTileM * kTopkC);
+#pragma unroll
+                    for (int i = 0; i < kTopkC; ++i) {
+                        mv[(slot * kTileM + rloc) * kTopkC + i] = tkv[i];
+                        mi[(slot * kTileM + rloc) * kTopkC + i] = tki[i];
+                    }
+                    asm volatile("bar.sync %0, 96;" ::"r"(3 + quarter) : "memory");
+                    if (slot == 0 && valid) {
+                        // three-way merge of the sorted lists, straight from shared memory (cold path: scalars only, so
+                        // that the hot loop's lists are the only long-lived registers)
+                        int h0 = 0, h1 = 0, h2 = 0;
+                        float vk = 0.f, v8 = -INFINITY;
+                        for (int i = 0; i < kTopkC; ++i) {
+                            const int e0 = rloc * kTopkC + h0, e1 = (kTileM + rloc) * kTopkC + h1, e2 = (2 * kTileM + rloc) * kTopkC + h2;
+                            const int n0 = h0 < kTopkC ? mi[e0] : -1, n1 = h1 < kTopkC ? mi[e1] : -1, n2 = h2 < kTopkC ? mi[e2] : -1;
+                            const float x0 = n0 >= 0 ? mv[e0] : -INFINITY, x1 = n1 >= 0 ? mv[e1] : -INFINITY, x2 = n2 >= 0 ? mv[e2] : -INFINITY;
+                            int w = -1, bn = -1;
+                            float bx = -INFINITY;
+                            if (n0 >= 0) { w = 0; bn = n0; bx = x0; }
+                            if (n1 >= 0 && (w < 0 || x1 > bx || (x1 == bx && n1 < bn))) { w = 1; bn = n1; bx = x1; }
+                            if (n2 >= 0 && (w < 0 || x2 > bx || (x2 == bx && n2 < bn))) { w = 2; bn = n2; bx = x2; }
+                            h0 += w == 0; h1 += w == 1; h2 += w == 2;
+                            p.topk_cand[row * kTopkC + i] = bn;
+                            if (i == p.topk_k - 1) vk = bx;
+                            if (i == kTopkC - 1) v8 = bx;
+                        }
+                        // fewer columns than candidates: every column is a candidate, nothing can be missed
+                        const bool thin = p.topk_n > kTopkC && !(vk - v8 > p.topk_eps);      // also true for NaN
+                        p.topk_flag[row] = thin ? 1 : 0;
+                    }
+                    asm volatile("bar.sync %0, 96;" ::"r"(3 + quarter) : "memory");          // scratch may be rewritten
+                }
+                tr.log(trole, 3, (int)tcount, 0);
+                continue;
+            }
             bool waited = false;
             for (int cg = slot; cg < n_groups; cg += 3) {
                 const int ch = ch0 + cg * 8;
@@ -795,6 +889,7 @@ int tc_pack_conv(const float* w, const float* b, int Cout, int Cin, int taps, co
 }
 
 constexpr int kTcMaxSmem = 200 * 1024;
+constexpr int kTcTopkSmem = 227 * 1024;         // the fused top-k kernel: a deeper ring beside its merge scratch
 
 static int g_num_sms = 148;
 bool g_force_generic = false;   // tests: run the runtime-flag instantiation
@@ -814,6 +909,7 @@ int tc_conv_init() {
     TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
     TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
     TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
+    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcTopkSmem));
     return 0;
 }
 
@@ -917,6 +1013,14 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     p.T = a.T; p.dil = a.dil; p.taps = W.taps; p.nkb = W.nkb; p.aux_nkb = W.aux_nkb; p.aux_mode = W.aux_mode;
     p.KB = W.KB; p.NT = W.NT; p.NTp = W.NTp; p.Cout = W.Cout;
     p.epi_act = a.epi_act; p.out_act = a.out_act;
+    const bool topk = a.topk_cand != nullptr;
+    TVC_REQUIRE(!topk || (a.topk_flag && W.taps == 1 && W.aux_mode == TC_AUX_NONE && !a.y32 && !a.y_hi && !a.res && a.a_pad == 0 &&
+                          a.topk_k >= 1 && a.topk_k <= 4 && a.topk_n >= 1 && a.topk_n <= W.Cout),
+                "tc_conv: the fused top-k needs a plain 1 x 1 conv without outputs, 1 <= k <= 4");
+    p.topk_cand = a.topk_cand; p.topk_flag = a.topk_flag; p.topk_k = a.topk_k; p.topk_n = a.topk_n; p.topk_eps = a.topk_eps;
+    p.row_major = topk ? 1 : 0;
+    const int topk_bytes = topk ? 3 * kTileM * kTopkC * 8 : 0;
+    const int smem_budget = topk ? kTcTopkSmem : kTcMaxSmem;
     static const int dbg = getenv("TVC_TC_DBG") ? atoi(getenv("TVC_TC_DBG")) : 0;
     p.dbg = dbg;
     p.trace = tc_trace_slot();
@@ -960,7 +1064,7 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     p.w_bytes = (wres_env && W.n_tiles == 1 && image_bytes <= 64 * 1024 && !(dbg & 1)) ? (uint32_t)image_bytes : 0u;
     if (p.w_bytes) p.b_stage_bytes = 0;
     const uint32_t stage = p.a_stage_bytes + p.b_stage_bytes;
-    int ring = (kTcMaxSmem - 256 - (int)p.w_bytes) / (int)stage;
+    int ring = (smem_budget - 256 - topk_bytes - (int)p.w_bytes) / (int)stage;
     ring = ring > 8 ? 8 : ring;
     TVC_REQUIRE(ring >= 1, "tc_conv: a K-stage of %u bytes does not fit shared memory", stage);
     p.ring = ring;
@@ -972,9 +1076,11 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     p.tmem_cols = tc;
     p.row_tiles = p.halo == 1 ? (long long)a.B * tpu : (p.rows_a + kTileM - 1) / kTileM;
     p.n_tiles = W.n_tiles;
-    const size_t smem = (size_t)ring * stage + p.w_bytes + 16 * ring + 64;
+    p.topk_smem = (uint32_t)align_up((int64_t)ring * stage + p.w_bytes + 16 * ring + 64, 16);
+    const size_t smem = topk ? (size_t)p.topk_smem + topk_bytes : (size_t)ring * stage + p.w_bytes + 16 * ring + 64;
     const long long tiles = p.row_tiles * p.n_tiles;
-    const unsigned grid = (unsigned)(tiles < g_num_sms ? tiles : g_num_sms);
+    const long long work = topk ? p.row_tiles : tiles;             // row-major: a CTA takes whole row tiles
+    const unsigned grid = (unsigned)(work < g_num_sms ? work : g_num_sms);
     // Two MMA-issuing warps (each with its own half of the ring) when a CTA has several tiles to alternate and the ring
     // is deep enough that half of it still prefetches ahead.
     // Same-box A/B (profiles/r01z_ab_issuer_modes.log): tiles of one K-stage gain 3-6 % from the second issuer, FiLM / deep-K
@@ -986,13 +1092,15 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     int spec = -1;
     for (int i = 0; i < kNumSpecs; ++i) {
         const EpiSpec e = epi_spec(i);
+        if ((e.topk != 0) != topk) continue;
         if ((e.film != 0) == (W.aux_mode == TC_AUX_FILM) && (e.res != 0) == (a.res != nullptr) && (e.y32 != 0) == (a.y32 != nullptr) &&
             (e.planes != 0) == (a.y_hi != nullptr) && e.epi_act == a.epi_act && (e.out_act == a.out_act || !a.y_hi)) {
             spec = i;
             break;
         }
     }
-    if (g_force_generic) spec = -1;
+    if (g_force_generic && !topk) spec = -1;
+    TVC_REQUIRE(!topk || spec == 8, "tc_conv: no fused top-k instantiation");
     switch (spec) {
         case 0: TVC_LAUNCH_PDL(tc_conv_kernel<0>, grid, kThreads, smem, s, p); break;
         case 1: TVC_LAUNCH_PDL(tc_conv_kernel<1>, grid, kThreads, smem, s, p); break;
@@ -1002,6 +1110,7 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
         case 5: TVC_LAUNCH_PDL(tc_conv_kernel<5>, grid, kThreads, smem, s, p); break;
         case 6: TVC_LAUNCH_PDL(tc_conv_kernel<6>, grid, kThreads, smem, s, p); break;
         case 7: TVC_LAUNCH_PDL(tc_conv_kernel<7>, grid, kThreads, smem, s, p); break;
+        case 8: TVC_LAUNCH_PDL(tc_conv_kernel<8>, grid, kThreads, smem, s, p); break;
         default: TVC_LAUNCH_PDL(tc_conv_kernel<-1>, grid, kThreads, smem, s, p); break;
     }
     TVC_LAUNCH_CHECK();

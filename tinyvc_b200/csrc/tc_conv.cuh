@@ -71,6 +71,13 @@ struct TcConvArgs {
     int y32_cs = 0;
     bf16 *y_hi = nullptr, *y_lo = nullptr;   // split-plane output (chunk-major, nullable)
     int y_cs = 0;
+    // Fused top-k (kNN screening): with topk_cand set the conv writes no tensor; per row it keeps the 8 largest of columns
+    // [0, topk_n) (ties: lower index) and stores their indices [rows][8] plus topk_flag[row] = 1 when the topk_k-th and the
+    // 8-th scores are closer than topk_eps.  1 x 1 convs without aux / residual only.
+    int* topk_cand = nullptr;
+    int* topk_flag = nullptr;
+    int topk_k = 0, topk_n = 0;
+    float topk_eps = 0.f;
     int epi_act = TC_ACT_NONE;         // applied to the value (both outputs)
     int out_act = TC_ACT_NONE;         // applied additionally to the split-plane copy only
 };

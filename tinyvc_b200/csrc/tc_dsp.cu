@@ -222,9 +222,17 @@ __global__ void __launch_bounds__(kOsc * 32, 2) osc_source_kernel(const float* _
     __shared__ float tile[kFrame][kOsc + 2];      // [sample][oscillator], 17-float rows: conflict-free both ways
     __shared__ float s_fsi[kFrame], s_uv[kFrame], s_al0[kFrame], s_al1[kFrame];
     __shared__ int s_ai0[kFrame];
+    __shared__ float s_amp[3][kOsc + 1];          // amplitudes of frames fr - 1, fr, fr + 1 (all a frame's samples interpolate between)
     const int fr = blockIdx.x, b = blockIdx.y;
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
     const float* f0b = f0 + (long long)b * Lf;
+    if (threadIdx.x < 3 * kOsc) {
+        const int w = threadIdx.x / kOsc, q = threadIdx.x - w * kOsc;
+        int f = fr - 1 + w;
+        f = f < 0 ? 0 : (f > Lf - 1 ? Lf - 1 : f);
+        const long long RF0 = (long long)gridDim.y * Lf;
+        s_amp[w][q] = __ldg(amps + cm((long long)b * Lf + f, q, RF0));
+    }
     {
         // per-sample quantities shared by all oscillators: interp(f0), interp(f0 > 20), amplitude interpolation coords
         const int n = fr * kFrame + threadIdx.x;
@@ -254,7 +262,6 @@ __global__ void __launch_bounds__(kOsc * 32, 2) osc_source_kernel(const float* _
     // exact in fp64, so the association does not change the fp32 rounding of I.
     double acc = __dadd_rn(carry[((long long)b * Lf + fr) * kOsc + k], __dadd_rn(ex, -v));
     const long long RF = (long long)gridDim.y * Lf;           // rows of the frame-rate tensors
-    const float* ab = amps + cm((long long)b * Lf, k, RF);     // amplitude k of frame 0 of this utterance; frames are 8 floats apart
 #pragma unroll 5
     for (int i = 0; i < kRun; ++i) {
         acc = __dadd_rn(acc, (double)osc_increment(s_fsi[r0 + i], kf));
@@ -264,7 +271,8 @@ __global__ void __launch_bounds__(kOsc * 32, 2) osc_source_kernel(const float* _
         const float h = __fmul_rn(sinf(theta), s_uv[r0 + i]);
         const int ai = s_ai0[r0 + i];
         const int i0 = ai & 0x3fffffff, i1 = i0 + (ai >> 30);
-        const float a = __fmaf_rn(__ldg(ab + (long long)i0 * 8), s_al0[r0 + i], __fmul_rn(__ldg(ab + (long long)i1 * 8), s_al1[r0 + i]));
+        // i0, i1 lie in [fr - 1, fr + 1] (clamped to the utterance exactly like lin_coord clamps them)
+        const float a = __fmaf_rn(s_amp[i0 - fr + 1][k], s_al0[r0 + i], __fmul_rn(s_amp[i1 - fr + 1][k], s_al1[r0 + i]));
         tile[r0 + i][k] = __fmul_rn(h, a);
     }
     __syncthreads();

@@ -1,9 +1,11 @@
-"""Fused 24-channel Upsample block (csrc/tc_block.cu, module/tinyvc/decoder.py:165-190) against the five tc_conv launches.
+"""Fused full-rate block (csrc/tc_block.cu: x5 resampler + 24-channel Upsample block + output layer,
+module/tinyvc/decoder.py:165-190,220,233) against the separate launches (tvc_set_option("fused_up", "0")).
 
-The fused kernel issues the same MMAs per tile in the same order and runs the same epilogue arithmetic, so the waveform
-must be bit-identical to the unfused plan (tvc_set_option("fused_up", "0")) for every shape: windows of 432 output rows
-with 40-row halos, first / last windows clamped to the utterance (replicate padding), utterances shorter than a window.
-"""
+Same resampler formula, same epilogue arithmetic, same output-conv summation order; the one difference is that the fused
+kernel forms x_hi*w_hi + x_lo*w_hi and x_hi*w_lo in two accumulators and adds them once (two MMAs per K-step instead of
+three), so the two plans agree to a few fp32 ulps of every intermediate, not bit for bit: max |d| < 2e-5 on waveforms of
+RMS ~0.27 (an indexing error -- window halos, replicate rows, utterance edges, short utterances -- shows up as O(0.1)).
+The fused plan itself must be reproducible bit for bit (eager run vs graph replay)."""
 import pytest
 import torch
 
@@ -11,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("B,Lf", [(1, 1), (2, 1), (3, 2), (5, 7), (64, 18), (2, 100)])
-def test_fused_block_bit_identical(cuda_models, B, Lf):
+def test_fused_block_matches_separate_launches(cuda_models, B, Lf):
     from tinyvc_b200 import _lib, synth
     _, dec = cuda_models
     inp = {k: v.to("cuda") for k, v in synth.decoder_inputs(B, Lf, 1236 + B).items()}
@@ -28,4 +30,5 @@ def test_fused_block_bit_identical(cuda_models, B, Lf):
     assert torch.equal(ref, ref2)
     assert torch.equal(got, got2)
     assert torch.isfinite(got).all()
-    assert torch.equal(got, ref), f"max|d| = {float((got - ref).abs().max()):.3e}"
+    d = float((got - ref).abs().max())
+    assert d < 2e-5, f"max|d| = {d:.3e}"

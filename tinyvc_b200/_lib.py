@@ -14,7 +14,8 @@ from typing import Dict, Optional, Tuple
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtinyvc_b200.so")
+# TVC_LIB: developer override (same-box A/B of two builds of the library, tools/gpu_ab_lib.sh)
+LIB_PATH = os.environ.get("TVC_LIB") or os.path.join(_HERE, "libtinyvc_b200.so")
 
 _lib: Optional[ctypes.CDLL] = None
 _lock = threading.Lock()

@@ -56,16 +56,16 @@ struct HostW {
 };
 
 int pack_named(const HostW& H, const std::string& prefix, int NT, TcConvW& out, const std::string& aux_prefix = "",
-               int aux_mode = TC_AUX_NONE) {
+               int aux_mode = TC_AUX_NONE, bool cat = false) {
     const ParamSpec* w = H.table->find(prefix + ".weight");
     TVC_REQUIRE(w && H.get(prefix + ".bias"), "tc weights: no conv named %s", prefix.c_str());
     const int Cout = w->d0, Cin = w->d1, K = w->d2;
-    if (aux_mode == TC_AUX_NONE) return tc_pack_conv(H.get(prefix + ".weight"), H.get(prefix + ".bias"), Cout, Cin, K, nullptr, nullptr, 0, 0, NT, out);
+    if (aux_mode == TC_AUX_NONE) return tc_pack_conv(H.get(prefix + ".weight"), H.get(prefix + ".bias"), Cout, Cin, K, nullptr, nullptr, 0, 0, NT, out, cat);
     if (aux_mode == TC_AUX_ACC) {
         const ParamSpec* aw = H.table->find(aux_prefix + ".weight");
         TVC_REQUIRE(aw && aw->d0 == Cout && aw->d2 == 1, "tc weights: bad residual conv %s", aux_prefix.c_str());
         return tc_pack_conv(H.get(prefix + ".weight"), H.get(prefix + ".bias"), Cout, Cin, K, H.get(aux_prefix + ".weight"),
-                            H.get(aux_prefix + ".bias"), aw->d1, TC_AUX_ACC, NT, out);
+                            H.get(aux_prefix + ".bias"), aw->d1, TC_AUX_ACC, NT, out, cat);
     }
     // FiLM: aux_prefix.to_scale / aux_prefix.to_shift, both Conv1d(C, C, 1)  (decoder.py:88-97)
     const ParamSpec* sw = H.table->find(aux_prefix + ".to_scale.weight");
@@ -77,7 +77,7 @@ int pack_named(const HostW& H, const std::string& prefix, int NT, TcConvW& out, 
     memcpy(fw.data() + (size_t)Cout * ac, H.get(aux_prefix + ".to_shift.weight"), sizeof(float) * Cout * ac);
     memcpy(fb.data(), H.get(aux_prefix + ".to_scale.bias"), sizeof(float) * Cout);
     memcpy(fb.data() + Cout, H.get(aux_prefix + ".to_shift.bias"), sizeof(float) * Cout);
-    return tc_pack_conv(H.get(prefix + ".weight"), H.get(prefix + ".bias"), Cout, Cin, K, fw.data(), fb.data(), ac, TC_AUX_FILM, NT, out);
+    return tc_pack_conv(H.get(prefix + ".weight"), H.get(prefix + ".bias"), Cout, Cin, K, fw.data(), fb.data(), ac, TC_AUX_FILM, NT, out, cat);
 }
 
 }  // namespace
@@ -87,6 +87,7 @@ DecoderTC::~DecoderTC() {
     for (auto& m : mid) { m.c2.free_all(); m.c3.free_all(); }
     for (auto& d : down) { d.c1.free_all(); d.c2.free_all(); d.c3.free_all(); }
     for (auto& u : up) { u.c1.free_all(); u.c2.free_all(); u.c3.free_all(); u.c4.free_all(); u.c5.free_all(); }
+    up4_cat.c1.free_all(); up4_cat.c2.free_all(); up4_cat.c3.free_all(); up4_cat.c4.free_all(); up4_cat.c5.free_all();
     if (w7_buf) cudaFree(w7_buf);
     if (rng_state) cudaFree(rng_state);
 }
@@ -185,6 +186,13 @@ int DecoderTC::init(const WeightStore& store) {
         TVC_TRY(pack_named(H, p + ".c3", kUpNT[i], up[i].c3));
         TVC_TRY(pack_named(H, p + ".c4", kUpNT[i], up[i].c4, p + ".film2", TC_AUX_FILM));
         TVC_TRY(pack_named(H, p + ".c5", kUpNT5[i], up[i].c5));
+        if (i == 4) {       // the fused block kernel's own images of the same convs ("cat" layout, tc_conv.cuh)
+            TVC_TRY(pack_named(H, p + ".c1", kUpNT[i], up4_cat.c1, "", TC_AUX_NONE, true));
+            TVC_TRY(pack_named(H, p + ".c2", kUpNT[i], up4_cat.c2, p + ".film1", TC_AUX_FILM, true));
+            TVC_TRY(pack_named(H, p + ".c3", kUpNT[i], up4_cat.c3, "", TC_AUX_NONE, true));
+            TVC_TRY(pack_named(H, p + ".c4", kUpNT[i], up4_cat.c4, p + ".film2", TC_AUX_FILM, true));
+            TVC_TRY(pack_named(H, p + ".c5", kUpNT5[i], up4_cat.c5, "", TC_AUX_NONE, true));
+        }
     }
     out_w = store.raw(fn + ".output_layer.weight");
     out_b = store.raw(fn + ".output_layer.bias");
@@ -205,8 +213,9 @@ int DecoderTC::init(const WeightStore& store) {
 #define ARENA_OK() TVC_REQUIRE(!A.overflow, "workspace too small: need at least %zu bytes, got %zu", A.peak, A.cap)
 
 namespace {
-// tvc_set_option("fused_up", "0"): run the 24-channel Upsample block as five tc_conv launches instead of the fused block
-// kernel (tc_block.cu).  The two are bit-identical (tests/test_gpu_fused_block.py); fused is 263 -> 146 us at config 2.
+// tvc_set_option("fused_up", "0"): run the x5 resampler, the 24-channel Upsample block and the output layer as separate
+// launches instead of the fused block kernel (tc_block.cu).  The fused kernel evaluates x_hi * [w_hi | w_lo] as one MMA, so the
+// two agree to the rounding of one fp32 addition per accumulator, not bit for bit (tests/test_gpu_fused_block.py).
 bool g_fused_up = true;
 // tvc_set_option("pad_max_t", "N"): levels whose utterances have at most N rows keep the replicate padding of their
 // k = 3 convs STORED in the activation planes (tc_conv.cuh, padded mode), so that every operand window is one contiguous
@@ -326,7 +335,8 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         const long long rows = (long long)B * tout;
         const Pl& cond = skipP[4 - i];
         TVC_REQUIRE(skipT[4 - i] == tout && cond.cs == c, "filter_net: skip %d shape mismatch", 4 - i);
-        const bool fused = g_fused_up && i == 4 && fac == 5 && c == 24 && tc_up24_block_supported(u.c1, u.c2, u.c3, u.c4, u.c5);
+        const Up& uc = up4_cat;
+        const bool fused = g_fused_up && i == 4 && fac == 5 && c == 24 && tc_up24_block_supported(uc.c1, uc.c2, uc.c3, uc.c4, uc.c5);
         if (fused) {
             // resampler, the five convs and the output layer in one kernel (tc_block.cu); same arithmetic as the launches below
             TcUpBlockArgs fa;
@@ -334,7 +344,7 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
             fa.B = B; fa.T = tout; fa.T4 = tin; fa.scale = (float)(1.0 / (double)fac);
             if (!A.dry) {
                 ProfScope ps("tc_up4_fused(", s);
-                TVC_TRY(tc_up24_block_launch(u.c1, u.c2, u.c3, u.c4, u.c5, fa, s));
+                TVC_TRY(tc_up24_block_launch(uc.c1, uc.c2, uc.c3, uc.c4, uc.c5, fa, s));
             }
             A.release(m0);
             return 0;

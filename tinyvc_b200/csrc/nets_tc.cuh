@@ -16,6 +16,7 @@ struct DecoderTC {
     TcConvW down0;
     struct Down { TcConvW c1, c2, c3; } down[4];
     struct Up { TcConvW c1, c2, c3, c4, c5; } up[5];
+    Up up4_cat;                   // ups.4 again as "cat" images for the fused block kernel
     const float *out_w = nullptr, *out_b = nullptr;
     float* w7_buf = nullptr;      // depth-wise weights repacked [3][7][128]
     unsigned long long* rng_state = nullptr;   // device {seed, step} of the noise generator (used when no draw is injected)

@@ -74,7 +74,7 @@ constexpr uint32_t kWBytes = 4 * kWMain + 2 * kWAux + kW5;
 constexpr uint32_t kOffOutW = kOffW + kWBytes;                            // output layer: [7 taps][24 channels] fp32, then the bias
 constexpr uint32_t kOffBar = kOffOutW + 1024;
 constexpr uint32_t kBlockSmem = kOffBar + 256;
-constexpr uint32_t kAccCols = 96;             // conv | FiLM scale | FiLM shift, 32 columns each
+constexpr uint32_t kAccCols = 128;            // conv x_hi*w_hi + x_lo*w_hi | conv x_hi*w_lo | FiLM scale | FiLM shift, 32 columns each
 constexpr uint32_t kYCol0 = 2 * kAccCols;     // TMEM columns of the fp32 residual y: 32 per tile
 constexpr int kBEpiWarps = 12, kBMmaWarp = 12, kBProdWarp = 13, kBLoadWarp0 = 14, kBLoadWarps = 4, kBThreads = 576;
 constexpr int kBEpiThreads = kBEpiWarps * 32;
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
         // ================= MMA issue (one elected lane; loops are warp-uniform) =================
         const bool leader = elect_one() != 0;
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);          // SBO = 128 bytes, descriptor version 1
-        const uint32_t idesc_m = umma_idesc(kBM, 32), idesc_x = umma_idesc(kBM, 64);
+        const uint32_t idesc_m = umma_idesc(kBM, 32), idesc_x = umma_idesc(kBM, 64);      // idesc_x: N = 64 (FiLM scale | shift; cat main)
         const uint32_t lbo16 = kActLbo >> 4, plane16 = kActPlane >> 4, clbo16 = kCondLbo >> 4, cplane16 = kCondPlane >> 4;
         const uint32_t a16 = ((sb + kOffA) & 0x3FFFFu) >> 4, b16 = ((sb + kOffB) & 0x3FFFFu) >> 4;
         const uint32_t c16 = ((sb + kOffCond) & 0x3FFFFu) >> 4, w16 = ((sb + kOffW) & 0x3FFFFu) >> 4;
@@ -224,10 +224,11 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
                     tc_fence_after();
                     const uint32_t dacc = tmem + buf * kAccCols;
                     const uint32_t a_lo0 = (lbo16 << 16) + src16 + (uint32_t)(g.sh + kBM * j) - d;   // tap 0 reads from row - dil
-                    const uint32_t b_lo0 = (32u << 16) + wl16;
+                    // "cat" weight images (tc_conv.cuh): chunk stride 64 rows (hi 32 | lo 32), two MMAs per K-step
+                    const uint32_t b_lo0 = (64u << 16) + wl16;
                     if (leader) {
-                        if (l < 4) issue_stage<3, 2>(dacc, a_lo0, b_lo0, d, 256u, 2u * lbo16, 64u, plane16, 128u, desc_hi, idesc_m, 0u);
-                        else issue_stage<1, 2>(dacc, a_lo0, b_lo0, 0u, 0u, 2u * lbo16, 64u, plane16, 128u, desc_hi, idesc_m, 0u);
+                        if (l < 4) issue_stage_cat<3, 2>(dacc, a_lo0, b_lo0, d, 256u, 2u * lbo16, 128u, plane16, desc_hi, idesc_m, idesc_x, 0u);
+                        else issue_stage_cat<1, 2>(dacc, a_lo0, b_lo0, 0u, 0u, 2u * lbo16, 128u, plane16, desc_hi, idesc_m, idesc_x, 0u);
                     }
                     if (film) {
                         mbar_wait(cond_full + 8u * cs, cph);
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
                         const uint32_t ax = (clbo16 << 16) + c16 + cs * (kCondStage >> 4) + off_x;
                         const uint32_t bx = (64u << 16) + wl16 + (kWMain >> 4);                       // FiLM image follows the 3 taps
                         if (leader) {
-                            issue_stage<1, 2>(dacc + 32u, ax, bx, 0u, 0u, 2u * clbo16, 128u, cplane16, 256u, desc_hi, idesc_x, 0u);
+                            issue_stage<1, 2>(dacc + 64u, ax, bx, 0u, 0u, 2u * clbo16, 128u, cplane16, 256u, desc_hi, idesc_x, 0u);
                             umma_commit(cond_empty + 8u * cs);
                         }
                         if (++cs == kCondRing) { cs = 0; cph ^= 1u; }
@@ -313,11 +314,14 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
                     tc_fence_after();
                     const uint32_t ta = tmem + buf * kAccCols + lane_sel + (uint32_t)(cg * 8);
                     const uint32_t ya = tmem + kYCol0 + (uint32_t)(j * 32 + cg * 8) + lane_sel;
-                    float v[8], sc[8], sf[8], yv[8];
+                    float v[8], v2[8], sc[8], sf[8], yv[8];
                     tmem_ld8(ta, v);
-                    if (film) { tmem_ld8(ta + 32u, sc); tmem_ld8(ta + 64u, sf); }
+                    tmem_ld8(ta + 32u, v2);                                          // x_hi * w_lo columns
+                    if (film) { tmem_ld8(ta + 64u, sc); tmem_ld8(ta + 96u, sf); }
                     if (l == 3) tmem_ld8(ya, yv);
                     tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = __fadd_rn(v[i], v2[i]);
                     v[0] = __fadd_rn(v[0], b0.x); v[1] = __fadd_rn(v[1], b0.y); v[2] = __fadd_rn(v[2], b0.z); v[3] = __fadd_rn(v[3], b0.w);
                     v[4] = __fadd_rn(v[4], b1.x); v[5] = __fadd_rn(v[5], b1.y); v[6] = __fadd_rn(v[6], b1.z); v[7] = __fadd_rn(v[7], b1.w);
                     if (film) {
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
 }
 
 bool k3_ok(const TcConvW& c, bool film) {
-    return c.taps == 3 && c.Cin == 24 && c.Cout == 24 && c.KB == 32 && c.nkb == 1 && c.NTp == 32 && c.n_tiles == 1 &&
+    return c.cat && c.taps == 3 && c.Cin == 24 && c.Cout == 24 && c.KB == 32 && c.nkb == 1 && c.NTp == 32 && c.n_tiles == 1 &&
            (film ? (c.aux_mode == TC_AUX_FILM && c.aux_cin == 24 && c.aux_nkb == 1 && c.tile_elems * 2 == kWMain + kWAux)
                  : (c.aux_mode == TC_AUX_NONE && c.tile_elems * 2 == kWMain));
 }
@@ -420,7 +424,7 @@ bool k3_ok(const TcConvW& c, bool film) {
 }  // namespace
 
 bool tc_up24_block_supported(const TcConvW& c1, const TcConvW& c2, const TcConvW& c3, const TcConvW& c4, const TcConvW& c5) {
-    return k3_ok(c1, false) && k3_ok(c2, true) && k3_ok(c3, false) && k3_ok(c4, true) && c5.taps == 1 && c5.Cin == 24 &&
+    return k3_ok(c1, false) && k3_ok(c2, true) && k3_ok(c3, false) && k3_ok(c4, true) && c5.cat && c5.taps == 1 && c5.Cin == 24 &&
            c5.Cout <= 24 && c5.KB == 32 && c5.nkb == 1 && c5.NTp == 32 && c5.n_tiles == 1 && c5.aux_mode == TC_AUX_NONE &&
            c5.tile_elems * 2 == kW5;
 }

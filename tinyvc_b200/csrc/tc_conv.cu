@@ -815,7 +815,7 @@ void TcConvW::free_all() {
 }
 
 int tc_pack_conv(const float* w, const float* b, int Cout, int Cin, int taps, const float* aux_w, const float* aux_b,
-                 int aux_cin, int aux_mode, int NT, TcConvW& o) {
+                 int aux_cin, int aux_mode, int NT, TcConvW& o, bool cat) {
     TVC_REQUIRE(Cout > 0 && Cin > 0 && (taps == 1 || taps == 3), "tc_pack_conv: bad shape Cout=%d Cin=%d taps=%d", Cout, Cin, taps);
     TVC_REQUIRE(NT % 8 == 0 && NT >= 8, "tc_pack_conv: NT=%d must be a multiple of 8", NT);
     o.Cin = Cin; o.Cout = Cout; o.taps = taps; o.aux_cin = aux_mode ? aux_cin : 0; o.aux_mode = aux_mode;
@@ -833,6 +833,7 @@ int tc_pack_conv(const float* w, const float* b, int Cout, int Cin, int taps, co
     std::vector<float> hb((size_t)o.n_tiles * o.NTp, 0.f), hf;
     if (aux_mode == TC_AUX_FILM) hf.assign((size_t)o.n_tiles * film_rows, 0.f);
 
+    o.cat = cat;
     auto put = [&](uint16_t* stage, int n_rows, int c, int n, int e, float v) {
         const uint16_t h = f2bf_host(v);
         const uint16_t l = f2bf_host(v - bf2f_host(h));
@@ -840,6 +841,14 @@ int tc_pack_conv(const float* w, const float* b, int Cout, int Cin, int taps, co
         const size_t off = ((size_t)c * n_rows + n) * 8 + e;
         stage[off] = h;
         stage[plane + off] = l;
+    };
+    // main stages of a "cat" image: [chunk][hi rows | lo rows][8]
+    auto put_cat = [&](uint16_t* stage, int c, int n, int e, float v) {
+        const uint16_t h = f2bf_host(v);
+        const uint16_t l = f2bf_host(v - bf2f_host(h));
+        const size_t off = ((size_t)c * 2 * o.NTp + n) * 8 + e;
+        stage[off] = h;
+        stage[off + (size_t)o.NTp * 8] = l;
     };
     for (int nt = 0; nt < o.n_tiles; ++nt) {
         uint16_t* tile = img.data() + o.tile_elems * nt;
@@ -850,7 +859,11 @@ int tc_pack_conv(const float* w, const float* b, int Cout, int Cin, int taps, co
                     for (int n = 0; n < NT; ++n)
                         for (int e = 0; e < 8; ++e) {
                             const int co = nt * NT + n, ci = kb * o.KB + c * 8 + e;
-                            if (co < Cout && ci < Cin) put(tile + so, o.NTp, c, n, e, w[((size_t)co * Cin + ci) * taps + tap]);
+                            if (co < Cout && ci < Cin) {
+                                const float wv = w[((size_t)co * Cin + ci) * taps + tap];
+                                if (o.cat) put_cat(tile + so, c, n, e, wv);
+                                else put(tile + so, o.NTp, c, n, e, wv);
+                            }
                         }
         for (int kb = 0; kb < o.aux_nkb; ++kb, so += aux_stage)
             for (int c = 0; c < chunks; ++c)
@@ -992,6 +1005,7 @@ int tc_make_plane_map(CUtensorMap* m, const bf16* base, long long rows, int nch,
 
 int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     TVC_REQUIRE(W.w && a.a_hi && a.a_lo, "tc_conv: missing weights or input");
+    TVC_REQUIRE(!W.cat, "tc_conv: \"cat\" weight images belong to the fused block kernel (tc_block.cu)");
     TVC_REQUIRE(a.B > 0 && a.T > 0, "tc_conv: empty problem B=%d T=%d", a.B, a.T);
     TVC_REQUIRE(a.a_cs % 8 == 0 && a.a_cs >= W.Cin, "tc_conv: input channel stride %d (need multiple of 8 >= %d)", a.a_cs, W.Cin);
     TVC_REQUIRE(W.aux_mode == TC_AUX_NONE || (a.x_hi && a.x_lo && a.x_cs % 8 == 0 && a.x_cs >= W.aux_cin), "tc_conv: aux input missing / bad stride");

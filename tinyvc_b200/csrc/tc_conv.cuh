@@ -40,6 +40,10 @@ struct TcConvW {
     int aux_cin = 0, aux_mode = TC_AUX_NONE;
     int KB = 0, nkb = 0, aux_nkb = 0;   // K-stage = KB channels of one tap
     int NT = 0, NTp = 0, n_tiles = 0;   // output channels per CTA, padded to 16
+    // "cat" images (the fused block kernel's, tc_block.cu): in the main K-stages the hi and lo rows of a chunk are adjacent
+    // ([chunk][hi NTp | lo NTp][8]), so x_hi * [w_hi | w_lo] is ONE MMA of N = 2 NTp and a K-step costs two instructions
+    // instead of three (tc_ptx.cuh issue_stage_cat).  tc_conv_kernel itself takes plain images only.
+    bool cat = false;
     size_t tile_elems = 0;              // bf16 elements of packed weights per n-tile
     void free_all();
 };
@@ -50,7 +54,7 @@ struct TcConvW {
 //   TC_AUX_FILM: aux_w [2][Cout][aux_cin] (scale rows then shift rows), aux_b [2][Cout]
 //                -> out = conv * (scale) + shift (+ res)            (decoder.py:88-97)
 int tc_pack_conv(const float* w, const float* b, int Cout, int Cin, int taps, const float* aux_w, const float* aux_b,
-                 int aux_cin, int aux_mode, int NT, TcConvW& out);
+                 int aux_cin, int aux_mode, int NT, TcConvW& out, bool cat = false);
 
 struct TcConvArgs {
     const bf16 *a_hi = nullptr, *a_lo = nullptr;   // main input planes, chunk-major, a_cs channels of capacity

@@ -169,5 +169,29 @@ __device__ __forceinline__ void issue_stage(uint32_t d, uint32_t a_lo0, uint32_t
     }
 }
 
+// The same K-stage with the weight planes concatenated along N ("cat" images, tc_conv.cuh): per K-step
+//   D[:, 0 : 2 NTp) += x_hi * [w_hi | w_lo]        one MMA of N = 2 NTp
+//   D[:, 0 : NTp)   += x_lo * w_hi                  one MMA of N = NTp
+// i.e. two instructions instead of three; the epilogue adds the two column halves.  A tcgen05.mma costs ~45 cycles of issue
+// whatever N <= 64 is (profiles/r02a_umma_bench.log), so small-N layers are issue-bound and gain ~30 %.
+// b_lo0's LBO field and b_ks describe the concatenated image (chunk stride 2 NTp rows).
+template <int TAPS, int KS>
+__device__ __forceinline__ void issue_stage_cat(uint32_t d, uint32_t a_lo0, uint32_t b_lo0, uint32_t a_tap, uint32_t b_tap,
+                                                uint32_t a_ks, uint32_t b_ks, uint32_t plane_a16, uint32_t desc_hi,
+                                                uint32_t idesc_n, uint32_t idesc_2n, uint32_t acc0) {
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) {
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)t * a_tap + (uint32_t)k * a_ks;
+            const uint32_t b_lo = b_lo0 + (uint32_t)t * b_tap + (uint32_t)k * b_ks;
+            const uint64_t a_h = ((uint64_t)desc_hi << 32) | a_lo, a_l = ((uint64_t)desc_hi << 32) | (a_lo + plane_a16);
+            const uint64_t b = ((uint64_t)desc_hi << 32) | b_lo;
+            umma_bf16(d, a_h, b, idesc_2n, (t == 0 && k == 0) ? acc0 : 1u);
+            umma_bf16(d, a_l, b, idesc_n, 1u);
+        }
+    }
+}
+
 }  // namespace
 }  // namespace tvc

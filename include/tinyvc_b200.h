@@ -39,7 +39,7 @@ const char* tvc_version(void);
  * ("graphs","1"|"0"): tvc_decoder_infer replays a captured CUDA
  * graph when it is called again with the same buffers (default on).  ("fused_up","1"|"0"): the 24-channel
  * Upsample block as one fused kernel (default) or five conv launches.  ("pdl","0"|"1"): programmatic dependent
- * launch (default off).  ("profile","0"|"1").
+ * launch (default on).  ("profile","0"|"1"): per-launcher event timing.  ("nvtx","0"|"1"): NVTX ranges per launcher.
  * Returns non-zero for unknown keys.                                                                */
 int tvc_set_option(const char* key, const char* value);
 /* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */

@@ -39,18 +39,30 @@ def test_config3_full_pipeline_b256_4s_n50k(cuda_models, weights, report):
     alone = gen.convert(wf[sub], index, 0.0, rand01=rand01[sub].cuda())
     assert torch.equal(alone, out[sub]), "an utterance's waveform depends on the rest of the batch"
     # (a) oracle on a few utterances: indices identical (or a reported numerical near-tie), decoder teacher-forced
-    bad_total, worst = 0, 0.0
+    bad_total, worst, worst_gap = 0, 0.0, 0.0
     for b in (0, 200):
         ref, rp = O.generator_convert(PE, PD, inp["wf"][b:b + 1], inp["index"], 0.0, rand01=rand01[b:b + 1], return_parts=True)
         z_rel = max_abs(parts["z"][b:b + 1], rp["z"]) / float(rp["z"].abs().max())
         assert z_rel < 2e-5
         bad = (idx[b].cpu() != rp["idx"][0]).any(dim=1)
         bad_total += int(bad.sum())
+        if int(bad.sum()):
+            # a different neighbour set is only acceptable at a numerical near-tie of the REFERENCE's own similarities: the
+            # gap between consecutive top-5 cosines (fp64, reference z) must be of the order of our z error (~1e-5 relative)
+            zq = rp["z"][0].t().double()
+            zq = zq / (zq.norm(dim=1, keepdim=True) + 1e-6)
+            rn = inp["index"][0].t().double()
+            rn = rn / (rn.norm(dim=1, keepdim=True) + 1e-6)
+            for q in bad.nonzero().flatten().tolist():
+                top = torch.topk(zq[q] @ rn.t(), 5).values
+                gap = float((top[:-1] - top[1:]).min())
+                worst_gap = max(worst_gap, gap)
         forced = dec.infer(rp["zm"].cuda(), rp["f0s"].cuda(), rp["energy"].cuda(), rand01=rand01[b:b + 1].cuda())
         worst = max(worst, rmse(forced, ref))
     report.add("config3_b256_n50k", idx_mismatched_queries=bad_total, queries_checked=2 * (T // 480),
-               teacher_forced_rmse=worst)
-    assert bad_total <= 1, f"{bad_total} of {2 * (T // 480)} queries picked different neighbours than the CPU reference"
+               teacher_forced_rmse=worst, max_top5_gap_at_mismatch=worst_gap)
+    assert bad_total <= 1 and worst_gap < 2e-5, (
+        f"{bad_total} of {2 * (T // 480)} queries picked different neighbours than the CPU reference (top-5 gap up to {worst_gap:.2e})")
     assert worst < 1e-4
 
 

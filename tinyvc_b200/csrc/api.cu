@@ -7,6 +7,8 @@
 #include <map>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>      // header-only: ranges cost nothing unless a profiler is attached
+
 #include "../../include/tinyvc_b200.h"
 #include "nets.cuh"
 #include "nets_tc.cuh"
@@ -44,7 +46,12 @@ static bool g_prof_on = false;
 static std::mutex g_prof_mu;
 static std::vector<ProfEntry> g_prof;
 
+static bool g_nvtx = false;          // tvc_set_option("nvtx", "1"): an NVTX range around every launcher of the plans (nsys / ncu --nvtx)
 ProfScope::ProfScope(const char* name, cudaStream_t s) : stream(s) {
+    if (g_nvtx) {
+        nvtxRangePushA(name);
+        nvtx = true;
+    }
     if (!g_prof_on) return;
     std::lock_guard<std::mutex> lock(g_prof_mu);
     ProfEntry e;
@@ -56,6 +63,7 @@ ProfScope::ProfScope(const char* name, cudaStream_t s) : stream(s) {
     g_prof.push_back(e);
 }
 ProfScope::~ProfScope() {
+    if (nvtx) nvtxRangePop();
     if (slot < 0) return;
     std::lock_guard<std::mutex> lock(g_prof_mu);
     cudaEventRecord(g_prof[slot].b, stream);
@@ -178,6 +186,7 @@ int tvc_set_option(const char* key, const char* value) {
         set_error("encoder_impl: unknown value '%s'", value);
         return 2;
     }
+    if (!strcmp(key, "nvtx")) { g_nvtx = !strcmp(value, "1"); return 0; }
     if (!strcmp(key, "pitch_impl")) {
         if (!strcmp(value, "fp32")) { g_pitch_tc = false; return 0; }
         if (!strcmp(value, "tc")) { g_pitch_tc = true; return 0; }

@@ -132,7 +132,8 @@ __global__ void knn_merge_kernel(const float* __restrict__ pv, const int* __rest
             const int n = pi[((long long)seg * ncol + col) * kKnnMaxK + i];
             if (n >= 0) topk_insert(v, id, k, pv[((long long)seg * ncol + col) * kKnnMaxK + i], n);
         }
-    for (int i = 0; i < k; ++i) idx_out[col * k + i] = id[i];
+    // fewer than k comparable similarities (NaN / Inf queries): fall back to row 0 rather than hand the gather index -1
+    for (int i = 0; i < k; ++i) idx_out[col * k + i] = id[i] >= 0 ? id[i] : 0;
 }
 
 int knn_topk(const float* sims, float* pv, int* pi, int* idx_out, int B, int T, int N, int k, cudaStream_t s) {

@@ -32,6 +32,7 @@ void count_launch();
 // A ProfScope brackets one launcher call with two events on the launch stream; disabled = no-op.
 struct ProfScope {
     int slot = -1;
+    bool nvtx = false;             // tvc_set_option("nvtx","1"): the scope is also an NVTX range named after the launcher
     cudaStream_t stream = 0;
     ProfScope(const char* name, cudaStream_t s);
     ~ProfScope();

@@ -8,7 +8,7 @@ import shutil
 import subprocess
 import sys
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01z"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02z"
 rows = list(csv.reader(open(f"gpurun_out/launches_{tag}.csv")))
 i0 = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
 h = rows[i0]
@@ -31,22 +31,25 @@ for r in out[1:]:
         v *= {"ns": 1e-3, "us": 1, "ms": 1e3}[u]
     e[m] = v
 own = {k: e for k, e in per.items() if "tvc" in e["name"] or "unnamed" in e["name"]}
-conv = [e for e in own.values() if "tc_conv_kernel" in e["name"]]
+conv = [e for e in own.values() if "tc_conv_kernel" in e["name"] or "tc_up24_block" in e["name"]]
 dram = lambda e: e["dram__bytes_read.sum"] + e["dram__bytes_write.sum"]
 t_conv = sum(e["gpu__time_duration.sum"] for e in conv)
 t_all = sum(e["gpu__time_duration.sum"] for e in own.values())
 json.dump({"source": f"profiles/{tag}_launches_one_step.csv (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,"
                      "dram__bytes_write.sum --clock-control none on `bench.py --steps 2 --warmup 3`; one Decoder.infer step; "
                      "cold-cache, serialised)",
-           "conv1d_dram_bytes_per_step": sum(map(dram, conv)), "all_kernels_dram_bytes_per_step": sum(map(dram, own.values())),
-           "conv_launches_per_step": len(conv), "launches_per_step": len(own), "conv_time_us_serialised": t_conv,
-           "step_time_us_serialised": t_all, "conv_share_serialised": t_conv / t_all},
+           "decoder_dram_bytes_per_step": sum(map(dram, own.values())),
+           "dense_conv_dram_bytes_per_step": sum(map(dram, conv)),
+           "dense_conv_launches_per_step": len(conv), "launches_per_step": len(own), "dense_conv_time_us_serialised": t_conv,
+           "step_time_us_serialised": t_all, "dense_conv_share_serialised": t_conv / t_all},
           open("profiles/roofline_traffic.json", "w"), indent=1)
-print(len(own), "launches,", len(conv), "convs, conv share", round(t_conv / t_all, 3))
-for t in ("up4", "knn"):
-    subprocess.run([sys.executable, "tools/ncu_summary.py", f"gpurun_out/prof_{tag}_{t}.ncu-rep", f"profiles/{tag}_{t}_ncu_full.csv"],
-                   stdout=subprocess.DEVNULL)
+print(len(own), "launches,", len(conv), "dense convs, share", round(t_conv / t_all, 3))
+import os
+for t in ("block", "up3c2", "encgemm", "knn", "fft"):
+    rep = f"gpurun_out/prof_{tag}_{t}.ncu-rep"
+    if os.path.exists(rep):
+        subprocess.run([sys.executable, "tools/ncu_summary.py", rep, f"profiles/{tag}_{t}_ncu_full.csv"], stdout=subprocess.DEVNULL)
 for src, dst in ((f"bench_{tag}.json", f"{tag}_bench.json"), (f"bench_ref_{tag}.json", f"{tag}_bench_reference_cpu.json"),
-                 (f"configs_{tag}.jsonl", f"{tag}_configs_3_4_5.jsonl"), ("parity_report.json", f"{tag}_parity_report.json"),
-                 (f"pytest_gpu_{tag}.log", f"{tag}_pytest_gpu.log")):
-    shutil.copy(f"gpurun_out/{src}", f"profiles/{dst}")
+                 ("parity_report.json", f"{tag}_parity_report.json"), (f"pytest_gpu_{tag}.log", f"{tag}_pytest_gpu.log")):
+    if os.path.exists(f"gpurun_out/{src}"):
+        shutil.copy(f"gpurun_out/{src}", f"profiles/{dst}")

@@ -225,3 +225,18 @@ def test_in_kernel_noise_draw(cuda_models, weights, report):
     ours = rmse(a1, oa)
     report.add("in_kernel_noise", rmse_vs_oracle_draw=ours, rmse_between_oracle_draws=between)
     assert 0.5 * between < ours < 2.0 * between
+
+
+@torch.inference_mode()
+def test_infer_into_pinned_host_memory(cuda_models):
+    """Decoder.infer(out=pinned host tensor): the last kernel writes the waveform through the PCIe mapping; same bits as the
+    device result."""
+    _, dec = cuda_models
+    inp = {k: v.cuda() for k, v in synth.decoder_inputs(3, 7, seed=31).items()}
+    want = dec.infer(inp["content"], inp["f0"], inp["energy"], rand01=inp["rand01"])
+    host = torch.empty(3, 7 * 480).pin_memory()
+    got = dec.infer(inp["content"], inp["f0"], inp["energy"], rand01=inp["rand01"], out=host)
+    torch.cuda.synchronize()
+    assert got.data_ptr() == host.data_ptr() and torch.equal(host, want.cpu())
+    with pytest.raises(RuntimeError):
+        dec.infer(inp["content"], inp["f0"], inp["energy"], out=torch.empty(3, 7 * 480))      # pageable host memory

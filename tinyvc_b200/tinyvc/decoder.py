@@ -192,7 +192,10 @@ class Decoder(nn.Module):
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """`out` (extension): write the waveform [B, L] into this fp32 buffer instead of a fresh tensor.  It may live on
         a peer GPU that this device can address (a `tinyvc_b200.peer` window): the last kernel then stores straight
-        into the peer's HBM over NVLink, which is how the sharded mode gathers without a copy."""
+        into the peer's HBM over NVLink, which is how the sharded mode gathers without a copy.  It may also be a PINNED
+        host tensor (`torch.empty(...).pin_memory()`): pinned memory is mapped into the device's address space, so the last
+        kernel's 4-byte-per-sample stores travel over PCIe while it computes and no device-to-host copy follows
+        (synchronise the stream before reading it on the host)."""
         content, f0, energy, B, Lf = self._prep(content, f0, energy)
         dev = content.device
         L = _lib.lib()
@@ -203,8 +206,10 @@ class Decoder(nn.Module):
             self.seed_noise()            # the draw of decoder.py:78 happens inside the noise kernel
         if out is None:
             out = torch.empty(B, Lf * FRAME, device=dev, dtype=torch.float32)
-        elif not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, Lf * FRAME)):
-            raise RuntimeError(f"Decoder.infer: out must be a contiguous CUDA fp32 tensor of shape {(B, Lf * FRAME)}")
+        elif not ((out.is_cuda or out.is_pinned()) and out.dtype == torch.float32 and out.is_contiguous()
+                  and tuple(out.shape) == (B, Lf * FRAME)):
+            raise RuntimeError(f"Decoder.infer: out must be a contiguous fp32 tensor of shape {(B, Lf * FRAME)} on a CUDA "
+                               "device or in pinned host memory")
         step = self._batch_chunk(B, Lf)
         with torch.cuda.device(dev):
             for b0 in range(0, B, step):

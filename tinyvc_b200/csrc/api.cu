@@ -196,6 +196,7 @@ int tvc_set_option(const char* key, const char* value) {
     if (!strcmp(key, "tc_trace")) return tc_trace_arm(value);          // developer: "k0,k1,..." launch ordinals
     if (!strcmp(key, "tc_trace_dump")) return tc_trace_dump(value);    // developer: write the timeline to a file
     if (!strcmp(key, "fused_up")) { set_fused_up(!strcmp(value, "1")); return 0; }
+    if (!strcmp(key, "fuse_down")) { set_fuse_down(!strcmp(value, "1")); return 0; }
     if (!strcmp(key, "pad_up_max_t")) { set_pad_max_t(atoi(value), -1); return 0; }
     if (!strcmp(key, "pad_down_max_t")) { set_pad_max_t(-1, atoi(value)); return 0; }
     if (!strcmp(key, "probe_pad")) {                                   // tests: tvc_tc_conv_probe in padded mode

@@ -222,6 +222,7 @@ bool g_fused_up = true;
 // tensor copy.  Short utterances (config 2: 36 / 108 / 432 rows at the three lowest rates) otherwise gather their clamped
 // windows row by row with cp.async, tap by tap.  0 = never.  Separate limits for the Downsample blocks (pads 1 / 2 / 4 rows:
 // the row count hardly grows) and the Upsample blocks (pads up to 27 rows: more row tiles re-stream the weights).
+bool g_fuse_down = true;      // tvc_set_option("fuse_down", "0"): separate interp_cl launches in front of the Downsample blocks
 int g_pad_max_t = 0, g_pad_down_max_t = 512;     // same-box A/B (profiles/r02f_pad_ab.log): down 1.010 -> 1.004 ms, up 1.010 -> 1.032 ms
 struct ConvCall {
     TcConvArgs a;
@@ -293,36 +294,70 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         A.release(m);
     }
     // ---- FilterNet down path (decoder.py:206-213,225-229): skips at L, L/5, L/20, L/80, L/240
-    float* skip32[5];
+    // g_fuse_down: the 1/f resampler in front of every Downsample block (decoder.py:148) is evaluated by the epilogue of the conv
+    // that produces its input (downs.0, then each block's c3), which writes the block's two operands directly: four launches
+    // fewer, and the fp32 copy of the skip tensors (96 B per sample at the full rate) is never written.
+    float* skip32[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     Pl skipP[5];
     int skipT[5];
     skipT[0] = L;
-    skip32[0] = A.f32(rowsL * 24);
+    const bool fuse_down = g_fuse_down;
+    if (!fuse_down) skip32[0] = A.f32(rowsL * 24);
     skipP[0] = planes(A, rowsL, 24);
+    // operands of the four Downsample blocks (raw planes for down_res, leaky-ReLU'd planes for c1, possibly padded)
+    Pl xr[4], xa[4];
+    int P1s[4];
+    {
+        int t = L;
+        for (int i = 0; i < 4; ++i) {
+            t /= kDownFac[i];
+            skipT[i + 1] = t;
+            P1s[i] = t <= g_pad_down_max_t ? 1 : 0;
+            if (fuse_down) {
+                xr[i] = planes(A, (long long)B * t, kDownIn[i]);
+                xa[i] = planes(A, (long long)B * (t + 2 * P1s[i]), kDownIn[i]);
+            }
+        }
+    }
     ARENA_OK();
-    CONV("tc_down0(", down0, ConvCall(src, B, L).f32(skip32[0], 24).out(skipP[0], TC_ACT_NONE));
+    auto with_dec = [&](ConvCall c, int i) {      // attach Downsample block i's resampled operands to the producing conv
+        const int fac = kDownFac[i];
+        c.a.dec_f = fac; c.a.dec_pad = P1s[i]; c.a.dec_scale = (float)(1.0 / (1.0 / (double)fac));
+        c.a.dec_r_hi = xr[i].hi; c.a.dec_r_lo = xr[i].lo; c.a.dec_a_hi = xa[i].hi; c.a.dec_a_lo = xa[i].lo;
+        return c;
+    };
+    if (fuse_down) CONV("tc_down0(", down0, with_dec(ConvCall(src, B, L).out(skipP[0], TC_ACT_NONE), 0));
+    else CONV("tc_down0(", down0, ConvCall(src, B, L).f32(skip32[0], 24).out(skipP[0], TC_ACT_NONE));
     for (int i = 0; i < 4; ++i) {
         const int cin = kDownIn[i], cout = kDownOut[i], fac = kDownFac[i];
-        const int tin = skipT[i], tout = tin / fac;       // exact: L = 480 * Lf
+        const int tin = skipT[i], tout = skipT[i + 1];    // exact: L = 480 * Lf
         const long long rows = (long long)B * tout;
-        skipT[i + 1] = tout;
-        skip32[i + 1] = A.f32(rows * cout);
+        const bool last = i == 3;
+        if (!fuse_down || last) skip32[i + 1] = A.f32(rows * cout);
         skipP[i + 1] = planes(A, rows, cout);
         const size_t m = A.mark();
         // stored replicate padding for short utterances: each tensor carries the dilation of the conv that reads it
-        const bool pad = tout <= g_pad_down_max_t;
+        const bool pad = P1s[i] != 0;
         const int P1 = pad ? 1 : 0, P2 = pad ? 2 : 0, P4 = pad ? 4 : 0;
-        Pl xr = planes(A, rows, cin), xa = planes(A, (long long)B * (tout + 2 * P1), cin),
-           a = planes(A, (long long)B * (tout + 2 * P2), cin), c = planes(A, (long long)B * (tout + 2 * P4), cin);
+        if (!fuse_down) {
+            xr[i] = planes(A, rows, cin);
+            xa[i] = planes(A, (long long)B * (tout + 2 * P1), cin);
+        }
+        Pl a = planes(A, (long long)B * (tout + 2 * P2), cin), c = planes(A, (long long)B * (tout + 2 * P4), cin);
         ARENA_OK();
-        const float scale = (float)(1.0 / (1.0 / (double)fac));   // F.interpolate(scale_factor=1/f)
-        RUN(interp_cl(skip32[i], B, tin, tout, scale, cin, nullptr, xr.hi, xr.lo, xa.hi, xa.lo, s, P1));
+        if (!fuse_down) {
+            const float scale = (float)(1.0 / (1.0 / (double)fac));   // F.interpolate(scale_factor=1/f)
+            RUN(interp_cl(skip32[i], B, tin, tout, scale, cin, nullptr, xr[i].hi, xr[i].lo, xa[i].hi, xa[i].lo, s, P1));
+        }
         const char* const n1[4] = {"tc_down1_c1(", "tc_down2_c1(", "tc_down3_c1(", "tc_down4_c1("};
         const char* const n2[4] = {"tc_down1_c2(", "tc_down2_c2(", "tc_down3_c2(", "tc_down4_c2("};
         const char* const n3[4] = {"tc_down1_c3(", "tc_down2_c3(", "tc_down3_c3(", "tc_down4_c3("};
-        CONV(n1[i], down[i].c1, ConvCall(xa, B, tout, 1).pad(P1, P2).out(a, TC_ACT_LRELU));
+        CONV(n1[i], down[i].c1, ConvCall(xa[i], B, tout, 1).pad(P1, P2).out(a, TC_ACT_LRELU));
         CONV(n2[i], down[i].c2, ConvCall(a, B, tout, 2).pad(P2, P4).out(c, TC_ACT_LRELU));
-        CONV(n3[i], down[i].c3, ConvCall(c, B, tout, 4).pad(P4, 0).aux(xr).f32(skip32[i + 1], cout).out(skipP[i + 1], TC_ACT_NONE));
+        if (fuse_down && !last)
+            CONV(n3[i], down[i].c3, with_dec(ConvCall(c, B, tout, 4).pad(P4, 0).aux(xr[i]).out(skipP[i + 1], TC_ACT_NONE), i + 1));
+        else
+            CONV(n3[i], down[i].c3, ConvCall(c, B, tout, 4).pad(P4, 0).aux(xr[i]).f32(skip32[i + 1], cout).out(skipP[i + 1], TC_ACT_NONE));
         A.release(m);
     }
     // ---- FilterNet up path (decoder.py:214-219,230-233)
@@ -488,11 +523,14 @@ int EncoderTC::forward(Arena& A, cudaStream_t s, const float* spec, float* z, fl
 }
 
 void set_fused_up(bool on) { g_fused_up = on; }
+void set_fuse_down(bool on) { g_fuse_down = on; }
 bool fused_up() { return g_fused_up; }
 void set_pad_max_t(int up, int down) {
     if (up >= 0) g_pad_max_t = up > 2047 ? 2047 : up;
     if (down >= 0) g_pad_down_max_t = down > 2047 ? 2047 : down;
 }
-unsigned plan_options() { return (g_fused_up ? 1u : 0u) | ((unsigned)g_pad_max_t << 1) | ((unsigned)g_pad_down_max_t << 12); }
+unsigned plan_options() {
+    return (g_fused_up ? 1u : 0u) | ((unsigned)g_pad_max_t << 1) | ((unsigned)g_pad_down_max_t << 12) | (g_fuse_down ? 1u << 23 : 0u);
+}
 
 }  // namespace tvc

@@ -78,6 +78,12 @@ struct alignas(64) TcKParams {
     float topk_eps;
     uint32_t topk_smem;            // byte offset of the merge scratch inside dynamic shared memory
     int row_major;                 // 1: tile id = row_tile * n_tiles + n_tile, whole row tiles per CTA
+    // fused down-resampler (SPEC 9): besides its own outputs the epilogue writes F.interpolate(y, scale_factor=1/dec_f,
+    // mode='linear') of the conv result as the next Downsample block's operands (decoder.py:148): raw planes (down_res input)
+    // and leaky-ReLU'd planes (c1 input, optionally with dec_pad stored replicate rows)
+    int dec_f, dec_pad;
+    float dec_scale;               // interp_cl's source-index scale, (float)dec_f
+    bf16 *dec_r_hi, *dec_r_lo, *dec_a_hi, *dec_a_lo;
     int dbg;   // ablation switches for profiling (TVC_TC_DBG): 1 no loads, 2 no MMAs, 4 no epilogue math/stores
     uint2* trace;   // developer timeline (TVC_TC_TRACE): CTA 0 logs {clock, role|event|tile|stage} per pipeline event
 };
@@ -87,11 +93,12 @@ struct alignas(64) TcKParams {
 // convs, so the combinations the decoder uses are compiled with their flags as constants; the generic
 // instantiation (flags read from the parameters) serves everything else (parity probes).
 // ---------------------------------------------------------------------------------------------
-struct EpiSpec { int film, res, y32, planes, epi_act, out_act, topk; };
-constexpr int kNumSpecs = 9;
+struct EpiSpec { int film, res, y32, planes, epi_act, out_act, topk, dec; };
+constexpr int kNumSpecs = 10;
 constexpr int kTopkC = 8;          // candidates kept per row by the fused top-k epilogue
 __host__ __device__ constexpr EpiSpec epi_spec(int i) {
-    return i == 8 ? EpiSpec{0, 0, 0, 0, TC_ACT_NONE, TC_ACT_NONE, 1}   // kNN screening: per-row top candidates, no output tensor
+    return i == 9 ? EpiSpec{0, 0, 0, 1, TC_ACT_NONE, TC_ACT_NONE, 0, 1}   // skip tensor + the next Downsample block's resampled operands
+         : i == 8 ? EpiSpec{0, 0, 0, 0, TC_ACT_NONE, TC_ACT_NONE, 1}   // kNN screening: per-row top candidates, no output tensor
          : i == 0 ? EpiSpec{0, 0, 1, 0, TC_ACT_NONE, TC_ACT_NONE}      // plain fp32 output
          : i == 1 ? EpiSpec{0, 0, 1, 0, TC_ACT_GELU, TC_ACT_NONE}      // ConvNeXt c2
          : i == 2 ? EpiSpec{0, 1, 1, 1, TC_ACT_NONE, TC_ACT_NONE}      // ConvNeXt c3 (+residual)
@@ -579,10 +586,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
             tr.log(trole, 0, (int)tcount, 0);
             long long row, rowp;                 // output row (residual, fp32 output) and row of the plane output
             bool valid, first = false, last = false;
+            [[maybe_unused]] int ut = 0;         // SPEC 9: time step inside the utterance and the utterance index
+            [[maybe_unused]] long long ub = 0;
             if (!p.halo) {
                 row = tw.row_tile * kTileM + rloc;
                 valid = row < p.rows;
                 rowp = row;
+                if constexpr (!kGeneric && kS.dec != 0) {
+                    ub = (long long)((unsigned)row / (unsigned)p.T);
+                    ut = (int)(row - ub * p.T);
+                }
             } else if (p.halo == 2) {
                 // padded mode: tile rows are padded input rows; pad rows produce nothing.  The plane output may carry its own
                 // padding (y_pad rows on either side of every utterance): the threads that own t = 0 and t = T - 1 also store
@@ -595,6 +608,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                     const int t = (int)(g - bq * (unsigned)p.Tp) - p.a_pad;
                     if (t >= 0 && t < p.T) {
                         valid = true;
+                        ut = t; ub = bq;
                         row = (long long)bq * p.T + t;
                         rowp = (long long)bq * (p.T + 2 * p.y_pad) + p.y_pad + t;
                         first = t == 0;
@@ -606,6 +620,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                 row = (long long)tw.bq * p.T + t;
                 valid = t < p.T;
                 rowp = row;
+                ut = t; ub = tw.bq;
             }
             const uint32_t lane_addr = tmem + buf * acc_cols + ((uint32_t)(quarter * 32) << 16);
             const float* bias = p.bias + n_tile * p.NTp;               // padded channel space
@@ -715,11 +730,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                 }
                 tmem_ld_wait();
                 tr.log(trole, 2, (int)tcount, cg);
-                if (!live) continue;
                 {
                     v[0] = __fadd_rn(v[0], b0.x); v[1] = __fadd_rn(v[1], b0.y); v[2] = __fadd_rn(v[2], b0.z); v[3] = __fadd_rn(v[3], b0.w);
                     v[4] = __fadd_rn(v[4], b1.x); v[5] = __fadd_rn(v[5], b1.y); v[6] = __fadd_rn(v[6], b1.z); v[7] = __fadd_rn(v[7], b1.w);
                 }
+                [[maybe_unused]] float vn[8];            // SPEC 9: the same channels of the next time row (the resampler's second tap)
+                if constexpr (!kGeneric && kS.dec != 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float nx = __shfl_down_sync(0xffffffffu, v[i], 1);
+                        vn[i] = lane == 31 ? v[i] : nx;  // only reached with weight 0 (factors 5 and 3 sample one row exactly)
+                    }
+                }
+                if (!live) continue;
                 if (film) {
                     const float sb[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                     const float hb[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
@@ -758,6 +781,44 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                         for (int q = 1; q <= p.y_pad; ++q) {
                             *reinterpret_cast<uint4*>(p.y_hi + op + 8 * q) = hv;
                             *reinterpret_cast<uint4*>(p.y_lo + op + 8 * q) = lv;
+                        }
+                    }
+                }
+                if constexpr (!kGeneric && kS.dec != 0) {
+                    // F.interpolate(scale_factor = 1 / f) of this conv's output, interp_cl's arithmetic: output d of the
+                    // utterance reads rows i0(d), i1(d); the thread that owns row i0 produces it (its neighbour lane owns i1).
+                    const int Tout = p.T / p.dec_f;
+                    const int d = ut / p.dec_f;
+                    if (d < Tout && ch + 8 <= p.y_cs) {
+                        const LinCoord c = lin_coord(d, p.dec_scale, p.T);
+                        if (c.i0 == ut) {
+                            float w[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) w[i] = lin_blend(v[i], c.i1 == ut ? v[i] : vn[i], c);
+                            const long long rows_r = (p.rows / p.T) * Tout;
+                            uint32_t h[4], l[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) split2(w[2 * i], w[2 * i + 1], h[i], l[i]);
+                            const long long orr = ((long long)(ch >> 3) * rows_r + ub * Tout + d) * 8;
+                            *reinterpret_cast<uint4*>(p.dec_r_hi + orr) = make_uint4(h[0], h[1], h[2], h[3]);
+                            *reinterpret_cast<uint4*>(p.dec_r_lo + orr) = make_uint4(l[0], l[1], l[2], l[3]);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) split2(leaky01(w[2 * i]), leaky01(w[2 * i + 1]), h[i], l[i]);
+                            const uint4 hv = make_uint4(h[0], h[1], h[2], h[3]), lv = make_uint4(l[0], l[1], l[2], l[3]);
+                            const long long Tpo = Tout + 2 * p.dec_pad;
+                            const long long oa = ((long long)(ch >> 3) * ((p.rows / p.T) * Tpo) + ub * Tpo + p.dec_pad + d) * 8;
+                            *reinterpret_cast<uint4*>(p.dec_a_hi + oa) = hv;
+                            *reinterpret_cast<uint4*>(p.dec_a_lo + oa) = lv;
+                            if (d == 0)
+                                for (int q = 1; q <= p.dec_pad; ++q) {
+                                    *reinterpret_cast<uint4*>(p.dec_a_hi + oa - 8 * q) = hv;
+                                    *reinterpret_cast<uint4*>(p.dec_a_lo + oa - 8 * q) = lv;
+                                }
+                            if (d == Tout - 1)
+                                for (int q = 1; q <= p.dec_pad; ++q) {
+                                    *reinterpret_cast<uint4*>(p.dec_a_hi + oa + 8 * q) = hv;
+                                    *reinterpret_cast<uint4*>(p.dec_a_lo + oa + 8 * q) = lv;
+                                }
                         }
                     }
                 }
@@ -923,6 +984,7 @@ int tc_conv_init() {
     TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
     TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
     TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcTopkSmem));
+    TVC_CUDA(cudaFuncSetAttribute(tc_conv_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcMaxSmem));
     return 0;
 }
 
@@ -1033,6 +1095,13 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
                 "tc_conv: the fused top-k needs a plain 1 x 1 conv without outputs, 1 <= k <= 4");
     p.topk_cand = a.topk_cand; p.topk_flag = a.topk_flag; p.topk_k = a.topk_k; p.topk_n = a.topk_n; p.topk_eps = a.topk_eps;
     p.row_major = topk ? 1 : 0;
+    const bool dec = a.dec_f > 0;
+    TVC_REQUIRE(!dec || (a.dec_r_hi && a.dec_r_lo && a.dec_a_hi && a.dec_a_lo && a.y_hi && !a.y32 && !a.res && W.aux_mode != TC_AUX_FILM &&
+                         a.epi_act == TC_ACT_NONE && a.out_act == TC_ACT_NONE && a.T % a.dec_f == 0 && a.dec_pad >= 0 &&
+                         (a.dec_f == 3 || a.dec_f == 5 || (a.dec_f == 4 && a.T % 4 == 0 && (a.a_pad % 4 == 0)))),
+                "tc_conv: the fused down-resampler needs a plain plane output and a factor of 3, 4 or 5 dividing T");
+    p.dec_f = a.dec_f; p.dec_pad = a.dec_pad; p.dec_scale = a.dec_scale;
+    p.dec_r_hi = a.dec_r_hi; p.dec_r_lo = a.dec_r_lo; p.dec_a_hi = a.dec_a_hi; p.dec_a_lo = a.dec_a_lo;
     const int topk_bytes = topk ? 3 * kTileM * kTopkC * 8 : 0;
     const int smem_budget = topk ? kTcTopkSmem : kTcMaxSmem;
     static const int dbg = getenv("TVC_TC_DBG") ? atoi(getenv("TVC_TC_DBG")) : 0;
@@ -1106,15 +1175,16 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     int spec = -1;
     for (int i = 0; i < kNumSpecs; ++i) {
         const EpiSpec e = epi_spec(i);
-        if ((e.topk != 0) != topk) continue;
+        if ((e.topk != 0) != topk || (e.dec != 0) != dec) continue;
         if ((e.film != 0) == (W.aux_mode == TC_AUX_FILM) && (e.res != 0) == (a.res != nullptr) && (e.y32 != 0) == (a.y32 != nullptr) &&
             (e.planes != 0) == (a.y_hi != nullptr) && e.epi_act == a.epi_act && (e.out_act == a.out_act || !a.y_hi)) {
             spec = i;
             break;
         }
     }
-    if (g_force_generic && !topk) spec = -1;
+    if (g_force_generic && !topk && !dec) spec = -1;
     TVC_REQUIRE(!topk || spec == 8, "tc_conv: no fused top-k instantiation");
+    TVC_REQUIRE(!dec || spec == 9, "tc_conv: no fused down-resampler instantiation");
     switch (spec) {
         case 0: TVC_LAUNCH_PDL(tc_conv_kernel<0>, grid, kThreads, smem, s, p); break;
         case 1: TVC_LAUNCH_PDL(tc_conv_kernel<1>, grid, kThreads, smem, s, p); break;
@@ -1125,6 +1195,7 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
         case 6: TVC_LAUNCH_PDL(tc_conv_kernel<6>, grid, kThreads, smem, s, p); break;
         case 7: TVC_LAUNCH_PDL(tc_conv_kernel<7>, grid, kThreads, smem, s, p); break;
         case 8: TVC_LAUNCH_PDL(tc_conv_kernel<8>, grid, kThreads, smem, s, p); break;
+        case 9: TVC_LAUNCH_PDL(tc_conv_kernel<9>, grid, kThreads, smem, s, p); break;
         default: TVC_LAUNCH_PDL(tc_conv_kernel<-1>, grid, kThreads, smem, s, p); break;
     }
     TVC_LAUNCH_CHECK();

@@ -82,6 +82,13 @@ struct TcConvArgs {
     int* topk_flag = nullptr;
     int topk_k = 0, topk_n = 0;
     float topk_eps = 0.f;
+    // Fused down-resampler: with dec_f in {3, 4, 5} the epilogue also writes F.interpolate(y, scale_factor = 1 / dec_f,
+    // mode='linear') of the conv's result (interp_cl's arithmetic) as the next Downsample block's two operands: raw planes
+    // dec_r (B * T / dec_f rows) and leaky-ReLU'd planes dec_a (with dec_pad stored replicate rows per utterance side).
+    // Needs a plane output and no fp32 output / residual / FiLM / activation.
+    int dec_f = 0, dec_pad = 0;
+    float dec_scale = 0.f;             // interp_cl's scale argument for this factor
+    bf16 *dec_r_hi = nullptr, *dec_r_lo = nullptr, *dec_a_hi = nullptr, *dec_a_lo = nullptr;
     int epi_act = TC_ACT_NONE;         // applied to the value (both outputs)
     int out_act = TC_ACT_NONE;         // applied additionally to the split-plane copy only
 };

@@ -74,7 +74,12 @@ int64_t tvc_param_total(int kind);
  * decoder.load_state_dict, infer.py:36-37).  Weights are repacked once into kernel layout.   */
 int tvc_decoder_create(const float* params, int64_t numel, tvc_decoder_t* out);
 int tvc_decoder_destroy(tvc_decoder_t h);
+/* Scratch bytes for this shape.  tvc_decoder_workspace_bytes fits every decoder entry point under any option;
+ * tvc_decoder_infer_workspace_bytes is what tvc_decoder_infer alone needs under the options in force when it is called
+ * (tvc_set_option: conv_impl, fused_up, fuse_down, pad limits -- ask again after changing one): the tensor-core plan
+ * needs 540 B per output sample, the exact-fp32 plan 862.                                                              */
 size_t tvc_decoder_workspace_bytes(int B, int Lf);
+size_t tvc_decoder_infer_workspace_bytes(int B, int Lf);
 
 /* Decoder.infer(content, f0, energy)  (decoder.py:253-257).
  *   content [B,768,Lf]  f0 [B,1,Lf]  energy [B,1,L]  rand01 [B,961,Lf]  ->  out [B,L]

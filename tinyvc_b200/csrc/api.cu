@@ -336,8 +336,9 @@ static void shapes_ok_msg(int B, int Lf) { set_error("invalid shape B=%d Lf=%d",
 size_t tvc_decoder_workspace_bytes(int B, int Lf) {
     if (B <= 0 || Lf <= 0) return 0;
     static DecoderModel shape_only;   // dry runs never touch weights (nor any mutable state of the model)
-    // the larger of the two execution plans, so the caller's buffer fits whichever option is active; the plan is passed
-    // explicitly (no global is touched: other threads may be inside tvc_decoder_infer)
+    // the larger of the two execution plans, so the caller's buffer fits every entry point (tvc_source_net / tvc_dsp /
+    // tvc_filter_net always run the exact-fp32 plan) whichever options are active; the plan is passed explicitly (no global is
+    // touched: other threads may be inside tvc_decoder_infer)
     size_t need = 0;
     for (int impl : {CONV_IMPL_FP32, CONV_IMPL_TC}) {
         Arena A(nullptr, 0, true);
@@ -345,6 +346,14 @@ size_t tvc_decoder_workspace_bytes(int B, int Lf) {
         need = A.peak > need ? A.peak : need;
     }
     return need + 256;
+}
+
+size_t tvc_decoder_infer_workspace_bytes(int B, int Lf) {
+    if (B <= 0 || Lf <= 0) return 0;
+    static DecoderModel shape_only;
+    Arena A(nullptr, 0, true);
+    if (shape_only.infer(A, 0, nullptr, nullptr, nullptr, nullptr, nullptr, B, Lf, g_conv_impl)) return 0;
+    return A.peak + 256;
 }
 
 int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, const float* energy,

@@ -371,7 +371,9 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         const Pl& cond = skipP[4 - i];
         TVC_REQUIRE(skipT[4 - i] == tout && cond.cs == c, "filter_net: skip %d shape mismatch", 4 - i);
         const Up& uc = up4_cat;
-        const bool fused = g_fused_up && i == 4 && fac == 5 && c == 24 && tc_up24_block_supported(uc.c1, uc.c2, uc.c3, uc.c4, uc.c5);
+        // (workspace sizing runs this plan dry on a weightless model: the architecture's shapes are the supported ones)
+        const bool fused = g_fused_up && i == 4 && fac == 5 && c == 24 &&
+                           (A.dry || tc_up24_block_supported(uc.c1, uc.c2, uc.c3, uc.c4, uc.c5));
         if (fused) {
             // resampler, the five convs and the output layer in one kernel (tc_block.cu); same arithmetic as the launches below
             TcUpBlockArgs fa;

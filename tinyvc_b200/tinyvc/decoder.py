@@ -7,11 +7,15 @@ infer_streaming.py:41-43 and train_decoder.py:105-107 (`decoder.source_net`, `de
 C-ABI in include/tinyvc_b200.h (`tvc_decoder_infer`, `tvc_source_net`, `tvc_dsp`,
 `tvc_filter_net`).  The nn.Conv1d objects below are parameter containers only.
 
-One extension over the reference signatures: the keyword-only `rand01=` argument carries the
-uniform [0,1) draw that the reference takes from torch's global generator inside
-`oscillate_noise` (decoder.py:78).  Passing the same tensor to the CPU reference (by seeding)
-and to this decoder makes the noise branch comparable; when omitted it is drawn with
-`torch.rand(..., device=content.device)` exactly like the reference does.
+Extensions over the reference signatures (keyword-only):
+* `rand01=` carries the uniform [0,1) draw that the reference takes from torch's global generator inside
+  `oscillate_noise` (decoder.py:78).  Passing the same tensor to the CPU reference (by seeding) and to this decoder makes
+  the noise branch comparable.  When omitted, `infer` draws inside the noise kernel (Philox-4x32-10, a fresh tensor per
+  call): the stream is seeded once per decoder from torch's CPU generator at first use, or explicitly with
+  `Decoder.seed_noise(seed)` -- a later `torch.manual_seed` does NOT reseed it (call `seed_noise` for reproducible runs;
+  `ShardedDecoder` gives every rank its own seed).  `dsp` / `filter_net` and the exact-fp32 plan draw `torch.rand` on the
+  device instead.
+* `out=` (infer only): destination buffer, possibly on a peer GPU or in pinned host memory.
 """
 from __future__ import annotations
 
@@ -183,7 +187,7 @@ class Decoder(nn.Module):
 
     @staticmethod
     def _batch_chunk(B: int, Lf: int) -> int:
-        per1 = _lib.lib().tvc_decoder_workspace_bytes(1, Lf)
+        per1 = _lib.lib().tvc_decoder_infer_workspace_bytes(1, Lf)
         return max(1, min(B, int(MAX_WORKSPACE_BYTES // max(per1, 1))))
 
     # ---- reference API ------------------------------------------------------------------------
@@ -214,7 +218,7 @@ class Decoder(nn.Module):
         with torch.cuda.device(dev):
             for b0 in range(0, B, step):
                 nb = min(step, B - b0)
-                nbytes = L.tvc_decoder_workspace_bytes(nb, Lf)
+                nbytes = L.tvc_decoder_infer_workspace_bytes(nb, Lf)
                 ws = _lib.WORKSPACE.get(nbytes, dev)
                 _lib.check(L.tvc_decoder_infer(h, content[b0:b0 + nb].data_ptr(), f0[b0:b0 + nb].data_ptr(),
                                                energy[b0:b0 + nb].data_ptr(),

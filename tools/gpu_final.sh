@@ -23,8 +23,8 @@ full() {  # name, kernel regex, skip, command...
 }
 : > gpurun_out/ncu_full_$TAG.log
 full block 'tc_up24_block_kernel' 3 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra-configs
-full up3c2 'tc_conv_kernel<6>' 15 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra-configs
-full encgemm 'tc_conv_kernel<1>' 0 python tools/bench_configs.py --configs 3 --steps 1
-full knn 'tc_conv_kernel<8>' 0 python tools/bench_configs.py --configs 3 --steps 1
+full up3c2 'tc_conv_kernel<.*6>' 15 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra-configs
+full encgemm 'tc_conv_kernel<.*1>' 0 python tools/bench_configs.py --configs 3 --steps 1
+full knn 'tc_conv_kernel<.*8>' 0 python tools/bench_configs.py --configs 3 --steps 1
 full fft 'stft_fft_kernel' 0 python tools/bench_configs.py --configs 3 --steps 1
 ls -la gpurun_out | tail -12

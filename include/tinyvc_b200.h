@@ -90,6 +90,14 @@ int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, co
                       const float* rand01, float* out, int B, int Lf, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* The same with output pruning: the caller reads only out[b][out_t0, out_t1) of every utterance (StreamInfer.audio_callback
+ * keeps y[-9600:-3840] of its 13 440-sample window, module/infer/stream.py:75).  The fused full-rate block skips the windows
+ * that produce none of those samples; the samples inside the range are bit-identical to tvc_decoder_infer's, the samples
+ * outside it are left unspecified.  0 <= out_t0 < out_t1 <= 480 * Lf.                                                     */
+int tvc_decoder_infer_range(tvc_decoder_t h, const float* content, const float* f0, const float* energy,
+                            const float* rand01, float* out, int B, int Lf, int64_t out_t0, int64_t out_t1,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* Seed of the in-kernel noise draw (the role torch.manual_seed plays for decoder.py:78).      */
 int tvc_decoder_seed(tvc_decoder_t h, uint64_t seed, void* stream);
 

@@ -53,3 +53,25 @@ def test_fused_down_resamplers_bit_identical(cuda_models, B, Lf):
     for g in got:
         assert torch.isfinite(g).all()
         assert torch.equal(g, ref), f"max|d| = {float((g - ref).abs().max()):.3e}"
+
+
+@pytest.mark.parametrize("B,Lf,t0,t1", [(2, 28, 3840, 9600), (3, 7, 0, 1), (3, 7, 3359, 3360), (1, 1, 100, 300), (5, 18, 425, 427),
+                                        (4, 28, 0, 13440), (2, 5, 426, 852)])
+def test_output_pruning_is_bit_identical_inside_the_kept_range(cuda_models, B, Lf, t0, t1):
+    """tvc_decoder_infer_range / Decoder.infer(keep=(t0, t1)): the fused block walks only the 426-sample windows that produce
+    kept samples (a streaming tick reads y[-9600:-3840] of 13 440, module/infer/stream.py:75).  The walked windows see complete
+    inputs, so the kept samples are the bits of the full run -- eager and under graph replay."""
+    from tinyvc_b200 import synth
+    _, dec = cuda_models
+    inp = {k: v.to("cuda") for k, v in synth.decoder_inputs(B, Lf, 77 + Lf + t0).items()}
+    full = dec.infer(inp["content"], inp["f0"], inp["energy"], rand01=inp["rand01"]).clone()
+    out = torch.full_like(full, float("nan"))
+    for _ in range(3):        # eager, capture, replay
+        out.fill_(float("nan"))
+        dec.infer(inp["content"], inp["f0"], inp["energy"], rand01=inp["rand01"], out=out, keep=(t0, t1))
+        assert torch.equal(out[:, t0:t1], full[:, t0:t1])
+    # what lies outside the walked windows was not touched (the pruning really skips work)
+    lo, hi = (t0 // 426) * 426, min(((t1 - 1) // 426 + 1) * 426, full.shape[1])
+    assert torch.isnan(out[:, :lo]).all() and torch.isnan(out[:, hi:]).all()
+    with pytest.raises(RuntimeError):
+        dec.infer(inp["content"], inp["f0"], inp["energy"], rand01=inp["rand01"], keep=(t1, t0))

@@ -73,6 +73,28 @@ def test_batched_streams_match_single(cuda_models):
 
 
 @torch.inference_mode()
+def test_output_pruning_does_not_change_a_tick(cuda_models):
+    """audio_callback asks the decoder for the 5 760 samples SOLA reads (stream.py:75) instead of all 13 440: same blocks."""
+    from tinyvc_b200.infer import Generator, BatchedStreamInfer
+    enc, dec = cuda_models
+    gen = Generator(enc, dec)
+    gi = torch.Generator().manual_seed(11)
+    index = torch.randn(1, 768, 2048, generator=gi).cuda()
+    S = 4
+    blocks = 0.1 * torch.randn(3, S, 1920, generator=gi)
+    rands = torch.rand(3, S, 961, 28, generator=gi)
+    a = BatchedStreamInfer(gen, S, target=index, device=torch.device("cuda"))
+    b = BatchedStreamInfer(gen, S, target=index, device=torch.device("cuda"))
+    b.prune_output = False
+    a.init_buffer(); b.init_buffer()
+    for tick in range(3):
+        oa = a.audio_callback(blocks[tick].cuda(), rand01=rands[tick].cuda())
+        ob = b.audio_callback(blocks[tick].cuda(), rand01=rands[tick].cuda())
+        assert torch.equal(a.last_shift, b.last_shift)
+        assert torch.equal(oa, ob), f"tick {tick}: max|d| = {float((oa - ob).abs().max()):.3e}"
+
+
+@torch.inference_mode()
 def test_phase_vocoder_matches_reference(report):
     """phase_vocoder(a, b, fade_out, fade_in) (reference stream.py:9-26) for several stream pairs, n = 1920 and an
     odd length (the reference doubles a different bin range for odd n)."""

@@ -118,9 +118,10 @@ struct DecoderGraphKey {
     const void *content, *f0, *energy, *rand01, *out, *ws;
     int B, Lf, impl;
     unsigned opts;                       // plan options (nets_tc.cuh plan_options): they change the launch sequence
+    int t0, t1;                          // output range (tvc_decoder_infer_range)
     bool operator==(const DecoderGraphKey& o) const {
         return content == o.content && f0 == o.f0 && energy == o.energy && rand01 == o.rand01 && out == o.out &&
-               ws == o.ws && B == o.B && Lf == o.Lf && impl == o.impl && opts == o.opts;
+               ws == o.ws && B == o.B && Lf == o.Lf && impl == o.impl && opts == o.opts && t0 == o.t0 && t1 == o.t1;
     }
 };
 struct DecoderGraph {
@@ -356,24 +357,28 @@ size_t tvc_decoder_infer_workspace_bytes(int B, int Lf) {
     return A.peak + 256;
 }
 
-int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, const float* energy,
-                      const float* rand01, float* out, int B, int Lf, void* workspace, size_t workspace_bytes,
-                      void* stream) {
+int tvc_decoder_infer_range(tvc_decoder_t h, const float* content, const float* f0, const float* energy,
+                            const float* rand01, float* out, int B, int Lf, int64_t out_t0, int64_t out_t1, void* workspace,
+                            size_t workspace_bytes, void* stream) {
     API_BEGIN
     TVC_REQUIRE(h && content && f0 && energy && out && workspace, "tvc_decoder_infer: null argument");
+    TVC_REQUIRE(Lf <= 0 || (out_t0 >= 0 && out_t0 < out_t1 && out_t1 <= (int64_t)Lf * kFrame),
+                "tvc_decoder_infer_range: range [%lld, %lld) outside the %lld output samples", (long long)out_t0, (long long)out_t1,
+                (long long)Lf * kFrame);
+    const int t0 = (int)out_t0, t1 = (int)out_t1;
     const int impl = g_conv_impl;     // read once: the whole call runs one plan
     TVC_REQUIRE(rand01 || impl == CONV_IMPL_TC, "tvc_decoder_infer: the fp32 plan needs an injected rand01 draw");
     CHECK_SHAPES();
     cudaStream_t s = (cudaStream_t)stream;
     if (!g_use_graphs || g_prof_on) {
         Arena A(workspace, workspace_bytes, false);
-        return h->m.infer(A, s, content, f0, energy, rand01, out, B, Lf, impl);
+        return h->m.infer(A, s, content, f0, energy, rand01, out, B, Lf, impl, t0, t1);
     }
     // CUDA-graph replay: the launch sequence for one exact set of buffers is captured the second time
     // that set is seen (callers that reuse their buffers -- serving loops, the Python wrapper's cached
     // workspace -- then pay one graph launch instead of ~100 kernel launches per call).
     std::lock_guard<std::mutex> lock(h->mu);
-    const DecoderGraphKey key{content, f0, energy, rand01, out, workspace, B, Lf, impl | (g_pdl ? 256 : 0), plan_options()};
+    const DecoderGraphKey key{content, f0, energy, rand01, out, workspace, B, Lf, impl | (g_pdl ? 256 : 0), plan_options(), t0, t1};
     ++h->tick;
     for (DecoderGraph& g : h->graphs)
         if (g.key == key) {
@@ -388,7 +393,7 @@ int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, co
         if (h->seen.size() >= 32) h->seen.erase(h->seen.begin());
         h->seen.push_back(key);
         Arena A(workspace, workspace_bytes, false);
-        return h->m.infer(A, s, content, f0, energy, rand01, out, B, Lf, impl);
+        return h->m.infer(A, s, content, f0, energy, rand01, out, B, Lf, impl, t0, t1);
     }
     if (!h->cap_stream) TVC_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
     const unsigned long long n0 = g_launches.load();
@@ -396,7 +401,7 @@ int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, co
     int rc = 0;
     {
         Arena A(workspace, workspace_bytes, false);
-        rc = h->m.infer(A, h->cap_stream, content, f0, energy, rand01, out, B, Lf, impl);
+        rc = h->m.infer(A, h->cap_stream, content, f0, energy, rand01, out, B, Lf, impl, t0, t1);
     }
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
@@ -423,6 +428,13 @@ int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, co
     TVC_CUDA(cudaGraphLaunch(g.exec, s));
     return 0;
     API_END
+}
+
+int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, const float* energy,
+                      const float* rand01, float* out, int B, int Lf, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+    return tvc_decoder_infer_range(h, content, f0, energy, rand01, out, B, Lf, 0, (int64_t)(Lf > 0 ? Lf : 1) * kFrame, workspace,
+                                   workspace_bytes, stream);
 }
 
 int tvc_decoder_seed(tvc_decoder_t h, uint64_t seed, void* stream) {

@@ -79,48 +79,57 @@ __global__ void __launch_bounds__(NTY* NTX) conv1d_f32_kernel(ConvParams p) {
     // Software pipeline: chunk c+1 travels global -> registers while chunk c is multiplied out of shared memory.
     constexpr int XROWS = (BK * KT + RSTEP - 1) / RSTEP;          // staged input rows per loader thread
     constexpr int WPT = (KT * BK * (BM / 4) + NT - 1) / NT;       // staged weight float4s per thread
+    // Loads are straight-line (indices clamped to legal addresses, masking and the producer-side op applied when the chunk
+    // is stored to shared memory): a value consumed inside its own guarded region would serialise the chunk's loads, one
+    // global-memory round trip per element (measured: 14 us per 32-row chunk with PRE_AFFINE on a streaming tick).
+    constexpr int SR = (KT == 1) ? XROWS : 1;                     // GRN affine operands exist for 1x1 convs only
     float xr[XROWS][CPT];
+    float sr[SR][CPT], hr[SR];
     float4 wr[WPT];
+    const int cin_last = p.Cin - 1;
     auto load_chunk = [&](int ci0) {
 #pragma unroll
         for (int r = 0; r < XROWS; ++r) {
-            const int row = rbase + r * RSTEP;
+            const int row = min(rbase + r * RSTEP, BK * KT - 1);
             const int k = row / KT, tap = row - k * KT;
-            const int ci = ci0 + k;
+            const int ci = min(ci0 + k, cin_last);
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                float v = 0.f;
-                if (row < BK * KT && colok[c] && ci < p.Cin) {
-                    v = __ldg(p.x + colbase[c] + (long long)ci * T + toff[c][tap]);
-                    if (pre == PRE_LRELU) {
-                        v = leaky01(v);
-                    } else if (pre == PRE_AFFINE) {
-                        v = fmaf(v, __ldg(p.pre_scale + (long long)colb[c] * p.Cin + ci), __ldg(p.pre_shift + ci));
-                    }
-                }
-                xr[r][c] = v;
+            for (int c = 0; c < CPT; ++c) xr[r][c] = __ldg(p.x + colbase[c] + (long long)ci * T + toff[c][tap]);
+        }
+        if (KT == 1 && pre == PRE_AFFINE) {
+#pragma unroll
+            for (int r = 0; r < SR; ++r) {
+                const int ci = min(ci0 + min(rbase + r * RSTEP, BK - 1), cin_last);
+                hr[r] = __ldg(p.pre_shift + ci);
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) sr[r][c] = __ldg(p.pre_scale + (long long)colb[c] * p.Cin + ci);
             }
         }
 #pragma unroll
         for (int q = 0; q < WPT; ++q) {
-            const int e = tid + q * NT;
+            const int e = min(tid + q * NT, KT * BK * (BM / 4) - 1);
             const int m4 = e % (BM / 4);
             const int rk = e / (BM / 4);          // tap*BK + k
             const int tap = rk / BK, k = rk - tap * BK;
             const int ci = ci0 + k, co = co0 + m4 * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e < KT * BK * (BM / 4) && ci < p.Cin && co < p.CoutP)
-                v = __ldg(reinterpret_cast<const float4*>(p.w + ((long long)tap * p.Cin + ci) * p.CoutP + co));
-            wr[q] = v;
+            const bool ok = ci < p.Cin && co < p.CoutP;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + ((long long)tap * p.Cin + min(ci, cin_last)) * p.CoutP + (ok ? co : 0)));
+            wr[q] = ok ? v : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
-    auto store_chunk = [&]() {
+    auto store_chunk = [&](int ci0) {
 #pragma unroll
         for (int r = 0; r < XROWS; ++r) {
             const int row = rbase + r * RSTEP;
             if (row < BK * KT) {
+                const int ci = ci0 + row / KT;
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) xs[row * BN + jbase + c * NT] = xr[r][c];
+                for (int c = 0; c < CPT; ++c) {
+                    float v = xr[r][c];
+                    if (pre == PRE_LRELU) v = leaky01(v);
+                    else if (KT == 1 && pre == PRE_AFFINE) v = fmaf(v, sr[r < SR ? r : 0][c], hr[r < SR ? r : 0]);
+                    xs[row * BN + jbase + c * NT] = (colok[c] && ci < p.Cin) ? v : 0.f;
+                }
             }
         }
 #pragma unroll
@@ -135,7 +144,7 @@ __global__ void __launch_bounds__(NTY* NTX) conv1d_f32_kernel(ConvParams p) {
     };
     load_chunk(0);
     for (int ci0 = 0; ci0 < p.Cin; ci0 += BK) {
-        store_chunk();
+        store_chunk(ci0);
         __syncthreads();
         if (ci0 + BK < p.Cin) load_chunk(ci0 + BK);
         // ---- FMA (per output: acc = fma(w, x, acc) with ci ascending, taps inner -- the order parity tests pin) ----
@@ -254,6 +263,10 @@ template <int KT> using F96 = ConvCfg<8, 12, 32, 8, KT>;    // 96 x 128, 256 thr
 template <int KT> using G64 = ConvCfg<8, 8, 32, 8, KT>;     // 64 x 128, 256 threads
 template <int KT> using G16 = ConvCfg<2, 8, 64, 8, KT>;     // 16 x 256, 128 threads (tiny Cout)
 using G128 = ConvCfg<8, 16, 32, 16, 1>;                      // 128 x 128, 256 threads, BK 16: the big 1x1 products (encoder, STFT, kNN)
+// 32 x 64, 64 threads, BK 32: 1x1 products over few columns (a streaming tick's PitchEstimator: 3 584 frames).  Four times
+// the CTAs of G64 and a quarter of the K-chunks, i.e. of the load -> stage -> multiply round trips that bound a CTA there;
+// the per-output FMA order (ci ascending) and therefore the result bits are those of every other configuration.
+using S32 = ConvCfg<4, 8, 16, 32, 1>;
 
 int conv1d_init() {
     TVC_TRY(F24<1>::init()); TVC_TRY(F24<3>::init());
@@ -262,6 +275,7 @@ int conv1d_init() {
     TVC_TRY(G64<1>::init()); TVC_TRY(G64<3>::init());
     TVC_TRY(G16<1>::init()); TVC_TRY(G16<3>::init());
     TVC_TRY(G128::init());
+    TVC_TRY(S32::init());
     return 0;
 }
 
@@ -280,11 +294,15 @@ int conv1d_launch(const ConvParams& p, cudaStream_t stream) {
     TVC_REQUIRE(p.CoutP % 4 == 0 && p.CoutP >= p.Cout, "conv1d: CoutP=%d must be a multiple of 4 >= Cout=%d", p.CoutP, p.Cout);
     TVC_REQUIRE(p.epi != EPI_FILM_RES || (p.film && p.res), "conv1d: FiLM epilogue needs film and res");
     TVC_REQUIRE(p.epi != EPI_RES || p.res, "conv1d: residual epilogue needs res");
-    TVC_REQUIRE(p.pre != PRE_AFFINE || (p.pre_scale && p.pre_shift), "conv1d: affine prologue needs scale/shift");
+    TVC_REQUIRE(p.pre != PRE_AFFINE || (p.pre_scale && p.pre_shift && p.K == 1), "conv1d: affine prologue needs scale/shift and a 1x1 conv");
     // large 1x1 products: 128 x 128 tiles when they still give every SM at least ~2 CTAs
     if (p.K == 1 && p.Cout >= 256) {
         const long long tiles = (((long long)p.B * p.T + 127) / 128) * ((p.Cout + 127) / 128);
         if (tiles >= 296) return G128::launch(p, stream);
+    }
+    if (p.K == 1 && p.Cout > 48 && p.Cout % 32 == 0) {
+        const long long g64 = (((long long)p.B * p.T + 127) / 128) * ((p.Cout + 63) / 64);
+        if (g64 < 2 * 148) return S32::launch(p, stream);
     }
     if (p.K == 1) return dispatch_cfg<1>(p, stream);
     if (p.K == 3) return dispatch_cfg<3>(p, stream);

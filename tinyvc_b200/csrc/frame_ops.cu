@@ -197,40 +197,71 @@ int grn_scale(const float* y, const float* gamma, float* scale, int B, int C, in
 // ---------------------------------------------------------------------------------------------
 // pitch_decode (encoder.py:48-67): top-4 of the 512 logits per frame, softmax over those four,
 // f0 = sum p_i * 20*2^(id_i/48) with frequencies <= 20 Hz zeroed, and the result zeroed if <= 20.
-// One thread per frame; consecutive threads read consecutive frames (coalesced over t).
 // ---------------------------------------------------------------------------------------------
-__global__ void pitch_decode_kernel(const float* __restrict__ logits, float* __restrict__ f0, int ncls, int T,
-                                    long long ncol) {
-    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per frame: lane l scans classes l, l + 32, ... (all loads in flight at once) keeping its own sorted top-4, then
+// four rounds of a warp arg-max (value descending, class index ascending on ties) pop the global top-4 in the order the
+// sequential scan of one thread would have produced; lane 0 evaluates the softmax-weighted frequency.
+__global__ void __launch_bounds__(256) pitch_decode_kernel(const float* __restrict__ logits, float* __restrict__ f0, int ncls, int T,
+                                                           long long ncol) {
+    const long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (n >= ncol) return;
     const long long b = n / T;
     const int t = (int)(n - b * T);
     const float* lp = logits + b * ncls * (long long)T + t;
     float v[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    int id[4] = {0, 0, 0, 0};
-    for (int c = 0; c < ncls; ++c) {
-        const float x = __ldg(lp + (long long)c * T);
-        if (x > v[3]) {
-            int pos = 3;
-            while (pos > 0 && x > v[pos - 1]) {
-                v[pos] = v[pos - 1];
-                id[pos] = id[pos - 1];
-                --pos;
+    int id[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    for (int c0 = 0; c0 < ncls; c0 += 32 * 8) {
+        float x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = c0 + u * 32 + lane;
+            x[u] = c < ncls ? __ldg(lp + (long long)c * T) : -INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = c0 + u * 32 + lane;
+            if (x[u] > v[3]) {                       // classes arrive in increasing order: strict '>' keeps the lower index
+                v[3] = x[u]; id[3] = c;
+#pragma unroll
+                for (int q = 3; q > 0; --q)
+                    if (v[q] > v[q - 1]) {
+                        const float tv = v[q]; v[q] = v[q - 1]; v[q - 1] = tv;
+                        const int ti = id[q]; id[q] = id[q - 1]; id[q - 1] = ti;
+                    }
             }
-            v[pos] = x;
-            id[pos] = c;
         }
     }
+    float tv[4];
+    int ti[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float bv = v[0];
+        int bi = id[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        tv[r] = bv;
+        ti[r] = bi == 0x7fffffff ? 0 : bi;           // fewer than four comparable logits (NaN / -inf rows): class 0 at -inf, as before
+        if (id[0] == bi && bi != 0x7fffffff) {       // the owner pops its head
+            v[0] = v[1]; id[0] = id[1]; v[1] = v[2]; id[1] = id[2]; v[2] = v[3]; id[2] = id[3];
+            v[3] = -INFINITY; id[3] = 0x7fffffff;
+        }
+    }
+    if (lane != 0) return;
     float e[4], se = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        e[i] = expf(v[i] - v[0]);
+        e[i] = expf(tv[i] - tv[0]);
         se += e[i];
     }
     float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        float fr = 20.0f * exp2f((float)id[i] / 48.0f);
+        float fr = 20.0f * exp2f((float)ti[i] / 48.0f);
         if (fr <= 20.0f) fr = 0.f;
         acc = __fadd_rn(acc, __fmul_rn(e[i] / se, fr));
     }
@@ -239,7 +270,7 @@ __global__ void pitch_decode_kernel(const float* __restrict__ logits, float* __r
 
 int pitch_decode(const float* logits, float* f0, int B, int ncls, int T, cudaStream_t s) {
     const long long ncol = (long long)B * T;
-    pitch_decode_kernel<<<cdiv(ncol, 128), 128, 0, s>>>(logits, f0, ncls, T, ncol);
+    pitch_decode_kernel<<<(unsigned)cdiv(ncol * 32, 256), 256, 0, s>>>(logits, f0, ncls, T, ncol);
     TVC_LAUNCH_CHECK();
     return 0;
 }

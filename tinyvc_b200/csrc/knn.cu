@@ -46,8 +46,12 @@ int knn_prepare(const float* index_cn, float* index_w, float* index_nc, float* b
 }
 
 // ---- query normalisation: qn[b,c,t] = s[b,c,t] / (|s[b,:,t]| + 1e-6)   (thread per frame) -----
-__global__ void knn_normalize_kernel(const float* __restrict__ src, float* __restrict__ qn, int C, int T, long long ncol,
-                                     int metric) {
+// The squared norm is one fmaf chain over ascending channels (the order the parity fixtures were taken with); the loads do
+// not depend on it, so they are issued 32 at a time.  Blocks of 32 frames: a streaming tick (3 584 frames) still covers
+// most SMs.
+constexpr int kNormBatch = 32;
+__global__ void __launch_bounds__(32) knn_normalize_kernel(const float* __restrict__ src, float* __restrict__ qn, int C, int T,
+                                                          long long ncol, int metric) {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= ncol) return;
     const long long b = n / T;
@@ -56,21 +60,31 @@ __global__ void knn_normalize_kernel(const float* __restrict__ src, float* __res
     float* qp = qn + b * C * (long long)T + t;
     float ss = 0.f;
     if (metric == 0) {
-        for (int c = 0; c < C; ++c) {
-            const float v = __ldg(sp + (long long)c * T);
-            ss = fmaf(v, v, ss);
+#pragma unroll 1
+        for (int c0 = 0; c0 < C; c0 += kNormBatch) {
+            float v[kNormBatch];
+#pragma unroll
+            for (int u = 0; u < kNormBatch; ++u) v[u] = c0 + u < C ? __ldg(sp + (long long)(c0 + u) * T) : 0.f;
+#pragma unroll
+            for (int u = 0; u < kNormBatch; ++u)
+                if (c0 + u < C) ss = fmaf(v[u], v[u], ss);
         }
     }
     const float nrm = __fadd_rn(sqrtf(ss), 1e-6f);
-    for (int c = 0; c < C; ++c) {
-        const float v = __ldg(sp + (long long)c * T);
-        qp[(long long)c * T] = metric == 0 ? __fdiv_rn(v, nrm) : v;
+#pragma unroll 1
+    for (int c0 = 0; c0 < C; c0 += kNormBatch) {
+        float v[kNormBatch];
+#pragma unroll
+        for (int u = 0; u < kNormBatch; ++u) v[u] = c0 + u < C ? __ldg(sp + (long long)(c0 + u) * T) : 0.f;
+#pragma unroll
+        for (int u = 0; u < kNormBatch; ++u)
+            if (c0 + u < C) qp[(long long)(c0 + u) * T] = metric == 0 ? __fdiv_rn(v[u], nrm) : v[u];
     }
 }
 
 int knn_normalize_queries(const float* src, float* qn, int B, int C, int T, int metric, cudaStream_t s) {
     const long long ncol = (long long)B * T;
-    knn_normalize_kernel<<<cdiv(ncol, 128), 128, 0, s>>>(src, qn, C, T, ncol, metric);
+    knn_normalize_kernel<<<cdiv(ncol, 32), 32, 0, s>>>(src, qn, C, T, ncol, metric);
     TVC_LAUNCH_CHECK();
     return 0;
 }
@@ -168,9 +182,26 @@ __device__ __forceinline__ bool knn_better(float x, int n, float y, int m) { ret
 
 // exact fp32 score of reference n for query (b, t): the CUDA-core path's operation order (conv1d.cu FMA loop)
 __device__ __forceinline__ float knn_exact_score(const float* __restrict__ wrow, const float* __restrict__ q, int T) {
+    // one fmaf chain over ascending channels; the loads are independent of it and go out 32 at a time (rows of the
+    // normalised index are 16-byte aligned: kContent * 4 bytes per row)
     float acc = 0.f;
-#pragma unroll 8
-    for (int ci = 0; ci < kContent; ++ci) acc = fmaf(__ldg(wrow + ci), __ldg(q + (long long)ci * T), acc);
+    static_assert(kContent % 32 == 0, "batching");
+#pragma unroll 1
+    for (int c0 = 0; c0 < kContent; c0 += 32) {
+        float4 w[8];
+        float x[32];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const float4*>(wrow + c0) + u);
+#pragma unroll
+        for (int u = 0; u < 32; ++u) x[u] = __ldg(q + (long long)(c0 + u) * T);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            acc = fmaf(w[u].x, x[4 * u], acc);
+            acc = fmaf(w[u].y, x[4 * u + 1], acc);
+            acc = fmaf(w[u].z, x[4 * u + 2], acc);
+            acc = fmaf(w[u].w, x[4 * u + 3], acc);
+        }
+    }
     return acc + 0.f;
 }
 

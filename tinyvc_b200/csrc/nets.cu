@@ -408,11 +408,11 @@ int DecoderModel::filter_net(Arena& A, cudaStream_t s, const float* content, con
 
 // Decoder.infer (decoder.py:253-257).
 int DecoderModel::infer(Arena& A, cudaStream_t s, const float* content, const float* f0, const float* energy,
-                        const float* rand01, float* out, int B, int Lf, int impl) {
+                        const float* rand01, float* out, int B, int Lf, int impl, int out_t0, int out_t1) {
     if (impl == CONV_IMPL_TC) {
         static const DecoderTC shape_only;   // dry runs (workspace sizing) never touch weights
         TVC_REQUIRE(A.dry || (tc && tc->ready), "decoder: tensor-core plan not initialised");
-        return (A.dry && !tc ? shape_only : *tc).infer(A, s, content, f0, energy, rand01, out, B, Lf);
+        return (A.dry && !tc ? shape_only : *tc).infer(A, s, content, f0, energy, rand01, out, B, Lf, out_t0, out_t1);
     }
     const int L = Lf * kFrame;
     const size_t m = A.mark();

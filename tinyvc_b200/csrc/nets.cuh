@@ -97,7 +97,8 @@ struct DecoderModel {
     int filter_net(Arena& A, cudaStream_t s, const float* content, const float* lf0, const float* src17, float* out,
                    int B, int Lf);
     int infer(Arena& A, cudaStream_t s, const float* content, const float* f0, const float* energy,
-              const float* rand01, float* out, int B, int Lf, int impl);   // impl: ConvImpl, chosen by the caller
+              const float* rand01, float* out, int B, int Lf, int impl,    // impl: ConvImpl, chosen by the caller
+              int out_t0 = 0, int out_t1 = -1);                            // samples that must be produced (tensor-core plan prunes)
 };
 
 struct EncoderTC;   // nets_tc.cuh: tensor-core execution plan

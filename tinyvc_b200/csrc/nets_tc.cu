@@ -247,7 +247,7 @@ int tc_conv_k(const char* name, const TcConvW& W, const ConvCall& c, cudaStream_
     } while (0)
 
 int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float* f0, const float* energy,
-                     const float* rand01, float* out, int B, int Lf) const {
+                     const float* rand01, float* out, int B, int Lf, int out_t0, int out_t1) const {
     const int L = Lf * kFrame;
     const long long rowsF = (long long)B * Lf, rowsL = (long long)B * L;
     const size_t m0 = A.mark();
@@ -379,6 +379,7 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
             TcUpBlockArgs fa;
             fa.x4 = x; fa.c_hi = cond.hi; fa.c_lo = cond.lo; fa.out_w = out_w; fa.out_b = out_b; fa.out = out;
             fa.B = B; fa.T = tout; fa.T4 = tin; fa.scale = (float)(1.0 / (double)fac);
+            fa.t_lo = out_t0; fa.t_hi = out_t1;
             if (!A.dry) {
                 ProfScope ps("tc_up4_fused(", s);
                 TVC_TRY(tc_up24_block_launch(uc.c1, uc.c2, uc.c3, uc.c4, uc.c5, fa, s));

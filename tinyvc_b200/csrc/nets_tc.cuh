@@ -24,8 +24,10 @@ struct DecoderTC {
     ~DecoderTC();
     int init(const WeightStore& store);
     // Decoder.infer (decoder.py:253-257) on the tensor-core path.
+    // out_t0 / out_t1: only out[b][out_t0, out_t1) has to be produced (out_t1 < 0: everything); the fused full-rate block
+    // then skips the windows outside the range.  Samples outside the range are unspecified.
     int infer(Arena& A, cudaStream_t s, const float* content, const float* f0, const float* energy, const float* rand01,
-              float* out, int B, int Lf) const;
+              float* out, int B, int Lf, int out_t0 = 0, int out_t1 = -1) const;
 };
 
 // Tensor-core execution plan of the Encoder (module/tinyvc/encoder.py:11-116): both ConvNeXt stacks with every dense 1x1

@@ -29,17 +29,55 @@ __global__ void __launch_bounds__(1024) sola_kernel(const float* __restrict__ y,
     __syncthreads();
     float bv = -INFINITY;
     int bi = 0x7fffffff;
-    for (int i = threadIdx.x; i <= search; i += blockDim.x) {
-        float nom = 0.f, den = 0.f;
-        for (int j = 0; j < cross; ++j) {
-            const float v = temp[i + j];
-            nom = fmaf(v, sola[j], nom);
-            den = fmaf(v, v, den);
+    if (cross % 4 == 0 && block >= 4) {
+        // four adjacent positions per thread: 3 vector loads feed 32 FMAs; per position the sums still run over j ascending
+        // (the order of the scalar loop below, so the ratio and the arg-max are the same bits)
+        const float4* t4 = reinterpret_cast<const float4*>(temp);
+        const float4* s4 = reinterpret_cast<const float4*>(sola);
+        for (int i0 = 4 * threadIdx.x; i0 <= search; i0 += 4 * blockDim.x) {
+            float nom[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
+            float4 a = t4[i0 >> 2];
+#pragma unroll 2
+            for (int j = 0; j < cross; j += 4) {
+                // positions i0 + 1 .. i0 + 3 read up to 3 elements past position i0's window: at most temp[search + cross + 3],
+                // inside temp[0, block + cross + search) for block >= 4
+                const float4 b = t4[((i0 + j) >> 2) + 1];
+                const float4 sv = s4[j >> 2];
+                const float w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                const float sj[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        nom[q] = fmaf(w[q + u], sj[u], nom[q]);
+                        den[q] = fmaf(w[q + u], w[q + u], den[q]);
+                    }
+                a = b;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + q;
+                if (i > search) break;
+                const float r = __fdiv_rn(nom[q], sqrtf(__fadd_rn(den[q], 1e-8f)));
+                if (r > bv || (r == bv && i < bi)) {
+                    bv = r;
+                    bi = i;
+                }
+            }
         }
-        const float r = __fdiv_rn(nom, sqrtf(__fadd_rn(den, 1e-8f)));
-        if (r > bv || (r == bv && i < bi)) {
-            bv = r;
-            bi = i;
+    } else {
+        for (int i = threadIdx.x; i <= search; i += blockDim.x) {
+            float nom = 0.f, den = 0.f;
+            for (int j = 0; j < cross; ++j) {
+                const float v = temp[i + j];
+                nom = fmaf(v, sola[j], nom);
+                den = fmaf(v, v, den);
+            }
+            const float r = __fdiv_rn(nom, sqrtf(__fadd_rn(den, 1e-8f)));
+            if (r > bv || (r == bv && i < bi)) {
+                bv = r;
+                bi = i;
+            }
         }
     }
     // block arg-max (first index on ties, like torch.argmax)

@@ -94,7 +94,7 @@ struct alignas(64) UpBlockParams {
     const float *out_w, *out_b;                       // output_layer.weight [1][24][7], .bias [1]
     float* out;                                       // waveform [B][T]
     long long rows, rows4, n_seg;
-    int T, T4, segs_per_utt;
+    int T, T4, segs_per_utt, seg_lo;                   // windows walked per utterance and the index of the first one (output pruning)
     float scale;                                      // resampler scale (float)(1 / 5)
     int dil[4];
 };
@@ -107,7 +107,7 @@ struct SegGeo {
     static constexpr int sh = kBPad;   // buffer slot of window row 0
     __device__ SegGeo(const UpBlockParams& p, long long seg) {
         const long long bq = seg / p.segs_per_utt;
-        const int k = (int)(seg - bq * p.segs_per_utt);
+        const int k = p.seg_lo + (int)(seg - bq * p.segs_per_utt);
         baseT = bq * p.T;
         base4 = bq * p.T4;
         w0 = k * kBS - kBHalo;
@@ -459,7 +459,10 @@ int tc_up24_block_launch(const TcConvW& c1, const TcConvW& c2, const TcConvW& c3
     p.film_bias[1] = c4.film_bias;
     p.x4 = a.x4; p.out_w = a.out_w; p.out_b = a.out_b; p.out = a.out;
     p.T = a.T; p.T4 = a.T4; p.scale = a.scale;
-    p.segs_per_utt = cdiv(a.T, kBS);
+    const int t_hi = a.t_hi < 0 ? a.T : a.t_hi;
+    TVC_REQUIRE(a.t_lo >= 0 && a.t_lo < t_hi && t_hi <= a.T, "tc_up24_block: output range [%d, %d) outside [0, %d)", a.t_lo, a.t_hi, a.T);
+    p.seg_lo = a.t_lo / kBS;                                  // window k produces samples [k * 426, (k + 1) * 426)
+    p.segs_per_utt = (t_hi - 1) / kBS - p.seg_lo + 1;
     p.n_seg = (long long)a.B * p.segs_per_utt;
     for (int i = 0; i < 4; ++i) p.dil[i] = a.dil[i];
     int dev = 0, sms = 148;

@@ -14,6 +14,11 @@ struct TcUpBlockArgs {
     int B = 0, T = 0, T4 = 0;                          // T = 5 * T4
     float scale = 0.2f;                                // F.interpolate's source-index scale, (float)(1 / 5)
     int dil[4] = {1, 3, 9, 27};                        // dilations of c1..c4 (c5 is 1x1)
+    // Output pruning: only out[b][t_lo, t_hi) has to be produced (t_hi < 0: the whole utterance).  Windows that produce none
+    // of those samples are not walked; the windows that are walked compute exactly what they compute in a full run (their
+    // inputs x4 / cond are complete tensors), so the samples written are bit-identical to the full run's.  A streaming tick
+    // keeps 5 760 of its 13 440 samples (module/infer/stream.py:75).
+    int t_lo = 0, t_hi = -1;
 };
 
 // c1..c5: the block's packed convs (tc_pack_conv; c2 / c4 with their TC_AUX_FILM images).

@@ -48,8 +48,8 @@ class Generator(nn.Module):
             zm, idx = _tv.match_features(z, tgt), None
         return zm, _ut.shift_frequency(f0, pitch_shift), idx
 
-    def synthesise(self, content, f0, energy, rand01: Optional[torch.Tensor] = None) -> torch.Tensor:
-        return self.decoder.infer(content, f0, energy, rand01=rand01)
+    def synthesise(self, content, f0, energy, rand01: Optional[torch.Tensor] = None, keep=None) -> torch.Tensor:
+        return self.decoder.infer(content, f0, energy, rand01=rand01, keep=keep)
 
     # ---- the reference's surface ------------------------------------------------------------------
     @torch.inference_mode()
@@ -60,16 +60,17 @@ class Generator(nn.Module):
 
     @torch.inference_mode()
     def convert(self, wf, tgt, pitch_shift, f0_estimation="default", device=torch.device("cpu"), *,
-                rand01: Optional[torch.Tensor] = None, return_parts: bool = False):
+                rand01: Optional[torch.Tensor] = None, return_parts: bool = False, keep=None):
         """wf [B,T], tgt [1|B,768,N] -> waveform [B, ceil(T/480)*480]   (generator.py:25-34).
 
         `f0_estimation` and `device` are accepted and ignored, exactly like the reference (its
         convert never reads them; infer.py:66 even passes the device string in the f0 slot).
         Keyword-only extras: `rand01` injects the noise draw (see Decoder.infer);
-        `return_parts` also returns the intermediates for stage-wise parity checks."""
+        `return_parts` also returns the intermediates for stage-wise parity checks; `keep=(t0, t1)`: only those output
+        samples will be read (Decoder.infer)."""
         a = self.analyse(wf)
         zm, f0s, idx = self.retarget(a.z, a.f0, tgt, pitch_shift, want_indices=return_parts)
-        out = self.synthesise(zm, f0s, a.energy, rand01)
+        out = self.synthesise(zm, f0s, a.energy, rand01, keep)
         if return_parts:
             return out, dict(spec=a.spec, energy=a.energy, z=a.z, f0=a.f0, idx=idx, zm=zm, f0s=f0s)
         return out

@@ -60,6 +60,7 @@ class BatchedStreamInfer:
         self.input_size = max(self.block_size + self.crossfade_size + self.sola_search_size + 2 * self.last_dilay_size,
                               self.block_size + self.extra_size)
         self.last_shift: Optional[torch.Tensor] = None
+        self.prune_output = True             # compute only the waveform samples the SOLA step reads (bit-identical there)
 
     def init_buffer(self) -> None:
         if self.device.type != "cuda":
@@ -84,7 +85,11 @@ class BatchedStreamInfer:
         nxt[:, : self.input_size - bs] = self.input_wav[:, bs:]
         nxt[:, self.input_size - bs:] = blocks
         self.input_wav = nxt
-        y = self.generator.convert(self.input_wav, self.target, self.pitch_shift, rand01=rand01).contiguous()
+        # stream.py:75 reads y[-(block+cross+search+delay) : -delay] and nothing else: tell the decoder (exact pruning)
+        Ly = -(-self.input_size // 480) * 480
+        keep = (max(0, Ly - bs - self.crossfade_size - self.sola_search_size - self.last_dilay_size), Ly - self.last_dilay_size)
+        y = self.generator.convert(self.input_wav, self.target, self.pitch_shift, rand01=rand01,
+                                   keep=keep if self.prune_output and keep[1] > keep[0] else None).contiguous()
         out = torch.empty(S, bs, device=self.device, dtype=torch.float32)
         L = _lib.lib()
         with torch.cuda.device(self.device):

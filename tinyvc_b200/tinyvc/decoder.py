@@ -193,8 +193,11 @@ class Decoder(nn.Module):
     # ---- reference API ------------------------------------------------------------------------
     @torch.inference_mode()
     def infer(self, content, f0, energy, *, rand01: Optional[torch.Tensor] = None,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """`out` (extension): write the waveform [B, L] into this fp32 buffer instead of a fresh tensor.  It may live on
+              out: Optional[torch.Tensor] = None, keep: Optional[tuple] = None) -> torch.Tensor:
+        """`keep=(t0, t1)` (extension): the caller will only read samples [t0, t1) of every waveform (a streaming tick keeps
+        5 760 of its 13 440, module/infer/stream.py:75); the full-rate block then skips the windows that produce none of them.
+        Samples inside the range are bit-identical to a full run; samples outside it are unspecified.
+        `out` (extension): write the waveform [B, L] into this fp32 buffer instead of a fresh tensor.  It may live on
         a peer GPU that this device can address (a `tinyvc_b200.peer` window): the last kernel then stores straight
         into the peer's HBM over NVLink, which is how the sharded mode gathers without a copy.  It may also be a PINNED
         host tensor (`torch.empty(...).pin_memory()`): pinned memory is mapped into the device's address space, so the last
@@ -214,17 +217,20 @@ class Decoder(nn.Module):
                   and tuple(out.shape) == (B, Lf * FRAME)):
             raise RuntimeError(f"Decoder.infer: out must be a contiguous fp32 tensor of shape {(B, Lf * FRAME)} on a CUDA "
                                "device or in pinned host memory")
+        t0, t1 = (0, Lf * FRAME) if keep is None else (int(keep[0]), int(keep[1]))
+        if not 0 <= t0 < t1 <= Lf * FRAME:
+            raise RuntimeError(f"Decoder.infer: keep={keep} is not a non-empty range inside [0, {Lf * FRAME}]")
         step = self._batch_chunk(B, Lf)
         with torch.cuda.device(dev):
             for b0 in range(0, B, step):
                 nb = min(step, B - b0)
                 nbytes = L.tvc_decoder_infer_workspace_bytes(nb, Lf)
                 ws = _lib.WORKSPACE.get(nbytes, dev)
-                _lib.check(L.tvc_decoder_infer(h, content[b0:b0 + nb].data_ptr(), f0[b0:b0 + nb].data_ptr(),
-                                               energy[b0:b0 + nb].data_ptr(),
-                                               rand01[b0:b0 + nb].data_ptr() if rand01 is not None else None,
-                                               out[b0:b0 + nb].data_ptr(), nb, Lf, ws.data_ptr(), ws.numel(),
-                                               _lib.stream_ptr(dev)), "tvc_decoder_infer")
+                _lib.check(L.tvc_decoder_infer_range(h, content[b0:b0 + nb].data_ptr(), f0[b0:b0 + nb].data_ptr(),
+                                                     energy[b0:b0 + nb].data_ptr(),
+                                                     rand01[b0:b0 + nb].data_ptr() if rand01 is not None else None,
+                                                     out[b0:b0 + nb].data_ptr(), nb, Lf, t0, t1, ws.data_ptr(), ws.numel(),
+                                                     _lib.stream_ptr(dev)), "tvc_decoder_infer")
         return out
 
     @torch.inference_mode()

@@ -154,6 +154,11 @@ int tvc_spectrogram(const float* wf, float* spec, int B, int L, void* workspace,
 size_t tvc_energy_workspace_bytes(int B, int L);
 int tvc_estimate_energy(const float* wf, float* energy, int B, int L, void* workspace, size_t workspace_bytes,
                         void* stream);
+/* Sample-rate conversion of input files (infer.py:45-46,63-64: torchaudio.functional.resample(wf, sr, 24000) with its
+ * defaults: sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99).  wf [B,L] -> out [B, tvc_resample_length(L, ...)]
+ * (= ceil(new_freq * L / orig_freq)); the polyphase filter bank is built once per (device, orig_freq, new_freq).        */
+int64_t tvc_resample_length(int64_t L, int orig_freq, int new_freq);
+int tvc_resample(const float* wf, float* out, int B, int64_t L, int orig_freq, int new_freq, void* stream);
 /* shift_frequency (utils/pitch_shift.py:5-15): n elements, in place allowed.                 */
 int tvc_shift_frequency(const float* f0, float* out, int64_t n, float semitones, void* stream);
 

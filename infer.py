@@ -52,16 +52,17 @@ def load_generator(encoder_path: str, decoder_path: str, device: torch.device):
     return Generator(enc.to(device), dec.to(device))
 
 
-def load_audio_24k(path: str) -> torch.Tensor:
+def load_audio_24k(path: str, device: torch.device) -> torch.Tensor:
+    """torchaudio.load decodes on the host; the resampling of infer.py:63-64 runs on the device (tvc_resample)."""
     import torchaudio
-    from torchaudio.functional import resample
+    from module.utils import resample
     wf, sr = torchaudio.load(path)
-    return resample(wf, sr, 24000)
+    return resample(wf.to(device), sr, 24000)
 
 
 def load_target(generator, args, device: torch.device) -> torch.Tensor:
     if args.index == "NONE":
-        tgt, _ = generator.encode(load_audio_24k(args.target).to(device))       # infer.py:45-47
+        tgt, _ = generator.encode(load_audio_24k(args.target, device))       # infer.py:45-47
         return tgt
     return torch.load(args.index, map_location="cpu").to(device)                 # [1,768,N]  (extract_index.py:58)
 
@@ -76,7 +77,7 @@ def main(argv=None) -> int:
     import torchaudio
     for path in paths:
         print(f"Converting {path} ...")
-        wf = load_audio_24k(path).mean(dim=0, keepdim=True).to(device)
+        wf = load_audio_24k(path, device).mean(dim=0, keepdim=True)
         out = generator.convert(wf, tgt, args.pitch_shift, args.f0_estimation, device).cpu()
         name = os.path.splitext(os.path.basename(path))[0]
         torchaudio.save(os.path.join(args.outputs, f"{name}.wav"), src=out, sample_rate=24000)

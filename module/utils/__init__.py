@@ -1,1 +1,1 @@
-from tinyvc_b200.utils import autopad_waveform, estimate_energy, shift_frequency, spectrogram  # noqa: F401
+from tinyvc_b200.utils import autopad_waveform, estimate_energy, resample, shift_frequency, spectrogram  # noqa: F401

@@ -103,3 +103,41 @@ def noise_ola(re: np.ndarray, im: np.ndarray, frame: int = 480, n_fft: int = 192
         env[t * frame:t * frame + n_fft] += 1.0
     half = n_fft // 2
     return (ola[half:half + lf * frame] / env[half:half + lf * frame])
+
+
+def sinc_resample_bank(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """Polyphase filter bank of `torchaudio.functional.resample` (sinc_interp_hann), the call reference infer.py:45-46,63-64
+    makes with its defaults.  torchaudio is an un-vendored, un-pinned dependency of the reference (requirements.txt; 2.11.0
+    here): this restates its published `_get_sinc_resample_kernel`.  Returns (bank [n][2*width+o] fp32, width, o, n)."""
+    g = math.gcd(int(orig_freq), int(new_freq))
+    o, n = int(orig_freq) // g, int(new_freq) // g
+    base = min(o, n) * rolloff
+    width = math.ceil(lowpass_filter_width * o / base)
+    idx = np.arange(-width, width + o, dtype=np.float64)[None, :] / o
+    # torch.arange(0, -n, -1) is int64; `/ new_freq` happens in fp32 (default dtype), the sum with idx in fp64
+    ph = (np.arange(0, -n, -1).astype(f32) / f32(n)).astype(np.float64)[:, None]
+    t = np.clip((ph + idx) * base, -lowpass_filter_width, lowpass_filter_width)
+    window = np.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t = t * math.pi
+    with np.errstate(invalid="ignore", divide="ignore"):
+        kern = np.where(t == 0, 1.0, np.sin(t) / t)
+    kern = kern * (window * (base / o))
+    return kern.astype(f32), width, o, n
+
+
+def sinc_resample(x: np.ndarray, orig_freq: int, new_freq: int) -> np.ndarray:
+    """x [..., L] -> [..., ceil(new * L / orig)]: `_apply_sinc_resample_kernel` (zero pad `width` in front and
+    `width + o` behind, conv1d with stride o, phases interleaved, cut to the target length); fp64 accumulation."""
+    x = np.asarray(x, f32)
+    if int(orig_freq) == int(new_freq):
+        return x.copy()
+    bank, width, o, n = sinc_resample_bank(orig_freq, new_freq)
+    L = x.shape[-1]
+    flat = x.reshape(-1, L)
+    pad = np.concatenate([np.zeros((flat.shape[0], width), f32), flat, np.zeros((flat.shape[0], width + o), f32)], axis=1)
+    klen = bank.shape[1]
+    nblk = (pad.shape[1] - klen) // o + 1
+    win = np.lib.stride_tricks.sliding_window_view(pad, klen, axis=1)[:, ::o][:, :nblk]      # [B][nblk][klen]
+    y = np.einsum("bjk,pk->bjp", win.astype(np.float64), bank.astype(np.float64)).reshape(flat.shape[0], -1)
+    target = -(-n * L // o)
+    return y[:, :target].astype(f32).reshape(*x.shape[:-1], target)

@@ -181,6 +181,24 @@ def golden_conditioning(enc, dec):
           f"f0 range {float(f0s[8].min()):.0f}..{float(f0s[8].max()):.0f} Hz")
 
 
+@torch.inference_mode()
+def golden_resample():
+    """torchaudio.functional.resample exactly as reference infer.py:63-64 calls it (defaults), for the rates input files come
+    in: 44.1 / 48 / 16 / 22.05 / 8 kHz -> 24 kHz, stereo and mono, lengths that do and do not divide."""
+    from torchaudio.functional import resample     # the reference's own import (infer.py:9)
+    import torchaudio
+    g = torch.Generator().manual_seed(2024)
+    out = {"torchaudio_version": np.array(torchaudio.__version__)}
+    cases = [(44100, 2, 4410), (48000, 1, 4801), (16000, 2, 1777), (22050, 1, 2205), (8000, 1, 331), (24000, 1, 100), (32000, 1, 7)]
+    out["cases"] = np.array(cases)
+    for sr, ch, n in cases:
+        wf = 0.3 * torch.randn(ch, n, generator=g)
+        out[f"in_{sr}"] = npy(wf)
+        out[f"out_{sr}"] = npy(resample(wf, sr, 24000))
+    np.savez_compressed(os.path.join(HERE, "resample.npz"), **out)
+    print("resample:", {sr: out[f"out_{sr}"].shape for sr, _, _ in cases})
+
+
 def golden_keys(enc, dec):
     """state_dict key order and shapes of the reference's Encoder / Decoder."""
     import json
@@ -193,6 +211,9 @@ def golden_keys(enc, dec):
 
 if __name__ == "__main__":
     enc, dec = build()
+    if "--resample-only" in sys.argv:
+        golden_resample()
+        sys.exit(0)
     if "--conditioning-only" in sys.argv:
         golden_conditioning(enc, dec)
         sys.exit(0)
@@ -202,5 +223,6 @@ if __name__ == "__main__":
     golden_pipeline(enc, dec)
     golden_match(enc, dec)
     golden_stream(enc, dec)
+    golden_resample()
     tot = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith(".npz"))
     print("fixtures total bytes:", tot)

@@ -189,3 +189,30 @@ def test_index_cache_survives_pointer_reuse():
         outs.append(out)
         del ref
     assert not torch.equal(outs[0], outs[1])
+
+
+def test_resample_matches_torchaudio(report):
+    """tvc_resample (infer.py:63-64's torchaudio.functional.resample, defaults) against torchaudio's own outputs and the oracle."""
+    import math
+    import numpy as np
+    from oracle import numerics_np as N
+    from tinyvc_b200.utils import resample
+    g = load_golden("resample.npz")
+    worst_g = worst_o = 0.0
+    for sr, ch, n in g["cases"]:
+        x = t(g[f"in_{sr}"]).cuda()
+        y = resample(x, int(sr), 24000)
+        assert tuple(y.shape) == (ch, math.ceil(24000 * n / sr))
+        worst_g = max(worst_g, max_abs(y.cpu(), t(g[f"out_{sr}"])))
+        worst_o = max(worst_o, float(np.abs(y.cpu().numpy() - N.sinc_resample(g[f"in_{sr}"], int(sr), 24000)).max()))
+    report.add("resample", max_abs_vs_torchaudio=worst_g, max_abs_vs_oracle=worst_o)
+    assert worst_g < 1e-5 and worst_o < 5e-6
+    # ragged shapes, batch dims, a long signal against the oracle
+    gen = torch.Generator().manual_seed(5)
+    x = 0.2 * torch.randn(3, 2, 48000, generator=gen)
+    y = resample(x.cuda(), 44100, 24000)
+    ref = N.sinc_resample(x.numpy(), 44100, 24000)
+    assert tuple(y.shape) == ref.shape
+    assert float(np.abs(y.cpu().numpy() - ref).max()) < 5e-6
+    with pytest.raises(RuntimeError):
+        resample(x, 44100, 24000)          # CPU tensor: there is no CPU path

@@ -68,3 +68,28 @@ def test_downsample_factors_pick_expected_taps():
     assert np.array_equal(N.interp_linear(x, 48, 1 / 5)[0], x[0, 2::5])
     assert np.array_equal(N.interp_linear(x, 80, 1 / 3)[0], x[0, 1::3])
     assert np.array_equal(N.interp_linear(x, 60, 1 / 4)[0], 0.5 * (x[0, 1::4] + x[0, 2::4]))
+
+
+def test_sinc_resample_restates_torchaudio():
+    """oracle/numerics_np.sinc_resample (the restated algorithm of torchaudio.functional.resample, reference infer.py:63-64)
+    against outputs of torchaudio itself (tests/golden/resample.npz, made by make_golden.py golden_resample): the filter bank
+    is bit-equal where torchaudio is importable; the resampled signals agree to fp32 accumulation error (torchaudio sums 171
+    taps in fp32, the oracle in fp64)."""
+    import math
+    import numpy as np
+    from conftest import load_golden
+    from oracle import numerics_np as N
+    g = load_golden("resample.npz")
+    for sr, ch, n in g["cases"]:
+        y = N.sinc_resample(g[f"in_{sr}"], int(sr), 24000)
+        ref = g[f"out_{sr}"]
+        assert y.shape == ref.shape == (ch, math.ceil(24000 * n / sr))
+        assert float(np.abs(y - ref).max()) < 1e-5, sr
+    try:
+        import torchaudio.functional.functional as FF
+    except Exception:
+        return
+    for sr in (44100, 48000, 16000, 22050, 8000, 32000, 11025):
+        k, w = FF._get_sinc_resample_kernel(sr, 24000, math.gcd(sr, 24000))
+        bank, width, o, nn = N.sinc_resample_bank(sr, 24000)
+        assert w == width and np.array_equal(k[:, 0].numpy(), bank), sr

@@ -750,6 +750,18 @@ int tvc_estimate_energy(const float* wf, float* energy, int B, int L, void* work
     API_END
 }
 
+int64_t tvc_resample_length(int64_t L, int orig_freq, int new_freq) {
+    if (L < 0 || orig_freq <= 0 || new_freq <= 0) return -1;
+    return (int64_t)resample_length((long long)L, orig_freq, new_freq);
+}
+int tvc_resample(const float* wf, float* out, int B, int64_t L, int orig_freq, int new_freq, void* stream) {
+    API_BEGIN
+    TVC_REQUIRE(wf && out, "tvc_resample: null argument");
+    TVC_REQUIRE(B > 0 && L > 0, "tvc_resample: invalid shape B=%d L=%lld", B, (long long)L);
+    return resample_run(wf, out, B, (long long)L, orig_freq, new_freq, (cudaStream_t)stream);
+    API_END
+}
+
 int tvc_shift_frequency(const float* f0, float* out, int64_t n, float semitones, void* stream) {
     API_BEGIN
     TVC_REQUIRE(f0 && out, "tvc_shift_frequency: null argument");

@@ -75,7 +75,15 @@ constexpr uint32_t kOffOutW = kOffW + kWBytes;                            // out
 constexpr uint32_t kOffBar = kOffOutW + 1024;
 constexpr uint32_t kBlockSmem = kOffBar + 256;
 constexpr uint32_t kAccCols = 128;            // conv x_hi*w_hi + x_lo*w_hi | conv x_hi*w_lo | FiLM scale | FiLM shift, 32 columns each
-constexpr uint32_t kYCol0 = 2 * kAccCols;     // TMEM columns of the fp32 residual y: 32 per tile
+#ifndef TVC_BLK_BUFS
+#define TVC_BLK_BUFS 3
+#endif
+#ifndef TVC_BLK_EARLY
+#define TVC_BLK_EARLY 1
+#endif
+constexpr uint32_t kAccBufs = TVC_BLK_BUFS;   // accumulator ring: tile-op k uses buffer k % kAccBufs (3 x 128 + 4 x 32 y columns = the 512 of TMEM)
+constexpr uint32_t kYCol0 = kAccBufs * kAccCols;   // TMEM columns of the fp32 residual y: 32 per tile
+static_assert(kYCol0 + 4 * 32 <= 512, "TMEM columns");
 constexpr int kBEpiWarps = 12, kBMmaWarp = 12, kBProdWarp = 13, kBLoadWarp0 = 14, kBLoadWarps = 4, kBThreads = 576;
 constexpr int kBEpiThreads = kBEpiWarps * 32;
 constexpr int kBInRows = kBW + 2;             // rows -1 .. 512 of the window: what c1 (dil 1) reads
@@ -131,13 +139,14 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
     const uint32_t sb = smem_u32(smem);
     const uint32_t bar = sb + kOffBar;
     const uint32_t wfull = bar, in_full = bar + 8, in_free = bar + 16, cond_full = bar + 24, cond_empty = bar + 40;
-    const uint32_t acc_full = bar + 56, acc_empty = bar + 72, act_ready = bar + 88;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 128);
+    const uint32_t acc_full = bar + 56, acc_empty = acc_full + 8 * kAccBufs, act_ready = acc_empty + 8 * kAccBufs;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 192);
+    static_assert(56 + 16 * kAccBufs + 8 * kBT <= 192, "barrier block");
 
     if (tid == 0) {
         mbar_init(wfull, 1); mbar_init(in_full, kBLoadWarps); mbar_init(in_free, 1);
         for (uint32_t s = 0; s < kCondRing; ++s) { mbar_init(cond_full + 8 * s, 1); mbar_init(cond_empty + 8 * s, 1); }
-        for (uint32_t b = 0; b < 2; ++b) { mbar_init(acc_full + 8 * b, 1); mbar_init(acc_empty + 8 * b, kBEpiWarps); }
+        for (uint32_t b = 0; b < kAccBufs; ++b) { mbar_init(acc_full + 8 * b, 1); mbar_init(acc_empty + 8 * b, kBEpiWarps); }
         for (uint32_t j = 0; j < kBT; ++j) mbar_init(act_ready + 8 * j, kBEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -209,7 +218,7 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
                 const uint32_t wl16 = w16 + p.w_off16[l];
 #pragma unroll
                 for (int j = 0; j < kBT; ++j) {
-                    const uint32_t buf = tcount & 1u, buse = tcount >> 1;
+                    const uint32_t buf = tcount % kAccBufs, buse = tcount / kAccBufs;
                     if (buse > 0) mbar_wait(acc_empty + 8u * buf, (buse - 1) & 1u);      // epilogue drained this accumulator
                     if (l > 0) {
                         // the rows this tile reads (its own and up to 27 of each neighbour's) must have been published; every
@@ -304,7 +313,7 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
                 const int nd = l < 3 ? p.dil[l + 1] : 0;                             // replicate slots the next conv reads
                 const int act = l == 3 ? TC_ACT_NONE : TC_ACT_LRELU;
                 for (int j = 0; j < kBT; ++j, ++tcount) {
-                    const uint32_t buf = tcount & 1u, buse = tcount >> 1;
+                    const uint32_t buf = tcount % kAccBufs, buse = tcount / kAccBufs;
                     const int r = j * kBM + rloc, t = g.w0 + r;
                     const bool inside = t >= 0 && t < p.T;
                     const long long row = g.baseT + t;
@@ -320,6 +329,12 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
                     if (film) { tmem_ld8(ta + 64u, sc); tmem_ld8(ta + 96u, sf); }
                     if (l == 3) tmem_ld8(ya, yv);
                     tmem_ld_wait();
+#if TVC_BLK_EARLY
+                    // the accumulator is in registers: hand the buffer back before the arithmetic and the shared-memory stores
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + 8u * buf);
+#endif
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = __fadd_rn(v[i], v2[i]);
                     v[0] = __fadd_rn(v[0], b0.x); v[1] = __fadd_rn(v[1], b0.y); v[2] = __fadd_rn(v[2], b0.z); v[3] = __fadd_rn(v[3], b0.w);
@@ -374,7 +389,9 @@ __global__ void __launch_bounds__(kBThreads, 1) tc_up24_block_kernel(const __gri
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
+#if !TVC_BLK_EARLY
                         mbar_arrive(acc_empty + 8u * buf);
+#endif
                         if (l < 4) mbar_arrive(act_ready + 8u * (uint32_t)j);
                     }
                 }

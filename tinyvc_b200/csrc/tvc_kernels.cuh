@@ -27,6 +27,10 @@ int energy_pooled_len(int L);
 int energy_estimate(const float* wf, float* energy, float* pooled, int B, int L, cudaStream_t s);
 int shift_frequency(const float* f0, float* out, long long n, float shift, cudaStream_t s);
 
+// resample.cu
+long long resample_length(long long L, int orig, int neu);
+int resample_run(const float* x, float* y, int B, long long L, int orig, int neu, cudaStream_t s);
+
 // knn.cu
 int knn_prepare(const float* index_cn, float* index_w, float* index_nc, float* bias, int C, int N, int NP, int metric,
                 cudaStream_t s);

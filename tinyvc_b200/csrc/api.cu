@@ -661,8 +661,10 @@ size_t tvc_match_workspace_bytes(tvc_index_t h, int B, int Lf) {
     const int bc = std::min(B, match_chunk_utts(N, Lf));
     size_t exact = align_up((size_t)bc * N * Lf * f, 256) + 2 * align_up((size_t)16 * bc * Lf * 8 * f, 256);
     // screened path: query planes, candidates, flags (the similarity matrix stays on chip)
+    // (a split sweep keeps up to 8 candidate lists + scores per query, and only for fewer than 148 x 128 queries)
+    const size_t lists = std::min(rows, (size_t)148 * 128) * 8 * 8;
     size_t screened = 2 * align_up(rows * kContent * sizeof(bf16), 256) + align_up(rows * 8 * sizeof(int), 256) +
-                      align_up(rows * sizeof(int), 256);
+                      align_up(rows * sizeof(int), 256) + 2 * align_up(lists * sizeof(int), 256);
     tot += h->m.screened ? std::max(exact, screened) : exact;
     return tot + 1024;
 }
@@ -688,18 +690,21 @@ int tvc_match_features(tvc_index_t h, const float* source, float* out, int32_t* 
         // the nominated candidates (knn.cu).  Nothing of size queries x N is ever written.
         bf16* q_hi = (bf16*)A.bytes((size_t)rows * kContent * sizeof(bf16));
         bf16* q_lo = (bf16*)A.bytes((size_t)rows * kContent * sizeof(bf16));
-        int* cand = A.i32(rows * 8);
+        const int splits = tc_conv_topk_splits(m.tc, rows);      // few queries (a streaming tick): cut the sweep so it covers the SMs
+        int* cand = A.i32(rows * 8 * splits);
+        float* cscore = splits > 1 ? A.f32(rows * 8 * splits) : nullptr;
         int* flag = A.i32(rows);
         TVC_REQUIRE(!A.overflow, "workspace too small: need at least %zu bytes, got %zu", A.peak, A.cap);
         TVC_TRY(cf_to_planes(qn, q_hi, q_lo, B, kContent, Lf, kContent, TC_ACT_NONE, s));
         TcConvArgs a;
         a.a_hi = q_hi; a.a_lo = q_lo; a.a_cs = kContent; a.B = B; a.T = Lf;
         a.topk_cand = cand; a.topk_flag = flag; a.topk_k = k; a.topk_n = m.N; a.topk_eps = kKnnScreenEps;
+        a.topk_score = cscore; a.topk_splits = splits;
         {
             ProfScope ps("tc_knn_screen(", s);
             TVC_TRY(tc_conv_launch(m.tc, a, s));
         }
-        TVC_TRY(knn_rescore_candidates(qn, m.index_wn, cand, flag, idx, B, Lf, m.N, k, s));
+        TVC_TRY(knn_rescore_candidates(qn, m.index_wn, cand, cscore, splits, flag, idx, B, Lf, m.N, k, s));
         return knn_gather_mean(source, m.index_nc, idx, out, B, kContent, Lf, k, alpha, s);
     }
     const int bc = std::min(B, match_chunk_utts(m.N, Lf));

@@ -45,46 +45,54 @@ int knn_prepare(const float* index_cn, float* index_w, float* index_nc, float* b
     return 0;
 }
 
-// ---- query normalisation: qn[b,c,t] = s[b,c,t] / (|s[b,:,t]| + 1e-6)   (thread per frame) -----
-// The squared norm is one fmaf chain over ascending channels (the order the parity fixtures were taken with); the loads do
-// not depend on it, so they are issued 32 at a time.  Blocks of 32 frames: a streaming tick (3 584 frames) still covers
-// most SMs.
-constexpr int kNormBatch = 32;
-__global__ void __launch_bounds__(32) knn_normalize_kernel(const float* __restrict__ src, float* __restrict__ qn, int C, int T,
-                                                          long long ncol, int metric) {
-    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= ncol) return;
-    const long long b = n / T;
-    const int t = (int)(n - b * T);
+// ---- query normalisation: qn[b,c,t] = s[b,c,t] / (|s[b,:,t]| + 1e-6) ------------------------------
+// Block = 32 frames: eight warps stage the [C][32] tile in shared memory (every load of a frame's column in flight at
+// once), warp 0 then forms each frame's squared norm as ONE fmaf chain over ascending channels (the order the parity
+// fixtures were taken with -- the values now come from shared memory, not from 768 dependent global round trips), and all
+// warps divide and store.  A streaming tick (3 584 frames) is 112 blocks.
+constexpr int kNormFrames = 32;
+__global__ void __launch_bounds__(256) knn_normalize_kernel(const float* __restrict__ src, float* __restrict__ qn, int C, int T,
+                                                           long long ncol, int metric) {
+    extern __shared__ float tile[];                 // [C][33]
+    __shared__ float s_nrm[kNormFrames];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long n = (long long)blockIdx.x * kNormFrames + lane;
+    const bool valid = n < ncol;
+    const long long b = valid ? n / T : 0;
+    const int t = valid ? (int)(n - b * T) : 0;
     const float* sp = src + b * C * (long long)T + t;
     float* qp = qn + b * C * (long long)T + t;
-    float ss = 0.f;
-    if (metric == 0) {
-#pragma unroll 1
-        for (int c0 = 0; c0 < C; c0 += kNormBatch) {
-            float v[kNormBatch];
-#pragma unroll
-            for (int u = 0; u < kNormBatch; ++u) v[u] = c0 + u < C ? __ldg(sp + (long long)(c0 + u) * T) : 0.f;
-#pragma unroll
-            for (int u = 0; u < kNormBatch; ++u)
-                if (c0 + u < C) ss = fmaf(v[u], v[u], ss);
+#pragma unroll 8
+    for (int c = warp; c < C; c += 8) tile[c * 33 + lane] = valid ? __ldg(sp + (long long)c * T) : 0.f;
+    __syncthreads();
+    if (warp == 0) {
+        float ss = 0.f;
+        if (metric == 0) {
+#pragma unroll 8
+            for (int c = 0; c < C; ++c) {
+                const float v = tile[c * 33 + lane];
+                ss = fmaf(v, v, ss);
+            }
         }
+        s_nrm[lane] = __fadd_rn(sqrtf(ss), 1e-6f);
     }
-    const float nrm = __fadd_rn(sqrtf(ss), 1e-6f);
-#pragma unroll 1
-    for (int c0 = 0; c0 < C; c0 += kNormBatch) {
-        float v[kNormBatch];
-#pragma unroll
-        for (int u = 0; u < kNormBatch; ++u) v[u] = c0 + u < C ? __ldg(sp + (long long)(c0 + u) * T) : 0.f;
-#pragma unroll
-        for (int u = 0; u < kNormBatch; ++u)
-            if (c0 + u < C) qp[(long long)(c0 + u) * T] = metric == 0 ? __fdiv_rn(v[u], nrm) : v[u];
+    __syncthreads();
+    if (!valid) return;
+    const float nrm = s_nrm[lane];
+#pragma unroll 8
+    for (int c = warp; c < C; c += 8) {
+        const float v = tile[c * 33 + lane];
+        qp[(long long)c * T] = metric == 0 ? __fdiv_rn(v, nrm) : v;
     }
 }
 
 int knn_normalize_queries(const float* src, float* qn, int B, int C, int T, int metric, cudaStream_t s) {
     const long long ncol = (long long)B * T;
-    knn_normalize_kernel<<<cdiv(ncol, 32), 32, 0, s>>>(src, qn, C, T, ncol, metric);
+    const size_t smem = sizeof(float) * 33 * (size_t)C;
+    TVC_REQUIRE(smem <= 200 * 1024, "knn_normalize: %d channels do not fit the shared-memory tile", C);
+    static PerDeviceOnce attr;
+    TVC_TRY(attr.run([] { TVC_CUDA(cudaFuncSetAttribute(knn_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); return 0; }));
+    knn_normalize_kernel<<<cdiv(ncol, kNormFrames), 256, smem, s>>>(src, qn, C, T, ncol, metric);
     TVC_LAUNCH_CHECK();
     return 0;
 }
@@ -205,16 +213,45 @@ __device__ __forceinline__ float knn_exact_score(const float* __restrict__ wrow,
     return acc + 0.f;
 }
 
-// pass 3: block = 32 queries x kKnnCand candidates; thread (q, j) re-scores candidate j exactly, thread (q, 0) selects
+// pass 3: block = 32 queries x kKnnCand candidates.  With a split sweep (S > 1 candidate lists per query, each sorted by
+// screening score descending / index ascending) thread (q, 0) first merges them into the query's 8 best -- the list the
+// single sweep would have produced -- and decides the "margin too thin" flag from it; then thread (q, j) re-scores
+// candidate j exactly and thread (q, 0) selects.
 __global__ void __launch_bounds__(32 * kKnnCand) knn_rescore_kernel(const float* __restrict__ qn, const float* __restrict__ index_wn,
-                                                                    const int* __restrict__ cand, int* __restrict__ idx_out,
-                                                                    int T, long long R, int k) {
+                                                                    const int* __restrict__ cand, const float* __restrict__ score,
+                                                                    int S, int* __restrict__ flag, float eps, int N,
+                                                                    int* __restrict__ idx_out, int T, long long R, int k) {
     __shared__ float sv[32][kKnnCand];
     __shared__ int si[32][kKnnCand];
     const int ql = threadIdx.x / kKnnCand, j = threadIdx.x % kKnnCand;
     const long long row = (long long)blockIdx.x * 32 + ql;
+    if (S > 1) {
+        if (row < R && j == 0) {
+            int head[8] = {0, 0, 0, 0, 0, 0, 0, 0};                      // S <= 8 lists
+            const int* cp = cand + row * S * kKnnCand;
+            const float* vp = score + row * S * kKnnCand;
+            float vk = 0.f, v8 = -INFINITY;
+            for (int i = 0; i < kKnnCand; ++i) {
+                int w = -1, bn = -1;
+                float bx = -INFINITY;
+                for (int sp = 0; sp < S; ++sp) {
+                    if (head[sp] >= kKnnCand) continue;
+                    const int n = cp[sp * kKnnCand + head[sp]];
+                    if (n < 0) continue;
+                    const float x = vp[sp * kKnnCand + head[sp]];
+                    if (w < 0 || x > bx || (x == bx && n < bn)) { w = sp; bn = n; bx = x; }
+                }
+                if (w >= 0) ++head[w];
+                si[ql][i] = bn;
+                if (i == k - 1) vk = bx;
+                if (i == kKnnCand - 1) v8 = bx;
+            }
+            flag[row] = (N > kKnnCand && !(vk - v8 > eps)) ? 1 : 0;      // same rule as the single sweep's epilogue
+        }
+        __syncthreads();
+    }
     if (row < R) {
-        const int n = cand[row * kKnnCand + j];
+        const int n = S > 1 ? si[ql][j] : cand[row * kKnnCand + j];
         const long long b = row / T;
         const int t = (int)(row - b * T);
         si[ql][j] = n;
@@ -290,11 +327,12 @@ __global__ void __launch_bounds__(256) knn_exact_fallback_kernel(const float* __
     }
 }
 
-int knn_rescore_candidates(const float* qn, const float* index_wn, const int* cand, const int* flag, int* idx_out, int B, int T,
-                           int N, int k, cudaStream_t s) {
+int knn_rescore_candidates(const float* qn, const float* index_wn, const int* cand, const float* score, int splits, int* flag,
+                           int* idx_out, int B, int T, int N, int k, cudaStream_t s) {
     TVC_REQUIRE(k >= 1 && k <= 4 && k < kKnnCand, "knn_rescore_candidates: k=%d unsupported", k);
+    TVC_REQUIRE(splits >= 1 && splits <= 8 && (splits == 1 || score), "knn_rescore_candidates: %d candidate lists per query", splits);
     const long long R = (long long)B * T;
-    knn_rescore_kernel<<<cdiv(R, 32), 32 * kKnnCand, 0, s>>>(qn, index_wn, cand, idx_out, T, R, k);
+    knn_rescore_kernel<<<cdiv(R, 32), 32 * kKnnCand, 0, s>>>(qn, index_wn, cand, score, splits, flag, kKnnScreenEps, N, idx_out, T, R, k);
     TVC_LAUNCH_CHECK();
     knn_exact_fallback_kernel<<<(unsigned)R, 256, 0, s>>>(qn, index_wn, flag, idx_out, T, N, k);
     TVC_LAUNCH_CHECK();

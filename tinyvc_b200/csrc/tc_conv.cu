@@ -76,6 +76,8 @@ struct alignas(64) TcKParams {
     int* topk_flag;                // [rows] 1 when score[k-1] - score[kTopkC-1] <= topk_eps (a true member may have been missed)
     int topk_k, topk_n;            // k of the final selection; number of real columns (channels >= topk_n are padding)
     float topk_eps;
+    float* topk_score;             // split sweep: [rows][topk_splits][kTopkC] scores next to the indices
+    int topk_splits, topk_nper;    // ranges the channel tiles are cut into, channel tiles per range
     uint32_t topk_smem;            // byte offset of the merge scratch inside dynamic shared memory
     int row_major;                 // 1: tile id = row_tile * n_tiles + n_tile, whole row tiles per CTA
     // fused down-resampler (SPEC 9): besides its own outputs the epilogue writes F.interpolate(y, scale_factor=1/dec_f,
@@ -118,10 +120,16 @@ constexpr int kMmaWarp2 = 17;     // second MMA-issuing warp: tiles alternate be
 struct TileWalk {
     long long row_tile;
     int n_tile, bq, tt0;     // halo mode: utterance index and first time step of the tile
+    int split, jn;           // row-major (top-k) walk: range of channel tiles this sweep covers, position inside it
     __device__ TileWalk(const TcKParams& p, long long tile) {
+        split = 0; jn = 0;
         if (p.row_major) {
-            row_tile = tile / p.n_tiles;
-            n_tile = (int)(tile - row_tile * p.n_tiles);
+            // tile id = ((row_tile * splits) + split) * nper + jn: a CTA takes whole (row tile, range) sweeps
+            const long long vr = tile / p.topk_nper;
+            jn = (int)(tile - vr * p.topk_nper);
+            row_tile = vr / p.topk_splits;
+            split = (int)(vr - row_tile * p.topk_splits);
+            n_tile = split * p.topk_nper + jn;
             bq = 0; tt0 = 0;
             return;
         }
@@ -132,7 +140,12 @@ struct TileWalk {
     }
     __device__ void next(const TcKParams& p) {
         if (p.row_major) {
-            if (++n_tile == p.n_tiles) { n_tile = 0; ++row_tile; }
+            ++n_tile;
+            if (++jn == p.topk_nper) {
+                jn = 0;
+                if (++split == p.topk_splits) { split = 0; ++row_tile; }
+                n_tile = split * p.topk_nper;
+            }
             return;
         }
         if (++row_tile == p.row_tiles) { row_tile = 0; ++n_tile; bq = 0; tt0 = 0; return; }
@@ -195,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     const uint32_t acc_cols = (uint32_t)(film ? 3 * p.NTp : p.NTp);
     const long long n_tiles_total = p.row_tiles * p.n_tiles;
     // contiguous tile range of this CTA; tile id = n_tile * row_tiles + row_tile
-    const long long per_cta = p.row_major ? ((p.row_tiles + gridDim.x - 1) / gridDim.x) * p.n_tiles
+    const long long per_cta = p.row_major ? ((p.row_tiles * p.topk_splits + gridDim.x - 1) / gridDim.x) * p.topk_nper
                                           : (n_tiles_total + gridDim.x - 1) / gridDim.x;
     const long long tile_beg = (long long)blockIdx.x * per_cta;
     const long long tile_end = tile_beg + per_cta < n_tiles_total ? tile_beg + per_cta : n_tiles_total;
@@ -630,7 +643,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                 // ---- kNN screening (feature_retrieval.py:27-28): the similarity tile never leaves the SM.  A thread sees the
                 //      columns of its row in increasing order (its column groups inside a tile, the tiles of the sweep), so a
                 //      strict '>' keeps the lower index on ties, like torch.topk on the CPU.
-                if (n_tile == 0) {
+                if (tw.jn == 0) {
 #pragma unroll
                     for (int i = 0; i < kTopkC; ++i) { tkv[i] = -INFINITY; tki[i] = -1; }
                 }
@@ -658,7 +671,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty + 8u * buf);
-                if (n_tile == p.n_tiles - 1) {
+                if (tw.jn == p.topk_nper - 1) {
                     // end of the row tile's sweep: the three column slots of a lane quarter merge their lists through shared memory
                     float* mv = reinterpret_cast<float*>(smem + p.topk_smem);            // [3 slots][128 rows][kTopkC]
                     int* mi = reinterpret_cast<int*>(mv + 3 * kTileM * kTopkC);
@@ -683,13 +696,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                             if (n1 >= 0 && (w < 0 || x1 > bx || (x1 == bx && n1 < bn))) { w = 1; bn = n1; bx = x1; }
                             if (n2 >= 0 && (w < 0 || x2 > bx || (x2 == bx && n2 < bn))) { w = 2; bn = n2; bx = x2; }
                             h0 += w == 0; h1 += w == 1; h2 += w == 2;
-                            p.topk_cand[row * kTopkC + i] = bn;
+                            const long long o = (row * p.topk_splits + tw.split) * kTopkC + i;
+                            p.topk_cand[o] = bn;
+                            if (p.topk_score) p.topk_score[o] = bx;
                             if (i == p.topk_k - 1) vk = bx;
                             if (i == kTopkC - 1) v8 = bx;
                         }
                         // fewer columns than candidates: every column is a candidate, nothing can be missed
                         const bool thin = p.topk_n > kTopkC && !(vk - v8 > p.topk_eps);      // also true for NaN
-                        p.topk_flag[row] = thin ? 1 : 0;
+                        if (p.topk_splits == 1) p.topk_flag[row] = thin ? 1 : 0;            // split sweep: decided after the merge
                     }
                     asm volatile("bar.sync %0, 96;" ::"r"(3 + quarter) : "memory");          // scratch may be rewritten
                 }
@@ -1065,6 +1080,16 @@ int tc_make_plane_map(CUtensorMap* m, const bf16* base, long long rows, int nch,
     return 0;
 }
 
+// Ranges to cut the top-k sweep into so that (row tiles x ranges) covers the SMs: the largest divisor of the channel tiles
+// (<= 8) that keeps the sweeps within one wave.  1 for anything with at least half a wave of row tiles.
+int tc_conv_topk_splits(const TcConvW& W, long long rows) {
+    const long long row_tiles = (rows + kTileM - 1) / kTileM;
+    int best = 1;
+    for (int sp = 2; sp <= 8; ++sp)
+        if (W.n_tiles % sp == 0 && row_tiles * sp <= g_num_sms) best = sp;
+    return best;
+}
+
 int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     TVC_REQUIRE(W.w && a.a_hi && a.a_lo, "tc_conv: missing weights or input");
     TVC_REQUIRE(!W.cat, "tc_conv: \"cat\" weight images belong to the fused block kernel (tc_block.cu)");
@@ -1095,6 +1120,11 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
                 "tc_conv: the fused top-k needs a plain 1 x 1 conv without outputs, 1 <= k <= 4");
     p.topk_cand = a.topk_cand; p.topk_flag = a.topk_flag; p.topk_k = a.topk_k; p.topk_n = a.topk_n; p.topk_eps = a.topk_eps;
     p.row_major = topk ? 1 : 0;
+    p.topk_splits = topk ? a.topk_splits : 1;
+    p.topk_score = a.topk_score;
+    TVC_REQUIRE(p.topk_splits >= 1 && W.n_tiles % p.topk_splits == 0 && (p.topk_splits == 1 || a.topk_score),
+                "tc_conv: %d top-k ranges do not divide %d channel tiles (or no score buffer)", p.topk_splits, W.n_tiles);
+    p.topk_nper = W.n_tiles / p.topk_splits;
     const bool dec = a.dec_f > 0;
     TVC_REQUIRE(!dec || (a.dec_r_hi && a.dec_r_lo && a.dec_a_hi && a.dec_a_lo && a.y_hi && !a.y32 && !a.res && W.aux_mode != TC_AUX_FILM &&
                          a.epi_act == TC_ACT_NONE && a.out_act == TC_ACT_NONE && a.T % a.dec_f == 0 && a.dec_pad >= 0 &&
@@ -1162,7 +1192,7 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     p.topk_smem = (uint32_t)align_up((int64_t)ring * stage + p.w_bytes + 16 * ring + 64, 16);
     const size_t smem = topk ? (size_t)p.topk_smem + topk_bytes : (size_t)ring * stage + p.w_bytes + 16 * ring + 64;
     const long long tiles = p.row_tiles * p.n_tiles;
-    const long long work = topk ? p.row_tiles : tiles;             // row-major: a CTA takes whole row tiles
+    const long long work = topk ? p.row_tiles * p.topk_splits : tiles;   // row-major: a CTA takes whole (row tile, range) sweeps
     const unsigned grid = (unsigned)(work < g_num_sms ? work : g_num_sms);
     // Two MMA-issuing warps (each with its own half of the ring) when a CTA has several tiles to alternate and the ring
     // is deep enough that half of it still prefetches ahead.

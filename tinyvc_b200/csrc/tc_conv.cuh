@@ -82,6 +82,12 @@ struct TcConvArgs {
     int* topk_flag = nullptr;
     int topk_k = 0, topk_n = 0;
     float topk_eps = 0.f;
+    // Split sweep (few query tiles, e.g. a streaming tick: 28 row tiles on 148 SMs): the channel tiles are cut into
+    // topk_splits equal ranges and (row tile, range) pairs are spread over the CTAs; every pair stores its own 8 candidates
+    // AND their scores -- topk_cand / topk_score are then [rows][topk_splits][8], topk_flag is not written, and the caller
+    // merges the lists (knn.cu: the merged list is exactly the single sweep's).  tc_conv_topk_splits() picks the count.
+    float* topk_score = nullptr;
+    int topk_splits = 1;
     // Fused down-resampler: with dec_f in {3, 4, 5} the epilogue also writes F.interpolate(y, scale_factor = 1 / dec_f,
     // mode='linear') of the conv's result (interp_cl's arithmetic) as the next Downsample block's two operands: raw planes
     // dec_r (B * T / dec_f rows) and leaky-ReLU'd planes dec_a (with dec_pad stored replicate rows per utterance side).
@@ -93,6 +99,7 @@ struct TcConvArgs {
     int out_act = TC_ACT_NONE;         // applied additionally to the split-plane copy only
 };
 int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s);
+int tc_conv_topk_splits(const TcConvW& W, long long rows);   // TcConvArgs::topk_splits for this many query rows
 int tc_conv_init();
 
 // developer timeline of selected tc_conv launches (ordinals counted from arming); see tc_conv.cu Tracer

@@ -38,8 +38,8 @@ int knn_normalize_queries(const float* src, float* qn, int B, int C, int T, int 
 int knn_topk(const float* sims, float* pv, int* pi, int* idx_out, int B, int T, int N, int k, cudaStream_t s);
 int knn_gather_mean(const float* src, const float* index_nc, const int* idx, float* out, int B, int C, int T, int k,
                     float alpha, cudaStream_t s);
-int knn_rescore_candidates(const float* qn, const float* index_wn, const int* cand, const int* flag, int* idx_out, int B, int T,
-                           int N, int k, cudaStream_t s);
+int knn_rescore_candidates(const float* qn, const float* index_wn, const int* cand, const float* score, int splits, int* flag,
+                           int* idx_out, int B, int T, int N, int k, cudaStream_t s);
 constexpr float kKnnScreenEps = 1e-4f;   // screening margin: >= 2 x the worst-case error of the split-bf16 similarity product
 int knn_transpose_index(const float* index_w, float* index_wn, int C, int N, int NP, cudaStream_t s);
 constexpr int kKnnMaxKDecl = 8;

@@ -95,6 +95,39 @@ def test_output_pruning_does_not_change_a_tick(cuda_models):
 
 
 @torch.inference_mode()
+@pytest.mark.parametrize("pv", [False, True])
+def test_tick_graph_replay_matches_eager_ticks(cuda_models, weights, pv):
+    """The whole tick as one CUDA graph (window slide, analyse, retarget, synthesise, SOLA; state updated in place) against the
+    eager launches, noise drawn in-kernel from identically seeded generators: same blocks bit for bit over several ticks, and
+    a change of target re-captures."""
+    from tinyvc_b200.infer import Generator, BatchedStreamInfer
+    from tinyvc_b200.tinyvc import Decoder
+    enc, dec_a = cuda_models
+    dec_b = Decoder().eval()
+    dec_b.load_state_dict(weights[1], strict=True)
+    dec_b = dec_b.to("cuda")
+    dec_a.seed_noise(99); dec_b.seed_noise(99)
+    gi = torch.Generator().manual_seed(21)
+    index = torch.randn(1, 768, 2048, generator=gi).cuda()
+    index2 = torch.randn(1, 768, 1100, generator=gi).cuda()
+    S = 3
+    blocks = 0.1 * torch.randn(6, S, 1920, generator=gi)
+    a = BatchedStreamInfer(Generator(enc, dec_a), S, target=index, device=torch.device("cuda"), use_phase_vocoder=pv)
+    b = BatchedStreamInfer(Generator(enc, dec_b), S, target=index, device=torch.device("cuda"), use_phase_vocoder=pv)
+    b.use_graph = False
+    a.init_buffer(); b.init_buffer()
+    for tick in range(6):
+        if tick == 4:
+            a.target = index2; b.target = index2
+        oa = a.audio_callback(blocks[tick].cuda())
+        ob = b.audio_callback(blocks[tick].cuda())
+        assert torch.equal(a.last_shift, b.last_shift), f"tick {tick}"
+        assert torch.equal(oa, ob), f"tick {tick}: max|d| = {float((oa - ob).abs().max()):.3e}"
+        assert torch.equal(a.input_wav, b.input_wav) and torch.equal(a.sola_buffer, b.sola_buffer)
+    assert a._graph is not None and b._graph is None
+
+
+@torch.inference_mode()
 def test_phase_vocoder_matches_reference(report):
     """phase_vocoder(a, b, fade_out, fade_in) (reference stream.py:9-26) for several stream pairs, n = 1920 and an
     odd length (the reference doubles a different bin range for odd n)."""

@@ -61,6 +61,10 @@ class BatchedStreamInfer:
                               self.block_size + self.extra_size)
         self.last_shift: Optional[torch.Tensor] = None
         self.prune_output = True             # compute only the waveform samples the SOLA step reads (bit-identical there)
+        self.use_graph = True                # replay the whole tick as one CUDA graph from the second tick on
+        self._graph = None
+        self._graph_key = None
+        self._ticks = 0
 
     def init_buffer(self) -> None:
         if self.device.type != "cuda":
@@ -72,25 +76,19 @@ class BatchedStreamInfer:
         self.input_wav = torch.zeros(self.num_streams, self.input_size, device=self.device)
         self.sola_buffer = torch.zeros(self.num_streams, cf, device=self.device)
         self._shift = torch.zeros(self.num_streams, dtype=torch.int32, device=self.device)
+        self._graph, self._graph_key, self._ticks = None, None, 0
 
-    @torch.inference_mode()
-    def audio_callback(self, blocks: torch.Tensor, *, rand01: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """blocks [S, block_size] -> converted [S, block_size]."""
-        S, bs = self.num_streams, self.block_size
-        blocks = _lib.dev_f32(blocks, "block")
-        if tuple(blocks.shape) != (S, bs):
-            raise RuntimeError(f"audio_callback: expected {(S, bs)}, got {tuple(blocks.shape)}")
-        # stream.py:69-70: slide the window left by one block and append the new samples
-        nxt = torch.empty_like(self.input_wav)
-        nxt[:, : self.input_size - bs] = self.input_wav[:, bs:]
-        nxt[:, self.input_size - bs:] = blocks
-        self.input_wav = nxt
+    # ---- one tick ---------------------------------------------------------------------------------------------------
+    def _keep_range(self):
         # stream.py:75 reads y[-(block+cross+search+delay) : -delay] and nothing else: tell the decoder (exact pruning)
         Ly = -(-self.input_size // 480) * 480
-        keep = (max(0, Ly - bs - self.crossfade_size - self.sola_search_size - self.last_dilay_size), Ly - self.last_dilay_size)
-        y = self.generator.convert(self.input_wav, self.target, self.pitch_shift, rand01=rand01,
-                                   keep=keep if self.prune_output and keep[1] > keep[0] else None).contiguous()
-        out = torch.empty(S, bs, device=self.device, dtype=torch.float32)
+        keep = (max(0, Ly - self.block_size - self.crossfade_size - self.sola_search_size - self.last_dilay_size),
+                Ly - self.last_dilay_size)
+        return keep if self.prune_output and keep[1] > keep[0] else None
+
+    def _convert_and_sola(self, window: torch.Tensor, out: torch.Tensor, rand01) -> None:
+        S, bs = self.num_streams, self.block_size
+        y = self.generator.convert(window, self.target, self.pitch_shift, rand01=rand01, keep=self._keep_range()).contiguous()
         L = _lib.lib()
         with torch.cuda.device(self.device):
             if self.use_phase_vocoder:        # stream.py:83-89
@@ -104,6 +102,61 @@ class BatchedStreamInfer:
                                       self.fade_in_window.data_ptr(), out.data_ptr(), self._shift.data_ptr(), S, bs,
                                       self.crossfade_size, self.sola_search_size, self.last_dilay_size,
                                       _lib.stream_ptr(self.device)), "tvc_sola")
+
+    def _graph_state(self):
+        tgt = self.target
+        return (tgt.data_ptr(), getattr(tgt, "_version", 0) if not tgt.is_inference() else -1, tuple(tgt.shape),
+                float(self.pitch_shift), bool(self.use_phase_vocoder), bool(self.prune_output))
+
+    def _tick_graph(self, blocks: torch.Tensor) -> torch.Tensor:
+        """The whole tick -- window slide, analyse, retarget, synthesise, SOLA -- as ONE CUDA graph per (S, window, target):
+        a tick then costs one graph launch on the host (a single stream's tick is host-bound otherwise: ~120 launches).
+        State (window, SOLA tail, noise generator) lives in fixed device buffers that the graph updates in place."""
+        n, bs = self.input_size, self.block_size
+        state = self._graph_state()
+        if self._graph is None or self._graph_key != state:
+            from ..tinyvc.feature_retrieval import _prepared
+            self._graph_index = _prepared(_lib.dev_f32(self.target[0], "reference"), _lib.METRICS["cos"])   # keep the native index alive
+            self._g_blocks = torch.empty_like(blocks)
+            self._g_slide = torch.empty(self.num_streams, n - bs, device=self.device)
+            self._g_out = torch.empty(self.num_streams, bs, device=self.device)
+            self._g_blocks.copy_(blocks)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                # stream.py:69-70, in place (two copies: the ranges overlap)
+                self._g_slide.copy_(self.input_wav[:, bs:])
+                self.input_wav[:, : n - bs].copy_(self._g_slide)
+                self.input_wav[:, n - bs:].copy_(self._g_blocks)
+                self._convert_and_sola(self.input_wav, self._g_out, None)
+            self._graph, self._graph_key = g, state
+        else:
+            self._g_blocks.copy_(blocks)
+        self._graph.replay()
+        self.last_shift = self._shift
+        return self._g_out.clone()
+
+    @torch.inference_mode()
+    def audio_callback(self, blocks: torch.Tensor, *, rand01: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """blocks [S, block_size] -> converted [S, block_size]."""
+        S, bs = self.num_streams, self.block_size
+        blocks = _lib.dev_f32(blocks, "block")
+        if tuple(blocks.shape) != (S, bs):
+            raise RuntimeError(f"audio_callback: expected {(S, bs)}, got {tuple(blocks.shape)}")
+        # graph mode: from the second tick on (the first one runs eagerly: it triggers every one-time set-up -- kernel
+        # attributes, the native index, workspaces -- none of which may happen inside a capture); injected noise draws
+        # (parity tests) and per-utterance targets stay on the eager path
+        if (self.use_graph and rand01 is None and self._ticks > 0 and isinstance(self.target, torch.Tensor)
+                and self.target.dim() == 3 and self.target.shape[0] == 1):
+            self._ticks += 1
+            return self._tick_graph(blocks)
+        self._ticks += 1
+        # stream.py:69-70: slide the window left by one block and append the new samples
+        nxt = torch.empty_like(self.input_wav)
+        nxt[:, : self.input_size - bs] = self.input_wav[:, bs:]
+        nxt[:, self.input_size - bs:] = blocks
+        self.input_wav = nxt
+        out = torch.empty(S, bs, device=self.device, dtype=torch.float32)
+        self._convert_and_sola(self.input_wav, out, rand01)
         self.last_shift = self._shift
         return out
 

@@ -93,19 +93,34 @@ __global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict_
         int q = t + (j - 3) * dil;
         tt[j] = q < 0 ? 0 : (q > T - 1 ? T - 1 : q);
     }
-    for (int c = warp; c < C; c += nwarp) {
-        float v = 0.f;
-        if (ok) {
+    // four channels per step with every load issued before the first use (frames past the end read a clamped, legal
+    // address and are masked afterwards): a short utterance batch is a chain of load round trips otherwise
+    const int tl = ok ? t : T - 1;
+    for (int c0 = warp; c0 < C; c0 += 4 * nwarp) {
+        float xv[4][7], wv[4][7], bv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = min(c0 + u * nwarp, C - 1);
             const float* xc = xb + (long long)c * T;
             if (w) {
-                v = __ldg(wb + c);
+                bv[u] = __ldg(wb + c);
 #pragma unroll
-                for (int j = 0; j < 7; ++j) v = fmaf(__ldg(w + c * 7 + j), __ldg(xc + tt[j]), v);
+                for (int j = 0; j < 7; ++j) { wv[u][j] = __ldg(w + c * 7 + j); xv[u][j] = __ldg(xc + tt[j]); }
             } else {
-                v = xc[t];
+                bv[u] = xc[tl];
             }
         }
-        tile[c * 33 + lane] = v;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = c0 + u * nwarp;
+            if (c >= C) break;
+            float v = bv[u];
+            if (w) {
+#pragma unroll
+                for (int j = 0; j < 7; ++j) v = fmaf(wv[u][j], xv[u][j], v);
+            }
+            tile[c * 33 + lane] = ok ? v : 0.f;
+        }
     }
     __syncthreads();
     // per-frame statistics: warp `warp` handles frames warp, warp+nwarp, ...
@@ -163,16 +178,24 @@ __global__ void __launch_bounds__(256) grn_scale_kernel(const float* __restrict_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int b = blockIdx.x;
     const float* yb = y + (long long)b * C * T;
-    for (int c = warp; c < C; c += nwarp) {
-        const float* yc = yb + (long long)c * T;
-        float s = 0.f;
+    // four channels per step, their loads in flight together; per channel the sum is still lane-strided partials + the same
+    // shuffle tree (bit-identical to one channel at a time)
+    for (int c0 = warp; c0 < C; c0 += 4 * nwarp) {
+        float sq[4] = {0.f, 0.f, 0.f, 0.f};
         for (int t = lane; t < T; t += 32) {
-            const float v = __ldg(yc + t);
-            s = fmaf(v, v, s);
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldg(yb + (long long)min(c0 + u * nwarp, C - 1) * T + t);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) sq[u] = fmaf(v[u], v[u], sq[u]);
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) g[c] = sqrtf(s);
+        for (int u = 0; u < 4; ++u) {
+            float s = sq[u];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0 && c0 + u * nwarp < C) g[c0 + u * nwarp] = sqrtf(s);
+        }
     }
     __syncthreads();
     float s = 0.f;

@@ -96,6 +96,9 @@ def test_decoder_infer_golden_fp32_plan(cuda_models, report):
     _lib.set_option("conv_impl", "fp32")
     try:
         out = dec.infer(*_cuda(t(g["content"]), t(g["f0"]), t(g["energy"])), rand01=t(g["rand01"]).cuda()).cpu()
+        # without an injected draw the public call draws torch.rand on the device (the fp32 plan has no in-kernel generator)
+        free = dec.infer(*_cuda(t(g["content"]), t(g["f0"]), t(g["energy"])))
+        assert free.shape == out.shape and torch.isfinite(free).all()
     finally:
         _lib.set_option("conv_impl", "tc")
     e = rmse(out, t(g["out"]))

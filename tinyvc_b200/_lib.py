@@ -98,10 +98,13 @@ def lib() -> ctypes.CDLL:
                 impl = os.environ.get("TVC_CONV_IMPL")
                 if impl and h.tvc_set_option(b"conv_impl", impl.encode()) != 0:
                     raise RuntimeError(f"tinyvc_b200: TVC_CONV_IMPL={impl!r} is not a known conv implementation")
+                if impl:
+                    _options["conv_impl"] = impl
                 for kv in filter(None, os.environ.get("TVC_OPTS", "").split(",")):      # e.g. TVC_OPTS=pdl=0,graphs=0
                     k, _, v = kv.partition("=")
                     if h.tvc_set_option(k.strip().encode(), v.strip().encode()) != 0:
                         raise RuntimeError(f"tinyvc_b200: TVC_OPTS entry {kv!r} was rejected by tvc_set_option")
+                    _options[k.strip()] = v.strip()
                 _lib = h
     return _lib
 
@@ -112,8 +115,18 @@ def check(status: int, what: str) -> None:
         raise RuntimeError(f"{what} failed ({status}): {msg.decode() if msg else 'unknown error'}")
 
 
+_options: dict = {}      # what this process has set through set_option / TVC_CONV_IMPL / TVC_OPTS (the library keeps the state)
+
+
 def set_option(key: str, value: str) -> None:
     check(lib().tvc_set_option(key.encode(), value.encode()), f"tvc_set_option({key})")
+    _options[key] = value
+
+
+def option(key: str, default: str = "") -> str:
+    """Last value this process gave `key` (set_option, TVC_CONV_IMPL, TVC_OPTS); `default` if it never set it."""
+    lib()
+    return _options.get(key, default)
 
 
 def launch_count() -> int:

@@ -207,8 +207,8 @@ class Decoder(nn.Module):
         dev = content.device
         L = _lib.lib()
         h = self._native.get()
-        if rand01 is not None:
-            rand01 = self._rand(rand01, B, Lf, dev)
+        if rand01 is not None or _lib.option("conv_impl", "tc") == "fp32":
+            rand01 = self._rand(rand01, B, Lf, dev)      # the exact-fp32 plan has no in-kernel generator: torch.rand, like decoder.py:78
         elif getattr(self, "_noise_seeded_for", None) != h.value:
             self.seed_noise()            # the draw of decoder.py:78 happens inside the noise kernel
         if out is None:

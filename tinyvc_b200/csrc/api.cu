@@ -35,7 +35,18 @@ static bool g_encoder_tc = true;     // tvc_set_option("encoder_impl", "tc"|"fp3
 // utterance, which amplifies an f0 error ~5 000 x into the waveform (DESIGN.md "conditioning of the reference"), while the
 // content vector only has to keep the kNN ranking.
 static bool g_pitch_tc = false;
+// tvc_set_option("encoder_share", "0"|"1"): on short batches cap the content stack's persistent kernels at kEncoderShareSms SMs
+// (and launch them without PDL) so that the fp32 pitch stack on the side stream gets SMs of its own.
+static bool g_encoder_share = true;
+// Measured (profiles/r02ah_encoder_share_ab.log): 128 streams x 28 frames 0.913 -> 0.687 ms, config 3 (51 200 frames) 7.74 -> 6.10 ms;
+// a single stream (28 frames) is 3 % slower with it, so batches under kEncoderShareMinFrames keep PDL and every SM.
+static bool g_encoder_share_force = false;
+static int g_encoder_share_sms = 0;                         // ("encoder_share", "<n>") forces this cap at every size (A/B runs)
+constexpr long long kEncoderShareMinFrames = 64, kEncoderShareFrames = 8192;
+constexpr int kEncoderShareSmsShort = 112, kEncoderShareSmsLong = 136;  // short batches are latency-bound in both stacks; long ones need the SMs on the tensor-core stack
 static int g_probe_pad_in = 0, g_probe_pad_out = 0;     // tvc_set_option("probe_pad", ...): tests only
+thread_local int t_sm_cap = 0;
+thread_local bool t_pdl_suppress = false;
 bool g_pdl = true;       // programmatic dependent launch between the decoder plan's kernels: the next kernel's CTAs start their
                          // set-up (mbarriers, TMEM, weight prefetch) on SMs the current one leaves idle (most layers of the
                          // low rates have fewer tiles than SMs); same-box A/B 0.986 -> 0.955 ms (profiles/r02h_pdl_ab.log)
@@ -188,6 +199,13 @@ int tvc_set_option(const char* key, const char* value) {
         return 2;
     }
     if (!strcmp(key, "nvtx")) { g_nvtx = !strcmp(value, "1"); return 0; }
+    if (!strcmp(key, "encoder_share")) {
+        const int n = atoi(value);
+        g_encoder_share = n != 0;
+        g_encoder_share_force = n > 1;                      // an explicit cap shares at every size (A/B runs)
+        if (n > 1) g_encoder_share_sms = n;
+        return 0;
+    }
     if (!strcmp(key, "pitch_impl")) {
         if (!strcmp(value, "fp32")) { g_pitch_tc = false; return 0; }
         if (!strcmp(value, "tc")) { g_pitch_tc = true; return 0; }
@@ -563,7 +581,15 @@ int tvc_encoder_forward(tvc_encoder_t h, const float* spec, float* z, float* log
             TVC_TRY(h->m.run_stack(Ap, h->side, h->m.pitch, spec, lg, B, Lf));
             if (f0) TVC_TRY(pitch_decode(lg, f0, B, 512, Lf, h->side));
             TVC_CUDA(cudaEventRecord(h->join, h->side));
+            // The content stack leaves some SMs to the pitch stack and gives up programmatic dependent launch (see t_sm_cap in
+            // tvc_common.cuh), so that the two chains really run side by side.
+            const long long frames = (long long)B * Lf;
+            const bool share = g_encoder_share && (g_encoder_share_force || frames >= kEncoderShareMinFrames);
+            t_sm_cap = !share ? 0 : g_encoder_share_force ? g_encoder_share_sms : frames <= kEncoderShareFrames ? kEncoderShareSmsShort : kEncoderShareSmsLong;
+            t_pdl_suppress = share;
             const int r = h->m.tc->forward(A, s, spec, z, nullptr, B, Lf);
+            t_sm_cap = 0;
+            t_pdl_suppress = false;
             TVC_CUDA(cudaStreamWaitEvent(s, h->join, 0));       // joined even if the content stack failed to launch
             return r;
         }

@@ -1193,7 +1193,8 @@ int tc_conv_launch(const TcConvW& W, const TcConvArgs& a, cudaStream_t s) {
     const size_t smem = topk ? (size_t)p.topk_smem + topk_bytes : (size_t)ring * stage + p.w_bytes + 16 * ring + 64;
     const long long tiles = p.row_tiles * p.n_tiles;
     const long long work = topk ? p.row_tiles * p.topk_splits : tiles;   // row-major: a CTA takes whole (row tile, range) sweeps
-    const unsigned grid = (unsigned)(work < g_num_sms ? work : g_num_sms);
+    const long long sms = (t_sm_cap > 0 && t_sm_cap < g_num_sms) ? t_sm_cap : g_num_sms;
+    const unsigned grid = (unsigned)(work < sms ? work : sms);
     // Two MMA-issuing warps (each with its own half of the ring) when a CTA has several tiles to alternate and the ring
     // is deep enough that half of it still prefetches ahead.
     // Same-box A/B (profiles/r01z_ab_issuer_modes.log): tiles of one K-stage gain 3-6 % from the second issuer, FiLM / deep-K

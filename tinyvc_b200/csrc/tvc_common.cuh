@@ -84,6 +84,12 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
         ::tvc::pdl_wait();                  \
     } while (0)
 extern bool g_pdl;      // tvc_set_option("pdl", "0"|"1")
+// Per-thread launch shaping while two plans share the GPU (tvc_encoder_forward: the fp32 pitch stack beside the tensor-core
+// content stack).  t_sm_cap > 0 caps the grid of the persistent tensor-core kernels, and t_pdl_suppress launches them without
+// the programmatic-dependent-launch attribute: with it the NEXT kernel's CTAs take every SM the running one leaves free (they
+// wait there for their turn), so the other stream's kernels would find no SM at all.
+extern thread_local int t_sm_cap;
+extern thread_local bool t_pdl_suppress;
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -95,7 +101,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = g_pdl ? 1 : 0;
+    cfg.numAttrs = (g_pdl && !t_pdl_suppress) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #define TVC_LAUNCH_PDL(kernel, grid, block, smem, stream, ...) \

@@ -50,6 +50,8 @@ for t in ("block", "up3c2", "encgemm", "knn", "fft"):
     if os.path.exists(rep):
         subprocess.run([sys.executable, "tools/ncu_summary.py", rep, f"profiles/{tag}_{t}_ncu_full.csv"], stdout=subprocess.DEVNULL)
 for src, dst in ((f"bench_{tag}.json", f"{tag}_bench.json"), (f"bench_ref_{tag}.json", f"{tag}_bench_reference_cpu.json"),
-                 ("parity_report.json", f"{tag}_parity_report.json"), (f"pytest_gpu_{tag}.log", f"{tag}_pytest_gpu.log")):
+                 ("parity_report.json", f"{tag}_parity_report.json"), (f"pytest_gpu_{tag}.log", f"{tag}_pytest_gpu.log"),
+                 (f"tick_latency_{tag}.log", f"{tag}_tick_latency.log"), (f"profile_tick_{tag}.log", f"{tag}_profile_tick.log"),
+                 (f"profile_c4_{tag}.log", f"{tag}_profile_c4.log"), (f"tick_launches_{tag}.csv", f"{tag}_tick_launches.csv")):
     if os.path.exists(f"gpurun_out/{src}"):
         shutil.copy(f"gpurun_out/{src}", f"profiles/{dst}")

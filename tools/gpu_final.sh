@@ -27,4 +27,9 @@ full up3c2 'tc_conv_kernel<.*6>' 15 python bench.py --steps 1 --warmup 3 --no-cp
 full encgemm 'tc_conv_kernel<.*1>' 0 python tools/bench_configs.py --configs 3 --steps 1
 full knn 'tc_conv_kernel<.*8>' 0 python tools/bench_configs.py --configs 3 --steps 1
 full fft 'stft_fft_kernel' 0 python tools/bench_configs.py --configs 3 --steps 1
+python tools/tick_latency.py 1 8 32 128 > gpurun_out/tick_latency_$TAG.log 2>&1; tail -4 gpurun_out/tick_latency_$TAG.log
+python tools/profile_tick.py > gpurun_out/profile_tick_$TAG.log 2>&1
+python tools/profile_shape.py 64 500 > gpurun_out/profile_c4_$TAG.log 2>&1; head -1 gpurun_out/profile_c4_$TAG.log
+timeout 600 $NCU --metrics gpu__time_duration.sum -c 700 --csv --log-file gpurun_out/tick_launches_$TAG.csv python tools/tick_once.py > gpurun_out/ncu_tick_$TAG.log 2>&1
+echo "ncu tick rc=$?"
 ls -la gpurun_out | tail -12

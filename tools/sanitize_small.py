@@ -25,5 +25,19 @@ sp = StreamInfer(gen, target=p["index"].to(dev), device=dev, use_phase_vocoder=T
 sp.init_buffer()
 o2 = sp.audio_callback(torch.randn(1920, device=dev) * 0.1)
 o2 = sp.audio_callback(torch.randn(1920, device=dev) * 0.1)
+# round-2 additions: device resampler, pruned decoder range, split kNN sweep (2048-vector index, few queries), streaming ticks on
+# the eager path with the shared-encoder launch shaping, several streams
+from tinyvc_b200.utils import resample
+from tinyvc_b200.infer import BatchedStreamInfer
+r = resample(torch.randn(2, 1001, device=dev), 44100, 24000)
+out3 = dec.infer(inp["content"], inp["f0"], inp["energy"], rand01=inp["rand01"], keep=(500, 901))
+idx2k = torch.randn(1, 768, 2048, device=dev)
+zq = torch.randn(3, 768, 28, device=dev)
+m2 = match_features(zq, idx2k)
+bsi = BatchedStreamInfer(gen, 3, target=idx2k, device=dev)
+bsi.use_graph = False
+bsi.init_buffer()
+for _ in range(2):
+    o3 = bsi.audio_callback(torch.randn(3, 1920, device=dev) * 0.1)
 torch.cuda.synchronize()
 print("sanitize_small ok", out.shape, y.shape, o.shape, float(out.abs().max()), float(y.abs().max()))

@@ -56,7 +56,8 @@ def test_fused_down_resamplers_bit_identical(cuda_models, B, Lf):
 
 
 @pytest.mark.parametrize("B,Lf,t0,t1", [(2, 28, 3840, 9600), (3, 7, 0, 1), (3, 7, 3359, 3360), (1, 1, 100, 300), (5, 18, 425, 427),
-                                        (4, 28, 0, 13440), (2, 5, 426, 852)])
+                                        (4, 28, 0, 13440), (2, 5, 426, 852), (1, 100, 20000, 21000), (2, 60, 0, 3000),
+                                        (2, 60, 26000, 28800), (3, 40, 9000, 9100)])
 def test_output_pruning_is_bit_identical_inside_the_kept_range(cuda_models, B, Lf, t0, t1):
     """tvc_decoder_infer_range / Decoder.infer(keep=(t0, t1)): the fused block walks only the 426-sample windows that produce
     kept samples (a streaming tick reads y[-9600:-3840] of 13 440, module/infer/stream.py:75).  The walked windows see complete

@@ -216,6 +216,7 @@ int tvc_set_option(const char* key, const char* value) {
     if (!strcmp(key, "tc_trace_dump")) return tc_trace_dump(value);    // developer: write the timeline to a file
     if (!strcmp(key, "fused_up")) { set_fused_up(!strcmp(value, "1")); return 0; }
     if (!strcmp(key, "fuse_down")) { set_fuse_down(!strcmp(value, "1")); return 0; }
+    if (!strcmp(key, "prune_levels")) { set_prune_levels(!strcmp(value, "1")); return 0; }
     if (!strcmp(key, "pad_up_max_t")) { set_pad_max_t(atoi(value), -1); return 0; }
     if (!strcmp(key, "pad_down_max_t")) { set_pad_max_t(-1, atoi(value)); return 0; }
     if (!strcmp(key, "probe_pad")) {                                   // tests: tvc_tc_conv_probe in padded mode
@@ -388,7 +389,12 @@ int tvc_decoder_infer_range(tvc_decoder_t h, const float* content, const float* 
     TVC_REQUIRE(rand01 || impl == CONV_IMPL_TC, "tvc_decoder_infer: the fp32 plan needs an injected rand01 draw");
     CHECK_SHAPES();
     cudaStream_t s = (cudaStream_t)stream;
-    if (!g_use_graphs || g_prof_on) {
+    // A caller that is itself capturing this stream (StreamInfer records the whole tick as one graph) gets plain launches:
+    // starting / instantiating / launching a graph of our own inside somebody else's capture is not allowed, and the buffer
+    // addresses of a capture's private pool can repeat between captures, which would otherwise look like "seen before".
+    cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+    TVC_CUDA(cudaStreamIsCapturing(s, &cap_status));
+    if (!g_use_graphs || g_prof_on || cap_status != cudaStreamCaptureStatusNone) {
         Arena A(workspace, workspace_bytes, false);
         return h->m.infer(A, s, content, f0, energy, rand01, out, B, Lf, impl, t0, t1);
     }

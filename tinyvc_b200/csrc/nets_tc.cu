@@ -222,6 +222,7 @@ bool g_fused_up = true;
 // tensor copy.  Short utterances (config 2: 36 / 108 / 432 rows at the three lowest rates) otherwise gather their clamped
 // windows row by row with cp.async, tap by tap.  0 = never.  Separate limits for the Downsample blocks (pads 1 / 2 / 4 rows:
 // the row count hardly grows) and the Upsample blocks (pads up to 27 rows: more row tiles re-stream the weights).
+bool g_prune_levels = true;   // tvc_set_option("prune_levels", "0"): output pruning stops at the fused block (the Upsample levels below it run in full)
 bool g_fuse_down = true;      // tvc_set_option("fuse_down", "0"): separate interp_cl launches in front of the Downsample blocks
 int g_pad_max_t = 0, g_pad_down_max_t = 512;     // same-box A/B (profiles/r02f_pad_ab.log): down 1.010 -> 1.004 ms, up 1.010 -> 1.032 ms
 struct ConvCall {
@@ -361,15 +362,44 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         A.release(m);
     }
     // ---- FilterNet up path (decoder.py:214-219,230-233)
+    // Output pruning (out_t0 / out_t1, fused block only): level i has to produce rows [wa[i], wb[i]) of its utterances only --
+    // the rows the level above reads, widened by the 40 rows (1 + 3 + 9 + 27) over which a wrong edge value of the block's
+    // dilated convs travels inward.  A pruned level works on compact tensors of wb - wa rows per utterance: the resampler
+    // writes just those rows (coordinates on the full lengths), the FiLM condition is a row slice of the skip tensor, the
+    // convs treat the window as an utterance (their replicate padding at a cut edge is wrong but stays inside the 40-row
+    // margin), so every kept output sample is computed from exactly the values of the full run.  Levels whose window is
+    // nearly everything, or too short to keep the conv kernels in the same (halo) tiling as the full run, are not pruned.
+    int wa[5], wb[5], Tlev[5];
+    {
+        int t = Lf;
+        for (int i = 0; i < 5; ++i) { t *= kUpFac[i]; Tlev[i] = t; wa[i] = 0; wb[i] = t; }
+        const bool prune = g_fused_up && g_prune_levels && out_t1 >= 0 && (out_t0 > 0 || out_t1 < L);
+        if (prune) {
+            // rows of x4 (= level 3's output) the walked windows of the block resample: window k covers block rows
+            // k * 426 - 44 .. k * 426 - 43 + 512 (tc_block.cu), clamped to the utterance
+            const int k_lo = out_t0 / 426, k_hi = (out_t1 - 1) / 426;
+            const int t_min = std::max(0, k_lo * 426 - 44), t_max = std::min(L - 1, k_hi * 426 - 43 + 512);
+            int na = std::max(0, t_min / 5 - 1), nb = std::min(Tlev[3], t_max / 5 + 2);        // needed rows of level 3
+            for (int i = 3; i >= 0; --i) {
+                const int ra = std::max(0, na - 40), rb = std::min(Tlev[i], nb + 40);
+                if ((rb - ra) * 100 > Tlev[i] * 85 || rb - ra < 384) break;                    // this level and all below: full
+                wa[i] = ra; wb[i] = rb;
+                const int f = kUpFac[i];
+                na = std::max(0, ra / f - 1);
+                nb = std::min(i > 0 ? Tlev[i - 1] : Lf, (rb - 1) / f + 2);
+            }
+        }
+    }
     const float* x = fx + cm(0, 128, rowsF);      // FilterNet x0 = channels [128, 512) of the frame-rate product
-    int tin = Lf;
+    int tin = Lf, tin_c = Lf, tin_off = 0;        // full length of the level input, rows it holds per utterance, first of them
     for (int i = 0; i < 5; ++i) {
         const Up& u = up[i];
         const int c = kUpCh[i], cn = kUpOut[i], fac = kUpFac[i];
-        const int tout = tin * fac;
+        const int tfull = tin * fac;
+        const int tout = wb[i] - wa[i];             // rows per utterance this level works on
         const long long rows = (long long)B * tout;
-        const Pl& cond = skipP[4 - i];
-        TVC_REQUIRE(skipT[4 - i] == tout && cond.cs == c, "filter_net: skip %d shape mismatch", 4 - i);
+        const Pl& cond_full = skipP[4 - i];
+        TVC_REQUIRE(skipT[4 - i] == tfull && cond_full.cs == c, "filter_net: skip %d shape mismatch", 4 - i);
         const Up& uc = up4_cat;
         // (workspace sizing runs this plan dry on a weightless model: the architecture's shapes are the supported ones)
         const bool fused = g_fused_up && i == 4 && fac == 5 && c == 24 &&
@@ -377,9 +407,10 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         if (fused) {
             // resampler, the five convs and the output layer in one kernel (tc_block.cu); same arithmetic as the launches below
             TcUpBlockArgs fa;
-            fa.x4 = x; fa.c_hi = cond.hi; fa.c_lo = cond.lo; fa.out_w = out_w; fa.out_b = out_b; fa.out = out;
-            fa.B = B; fa.T = tout; fa.T4 = tin; fa.scale = (float)(1.0 / (double)fac);
+            fa.x4 = x; fa.c_hi = cond_full.hi; fa.c_lo = cond_full.lo; fa.out_w = out_w; fa.out_b = out_b; fa.out = out;
+            fa.B = B; fa.T = tfull; fa.T4 = tin; fa.scale = (float)(1.0 / (double)fac);
             fa.t_lo = out_t0; fa.t_hi = out_t1;
+            fa.x4_rows = tin_c; fa.x4_off = tin_off;
             if (!A.dry) {
                 ProfScope ps("tc_up4_fused(", s);
                 TVC_TRY(tc_up24_block_launch(uc.c1, uc.c2, uc.c3, uc.c4, uc.c5, fa, s));
@@ -387,17 +418,26 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
             A.release(m0);
             return 0;
         }
+        TVC_REQUIRE(i < 4 || (tout == tfull && tin_c == tin), "filter_net: pruned levels need the fused block");
         float* xo = A.f32(rows * cn);
         const size_t m = A.mark();
         float* xi = A.f32(rows * c);
         float* y = A.f32(rows * c);
         // stored replicate padding (see g_pad_max_t): p0 holds c1's input (1 row), later c3's (9); p1 c2's (3), later c4's (27)
-        const bool pad = !fused && tout <= g_pad_max_t;
+        const bool windowed = tout != tfull || tin_c != tin;
+        const bool pad = !fused && !windowed && tout <= g_pad_max_t;
         const int Q1 = pad ? 1 : 0, Q3 = pad ? 3 : 0, Q9 = pad ? 9 : 0, Q27 = pad ? 27 : 0;
         Pl p0 = planes(A, (long long)B * (tout + 2 * Q9), c), p1 = planes(A, (long long)B * (tout + 2 * Q27), c);
+        Pl cond = cond_full;
+        if (tout != tfull || A.dry) cond = planes(A, rows, c);      // (sizing runs reserve the slice: a pruned call then never needs more than the full plan)
         ARENA_OK();
         const float scale = (float)(1.0 / (double)fac);           // F.interpolate(scale_factor=f)
-        RUN(interp_cl(x, B, tin, tout, scale, c, xi, nullptr, nullptr, p0.hi, p0.lo, s, Q1));
+        if (windowed) {
+            RUN(interp_cl(x, B, tin, tout, scale, c, xi, nullptr, nullptr, p0.hi, p0.lo, s, 0, tin_c, tin_off, wa[i]));
+            if (tout != tfull) RUN(slice_planes_cl(cond_full.hi, cond_full.lo, cond.hi, cond.lo, B, tfull, c, wa[i], tout, s));
+        } else {
+            RUN(interp_cl(x, B, tin, tout, scale, c, xi, nullptr, nullptr, p0.hi, p0.lo, s, Q1));
+        }
         const char* const un[5][5] = {{"tc_up0_c1(", "tc_up0_c2(", "tc_up0_c3(", "tc_up0_c4(", "tc_up0_c5("},
                                       {"tc_up1_c1(", "tc_up1_c2(", "tc_up1_c3(", "tc_up1_c4(", "tc_up1_c5("},
                                       {"tc_up2_c1(", "tc_up2_c2(", "tc_up2_c3(", "tc_up2_c4(", "tc_up2_c5("},
@@ -409,7 +449,7 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         CONV(un[i][3], u.c4, ConvCall(p1, B, tout, 27).pad(Q27, 0).aux(cond).res(y, c).out(p0, TC_ACT_NONE));
         CONV(un[i][4], u.c5, ConvCall(p0, B, tout, 1).f32(xo, cn));
         A.release(m);
-        x = xo; tin = tout;
+        x = xo; tin = tfull; tin_c = tout; tin_off = wa[i];
     }
     RUN(out_conv_k7_cl(x, out_w, out_b, out, B, L, s));
     A.release(m0);
@@ -527,13 +567,14 @@ int EncoderTC::forward(Arena& A, cudaStream_t s, const float* spec, float* z, fl
 
 void set_fused_up(bool on) { g_fused_up = on; }
 void set_fuse_down(bool on) { g_fuse_down = on; }
+void set_prune_levels(bool on) { g_prune_levels = on; }
 bool fused_up() { return g_fused_up; }
 void set_pad_max_t(int up, int down) {
     if (up >= 0) g_pad_max_t = up > 2047 ? 2047 : up;
     if (down >= 0) g_pad_down_max_t = down > 2047 ? 2047 : down;
 }
 unsigned plan_options() {
-    return (g_fused_up ? 1u : 0u) | ((unsigned)g_pad_max_t << 1) | ((unsigned)g_pad_down_max_t << 12) | (g_fuse_down ? 1u << 23 : 0u);
+    return (g_fused_up ? 1u : 0u) | ((unsigned)g_pad_max_t << 1) | ((unsigned)g_pad_down_max_t << 12) | (g_fuse_down ? 1u << 23 : 0u) | (g_prune_levels ? 1u << 24 : 0u);
 }
 
 }  // namespace tvc

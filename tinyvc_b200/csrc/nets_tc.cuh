@@ -55,6 +55,7 @@ struct EncoderTC {
 
 void set_fused_up(bool on);          // tvc_set_option("fused_up", "0"|"1"): fused 24-channel Upsample block (default on)
 bool fused_up();
+void set_prune_levels(bool on);      // tvc_set_option("prune_levels", "0"|"1"): output pruning below the fused block (default on)
 void set_fuse_down(bool on);         // tvc_set_option("fuse_down", "0"|"1"): Downsample resamplers inside the producing conv's epilogue (default on)
 // tvc_set_option("pad_up_max_t" | "pad_down_max_t", "N"): Upsample / Downsample blocks of levels whose utterances have
 // <= N rows store the replicate padding of their k = 3 convs (tc_conv.cuh, padded mode); -1 leaves a limit unchanged

@@ -103,6 +103,7 @@ struct alignas(64) UpBlockParams {
     float* out;                                       // waveform [B][T]
     long long rows, rows4, n_seg;
     int T, T4, segs_per_utt, seg_lo;                   // windows walked per utterance and the index of the first one (output pruning)
+    int T4c, x4_off;                                   // x4 holds rows [x4_off, x4_off + T4c) of every utterance's low-rate tensor
     float scale;                                      // resampler scale (float)(1 / 5)
     int dil[4];
 };
@@ -117,7 +118,7 @@ struct SegGeo {
         const long long bq = seg / p.segs_per_utt;
         const int k = p.seg_lo + (int)(seg - bq * p.segs_per_utt);
         baseT = bq * p.T;
-        base4 = bq * p.T4;
+        base4 = bq * p.T4c - p.x4_off;                   // so that base4 + (row of the full-length tensor) addresses the window
         w0 = k * kBS - kBHalo;
     }
 };
@@ -459,7 +460,10 @@ int tc_up24_block_launch(const TcConvW& c1, const TcConvW& c2, const TcConvW& c3
     UpBlockParams p;
     memset(&p, 0, sizeof(p));
     p.rows = (long long)a.B * a.T;
-    p.rows4 = (long long)a.B * a.T4;
+    const int T4c = a.x4_rows > 0 ? a.x4_rows : a.T4;
+    TVC_REQUIRE(a.x4_off >= 0 && a.x4_off + T4c <= a.T4, "tc_up24_block: input window [%d, %d) outside the %d low-rate rows", a.x4_off, a.x4_off + T4c, a.T4);
+    p.rows4 = (long long)a.B * T4c;
+    p.T4c = T4c; p.x4_off = a.x4_off;
     TVC_TRY(tc_make_plane_map(&p.tm_c_hi, a.c_hi, p.rows, 3, 3, kCondG));
     TVC_TRY(tc_make_plane_map(&p.tm_c_lo, a.c_lo, p.rows, 3, 3, kCondG));
     const TcConvW* cw[5] = {&c1, &c2, &c3, &c4, &c5};

@@ -19,6 +19,9 @@ struct TcUpBlockArgs {
     // inputs x4 / cond are complete tensors), so the samples written are bit-identical to the full run's.  A streaming tick
     // keeps 5 760 of its 13 440 samples (module/infer/stream.py:75).
     int t_lo = 0, t_hi = -1;
+    // x4 may hold only rows [x4_off, x4_off + x4_rows) of every utterance's low-rate tensor (x4_rows <= 0: all T4 rows): the
+    // rows the walked windows resample must lie inside (the plan computes the range, nets_tc.cu)
+    int x4_rows = 0, x4_off = 0;
 };
 
 // c1..c5: the block's packed convs (tc_pack_conv; c2 / c4 with their TC_AUX_FILM images).

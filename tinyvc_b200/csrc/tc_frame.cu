@@ -45,10 +45,14 @@ __device__ __forceinline__ void store_planes8(bf16* hi, bf16* lo, long long off,
 // leaky_relu(0.1) split planes (the convs that follow apply leaky_relu first), all with B*Tout rows.
 // One thread per (8-channel chunk, output row): blockIdx.y = chunk, consecutive threads = consecutive rows of it.
 // ---------------------------------------------------------------------------------------------
+// Windowed form (output pruning, nets_tc.cu): the output tensor holds rows [out_off, out_off + Tout) of every utterance's
+// full-length result and the input tensor rows [in_off, in_off + Tin_c) of its full-length input (Tin rows); coordinates are
+// evaluated on the full lengths, so the values are those of the full-length call.
 __global__ void __launch_bounds__(256) interp_cl_kernel(const float* __restrict__ x, int Tin, int Tout, float scale,
                                                         long long rows_in, long long rows_out, float* __restrict__ y32,
                                                         bf16* __restrict__ r_hi, bf16* __restrict__ r_lo,
-                                                        bf16* __restrict__ a_hi, bf16* __restrict__ a_lo, int a_pad) {
+                                                        bf16* __restrict__ a_hi, bf16* __restrict__ a_lo, int a_pad,
+                                                        int Tin_c, int in_off, int out_off) {
     TVC_PDL_PROLOGUE();
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows_out) return;
@@ -56,9 +60,9 @@ __global__ void __launch_bounds__(256) interp_cl_kernel(const float* __restrict_
     const unsigned bu = (unsigned)row / (unsigned)Tout;      // rows < 2^31 (checked at the API)
     const long long b = bu;
     const int t = (int)((unsigned)row - bu * (unsigned)Tout);
-    const LinCoord c = lin_coord(t, scale, Tin);
-    const float4* p0 = reinterpret_cast<const float4*>(x + (q * rows_in + b * Tin + c.i0) * 8);
-    const float4* p1 = reinterpret_cast<const float4*>(x + (q * rows_in + b * Tin + c.i1) * 8);
+    const LinCoord c = lin_coord(t + out_off, scale, Tin);
+    const float4* p0 = reinterpret_cast<const float4*>(x + (q * rows_in + b * Tin_c + (c.i0 - in_off)) * 8);
+    const float4* p1 = reinterpret_cast<const float4*>(x + (q * rows_in + b * Tin_c + (c.i1 - in_off)) * 8);
     const float4 x0 = __ldg(p0), x1 = __ldg(p0 + 1), z0 = __ldg(p1), z1 = __ldg(p1 + 1);
     float v[8] = {lin_blend(x0.x, z0.x, c), lin_blend(x0.y, z0.y, c), lin_blend(x0.z, z0.z, c), lin_blend(x0.w, z0.w, c),
                   lin_blend(x1.x, z1.x, c), lin_blend(x1.y, z1.y, c), lin_blend(x1.z, z1.z, c), lin_blend(x1.w, z1.w, c)};
@@ -337,11 +341,36 @@ __global__ void __launch_bounds__(256) out_conv_k7_cl_kernel(const float* __rest
 }  // namespace
 
 int interp_cl(const float* x, int B, int Tin, int Tout, float scale, int C, float* y32, bf16* r_hi, bf16* r_lo, bf16* a_hi,
-              bf16* a_lo, cudaStream_t s, int a_pad) {
+              bf16* a_lo, cudaStream_t s, int a_pad, int Tin_c, int in_off, int out_off) {
     TVC_REQUIRE(C % 8 == 0, "interp_cl: channel count %d must be a multiple of 8", C);
-    const long long rows_in = (long long)B * Tin, rows_out = (long long)B * Tout;
+    if (Tin_c <= 0) Tin_c = Tin;
+    TVC_REQUIRE((Tin_c == Tin && in_off == 0 && out_off == 0) || a_pad == 0, "interp_cl: the windowed form has no stored padding");
+    const long long rows_in = (long long)B * Tin_c, rows_out = (long long)B * Tout;
     TVC_REQUIRE(rows_out < (1LL << 31) && rows_in < (1LL << 31), "interp_cl: too many rows");
-    TVC_LAUNCH_PDL(interp_cl_kernel, dim3(cdiv(rows_out, 256), C / 8), 256, 0, s, x, Tin, Tout, scale, rows_in, rows_out, y32, r_hi, r_lo, a_hi, a_lo, a_pad);
+    TVC_LAUNCH_PDL(interp_cl_kernel, dim3(cdiv(rows_out, 256), C / 8), 256, 0, s, x, Tin, Tout, scale, rows_in, rows_out, y32, r_hi, r_lo, a_hi, a_lo, a_pad,
+                   Tin_c, in_off, out_off);
+    TVC_LAUNCH_CHECK();
+    return 0;
+}
+
+// rows [t0, t0 + Tc) of every utterance of a chunk-major plane pair -> a compact pair with Tc rows per utterance
+__global__ void __launch_bounds__(256) slice_planes_cl_kernel(const bf16* __restrict__ s_hi, const bf16* __restrict__ s_lo,
+                                                              bf16* __restrict__ d_hi, bf16* __restrict__ d_lo, int T, int Tc, int t0,
+                                                              long long rows_in, long long rows_out) {
+    TVC_PDL_PROLOGUE();
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows_out) return;
+    const long long q = blockIdx.y;
+    const long long b = row / Tc;
+    const int r = (int)(row - b * Tc);
+    const long long si = (q * rows_in + b * T + t0 + r) * 8, di = (q * rows_out + row) * 8;
+    *reinterpret_cast<uint4*>(d_hi + di) = __ldg(reinterpret_cast<const uint4*>(s_hi + si));
+    *reinterpret_cast<uint4*>(d_lo + di) = __ldg(reinterpret_cast<const uint4*>(s_lo + si));
+}
+int slice_planes_cl(const bf16* s_hi, const bf16* s_lo, bf16* d_hi, bf16* d_lo, int B, int T, int C, int t0, int Tc, cudaStream_t s) {
+    TVC_REQUIRE(C % 8 == 0 && t0 >= 0 && Tc > 0 && t0 + Tc <= T, "slice_planes_cl: rows [%d, %d) of %d, %d channels", t0, t0 + Tc, T, C);
+    const long long rows_in = (long long)B * T, rows_out = (long long)B * Tc;
+    TVC_LAUNCH_PDL(slice_planes_cl_kernel, dim3(cdiv(rows_out, 256), C / 8), 256, 0, s, s_hi, s_lo, d_hi, d_lo, T, Tc, t0, rows_in, rows_out);
     TVC_LAUNCH_CHECK();
     return 0;
 }

@@ -7,8 +7,12 @@ namespace tvc {
 // tc_frame.cu
 // all channels-last tensors are chunk-major (tc_conv.cuh); row counts follow from B and T
 // a_pad > 0: the activation planes (a_hi / a_lo) are written with stored replicate padding (tc_conv.cuh, padded mode)
+// windowed form (output pruning): the output holds rows [out_off, out_off + Tout) of the full-length result, the input rows
+// [in_off, in_off + Tin_c) of the full-length (Tin rows) input; Tin_c <= 0: the plain full-length call
 int interp_cl(const float* x, int B, int Tin, int Tout, float scale, int C, float* y32, bf16* r_hi, bf16* r_lo, bf16* a_hi,
-              bf16* a_lo, cudaStream_t s, int a_pad = 0);
+              bf16* a_lo, cudaStream_t s, int a_pad = 0, int Tin_c = 0, int in_off = 0, int out_off = 0);
+// rows [t0, t0 + Tc) of every utterance of a plane pair (B * T rows, C channels of capacity) -> compact planes (B * Tc rows)
+int slice_planes_cl(const bf16* s_hi, const bf16* s_lo, bf16* d_hi, bf16* d_lo, int B, int T, int C, int t0, int Tc, cudaStream_t s);
 int dwconv_ln_cl(const float* x, const float* w7, const float* wb, const float* gamma, const float* beta,
                  bf16* hi, bf16* lo, int B, int T, cudaStream_t s);
 // general ConvNeXt front half: depth-wise k = 7 (dilation `dil`; w7 [7][C] repacked, nullptr = none) + LayerNorm over C

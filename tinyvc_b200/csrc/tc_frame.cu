@@ -216,52 +216,50 @@ __global__ void __launch_bounds__(256) cnxt_ln_cl_kernel(const float* __restrict
 // grn_apply_wide_cl: GRN (convnext.py:23-34) for any channel count (the Encoder's 768 / 256): one block per utterance,
 // a thread owns channels tid, tid + 256, ...; fixed summation order (deterministic).
 // ---------------------------------------------------------------------------------------------
-template <int PER>
-__global__ void __launch_bounds__(256) grn_apply_wide_cl_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
-                                                                const float* __restrict__ beta, bf16* __restrict__ hi,
-                                                                bf16* __restrict__ lo, int C, int T) {
+// One thread per channel (up to 1024 channels): a thread's two passes over its T rows are short chains of independent loads.
+__global__ void __launch_bounds__(1024) grn_apply_wide_cl_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, bf16* __restrict__ hi,
+                                                                 bf16* __restrict__ lo, int C, int T) {
     TVC_PDL_PROLOGUE();
-    __shared__ float part[8];
-    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ float part[32];
+    const int b = blockIdx.x, c = threadIdx.x, lane = c & 31, warp = c >> 5;
     const long long R = (long long)gridDim.x * T;
-    float g[PER];
-    float tot = 0.f;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        const int c = threadIdx.x + 256 * i;
-        g[i] = 0.f;
-        if (c < C) {
-            const long long base = cm((long long)b * T, c, R);
-            float s = 0.f;
-            for (int t = 0; t < T; ++t) {
-                const float v = __ldg(y + base + (long long)t * 8);
-                s = fmaf(v, v, s);
-            }
-            g[i] = sqrtf(s);
-            tot += g[i];
+    const long long base = cm((long long)b * T, c < C ? c : 0, R);
+    float s = 0.f;
+    if (c < C) {
+#pragma unroll 4
+        for (int t = 0; t < T; ++t) {
+            const float v = __ldg(y + base + (long long)t * 8);
+            s = fmaf(v, v, s);
         }
     }
+    const float g = sqrtf(s);
+    // the block total is formed in the order of the 256-thread version (thread tid summed its channels tid, tid + 256, tid + 512,
+    // then a shuffle tree per warp, then the eight warp sums in order), so the statistic keeps its bits
+    __shared__ float gs[1024];
+    gs[c] = c < C ? g : 0.f;
+    __syncthreads();
+    if (c < 256) {
+        float tot = 0.f;
+        for (int cc = c; cc < C; cc += 256) tot += gs[cc];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0) part[warp] = tot;
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (lane == 0) part[warp] = tot;
+    }
     __syncthreads();
     float all = 0.f;
     for (int i = 0; i < 8; ++i) all += part[i];
+    if (c >= C) return;
     const float denom = all / (float)C + 1e-6f;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        const int c = threadIdx.x + 256 * i;
-        if (c >= C) continue;
-        const long long base = cm((long long)b * T, c, R);
-        const float scale = fmaf(__ldg(gamma + c), g[i] / denom, 1.0f);
-        const float bt = __ldg(beta + c);
-        for (int t = 0; t < T; ++t) {
-            const long long o = base + (long long)t * 8;
-            bf16 h, l;
-            split_bf16(fmaf(__ldg(y + o), scale, bt), h, l);
-            hi[o] = h;
-            lo[o] = l;
-        }
+    const float scale = fmaf(__ldg(gamma + c), g / denom, 1.0f);
+    const float bt = __ldg(beta + c);
+#pragma unroll 4
+    for (int t = 0; t < T; ++t) {
+        const long long o = base + (long long)t * 8;
+        bf16 h, l;
+        split_bf16(fmaf(__ldg(y + o), scale, bt), h, l);
+        hi[o] = h;
+        lo[o] = l;
     }
 }
 
@@ -396,8 +394,8 @@ int cnxt_ln_cl(const float* x, const float* w7, const float* wb, const float* ga
 int grn_apply_cl(const float* y, const float* gamma, const float* beta, bf16* hi, bf16* lo, int B, int C, int T,
                  cudaStream_t s) {
     if (C > 256) {
-        TVC_REQUIRE(C <= 768, "grn_apply_cl: C=%d > 768", C);
-        TVC_LAUNCH_PDL(grn_apply_wide_cl_kernel<3>, B, 256, 0, s, y, gamma, beta, hi, lo, C, T);
+        TVC_REQUIRE(C <= 1024, "grn_apply_cl: C=%d > 1024", C);
+        TVC_LAUNCH_PDL(grn_apply_wide_cl_kernel, B, (C + 31) / 32 * 32, 0, s, y, gamma, beta, hi, lo, C, T);
         TVC_LAUNCH_CHECK();
         return 0;
     }

@@ -125,6 +125,14 @@ def test_tick_graph_replay_matches_eager_ticks(cuda_models, weights, pv):
         assert torch.equal(oa, ob), f"tick {tick}: max|d| = {float((oa - ob).abs().max()):.3e}"
         assert torch.equal(a.input_wav, b.input_wav) and torch.equal(a.sola_buffer, b.sola_buffer)
     assert a._graph is not None and b._graph is None
+    # eager ticks (an injected draw) and replayed ticks alternate on the same state
+    r = torch.rand(S, 961, 28, generator=gi).cuda()
+    oa = a.audio_callback(blocks[0].cuda(), rand01=r)
+    ob = b.audio_callback(blocks[0].cuda(), rand01=r)
+    assert torch.equal(oa, ob)
+    oa = a.audio_callback(blocks[1].cuda())
+    ob = b.audio_callback(blocks[1].cuda())
+    assert torch.equal(oa, ob) and torch.equal(a.input_wav, b.input_wav)
 
 
 @torch.inference_mode()

@@ -150,11 +150,11 @@ class BatchedStreamInfer:
             self._ticks += 1
             return self._tick_graph(blocks)
         self._ticks += 1
-        # stream.py:69-70: slide the window left by one block and append the new samples
-        nxt = torch.empty_like(self.input_wav)
-        nxt[:, : self.input_size - bs] = self.input_wav[:, bs:]
-        nxt[:, self.input_size - bs:] = blocks
-        self.input_wav = nxt
+        # stream.py:69-70: slide the window left by one block and append the new samples -- in place, like the graph path, so
+        # that eager and replayed ticks of one object can alternate (an injected rand01 takes this path) on the same state
+        keep_part = self.input_wav[:, bs:].clone()
+        self.input_wav[:, : self.input_size - bs] = keep_part
+        self.input_wav[:, self.input_size - bs:] = blocks
         out = torch.empty(S, bs, device=self.device, dtype=torch.float32)
         self._convert_and_sola(self.input_wav, out, rand01)
         self.last_shift = self._shift

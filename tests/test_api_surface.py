@@ -73,6 +73,30 @@ def test_no_cpu_fallback():
         match_features(torch.zeros(1, 768, 4), torch.zeros(1, 768, 16))
 
 
+def test_round2_host_logic_without_a_gpu():
+    """Host-side pieces of the round-2 additions: the resampler's length contract (torchaudio: ceil(new * L / orig)), its refusal of
+    CPU tensors, the sample range a streaming tick asks the decoder for (stream.py:75: y[-9600:-3840] of 13 440), and that
+    the keep= range is validated before anything is launched."""
+    import math
+    from tinyvc_b200 import _lib
+    from tinyvc_b200.infer import BatchedStreamInfer, StreamInfer
+    from tinyvc_b200.utils import resample
+    L = _lib.lib()
+    for n, o, nw in [(4410, 44100, 24000), (4801, 48000, 24000), (1777, 16000, 24000), (7, 32000, 24000), (100, 24000, 24000)]:
+        assert L.tvc_resample_length(n, o, nw) == math.ceil(nw * n / o)
+    assert L.tvc_resample_length(-1, 44100, 24000) == -1 and L.tvc_resample_length(10, 0, 24000) == -1
+    with pytest.raises(RuntimeError, match="CUDA"):
+        resample(torch.zeros(1, 100), 44100, 24000)
+    si = StreamInfer(None, device=torch.device("cuda"))
+    assert si.input_size == 13440 and si._keep_range() == (3840, 9600)
+    bs = BatchedStreamInfer(None, 4, block_size=960, extra_size=20000)     # window = block + extra, padded to whole frames
+    assert bs.input_size == 20960 and bs._keep_range() == (21120 - 960 - 1920 - 1920 - 3840, 21120 - 3840)
+    bs.prune_output = False
+    assert bs._keep_range() is None
+    with pytest.raises(RuntimeError):
+        BatchedStreamInfer(None, 2, device=torch.device("cpu")).init_buffer()
+
+
 def test_workspace_queries_are_monotone():
     from tinyvc_b200 import _lib
     L = _lib.lib()

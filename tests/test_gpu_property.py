@@ -63,3 +63,35 @@ def test_decoder_infer_matches_oracle_for_any_shape_and_voicing(cuda_models, wei
         alone = dec.infer(inp["content"][b:b + 1].cuda(), f0[b:b + 1].cuda(), inp["energy"][b:b + 1].cuda(),
                           rand01=inp["rand01"][b:b + 1].cuda())
         assert torch.equal(alone[0], out[b]), case
+
+
+@st.composite
+def keep_case(draw):
+    lf = draw(st.one_of(st.integers(1, 12), st.integers(13, 60), st.integers(61, 160)))
+    L = lf * 480
+    a = draw(st.integers(0, L - 1))
+    b = draw(st.integers(a + 1, L))
+    # bias towards short ranges in long utterances (where the levels below the block get pruned) and towards the two ends
+    kind = draw(st.sampled_from(["any", "short", "head", "tail"]))
+    if kind == "short":
+        b = min(L, a + draw(st.integers(1, 4000)))
+    elif kind == "head":
+        a = 0
+    elif kind == "tail":
+        b = L
+    return lf, draw(st.integers(1, 3)), draw(st.integers(0, 2**20)), a, b
+
+
+@settings(max_examples=25, deadline=None, derandomize=True,
+          suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(case=keep_case())
+def test_output_pruning_is_exact_for_any_range(cuda_models, case):
+    """Decoder.infer(keep=(t0, t1)) for arbitrary utterance lengths and ranges: the kept samples are the full run's bits (the
+    fused block walks only the windows that produce them; on long utterances the Upsample levels below it run on compact
+    tensors, nets_tc.cu)."""
+    lf, batch, seed, t0, t1 = case
+    _, dec = cuda_models
+    inp = {k: v.cuda() for k, v in synth.decoder_inputs(batch, lf, seed=seed).items()}
+    full = dec.infer(inp["content"], inp["f0"], inp["energy"], rand01=inp["rand01"]).clone()
+    part = dec.infer(inp["content"], inp["f0"], inp["energy"], rand01=inp["rand01"], keep=(t0, t1))
+    assert torch.equal(part[:, t0:t1], full[:, t0:t1]), (case, float((part[:, t0:t1] - full[:, t0:t1]).abs().max()))

@@ -441,7 +441,6 @@ def run_ours(args) -> None:
     dec = dec.to(dev)
     host = synth.decoder_inputs(BATCH, LF, seed=1234 + 2 + rank)     # every rank its own utterances
     inp = {k: v.to(dev) for k, v in host.items()}
-    pinned = {k: v.pin_memory() for k, v in host.items()}
     out_pinned = torch.empty(BATCH, LF * FRAME).pin_memory()
     samples = BATCH * LF * FRAME
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
@@ -453,13 +452,23 @@ def run_ours(args) -> None:
     def step():
         return dec.infer(inp["content"], inp["f0"], inp["energy"])
 
-    e2e_dev = {k: torch.empty_like(inp[k]) for k in ("content", "f0", "energy")}    # fixed device staging buffers
+    # e2e staging: the three inputs are views of ONE pinned host buffer and ONE device buffer, so a step's host -> device
+    # traffic is a single copy (three separate copies cost ~10 us of launch / completion overhead each on a ~1 ms step)
+    names = ("content", "f0", "energy")
+    sizes = [host[k].numel() for k in names]
+    offs = [sum(-(-n // 64) * 64 for n in sizes[:i]) for i in range(3)]            # 256-byte aligned views
+    total = offs[2] + sizes[2]
+    stage_host = torch.empty(total, dtype=torch.float32).pin_memory()
+    stage_dev = torch.empty(total, dtype=torch.float32, device=dev)
+    e2e_dev = {}
+    for k, o, n in zip(names, offs, sizes):
+        stage_host[o:o + n].copy_(host[k].reshape(-1))
+        e2e_dev[k] = stage_dev[o:o + n].view(host[k].shape)
 
     def step_e2e():
         # host -> device: the step's inputs from pinned memory; device -> host: the waveform goes straight into the pinned
         # result buffer (Decoder.infer(out=pinned): the last kernel stores over PCIe, no separate copy)
-        for k in ("content", "f0", "energy"):
-            e2e_dev[k].copy_(pinned[k], non_blocking=True)
+        stage_dev.copy_(stage_host, non_blocking=True)
         return dec.infer(e2e_dev["content"], e2e_dev["f0"], e2e_dev["energy"], out=out_pinned)
 
     for _ in range(max(args.warmup, 3)):
@@ -563,7 +572,7 @@ def run_ours(args) -> None:
                    "sample": f"{utts} of the {BATCH} utterances ({utts * LF * FRAME} samples), median of 5 after 1 warm-up, "
                              "oracle port of decoder.py on torch-CPU",
                    "value_1thread": rate1, "sample_1thread": f"4 utterances ({4 * LF * FRAME} samples), median of 2, 1 thread"}
-        h2d = sum(pinned[k].numel() * 4 for k in ("content", "f0", "energy"))
+        h2d = stage_host.numel() * 4                         # the one staged copy: content + f0 + energy (+ alignment gaps)
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

@@ -8,6 +8,7 @@
 //   out    = temp[shift : shift+block+cross];  out[:cross] = out[:cross]*fade_in + sola*fade_out  (:80,90-92)
 //   sola'  = out[-cross:] ; return out[:block]                                                   (:94-95)
 #include <cooperative_groups.h>
+#include <cstdint>
 
 #include "tvc_kernels.cuh"
 
@@ -163,8 +164,17 @@ __global__ void __cluster_dims__(kSolaCluster, 1, 1) __launch_bounds__(kSolaThre
     const int s = blockIdx.x / kSolaCluster;
     const int tl = block + cross + search;
     const float* ys = y + (long long)s * y_len + (y_len - tl - delay);
-    for (int i = threadIdx.x; i < tl; i += blockDim.x) temp[i] = ys[i];
-    for (int i = threadIdx.x; i < cross; i += blockDim.x) sola[i] = sola_buf[(long long)s * cross + i];
+    // 128 threads stage 30 KB: 16-byte loads, four in flight per thread (the loops below are latency chains otherwise)
+    const float* sb = sola_buf + (long long)s * cross;
+    if ((reinterpret_cast<uintptr_t>(ys) & 15) == 0 && (reinterpret_cast<uintptr_t>(sb) & 15) == 0 && tl % 4 == 0) {
+#pragma unroll 4
+        for (int i = threadIdx.x; i < tl / 4; i += blockDim.x) reinterpret_cast<float4*>(temp)[i] = __ldg(reinterpret_cast<const float4*>(ys) + i);
+#pragma unroll 4
+        for (int i = threadIdx.x; i < cross / 4; i += blockDim.x) reinterpret_cast<float4*>(sola)[i] = __ldg(reinterpret_cast<const float4*>(sb) + i);
+    } else {
+        for (int i = threadIdx.x; i < tl; i += blockDim.x) temp[i] = ys[i];
+        for (int i = threadIdx.x; i < cross; i += blockDim.x) sola[i] = sb[i];
+    }
     __syncthreads();
     float bv = -INFINITY;
     int bi = 0x7fffffff;
@@ -236,6 +246,7 @@ __global__ void __cluster_dims__(kSolaCluster, 1, 1) __launch_bounds__(kSolaThre
             pv_ab[((long long)s * 2 + 1) * cross + i] = temp[sh + i];
         }
     }
+#pragma unroll 4
     for (int i = threadIdx.x + (pv_ab ? cross : 0); i < block; i += blockDim.x) {
         float v = temp[sh + i];
         if (i < cross) {
@@ -245,6 +256,7 @@ __global__ void __cluster_dims__(kSolaCluster, 1, 1) __launch_bounds__(kSolaThre
         out_block[(long long)s * block + i] = v;
     }
     __syncthreads();   // every read of the old sola buffer is done
+#pragma unroll 4
     for (int i = threadIdx.x; i < cross; i += blockDim.x) {
         const int p = block + i;
         float v = temp[sh + p];

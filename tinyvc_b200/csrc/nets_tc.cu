@@ -84,6 +84,10 @@ int pack_named(const HostW& H, const std::string& prefix, int NT, TcConvW& out, 
 
 DecoderTC::~DecoderTC() {
     frame_in.free_all(); heads.free_all(); dft_cos.free_all(); dft_sin.free_all(); down0.free_all();
+    dft_cos_w.free_all(); dft_sin_w.free_all();
+    if (fork) cudaEventDestroy(fork);
+    if (join) cudaEventDestroy(join);
+    if (side) cudaStreamDestroy(side);
     for (auto& m : mid) { m.c2.free_all(); m.c3.free_all(); }
     for (auto& d : down) { d.c1.free_all(); d.c2.free_all(); d.c3.free_all(); }
     for (auto& u : up) { u.c1.free_all(); u.c2.free_all(); u.c3.free_all(); u.c4.free_all(); u.c5.free_all(); }
@@ -170,6 +174,11 @@ int DecoderTC::init(const WeightStore& store) {
             }
         TVC_TRY(tc_pack_conv(wc.data(), nullptr, kBins, kBins, 1, nullptr, nullptr, 0, 0, 64, dft_cos));
         TVC_TRY(tc_pack_conv(ws.data(), nullptr, kBins, kBins, 1, nullptr, nullptr, 0, 0, 64, dft_sin));
+        TVC_TRY(tc_pack_conv(wc.data(), nullptr, kBins, kBins, 1, nullptr, nullptr, 0, 0, 128, dft_cos_w));
+        TVC_TRY(tc_pack_conv(ws.data(), nullptr, kBins, kBins, 1, nullptr, nullptr, 0, 0, 128, dft_sin_w));
+        TVC_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        TVC_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        TVC_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
     }
     // ---- FilterNet
     TVC_TRY(pack_named(H, fn + ".downs.0", 24, down0));
@@ -222,6 +231,7 @@ bool g_fused_up = true;
 // tensor copy.  Short utterances (config 2: 36 / 108 / 432 rows at the three lowest rates) otherwise gather their clamped
 // windows row by row with cp.async, tap by tap.  0 = never.  Separate limits for the Downsample blocks (pads 1 / 2 / 4 rows:
 // the row count hardly grows) and the Upsample blocks (pads up to 27 rows: more row tiles re-stream the weights).
+bool g_idft_pair = true;      // tvc_set_option("idft_pair", "0"): the noise branch's two inverse-DFT products one after the other at every size
 bool g_prune_levels = true;   // tvc_set_option("prune_levels", "0"): output pruning stops at the fused block (the Upsample levels below it run in full)
 bool g_fuse_down = true;      // tvc_set_option("fuse_down", "0"): separate interp_cl launches in front of the Downsample blocks
 int g_pad_max_t = 0, g_pad_down_max_t = 512;     // same-box A/B (profiles/r02f_pad_ab.log): down 1.010 -> 1.004 ms, up 1.010 -> 1.032 ms
@@ -288,8 +298,25 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         }
         CONV("tc_heads(", heads, ConvCall(xp, B, Lf).f32(hk, kHeadsCs).epi(TC_ACT_ELU1));
         RUN(noise_spectrum_cl(hk, rand01, rng_state, yr.hi, yr.lo, yi.hi, yi.lo, kBinsCs, B, Lf, s));
-        CONV("tc_idft(", dft_cos, ConvCall(yr, B, Lf).f32(cc, kBinsCs));
-        CONV("tc_idft(", dft_sin, ConvCall(yi, B, Lf).f32(ss, kBinsCs));
+        // The cosine and sine products are independent.  On short batches each is one tile per CTA on fewer than half of the
+        // SMs when the channel tiles are 128 wide, so they run side by side: the sine product on a forked branch, both
+        // without programmatic dependent launch (a PDL successor would take the free SMs, tvc_common.cuh t_sm_cap).
+        const long long idft_tiles_w = ((rowsF + 127) / 128) * dft_cos_w.n_tiles;
+        if (g_idft_pair && !A.dry && side && 2 * idft_tiles_w <= 148) {
+            TVC_CUDA(cudaEventRecord(fork, s));
+            TVC_CUDA(cudaStreamWaitEvent(side, fork, 0));
+            const bool pdl_was = t_pdl_suppress;
+            t_pdl_suppress = true;
+            int rc = tc_conv_k("tc_idft(", dft_sin_w, ConvCall(yi, B, Lf).f32(ss, kBinsCs), side);
+            if (!rc) rc = cudaEventRecord(join, side) != cudaSuccess;
+            if (!rc) rc = tc_conv_k("tc_idft(", dft_cos_w, ConvCall(yr, B, Lf).f32(cc, kBinsCs), s);
+            t_pdl_suppress = pdl_was;
+            cudaStreamWaitEvent(s, join, 0);               // joined even after a failure: a capture must end on one stream
+            TVC_TRY(rc);
+        } else {
+            CONV("tc_idft(", dft_cos, ConvCall(yr, B, Lf).f32(cc, kBinsCs));
+            CONV("tc_idft(", dft_sin, ConvCall(yi, B, Lf).f32(ss, kBinsCs));
+        }
         RUN(noise_ola_cl(cc, ss, noise, B, Lf, s));
         RUN(harmonic_source_cl(f0, hk + cm(0, kAmpsOff, rowsF), noise, energy, src.hi, src.lo, osc, B, Lf, s));
         A.release(m);
@@ -568,13 +595,14 @@ int EncoderTC::forward(Arena& A, cudaStream_t s, const float* spec, float* z, fl
 void set_fused_up(bool on) { g_fused_up = on; }
 void set_fuse_down(bool on) { g_fuse_down = on; }
 void set_prune_levels(bool on) { g_prune_levels = on; }
+void set_idft_pair(bool on) { g_idft_pair = on; }
 bool fused_up() { return g_fused_up; }
 void set_pad_max_t(int up, int down) {
     if (up >= 0) g_pad_max_t = up > 2047 ? 2047 : up;
     if (down >= 0) g_pad_down_max_t = down > 2047 ? 2047 : down;
 }
 unsigned plan_options() {
-    return (g_fused_up ? 1u : 0u) | ((unsigned)g_pad_max_t << 1) | ((unsigned)g_pad_down_max_t << 12) | (g_fuse_down ? 1u << 23 : 0u) | (g_prune_levels ? 1u << 24 : 0u);
+    return (g_fused_up ? 1u : 0u) | ((unsigned)g_pad_max_t << 1) | ((unsigned)g_pad_down_max_t << 12) | (g_fuse_down ? 1u << 23 : 0u) | (g_prune_levels ? 1u << 24 : 0u) | (g_idft_pair ? 1u << 25 : 0u);
 }
 
 }  // namespace tvc

@@ -13,6 +13,9 @@ struct DecoderTC {
     } mid[3];
     TcConvW heads;                // 128 -> [kernel 961 | 7 pad | amps 15]
     TcConvW dft_cos, dft_sin;     // inverse real-DFT bases, 961 -> 961
+    TcConvW dft_cos_w, dft_sin_w; // the same with 128-wide channel tiles: on short batches the two products run side by side
+    cudaStream_t side = nullptr;  // branch for the sine product (forked from / joined to the caller's stream, also under capture)
+    cudaEvent_t fork = nullptr, join = nullptr;
     TcConvW down0;
     struct Down { TcConvW c1, c2, c3; } down[4];
     struct Up { TcConvW c1, c2, c3, c4, c5; } up[5];
@@ -55,6 +58,7 @@ struct EncoderTC {
 
 void set_fused_up(bool on);          // tvc_set_option("fused_up", "0"|"1"): fused 24-channel Upsample block (default on)
 bool fused_up();
+void set_idft_pair(bool on);         // tvc_set_option("idft_pair", "0"|"1"): the two inverse-DFT products side by side on short batches (default on)
 void set_prune_levels(bool on);      // tvc_set_option("prune_levels", "0"|"1"): output pruning below the fused block (default on)
 void set_fuse_down(bool on);         // tvc_set_option("fuse_down", "0"|"1"): Downsample resamplers inside the producing conv's epilogue (default on)
 // tvc_set_option("pad_up_max_t" | "pad_down_max_t", "N"): Upsample / Downsample blocks of levels whose utterances have

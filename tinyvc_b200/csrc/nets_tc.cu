@@ -87,6 +87,7 @@ DecoderTC::~DecoderTC() {
     dft_cos_w.free_all(); dft_sin_w.free_all();
     if (fork) cudaEventDestroy(fork);
     if (join) cudaEventDestroy(join);
+    if (scan_ev) cudaEventDestroy(scan_ev);
     if (side) cudaStreamDestroy(side);
     for (auto& m : mid) { m.c2.free_all(); m.c3.free_all(); }
     for (auto& d : down) { d.c1.free_all(); d.c2.free_all(); d.c3.free_all(); }
@@ -179,6 +180,7 @@ int DecoderTC::init(const WeightStore& store) {
         TVC_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
         TVC_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
         TVC_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+        TVC_CUDA(cudaEventCreateWithFlags(&scan_ev, cudaEventDisableTiming));
     }
     // ---- FilterNet
     TVC_TRY(pack_named(H, fn + ".downs.0", 24, down0));
@@ -268,6 +270,18 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
     float* lf0 = A.f32(rowsF);
     float* fx = A.f32(rowsF * 512);
     Pl src = planes(A, rowsL, 24);
+    // The oscillator's first two scan levels need f0 only: on short batches they run on the side branch from the start, beside
+    // the frame-rate input conv and the SourceNet (joined in front of the third level, harmonic_source_cl).
+    void* osc = A.bytes(osc_scratch_bytes(B, Lf));
+    ARENA_OK();
+    const bool scan_early = g_idft_pair && !A.dry && side && rowsF <= 8192;
+    if (scan_early) {
+        TVC_CUDA(cudaEventRecord(fork, s));
+        TVC_CUDA(cudaStreamWaitEvent(side, fork, 0));
+        const int rc = osc_phase_scan(f0, osc, B, Lf, side);
+        cudaEventRecord(scan_ev, side);                  // waited for in front of harmonic_source_cl (also after a failure:
+        if (rc) { cudaStreamWaitEvent(s, scan_ev, 0); return rc; }          // a capture must end with every branch joined)
+    }
     {
         const size_t m = A.mark();
         Pl cin = planes(A, rowsF, kFrameInCs);
@@ -287,7 +301,6 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         float* cc = A.f32(rowsF * kBinsCs);
         float* ss = A.f32(rowsF * kBinsCs);
         float* noise = A.f32(rowsL);
-        void* osc = A.bytes(osc_scratch_bytes(B, Lf));
         ARENA_OK();
         for (int i = 0; i < 3; ++i) {
             const Cnxt& c = mid[i];
@@ -318,7 +331,8 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
             CONV("tc_idft(", dft_sin, ConvCall(yi, B, Lf).f32(ss, kBinsCs));
         }
         RUN(noise_ola_cl(cc, ss, noise, B, Lf, s));
-        RUN(harmonic_source_cl(f0, hk + cm(0, kAmpsOff, rowsF), noise, energy, src.hi, src.lo, osc, B, Lf, s));
+        if (scan_early) TVC_CUDA(cudaStreamWaitEvent(s, scan_ev, 0));
+        RUN(harmonic_source_cl(f0, hk + cm(0, kAmpsOff, rowsF), noise, energy, src.hi, src.lo, osc, B, Lf, s, scan_early));
         A.release(m);
     }
     // ---- FilterNet down path (decoder.py:206-213,225-229): skips at L, L/5, L/20, L/80, L/240

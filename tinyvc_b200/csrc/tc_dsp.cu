@@ -334,17 +334,28 @@ int noise_ola_cl(const float* c, const float* sn, float* noise, int B, int Lf, c
 
 size_t osc_scratch_bytes(int B, int Lf) { return sizeof(double) * (size_t)B * Lf * kOsc; }
 
-int harmonic_source_cl(const float* f0, const float* amps, const float* noise, const float* energy,
-                       bf16* src_hi, bf16* src_lo, void* scratch, int B, int Lf, cudaStream_t s) {
+// the first two levels of the oscillator's scan (per-frame totals, per-utterance frame scan): they depend on f0 only, so the
+// plan may run them early on a side branch (harmonic_source_cl(..., scan_done = true) then starts at the third level)
+int osc_phase_scan(const float* f0, void* scratch, int B, int Lf, cudaStream_t s) {
     const int L = Lf * kFrame;
     const float scale_size = (float)Lf / (float)L;              // F.interpolate(size=L)
-    const float scale_factor = (float)(1.0 / (double)kFrame);   // F.interpolate(scale_factor=480)
     double* totals = (double*)scratch;
     dim3 grid(Lf, B);
     TVC_LAUNCH_PDL(osc_frame_sums_kernel, grid, kOsc * 32, 0, s, f0, totals, Lf, scale_size);
     TVC_LAUNCH_CHECK();
     TVC_LAUNCH_PDL(osc_scan_frames_kernel, B, kOsc * 32, 0, s, totals, Lf);
     TVC_LAUNCH_CHECK();
+    return 0;
+}
+
+int harmonic_source_cl(const float* f0, const float* amps, const float* noise, const float* energy,
+                       bf16* src_hi, bf16* src_lo, void* scratch, int B, int Lf, cudaStream_t s, bool scan_done) {
+    const int L = Lf * kFrame;
+    const float scale_size = (float)Lf / (float)L;              // F.interpolate(size=L)
+    const float scale_factor = (float)(1.0 / (double)kFrame);   // F.interpolate(scale_factor=480)
+    double* totals = (double*)scratch;
+    dim3 grid(Lf, B);
+    if (!scan_done) TVC_TRY(osc_phase_scan(f0, scratch, B, Lf, s));
     TVC_LAUNCH_PDL(osc_source_kernel, grid, kOsc * 32, 0, s, f0, totals, amps, noise, energy, src_hi, src_lo, Lf,
                                                scale_size, scale_factor);
     TVC_LAUNCH_CHECK();

@@ -32,6 +32,8 @@ int noise_ola_cl(const float* c, const float* sn, float* noise, int B, int Lf, c
 size_t osc_scratch_bytes(int B, int Lf);
 // amps: view on the 15 amplitude channels (chunk-major, B*Lf rows); src planes: 24 channels of capacity, B*L rows
 int harmonic_source_cl(const float* f0, const float* amps, const float* noise, const float* energy,
-                       bf16* src_hi, bf16* src_lo, void* scratch, int B, int Lf, cudaStream_t s);
+                       bf16* src_hi, bf16* src_lo, void* scratch, int B, int Lf, cudaStream_t s, bool scan_done = false);
+// levels one and two of the oscillator's phase scan alone (f0 only): may run ahead on another stream
+int osc_phase_scan(const float* f0, void* scratch, int B, int Lf, cudaStream_t s);
 
 }  // namespace tvc

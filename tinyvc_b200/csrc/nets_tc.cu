@@ -88,6 +88,7 @@ DecoderTC::~DecoderTC() {
     if (fork) cudaEventDestroy(fork);
     if (join) cudaEventDestroy(join);
     if (scan_ev) cudaEventDestroy(scan_ev);
+    if (up0_ev) cudaEventDestroy(up0_ev);
     if (side) cudaStreamDestroy(side);
     for (auto& m : mid) { m.c2.free_all(); m.c3.free_all(); }
     for (auto& d : down) { d.c1.free_all(); d.c2.free_all(); d.c3.free_all(); }
@@ -181,6 +182,7 @@ int DecoderTC::init(const WeightStore& store) {
         TVC_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
         TVC_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
         TVC_CUDA(cudaEventCreateWithFlags(&scan_ev, cudaEventDisableTiming));
+        TVC_CUDA(cudaEventCreateWithFlags(&up0_ev, cudaEventDisableTiming));
     }
     // ---- FilterNet
     TVC_TRY(pack_named(H, fn + ".downs.0", 24, down0));
@@ -290,6 +292,33 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         RUN(cf_to_planes(content, cin.hi, cin.lo, B, kContent, Lf, kFrameInCs, TC_ACT_NONE, s, e_fr, lf0));
         CONV("tc_frame_in(", frame_in, ConvCall(cin, B, Lf).f32(fx, 512));
         A.release(m);
+    }
+    // ---- head start for the first Upsample block (decoder.py:174-176): its x2 resampler and c1 read the frame-rate product
+    // only, not the down path.  On short batches they run on the side branch beside the SourceNet (whose kernels leave most SMs
+    // idle); the block joins in front of c2, the first layer that needs the skip tensor.
+    // (the buffers are reserved in sizing runs as well: they live from here to the block, on top of everything in between)
+    const bool up0_bufs = g_idft_pair && rowsF <= 8192 && kUpFac[0] * Lf < 384 && g_pad_max_t == 0;   // (< 384 rows: never a pruned level)
+    const bool up0_early = up0_bufs && scan_early;
+    float* xi_e = nullptr;
+    Pl p0_e, p1_e;
+    if (up0_bufs) {
+        const int t0r = kUpFac[0] * Lf;
+        xi_e = A.f32((long long)B * t0r * kUpCh[0]);
+        p0_e = planes(A, (long long)B * t0r, kUpCh[0]);
+        p1_e = planes(A, (long long)B * t0r, kUpCh[0]);
+        ARENA_OK();
+    }
+    if (up0_early) {
+        const int t0r = kUpFac[0] * Lf;
+        TVC_CUDA(cudaEventRecord(fork, s));
+        TVC_CUDA(cudaStreamWaitEvent(side, fork, 0));
+        const bool pdl_was = t_pdl_suppress;
+        t_pdl_suppress = true;
+        int rc = interp_cl(fx + cm(0, 128, rowsF), B, Lf, t0r, (float)(1.0 / (double)kUpFac[0]), kUpCh[0], xi_e, nullptr, nullptr, p0_e.hi, p0_e.lo, side, 0);
+        if (!rc) rc = tc_conv_k("tc_up0_c1(", up[0].c1, ConvCall(p0_e, B, t0r, 1).out(p1_e, TC_ACT_LRELU), side);
+        t_pdl_suppress = pdl_was;
+        cudaEventRecord(up0_ev, side);
+        if (rc) { cudaStreamWaitEvent(s, up0_ev, 0); return rc; }
     }
     // ---- SourceNet (decoder.py:126-134) + dsp (decoder.py:259-266)
     {
@@ -460,20 +489,23 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
             return 0;
         }
         TVC_REQUIRE(i < 4 || (tout == tfull && tin_c == tin), "filter_net: pruned levels need the fused block");
+        const bool early = up0_early && i == 0, ebuf = up0_bufs && i == 0;
         float* xo = A.f32(rows * cn);
         const size_t m = A.mark();
-        float* xi = A.f32(rows * c);
+        float* xi = ebuf ? xi_e : A.f32(rows * c);
         float* y = A.f32(rows * c);
         // stored replicate padding (see g_pad_max_t): p0 holds c1's input (1 row), later c3's (9); p1 c2's (3), later c4's (27)
         const bool windowed = tout != tfull || tin_c != tin;
         const bool pad = !fused && !windowed && tout <= g_pad_max_t;
         const int Q1 = pad ? 1 : 0, Q3 = pad ? 3 : 0, Q9 = pad ? 9 : 0, Q27 = pad ? 27 : 0;
-        Pl p0 = planes(A, (long long)B * (tout + 2 * Q9), c), p1 = planes(A, (long long)B * (tout + 2 * Q27), c);
+        Pl p0 = ebuf ? p0_e : planes(A, (long long)B * (tout + 2 * Q9), c), p1 = ebuf ? p1_e : planes(A, (long long)B * (tout + 2 * Q27), c);
         Pl cond = cond_full;
         if (tout != tfull || A.dry) cond = planes(A, rows, c);      // (sizing runs reserve the slice: a pruned call then never needs more than the full plan)
         ARENA_OK();
         const float scale = (float)(1.0 / (double)fac);           // F.interpolate(scale_factor=f)
-        if (windowed) {
+        if (early) {
+            TVC_CUDA(cudaStreamWaitEvent(s, up0_ev, 0));      // resampler and c1 ran on the side branch
+        } else if (windowed) {
             RUN(interp_cl(x, B, tin, tout, scale, c, xi, nullptr, nullptr, p0.hi, p0.lo, s, 0, tin_c, tin_off, wa[i]));
             if (tout != tfull) RUN(slice_planes_cl(cond_full.hi, cond_full.lo, cond.hi, cond.lo, B, tfull, c, wa[i], tout, s));
         } else {
@@ -484,7 +516,7 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
                                       {"tc_up2_c1(", "tc_up2_c2(", "tc_up2_c3(", "tc_up2_c4(", "tc_up2_c5("},
                                       {"tc_up3_c1(", "tc_up3_c2(", "tc_up3_c3(", "tc_up3_c4(", "tc_up3_c5("},
                                       {"tc_up4_c1(", "tc_up4_c2(", "tc_up4_c3(", "tc_up4_c4(", "tc_up4_c5("}};
-        CONV(un[i][0], u.c1, ConvCall(p0, B, tout, 1).pad(Q1, Q3).out(p1, TC_ACT_LRELU));
+        if (!early) CONV(un[i][0], u.c1, ConvCall(p0, B, tout, 1).pad(Q1, Q3).out(p1, TC_ACT_LRELU));
         CONV(un[i][1], u.c2, ConvCall(p1, B, tout, 3).pad(Q3, Q9).aux(cond).res(xi, c).f32(y, c).out(p0, TC_ACT_LRELU));
         CONV(un[i][2], u.c3, ConvCall(p0, B, tout, 9).pad(Q9, Q27).out(p1, TC_ACT_LRELU));
         CONV(un[i][3], u.c4, ConvCall(p1, B, tout, 27).pad(Q27, 0).aux(cond).res(y, c).out(p0, TC_ACT_NONE));

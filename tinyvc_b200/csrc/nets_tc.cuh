@@ -15,7 +15,7 @@ struct DecoderTC {
     TcConvW dft_cos, dft_sin;     // inverse real-DFT bases, 961 -> 961
     TcConvW dft_cos_w, dft_sin_w; // the same with 128-wide channel tiles: on short batches the two products run side by side
     cudaStream_t side = nullptr;  // branch for the sine product (forked from / joined to the caller's stream, also under capture)
-    cudaEvent_t fork = nullptr, join = nullptr, scan_ev = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, scan_ev = nullptr, up0_ev = nullptr;
     TcConvW down0;
     struct Down { TcConvW c1, c2, c3; } down[4];
     struct Up { TcConvW c1, c2, c3, c4, c5; } up[5];

@@ -93,6 +93,7 @@ DecoderTC::~DecoderTC() {
     for (auto& m : mid) { m.c2.free_all(); m.c3.free_all(); }
     for (auto& d : down) { d.c1.free_all(); d.c2.free_all(); d.c3.free_all(); }
     for (auto& u : up) { u.c1.free_all(); u.c2.free_all(); u.c3.free_all(); u.c4.free_all(); u.c5.free_all(); }
+    for (auto& u : up_w) { u.c1.free_all(); u.c2.free_all(); u.c3.free_all(); u.c4.free_all(); }
     up4_cat.c1.free_all(); up4_cat.c2.free_all(); up4_cat.c3.free_all(); up4_cat.c4.free_all(); up4_cat.c5.free_all();
     if (w7_buf) cudaFree(w7_buf);
     if (rng_state) cudaFree(rng_state);
@@ -199,6 +200,12 @@ int DecoderTC::init(const WeightStore& store) {
         TVC_TRY(pack_named(H, p + ".c3", kUpNT[i], up[i].c3));
         TVC_TRY(pack_named(H, p + ".c4", kUpNT[i], up[i].c4, p + ".film2", TC_AUX_FILM));
         TVC_TRY(pack_named(H, p + ".c5", kUpNT5[i], up[i].c5));
+        if (i < 2) {        // wide variants (up_w): same arithmetic per output channel, other tiling
+            TVC_TRY(pack_named(H, p + ".c1", 96, up_w[i].c1));
+            TVC_TRY(pack_named(H, p + ".c2", 80, up_w[i].c2, p + ".film1", TC_AUX_FILM));
+            TVC_TRY(pack_named(H, p + ".c3", 96, up_w[i].c3));
+            TVC_TRY(pack_named(H, p + ".c4", 80, up_w[i].c4, p + ".film2", TC_AUX_FILM));
+        }
         if (i == 4) {       // the fused block kernel's own images of the same convs ("cat" layout, tc_conv.cuh)
             TVC_TRY(pack_named(H, p + ".c1", kUpNT[i], up4_cat.c1, "", TC_AUX_NONE, true));
             TVC_TRY(pack_named(H, p + ".c2", kUpNT[i], up4_cat.c2, p + ".film1", TC_AUX_FILM, true));
@@ -235,6 +242,7 @@ bool g_fused_up = true;
 // tensor copy.  Short utterances (config 2: 36 / 108 / 432 rows at the three lowest rates) otherwise gather their clamped
 // windows row by row with cp.async, tap by tap.  0 = never.  Separate limits for the Downsample blocks (pads 1 / 2 / 4 rows:
 // the row count hardly grows) and the Upsample blocks (pads up to 27 rows: more row tiles re-stream the weights).
+bool g_wide_tiles = true;     // tvc_set_option("wide_tiles", "0"): always the narrow channel tiles of ups.0 / ups.1
 bool g_idft_pair = true;      // tvc_set_option("idft_pair", "0"): the noise branch's two inverse-DFT products one after the other at every size
 bool g_prune_levels = true;   // tvc_set_option("prune_levels", "0"): output pruning stops at the fused block (the Upsample levels below it run in full)
 bool g_fuse_down = true;      // tvc_set_option("fuse_down", "0"): separate interp_cl launches in front of the Downsample blocks
@@ -251,6 +259,21 @@ struct ConvCall {
     ConvCall& epi(int act) { a.epi_act = act; return *this; }
     ConvCall& pad(int in, int out) { a.a_pad = in; a.y_pad = out; return *this; }
 };
+// Narrow or wide image of the same conv for `rows` output rows: estimated time = waves x bytes a tile streams per K-stage (its
+// activation window, 128 + 2 dil rows, + its weight tile; the FiLM pair counts its second accumulator's weights).
+const TcConvW& pick_tiling(const TcConvW& narrow, const TcConvW& wide, long long rows, int dil) {
+    if (!g_wide_tiles || !wide.w) return narrow;
+    // many waves: the tile quantisation the wide tiles fix no longer matters, and their FiLM stages leave a two-deep ring
+    // (measured: 64 x 500 frames 16.51 -> 16.61 ms with wide tiles, a 128-stream tick 2.77 -> 2.65 ms)
+    if (((rows + 127) / 128) * narrow.n_tiles > 6 * 148) return narrow;
+    auto cost = [&](const TcConvW& W) {
+        const long long tiles = ((rows + 127) / 128) * W.n_tiles;
+        const long long waves = (tiles + 147) / 148;
+        const double a = 128.0 + 2.0 * dil, b = (W.aux_mode == TC_AUX_FILM ? 1.7 : 1.0) * W.NTp;
+        return (double)waves * (a + b);
+    };
+    return cost(wide) < cost(narrow) ? wide : narrow;
+}
 int tc_conv_k(const char* name, const TcConvW& W, const ConvCall& c, cudaStream_t s) {
     ProfScope ps(name, s);
     return tc_conv_launch(W, c.a, s);
@@ -516,10 +539,15 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
                                       {"tc_up2_c1(", "tc_up2_c2(", "tc_up2_c3(", "tc_up2_c4(", "tc_up2_c5("},
                                       {"tc_up3_c1(", "tc_up3_c2(", "tc_up3_c3(", "tc_up3_c4(", "tc_up3_c5("},
                                       {"tc_up4_c1(", "tc_up4_c2(", "tc_up4_c3(", "tc_up4_c4(", "tc_up4_c5("}};
-        if (!early) CONV(un[i][0], u.c1, ConvCall(p0, B, tout, 1).pad(Q1, Q3).out(p1, TC_ACT_LRELU));
-        CONV(un[i][1], u.c2, ConvCall(p1, B, tout, 3).pad(Q3, Q9).aux(cond).res(xi, c).f32(y, c).out(p0, TC_ACT_LRELU));
-        CONV(un[i][2], u.c3, ConvCall(p0, B, tout, 9).pad(Q9, Q27).out(p1, TC_ACT_LRELU));
-        CONV(un[i][3], u.c4, ConvCall(p1, B, tout, 27).pad(Q27, 0).aux(cond).res(y, c).out(p0, TC_ACT_NONE));
+        const bool has_w = i < 2 && !pad && !A.dry;
+        const TcConvW& w1 = has_w ? pick_tiling(u.c1, up_w[i].c1, rows, 1) : u.c1;
+        const TcConvW& w2 = has_w ? pick_tiling(u.c2, up_w[i].c2, rows, 3) : u.c2;
+        const TcConvW& w3 = has_w ? pick_tiling(u.c3, up_w[i].c3, rows, 9) : u.c3;
+        const TcConvW& w4 = has_w ? pick_tiling(u.c4, up_w[i].c4, rows, 27) : u.c4;
+        if (!early) CONV(un[i][0], w1, ConvCall(p0, B, tout, 1).pad(Q1, Q3).out(p1, TC_ACT_LRELU));
+        CONV(un[i][1], w2, ConvCall(p1, B, tout, 3).pad(Q3, Q9).aux(cond).res(xi, c).f32(y, c).out(p0, TC_ACT_LRELU));
+        CONV(un[i][2], w3, ConvCall(p0, B, tout, 9).pad(Q9, Q27).out(p1, TC_ACT_LRELU));
+        CONV(un[i][3], w4, ConvCall(p1, B, tout, 27).pad(Q27, 0).aux(cond).res(y, c).out(p0, TC_ACT_NONE));
         CONV(un[i][4], u.c5, ConvCall(p0, B, tout, 1).f32(xo, cn));
         A.release(m);
         x = xo; tin = tfull; tin_c = tout; tin_off = wa[i];
@@ -642,13 +670,14 @@ void set_fused_up(bool on) { g_fused_up = on; }
 void set_fuse_down(bool on) { g_fuse_down = on; }
 void set_prune_levels(bool on) { g_prune_levels = on; }
 void set_idft_pair(bool on) { g_idft_pair = on; }
+void set_wide_tiles(bool on) { g_wide_tiles = on; }
 bool fused_up() { return g_fused_up; }
 void set_pad_max_t(int up, int down) {
     if (up >= 0) g_pad_max_t = up > 2047 ? 2047 : up;
     if (down >= 0) g_pad_down_max_t = down > 2047 ? 2047 : down;
 }
 unsigned plan_options() {
-    return (g_fused_up ? 1u : 0u) | ((unsigned)g_pad_max_t << 1) | ((unsigned)g_pad_down_max_t << 12) | (g_fuse_down ? 1u << 23 : 0u) | (g_prune_levels ? 1u << 24 : 0u) | (g_idft_pair ? 1u << 25 : 0u);
+    return (g_fused_up ? 1u : 0u) | ((unsigned)g_pad_max_t << 1) | ((unsigned)g_pad_down_max_t << 12) | (g_fuse_down ? 1u << 23 : 0u) | (g_prune_levels ? 1u << 24 : 0u) | (g_idft_pair ? 1u << 25 : 0u) | (g_wide_tiles ? 1u << 26 : 0u);
 }
 
 }  // namespace tvc

@@ -20,6 +20,11 @@ struct DecoderTC {
     struct Down { TcConvW c1, c2, c3; } down[4];
     struct Up { TcConvW c1, c2, c3, c4, c5; } up[5];
     Up up4_cat;                   // ups.4 again as "cat" images for the fused block kernel
+    // Wider channel tiles of the 384- and 192-channel Upsample blocks (96 / 80 wide; FiLM layers need 3 x 2 accumulator columns per
+    // output channel in TMEM, so 80 is their limit).  Which image a launch uses is decided per batch: the narrow tiles give a
+    // short batch one tile per CTA, the wide ones cut the waves (and the re-streaming of the activation windows) of larger ones
+    // -- a streaming tick has 56 row tiles at L/240: 448 narrow tiles = 4 per CTA on 112 CTAs, 224 wide ones = 2 per CTA.
+    Up up_w[2];
     const float *out_w = nullptr, *out_b = nullptr;
     float* w7_buf = nullptr;      // depth-wise weights repacked [3][7][128]
     unsigned long long* rng_state = nullptr;   // device {seed, step} of the noise generator (used when no draw is injected)
@@ -58,6 +63,7 @@ struct EncoderTC {
 
 void set_fused_up(bool on);          // tvc_set_option("fused_up", "0"|"1"): fused 24-channel Upsample block (default on)
 bool fused_up();
+void set_wide_tiles(bool on);        // tvc_set_option("wide_tiles", "0"|"1"): per-batch choice between narrow and wide channel tiles of ups.0 / ups.1 (default on)
 void set_idft_pair(bool on);         // tvc_set_option("idft_pair", "0"|"1"): the two inverse-DFT products side by side on short batches (default on)
 void set_prune_levels(bool on);      // tvc_set_option("prune_levels", "0"|"1"): output pruning below the fused block (default on)
 void set_fuse_down(bool on);         // tvc_set_option("fuse_down", "0"|"1"): Downsample resamplers inside the producing conv's epilogue (default on)

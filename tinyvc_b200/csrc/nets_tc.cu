@@ -200,11 +200,13 @@ int DecoderTC::init(const WeightStore& store) {
         TVC_TRY(pack_named(H, p + ".c3", kUpNT[i], up[i].c3));
         TVC_TRY(pack_named(H, p + ".c4", kUpNT[i], up[i].c4, p + ".film2", TC_AUX_FILM));
         TVC_TRY(pack_named(H, p + ".c5", kUpNT5[i], up[i].c5));
-        if (i < 2) {        // wide variants (up_w): same arithmetic per output channel, other tiling
+        if (i < 3) {        // wide variants (up_w): same arithmetic per output channel, other tiling
             TVC_TRY(pack_named(H, p + ".c1", 96, up_w[i].c1));
-            TVC_TRY(pack_named(H, p + ".c2", 80, up_w[i].c2, p + ".film1", TC_AUX_FILM));
             TVC_TRY(pack_named(H, p + ".c3", 96, up_w[i].c3));
-            TVC_TRY(pack_named(H, p + ".c4", 80, up_w[i].c4, p + ".film2", TC_AUX_FILM));
+            if (i < 2) {
+                TVC_TRY(pack_named(H, p + ".c2", 80, up_w[i].c2, p + ".film1", TC_AUX_FILM));
+                TVC_TRY(pack_named(H, p + ".c4", 80, up_w[i].c4, p + ".film2", TC_AUX_FILM));
+            }
         }
         if (i == 4) {       // the fused block kernel's own images of the same convs ("cat" layout, tc_conv.cuh)
             TVC_TRY(pack_named(H, p + ".c1", kUpNT[i], up4_cat.c1, "", TC_AUX_NONE, true));
@@ -539,7 +541,7 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
                                       {"tc_up2_c1(", "tc_up2_c2(", "tc_up2_c3(", "tc_up2_c4(", "tc_up2_c5("},
                                       {"tc_up3_c1(", "tc_up3_c2(", "tc_up3_c3(", "tc_up3_c4(", "tc_up3_c5("},
                                       {"tc_up4_c1(", "tc_up4_c2(", "tc_up4_c3(", "tc_up4_c4(", "tc_up4_c5("}};
-        const bool has_w = i < 2 && !pad && !A.dry;
+        const bool has_w = i < 3 && !pad && !A.dry;
         const TcConvW& w1 = has_w ? pick_tiling(u.c1, up_w[i].c1, rows, 1) : u.c1;
         const TcConvW& w2 = has_w ? pick_tiling(u.c2, up_w[i].c2, rows, 3) : u.c2;
         const TcConvW& w3 = has_w ? pick_tiling(u.c3, up_w[i].c3, rows, 9) : u.c3;
@@ -563,8 +565,8 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
 EncoderTC::~EncoderTC() {
     in.free_all();
     for (Stack* st : {&ssl, &pitch}) {
-        st->out.free_all();
-        for (auto& b : st->mid) { b.c2.free_all(); b.c3.free_all(); }
+        st->out.free_all(); st->out_w.free_all();
+        for (auto& b : st->mid) { b.c2.free_all(); b.c2_w.free_all(); b.c3.free_all(); }
     }
     if (w7_buf) cudaFree(w7_buf);
 }
@@ -617,9 +619,11 @@ int EncoderTC::init(const WeightStore& store) {
             k.grn_g = store.raw(q + ".grn.gamma"); k.grn_b = store.raw(q + ".grn.beta");
             TVC_REQUIRE(k.wb && k.ln_g && k.ln_b && k.grn_g && k.grn_b, "tc encoder weights: incomplete %s", q.c_str());
             TVC_TRY(pack_named(H, q + ".c2", 128, k.c2));
+            if (d.C == 384) TVC_TRY(pack_named(H, q + ".c2", 192, k.c2_w));
             TVC_TRY(pack_named(H, q + ".c3", d.C == 384 ? 96 : 64, k.c3));
         }
         TVC_TRY(pack_named(H, p + ".output_layer", 128, st.out));
+        if (d.C == 384) TVC_TRY(pack_named(H, p + ".output_layer", 192, st.out_w));
     }
     TVC_CUDA(cudaMemcpy(w7_buf, w7.data(), sizeof(float) * w7_total, cudaMemcpyHostToDevice));
     ready = true;
@@ -654,11 +658,11 @@ int EncoderTC::forward(Arena& A, cudaStream_t s, const float* spec, float* z, fl
         RUN(cnxt_ln_cl(x, nullptr, nullptr, st.ln_g, st.ln_b, xp.hi, xp.lo, x, B, C, Lf, 1, s));       // encoder.py:29,86
         for (const Blk& b : st.mid) {              // convnext.py:49-58
             RUN(cnxt_ln_cl(x, b.w7, b.wb, b.ln_g, b.ln_b, t1.hi, t1.lo, nullptr, B, C, Lf, b.dil, s));
-            CONV("tc_enc_c2(", b.c2, ConvCall(t1, B, Lf).f32(t2, 2 * C).epi(TC_ACT_GELU));
+            CONV("tc_enc_c2(", A.dry ? b.c2 : pick_tiling(b.c2, b.c2_w, rows, 0), ConvCall(t1, B, Lf).f32(t2, 2 * C).epi(TC_ACT_GELU));
             RUN(grn_apply_cl(t2, b.grn_g, b.grn_b, t2p.hi, t2p.lo, B, 2 * C, Lf, s));
             CONV("tc_enc_c3(", b.c3, ConvCall(t2p, B, Lf).res(x, C).f32(x, C).out(xp, TC_ACT_NONE));
         }
-        CONV("tc_enc_out(", st.out, ConvCall(xp, B, Lf).f32(y, Cout));
+        CONV("tc_enc_out(", A.dry ? st.out : pick_tiling(st.out, st.out_w, rows, 0), ConvCall(xp, B, Lf).f32(y, Cout));
         RUN(cl_to_cf(y, outs[k], B, Cout, Lf, Cout, s));
         A.release(m);
     }

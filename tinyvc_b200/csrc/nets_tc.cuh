@@ -24,7 +24,7 @@ struct DecoderTC {
     // output channel in TMEM, so 80 is their limit).  Which image a launch uses is decided per batch: the narrow tiles give a
     // short batch one tile per CTA, the wide ones cut the waves (and the re-streaming of the activation windows) of larger ones
     // -- a streaming tick has 56 row tiles at L/240: 448 narrow tiles = 4 per CTA on 112 CTAs, 224 wide ones = 2 per CTA.
-    Up up_w[2];
+    Up up_w[3];                   // (ups.2: c1 / c3 only -- its FiLM layers cannot be wider than they are)
     const float *out_w = nullptr, *out_b = nullptr;
     float* w7_buf = nullptr;      // depth-wise weights repacked [3][7][128]
     unsigned long long* rng_state = nullptr;   // device {seed, step} of the noise generator (used when no draw is injected)
@@ -44,13 +44,14 @@ struct EncoderTC {
     struct Blk {
         const float *w7 = nullptr, *wb = nullptr, *ln_g = nullptr, *ln_b = nullptr, *grn_g = nullptr, *grn_b = nullptr;
         TcConvW c2, c3;
+        TcConvW c2_w;             // c2 again with 192-wide channel tiles (384-channel stack): one wave for a short batch
         int dil = 1;
     };
     struct Stack {
         int C = 0, c0 = 0;            // width, first channel inside the merged input product
         const float *ln_g = nullptr, *ln_b = nullptr;
         std::vector<Blk> mid;
-        TcConvW out;
+        TcConvW out, out_w;       // output layer (+ its 192-wide variant for the 384-channel stack)
     } ssl, pitch;
     TcConvW in;                   // both input layers as one product over the spectrogram: 961 -> [ssl 384 | pitch 128]
     float* w7_buf = nullptr;      // depth-wise weights repacked [7][C] per block

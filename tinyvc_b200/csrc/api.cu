@@ -217,7 +217,7 @@ int tvc_set_option(const char* key, const char* value) {
     if (!strcmp(key, "fused_up")) { set_fused_up(!strcmp(value, "1")); return 0; }
     if (!strcmp(key, "fuse_down")) { set_fuse_down(!strcmp(value, "1")); return 0; }
     if (!strcmp(key, "prune_levels")) { set_prune_levels(!strcmp(value, "1")); return 0; }
-    if (!strcmp(key, "idft_pair")) { set_idft_pair(!strcmp(value, "1")); return 0; }
+    if (!strcmp(key, "side_branch") || !strcmp(key, "idft_pair")) { set_side_branch(!strcmp(value, "1")); return 0; }   // (idft_pair: the name in the A/B logs)
     if (!strcmp(key, "wide_tiles")) { set_wide_tiles(!strcmp(value, "1")); return 0; }
     if (!strcmp(key, "pad_up_max_t")) { set_pad_max_t(atoi(value), -1); return 0; }
     if (!strcmp(key, "pad_down_max_t")) { set_pad_max_t(-1, atoi(value)); return 0; }

@@ -245,7 +245,8 @@ bool g_fused_up = true;
 // windows row by row with cp.async, tap by tap.  0 = never.  Separate limits for the Downsample blocks (pads 1 / 2 / 4 rows:
 // the row count hardly grows) and the Upsample blocks (pads up to 27 rows: more row tiles re-stream the weights).
 bool g_wide_tiles = true;     // tvc_set_option("wide_tiles", "0"): always the narrow channel tiles of ups.0 / ups.1
-bool g_idft_pair = true;      // tvc_set_option("idft_pair", "0"): the noise branch's two inverse-DFT products one after the other at every size
+bool g_side_branch = true;    // tvc_set_option("side_branch", "0"): no forked branch inside a decoder step (short batches otherwise run the two inverse-DFT
+                              // products side by side and give the oscillator's f0-only scan and ups.0's resampler + c1 a head start)
 bool g_prune_levels = true;   // tvc_set_option("prune_levels", "0"): output pruning stops at the fused block (the Upsample levels below it run in full)
 bool g_fuse_down = true;      // tvc_set_option("fuse_down", "0"): separate interp_cl launches in front of the Downsample blocks
 int g_pad_max_t = 0, g_pad_down_max_t = 512;     // same-box A/B (profiles/r02f_pad_ab.log): down 1.010 -> 1.004 ms, up 1.010 -> 1.032 ms
@@ -301,7 +302,7 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
     // the frame-rate input conv and the SourceNet (joined in front of the third level, harmonic_source_cl).
     void* osc = A.bytes(osc_scratch_bytes(B, Lf));
     ARENA_OK();
-    const bool scan_early = g_idft_pair && !A.dry && side && rowsF <= 8192;
+    const bool scan_early = g_side_branch && !A.dry && side && rowsF <= 8192;
     if (scan_early) {
         TVC_CUDA(cudaEventRecord(fork, s));
         TVC_CUDA(cudaStreamWaitEvent(side, fork, 0));
@@ -322,7 +323,7 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
     // only, not the down path.  On short batches they run on the side branch beside the SourceNet (whose kernels leave most SMs
     // idle); the block joins in front of c2, the first layer that needs the skip tensor.
     // (the buffers are reserved in sizing runs as well: they live from here to the block, on top of everything in between)
-    const bool up0_bufs = g_idft_pair && rowsF <= 8192 && kUpFac[0] * Lf < 384 && g_pad_max_t == 0;   // (< 384 rows: never a pruned level)
+    const bool up0_bufs = g_side_branch && rowsF <= 8192 && kUpFac[0] * Lf < 384 && g_pad_max_t == 0;   // (< 384 rows: never a pruned level)
     const bool up0_early = up0_bufs && scan_early;
     float* xi_e = nullptr;
     Pl p0_e, p1_e;
@@ -369,7 +370,7 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
         // SMs when the channel tiles are 128 wide, so they run side by side: the sine product on a forked branch, both
         // without programmatic dependent launch (a PDL successor would take the free SMs, tvc_common.cuh t_sm_cap).
         const long long idft_tiles_w = ((rowsF + 127) / 128) * dft_cos_w.n_tiles;
-        if (g_idft_pair && !A.dry && side && 2 * idft_tiles_w <= 148) {
+        if (g_side_branch && !A.dry && side && 2 * idft_tiles_w <= 148) {
             TVC_CUDA(cudaEventRecord(fork, s));
             TVC_CUDA(cudaStreamWaitEvent(side, fork, 0));
             const bool pdl_was = t_pdl_suppress;
@@ -673,7 +674,7 @@ int EncoderTC::forward(Arena& A, cudaStream_t s, const float* spec, float* z, fl
 void set_fused_up(bool on) { g_fused_up = on; }
 void set_fuse_down(bool on) { g_fuse_down = on; }
 void set_prune_levels(bool on) { g_prune_levels = on; }
-void set_idft_pair(bool on) { g_idft_pair = on; }
+void set_side_branch(bool on) { g_side_branch = on; }
 void set_wide_tiles(bool on) { g_wide_tiles = on; }
 bool fused_up() { return g_fused_up; }
 void set_pad_max_t(int up, int down) {
@@ -681,7 +682,7 @@ void set_pad_max_t(int up, int down) {
     if (down >= 0) g_pad_down_max_t = down > 2047 ? 2047 : down;
 }
 unsigned plan_options() {
-    return (g_fused_up ? 1u : 0u) | ((unsigned)g_pad_max_t << 1) | ((unsigned)g_pad_down_max_t << 12) | (g_fuse_down ? 1u << 23 : 0u) | (g_prune_levels ? 1u << 24 : 0u) | (g_idft_pair ? 1u << 25 : 0u) | (g_wide_tiles ? 1u << 26 : 0u);
+    return (g_fused_up ? 1u : 0u) | ((unsigned)g_pad_max_t << 1) | ((unsigned)g_pad_down_max_t << 12) | (g_fuse_down ? 1u << 23 : 0u) | (g_prune_levels ? 1u << 24 : 0u) | (g_side_branch ? 1u << 25 : 0u) | (g_wide_tiles ? 1u << 26 : 0u);
 }
 
 }  // namespace tvc

@@ -65,7 +65,7 @@ struct EncoderTC {
 void set_fused_up(bool on);          // tvc_set_option("fused_up", "0"|"1"): fused 24-channel Upsample block (default on)
 bool fused_up();
 void set_wide_tiles(bool on);        // tvc_set_option("wide_tiles", "0"|"1"): per-batch choice between narrow and wide channel tiles of ups.0 / ups.1 (default on)
-void set_idft_pair(bool on);         // tvc_set_option("idft_pair", "0"|"1"): the two inverse-DFT products side by side on short batches (default on)
+void set_side_branch(bool on);       // tvc_set_option("side_branch", "0"|"1"): forked branch inside a decoder step on short batches (default on)
 void set_prune_levels(bool on);      // tvc_set_option("prune_levels", "0"|"1"): output pruning below the fused block (default on)
 void set_fuse_down(bool on);         // tvc_set_option("fuse_down", "0"|"1"): Downsample resamplers inside the producing conv's epilogue (default on)
 // tvc_set_option("pad_up_max_t" | "pad_down_max_t", "N"): Upsample / Downsample blocks of levels whose utterances have

@@ -98,6 +98,11 @@ int tvc_decoder_infer_range(tvc_decoder_t h, const float* content, const float* 
                             const float* rand01, float* out, int B, int Lf, int64_t out_t0, int64_t out_t1,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* Test / planning aid (host arithmetic only, no GPU work): the rows [wa[i], wb[i]) of every utterance that Upsample level i of the
+ * FilterNet (i = 0 .. 4: rates L/240, L/80, L/20, L/5, L) works on when tvc_decoder_infer_range is asked for [out_t0, out_t1).
+ * Level 4 (the fused block) always reports its full length: it prunes by 426-sample windows itself.                        */
+int tvc_decoder_plan_windows(int Lf, int64_t out_t0, int64_t out_t1, int32_t* wa, int32_t* wb);
+
 /* Seed of the in-kernel noise draw (the role torch.manual_seed plays for decoder.py:78).      */
 int tvc_decoder_seed(tvc_decoder_t h, uint64_t seed, void* stream);
 

@@ -46,6 +46,7 @@ _SIGNATURES = {
     "tvc_decoder_workspace_bytes": (c_size_t, [c_int, c_int]),
     "tvc_decoder_infer_workspace_bytes": (c_size_t, [c_int, c_int]),
     "tvc_decoder_infer": (c_int, [c_void_p, _P, _P, _P, _P, _P, c_int, c_int, _P, c_size_t, c_void_p]),
+    "tvc_decoder_plan_windows": (c_int, [c_int, c_int64, c_int64, _P, _P]),
     "tvc_resample_length": (c_int64, [c_int64, c_int, c_int]),
     "tvc_resample": (c_int, [_P, _P, c_int, c_int64, c_int, c_int, c_void_p]),
     "tvc_decoder_infer_range": (c_int, [c_void_p, _P, _P, _P, _P, _P, c_int, c_int, c_int64, c_int64, _P, c_size_t, c_void_p]),

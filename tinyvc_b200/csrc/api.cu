@@ -463,6 +463,16 @@ int tvc_decoder_infer(tvc_decoder_t h, const float* content, const float* f0, co
                                    workspace_bytes, stream);
 }
 
+int tvc_decoder_plan_windows(int Lf, int64_t out_t0, int64_t out_t1, int32_t* wa, int32_t* wb) {
+    API_BEGIN
+    TVC_REQUIRE(wa && wb && Lf > 0 && out_t0 >= 0 && out_t0 < out_t1 && out_t1 <= (int64_t)Lf * kFrame, "tvc_decoder_plan_windows: bad arguments");
+    int a[5], b[5];
+    decoder_plan_windows(Lf, (int)out_t0, (int)out_t1, true, a, b);
+    for (int i = 0; i < 5; ++i) { wa[i] = a[i]; wb[i] = b[i]; }
+    return 0;
+    API_END
+}
+
 int tvc_decoder_seed(tvc_decoder_t h, uint64_t seed, void* stream) {
     API_BEGIN
     TVC_REQUIRE(h && h->m.tc && h->m.tc->rng_state, "tvc_decoder_seed: decoder has no tensor-core plan");

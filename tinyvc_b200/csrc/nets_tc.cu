@@ -287,6 +287,33 @@ int tc_conv_k(const char* name, const TcConvW& W, const ConvCall& c, cudaStream_
         if (!A.dry) TVC_TRY(tc_conv_k(name, W, call, s));     \
     } while (0)
 
+// Rows [wa[i], wb[i]) of every utterance that Upsample level i (0 .. 4, 4 = the fused full-rate block) has to produce when only
+// the output samples [out_t0, out_t1) are needed (out_t1 < 0: everything).  Level 4 is always "full" here (the block prunes by
+// windows itself); the levels below get the rows the level above reads, widened by 40 rows, or everything (see DecoderTC::infer).
+// Host arithmetic only: exported as tvc_decoder_plan_windows so that the CPU tests can check it against a brute-force
+// dependency trace.
+void decoder_plan_windows(int Lf, int out_t0, int out_t1, bool prune_enabled, int wa[5], int wb[5]) {
+    const int L = Lf * kFrame;
+    int Tlev[5];
+    int t = Lf;
+    for (int i = 0; i < 5; ++i) { t *= kUpFac[i]; Tlev[i] = t; wa[i] = 0; wb[i] = t; }
+    const bool prune = prune_enabled && out_t1 >= 0 && (out_t0 > 0 || out_t1 < L);
+    if (!prune) return;
+    // rows of x4 (= level 3's output) the walked windows of the block resample: window k covers block rows
+    // k * 426 - 44 .. k * 426 - 43 + 512 (tc_block.cu), clamped to the utterance
+    const int k_lo = out_t0 / 426, k_hi = (out_t1 - 1) / 426;
+    const int t_min = std::max(0, k_lo * 426 - 44), t_max = std::min(L - 1, k_hi * 426 - 43 + 512);
+    int na = std::max(0, t_min / 5 - 1), nb = std::min(Tlev[3], t_max / 5 + 2);        // needed rows of level 3
+    for (int i = 3; i >= 0; --i) {
+        const int ra = std::max(0, na - 40), rb = std::min(Tlev[i], nb + 40);
+        if ((rb - ra) * 100 > Tlev[i] * 85 || rb - ra < 384) break;                    // this level and all below: full
+        wa[i] = ra; wb[i] = rb;
+        const int f = kUpFac[i];
+        na = std::max(0, ra / f - 1);
+        nb = std::min(i > 0 ? Tlev[i - 1] : Lf, (rb - 1) / f + 2);
+    }
+}
+
 int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float* f0, const float* energy,
                      const float* rand01, float* out, int B, int Lf, int out_t0, int out_t1) const {
     const int L = Lf * kFrame;
@@ -465,27 +492,8 @@ int DecoderTC::infer(Arena& A, cudaStream_t s, const float* content, const float
     // convs treat the window as an utterance (their replicate padding at a cut edge is wrong but stays inside the 40-row
     // margin), so every kept output sample is computed from exactly the values of the full run.  Levels whose window is
     // nearly everything, or too short to keep the conv kernels in the same (halo) tiling as the full run, are not pruned.
-    int wa[5], wb[5], Tlev[5];
-    {
-        int t = Lf;
-        for (int i = 0; i < 5; ++i) { t *= kUpFac[i]; Tlev[i] = t; wa[i] = 0; wb[i] = t; }
-        const bool prune = g_fused_up && g_prune_levels && out_t1 >= 0 && (out_t0 > 0 || out_t1 < L);
-        if (prune) {
-            // rows of x4 (= level 3's output) the walked windows of the block resample: window k covers block rows
-            // k * 426 - 44 .. k * 426 - 43 + 512 (tc_block.cu), clamped to the utterance
-            const int k_lo = out_t0 / 426, k_hi = (out_t1 - 1) / 426;
-            const int t_min = std::max(0, k_lo * 426 - 44), t_max = std::min(L - 1, k_hi * 426 - 43 + 512);
-            int na = std::max(0, t_min / 5 - 1), nb = std::min(Tlev[3], t_max / 5 + 2);        // needed rows of level 3
-            for (int i = 3; i >= 0; --i) {
-                const int ra = std::max(0, na - 40), rb = std::min(Tlev[i], nb + 40);
-                if ((rb - ra) * 100 > Tlev[i] * 85 || rb - ra < 384) break;                    // this level and all below: full
-                wa[i] = ra; wb[i] = rb;
-                const int f = kUpFac[i];
-                na = std::max(0, ra / f - 1);
-                nb = std::min(i > 0 ? Tlev[i - 1] : Lf, (rb - 1) / f + 2);
-            }
-        }
-    }
+    int wa[5], wb[5];
+    decoder_plan_windows(Lf, out_t0, out_t1, g_fused_up && g_prune_levels, wa, wb);
     const float* x = fx + cm(0, 128, rowsF);      // FilterNet x0 = channels [128, 512) of the frame-rate product
     int tin = Lf, tin_c = Lf, tin_off = 0;        // full length of the level input, rows it holds per utterance, first of them
     for (int i = 0; i < 5; ++i) {

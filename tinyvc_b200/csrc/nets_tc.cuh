@@ -66,6 +66,8 @@ void set_fused_up(bool on);          // tvc_set_option("fused_up", "0"|"1"): fus
 bool fused_up();
 void set_wide_tiles(bool on);        // tvc_set_option("wide_tiles", "0"|"1"): per-batch choice between narrow and wide channel tiles of ups.0 / ups.1 (default on)
 void set_side_branch(bool on);       // tvc_set_option("side_branch", "0"|"1"): forked branch inside a decoder step on short batches (default on)
+// rows [wa[i], wb[i]) Upsample level i must produce for output samples [out_t0, out_t1) (nets_tc.cu; host arithmetic only)
+void decoder_plan_windows(int Lf, int out_t0, int out_t1, bool prune_enabled, int wa[5], int wb[5]);
 void set_prune_levels(bool on);      // tvc_set_option("prune_levels", "0"|"1"): output pruning below the fused block (default on)
 void set_fuse_down(bool on);         // tvc_set_option("fuse_down", "0"|"1"): Downsample resamplers inside the producing conv's epilogue (default on)
 // tvc_set_option("pad_up_max_t" | "pad_down_max_t", "N"): Upsample / Downsample blocks of levels whose utterances have
